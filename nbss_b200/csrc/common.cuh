@@ -1,0 +1,44 @@
+// common.cuh — status codes and small device helpers shared by all kernels of libnbss_b200.so.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+// Status codes returned by every extern "C" entry point (see include/nbss_b200.h):
+//   0 ok; < 0 argument / shape error; > 0 cudaError_t of the launch.
+#define NBSS_OK 0
+#define NBSS_ERR_SHAPE (-1)
+#define NBSS_ERR_NULL (-2)
+#define NBSS_ERR_UNSUPPORTED (-3)
+#define NBSS_ERR_WORKSPACE (-4)
+
+#define NBSS_LAUNCH_CHECK()                       \
+    do {                                          \
+        cudaError_t e__ = cudaGetLastError();     \
+        if (e__ != cudaSuccess) return (int)e__;  \
+    } while (0)
+
+namespace nbss {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// SiLU and its derivative (fp32, accurate exp: the parity budget is spent on 16-bit MMA operands, not here).
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return x * sigmoidf_(x); }
+__device__ __forceinline__ float silu_grad(float x) {
+    float s = sigmoidf_(x);
+    return s * (1.f + x * (1.f - s));
+}
+
+__device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+}  // namespace nbss

@@ -1,0 +1,352 @@
+"""CPU oracle for the NBSS SpatialNet hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference`` leg may import
+this module.  ``nbss_b200`` itself never does: the product path is CUDA only and fails loudly without its library.
+
+It is a functional restatement (explicit math on torch CPU tensors, fp32 or fp64) of the reference's algorithm for
+the path ``TrainModule.forward`` (SharedTrainer.py:104-132):
+
+    STFT.stft            models/io/stft.py:49-66      -> stft()
+    Norm.norm            models/io/norm.py:61-95      -> norm_frequency_online()
+    pack                 SharedTrainer.py:116-117     -> pack()
+    SpatialNet.forward   models/arch/SpatialNet.py:202-220 -> spatialnet_forward()
+      SpatialNetLayer    models/arch/SpatialNet.py:76-146  -> fconv(), full(), mhsa(), tconvffn()
+      LayerNorm/GroupNorm models/arch/base/norm.py:11-27,79-91
+      LinearGroup        models/arch/base/linear_group.py:29-34
+      nn.MultiheadAttention (torch: packed in-proj, q*dh^-0.5, softmax, out-proj)
+    unpack + Norm.inorm  SharedTrainer.py:121-128, models/io/norm.py:97-108 -> unpack_inorm()
+    STFT.istft           models/io/stft.py:68-97      -> istft()
+
+Parameters are passed as a flat ``dict`` using the reference's state_dict key names.  Everything is
+differentiable, so gradients come from ``torch.autograd`` on this restatement.
+
+PINNING: the reference has no tests or golden vectors for this path.  The oracle is pinned
+against outputs of the reference modules themselves, generated in the build container by
+``tests/golden/make_golden.py`` (imports /root/reference) and committed as ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` checks forward outputs and gradients, and additionally compares against the live
+reference when /root/reference is present.
+
+``opround`` (optional) emulates 16-bit MMA-operand rounding at exactly the points where the CUDA kernels feed
+tensor cores, for error budgeting; the default ``None`` is the exact fp32/fp64 algorithm.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+Params = Dict[str, Tensor]
+
+SMALL_CFG = dict(dim_input=12, dim_output=4, dim_squeeze=8, num_layers=8, num_freqs=129, encoder_kernel_size=5,
+                 dim_hidden=96, dim_ffn=192, num_heads=4, kernel_size=(5, 3), conv_groups=(8, 8))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# parameter shapes (printed from the live reference module) and a deterministic synthetic init
+# ----------------------------------------------------------------------------------------------------------------
+def param_shapes(cfg: dict) -> Dict[str, Tuple[int, ...]]:
+    H, Hf, Hs, F_, nl = cfg["dim_hidden"], cfg["dim_ffn"], cfg["dim_squeeze"], cfg["num_freqs"], cfg["num_layers"]
+    Cin, Cout, ek = cfg["dim_input"], cfg["dim_output"], cfg["encoder_kernel_size"]
+    kf, kt = cfg["kernel_size"]
+    gf, gt = cfg["conv_groups"]
+    s: Dict[str, Tuple[int, ...]] = {"encoder.weight": (H, Cin, ek), "encoder.bias": (H,)}
+    for i in range(nl):
+        p = f"layers.{i}."
+        for fc in ("fconv1", "fconv2"):
+            s[p + fc + ".0.weight"] = (H,)
+            s[p + fc + ".0.bias"] = (H,)
+            s[p + fc + ".1.weight"] = (H, H // gf, kf)
+            s[p + fc + ".1.bias"] = (H,)
+            s[p + fc + ".2.weight"] = (H,)
+        s[p + "norm_full.weight"] = (H,)
+        s[p + "norm_full.bias"] = (H,)
+        s[p + "squeeze.0.weight"] = (Hs, H, 1)
+        s[p + "squeeze.0.bias"] = (Hs,)
+        s[p + "full.weight"] = (Hs, F_, F_)  # one tensor shared by every layer (SpatialNet.py:192-195)
+        s[p + "full.bias"] = (Hs, F_)
+        s[p + "unsqueeze.0.weight"] = (H, Hs, 1)
+        s[p + "unsqueeze.0.bias"] = (H,)
+        s[p + "norm_mhsa.weight"] = (H,)
+        s[p + "norm_mhsa.bias"] = (H,)
+        s[p + "mhsa.in_proj_weight"] = (3 * H, H)
+        s[p + "mhsa.in_proj_bias"] = (3 * H,)
+        s[p + "mhsa.out_proj.weight"] = (H, H)
+        s[p + "mhsa.out_proj.bias"] = (H,)
+        s[p + "tconvffn.0.weight"] = (H,)
+        s[p + "tconvffn.0.bias"] = (H,)
+        s[p + "tconvffn.1.weight"] = (Hf, H, 1)
+        s[p + "tconvffn.1.bias"] = (Hf,)
+        for j in (3, 5, 8):
+            s[p + f"tconvffn.{j}.weight"] = (Hf, Hf // gt, kt)
+            s[p + f"tconvffn.{j}.bias"] = (Hf,)
+        s[p + "tconvffn.6.weight"] = (Hf,)
+        s[p + "tconvffn.6.bias"] = (Hf,)
+        s[p + "tconvffn.10.weight"] = (H, Hf, 1)
+        s[p + "tconvffn.10.bias"] = (H,)
+    s["decoder.weight"] = (Cout, H)
+    s["decoder.bias"] = (Cout,)
+    return s
+
+
+def synth_params(cfg: dict, seed: int, dtype=torch.float32) -> Params:
+    """Deterministic synthetic parameters (NOT the reference init): fan-in-scaled normals for weights, small normals
+    for biases, norm gains around 1, PReLU slopes around 0.25.  ``full.*`` is shared across layers like the
+    reference (same tensor object under every ``layers.i.full`` key)."""
+    g = torch.Generator().manual_seed(seed)
+    out: Params = {}
+    shared_full: Dict[str, Tensor] = {}
+    for name, shp in param_shapes(cfg).items():
+        leaf = name.split(".", 2)[-1] if name.startswith("layers.") else name
+        if leaf in ("full.weight", "full.bias"):
+            if leaf in shared_full:
+                out[name] = shared_full[leaf]
+                continue
+        is_norm_gain = name.endswith(".weight") and len(shp) == 1 and ".2.weight" not in name
+        if ".2.weight" in name and ("fconv1" in name or "fconv2" in name):  # PReLU slope
+            t = 0.25 + 0.05 * torch.randn(shp, generator=g)
+        elif is_norm_gain:
+            t = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        elif name.endswith(".bias"):
+            t = 0.05 * torch.randn(shp, generator=g)
+        else:
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            t = torch.randn(shp, generator=g) / math.sqrt(fan_in)
+        t = t.to(dtype)
+        out[name] = t
+        if leaf in ("full.weight", "full.bias"):
+            shared_full[leaf] = t
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# norms (models/arch/base/norm.py:11-27 LayerNorm, :79-91 GroupNorm; torch semantics: biased variance, eps in sqrt)
+# ----------------------------------------------------------------------------------------------------------------
+def layer_norm(x: Tensor, w: Tensor, b: Tensor, eps: float = 1e-5) -> Tensor:
+    mu = x.mean(dim=-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def group_norm_seq_last(x: Tensor, groups: int, w: Tensor, b: Tensor, eps: float = 1e-5) -> Tensor:
+    """x: [N, C, T]; statistics per (n, group) over (C/groups channels x T) — nn.GroupNorm."""
+    N, C, T = x.shape
+    xg = x.reshape(N, groups, (C // groups) * T)
+    mu = xg.mean(dim=-1, keepdim=True)
+    var = ((xg - mu) ** 2).mean(dim=-1, keepdim=True)
+    xn = ((xg - mu) / torch.sqrt(var + eps)).reshape(N, C, T)
+    return xn * w[None, :, None] + b[None, :, None]
+
+
+def _id(x: Tensor) -> Tensor:
+    return x
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# SpatialNetLayer pieces (models/arch/SpatialNet.py)
+# ----------------------------------------------------------------------------------------------------------------
+def fconv(x: Tensor, P: Params, pre: str, groups: int) -> Tensor:
+    """_fconv (SpatialNet.py:116-127) with modules :36-40: LN(H) -> grouped Conv1d along F ('same', zeros) ->
+    PReLU(H).  x: [B,F,T,H] -> branch output [B,F,T,H] (the residual add happens in the caller, :85,87)."""
+    B, F_, T, H = x.shape
+    h = layer_norm(x, P[pre + ".0.weight"], P[pre + ".0.bias"])  # LayerNorm(seq_last=True) == LN over H
+    h = h.permute(0, 2, 3, 1).reshape(B * T, H, F_)
+    w = P[pre + ".1.weight"]
+    h = F.conv1d(h, w, P[pre + ".1.bias"], padding=w.shape[-1] // 2, groups=groups)
+    a = P[pre + ".2.weight"][None, :, None]
+    h = torch.where(h >= 0, h, a * h)  # PReLU
+    return h.reshape(B, T, H, F_).permute(0, 3, 1, 2)
+
+
+def full(x: Tensor, P: Params, pre: str) -> Tensor:
+    """_full (SpatialNet.py:129-146): LN(H) -> 1x1 H->Hs + SiLU -> LinearGroup over F (linear_group.py:29-34) ->
+    1x1 Hs->H + SiLU."""
+    B, F_, T, H = x.shape
+    h = layer_norm(x, P[pre + "norm_full.weight"], P[pre + "norm_full.bias"])
+    h = h.permute(0, 2, 3, 1).reshape(B * T, H, F_)
+    h = F.silu(torch.einsum("nhf,sh->nsf", h, P[pre + "squeeze.0.weight"][:, :, 0]) + P[pre + "squeeze.0.bias"][None, :, None])
+    h = torch.einsum("ngf,gkf->ngk", h, P[pre + "full.weight"]) + P[pre + "full.bias"][None]
+    h = F.silu(torch.einsum("nsf,hs->nhf", h, P[pre + "unsqueeze.0.weight"][:, :, 0]) + P[pre + "unsqueeze.0.bias"][None, :, None])
+    return h.reshape(B, T, H, F_).permute(0, 3, 1, 2)
+
+
+def mhsa(x: Tensor, P: Params, pre: str, num_heads: int, opround: Callable[[Tensor], Tensor] = _id) -> Tensor:
+    """_tsa (SpatialNet.py:93-100): LN(H) -> nn.MultiheadAttention(batch_first) over T per (b,f); no mask, no
+    dropout.  torch semantics: q,k,v = x W_in^T + b_in; q *= dh^-0.5; softmax(q k^T) v; out_proj."""
+    B, F_, T, H = x.shape
+    dh = H // num_heads
+    h = layer_norm(x, P[pre + "norm_mhsa.weight"], P[pre + "norm_mhsa.bias"]).reshape(B * F_, T, H)
+    qkv = opround(h) @ opround(P[pre + "mhsa.in_proj_weight"]).t() + P[pre + "mhsa.in_proj_bias"]
+    q, k, v = qkv.split(H, dim=-1)
+
+    def heads(t):
+        return t.reshape(B * F_, T, num_heads, dh).permute(0, 2, 1, 3)
+
+    q, k, v = heads(q) * (dh ** -0.5), heads(k), heads(v)
+    s = opround(q) @ opround(k).transpose(-1, -2)
+    p = torch.softmax(s, dim=-1)
+    o = opround(p) @ opround(v)
+    o = o.permute(0, 2, 1, 3).reshape(B * F_, T, H)
+    y = opround(o) @ opround(P[pre + "mhsa.out_proj.weight"]).t() + P[pre + "mhsa.out_proj.bias"]
+    return y.reshape(B, F_, T, H)
+
+
+def tconvffn(x: Tensor, P: Params, pre: str, groups: int, opround: Callable[[Tensor], Tensor] = _id,
+             convround: Callable[[Tensor], Tensor] = _id) -> Tensor:
+    """_tconvffn (SpatialNet.py:102-114) with modules :61-73: LN(H) -> 1x1 H->Hf -> SiLU -> gconv3(T) -> SiLU ->
+    gconv3 -> GroupNorm(groups, Hf) -> SiLU -> gconv3 -> SiLU -> 1x1 Hf->H."""
+    B, F_, T, H = x.shape
+    t = pre + "tconvffn."
+    h = layer_norm(x, P[t + "0.weight"], P[t + "0.bias"]).reshape(B * F_, T, H)
+    h = opround(h) @ opround(P[t + "1.weight"][:, :, 0]).t() + P[t + "1.bias"]
+    h = F.silu(h).transpose(1, 2)  # [BF, Hf, T]
+
+    def gconv(z, j):
+        w = P[t + f"{j}.weight"]
+        return F.conv1d(convround(z), convround(w), P[t + f"{j}.bias"], padding=w.shape[-1] // 2, groups=groups)
+
+    h = F.silu(gconv(h, 3))
+    h = gconv(h, 5)
+    h = F.silu(group_norm_seq_last(h, groups, P[t + "6.weight"], P[t + "6.bias"]))
+    h = F.silu(gconv(h, 8))
+    h = h.transpose(1, 2)
+    y = opround(h) @ opround(P[t + "10.weight"][:, :, 0]).t() + P[t + "10.bias"]
+    return y.reshape(B, F_, T, H)
+
+
+def encoder(x: Tensor, P: Params) -> Tensor:
+    """SpatialNet.py:175,205: Conv1d(Cin->H, k, 'same') along T on [B*F, Cin, T]."""
+    B, F_, T, Cin = x.shape
+    w = P["encoder.weight"]
+    h = F.conv1d(x.reshape(B * F_, T, Cin).permute(0, 2, 1), w, P["encoder.bias"], padding=w.shape[-1] // 2)
+    return h.permute(0, 2, 1).reshape(B, F_, T, -1)
+
+
+def decoder(x: Tensor, P: Params) -> Tensor:
+    """SpatialNet.py:200,216: Linear(H -> Cout)."""
+    return x @ P["decoder.weight"].t() + P["decoder.bias"]
+
+
+def layer_forward(x: Tensor, P: Params, i: int, cfg: dict, opround=_id, convround=_id, taps: Optional[dict] = None) -> Tensor:
+    """SpatialNetLayer.forward (SpatialNet.py:76-91): five residual sub-blocks."""
+    pre = f"layers.{i}."
+    gf, gt = cfg["conv_groups"]
+    x = x + fconv(x, P, pre + "fconv1", gf)
+    if taps is not None: taps[f"l{i}.c1"] = x
+    x = x + full(x, P, pre)
+    if taps is not None: taps[f"l{i}.c2"] = x
+    x = x + fconv(x, P, pre + "fconv2", gf)
+    if taps is not None: taps[f"l{i}.c3"] = x
+    x = x + mhsa(x, P, pre, cfg["num_heads"], opround)
+    if taps is not None: taps[f"l{i}.n1"] = x
+    x = x + tconvffn(x, P, pre, gt, opround, convround)
+    if taps is not None: taps[f"l{i}.n2"] = x
+    return x
+
+
+def spatialnet_forward(P: Params, x: Tensor, cfg: dict, opround=_id, convround=_id, taps: Optional[dict] = None) -> Tensor:
+    """SpatialNet.forward (SpatialNet.py:202-220). x: [B,F,T,dim_input] -> [B,F,T,dim_output]."""
+    h = encoder(x, P)
+    if taps is not None: taps["enc"] = h
+    for i in range(cfg["num_layers"]):
+        h = layer_forward(h, P, i, cfg, opround, convround, taps)
+    return decoder(h, P).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# framing: STFT / Norm / pack / unpack / iSTFT
+# ----------------------------------------------------------------------------------------------------------------
+def hann_periodic(n: int, dtype=torch.float32) -> Tensor:
+    """torch.hann_window(n) (periodic): 0.5 - 0.5 cos(2 pi k / n)  (models/io/stft.py:30)."""
+    k = torch.arange(n, dtype=torch.float64)
+    return (0.5 - 0.5 * torch.cos(2 * math.pi * k / n)).to(dtype)
+
+
+def stft(x: Tensor, n_fft: int, n_hop: int) -> Tensor:
+    """STFT.stft (models/io/stft.py:49-66): torch.stft defaults — center=True with reflect padding n_fft//2,
+    periodic Hann, onesided, not normalised.  x: [..., Ts] -> complex [..., F=n_fft/2+1, T=1+Ts//n_hop]."""
+    shape = x.shape
+    w = hann_periodic(n_fft, x.dtype)
+    xp = F.pad(x.reshape(-1, 1, shape[-1]), (n_fft // 2, n_fft // 2), mode="reflect")[:, 0]
+    frames = xp.unfold(-1, n_fft, n_hop)  # [N, T, n_fft]
+    X = torch.fft.rfft(frames * w, dim=-1)  # [N, T, F]
+    return X.transpose(-1, -2).reshape(*shape[:-1], n_fft // 2 + 1, frames.shape[1])
+
+
+def norm_frequency_online(X: Tensor, ref_channel: int, eps: float = 1e-6) -> Tuple[Tensor, Tensor, Tensor]:
+    """Norm.norm, mode='frequency', online=True (models/io/norm.py:75-81,94): XrMM = |X_ref| + eps per T-F bin;
+    every channel divided by it.  X: [B,C,F,T] complex -> (X/XrMM, Xr [B,1,F,T], XrMM [B,1,F,T])."""
+    Xr = X[:, [ref_channel]].clone()
+    XrMM = torch.abs(Xr) + eps
+    return X / XrMM, Xr, XrMM
+
+
+def pack(X: Tensor) -> Tensor:
+    """SharedTrainer.py:116-117: [B,C,F,T] complex -> [B,F,T,2C] real, (c0.re, c0.im, c1.re, ...)."""
+    B, C, F_, T = X.shape
+    return torch.view_as_real(X.permute(0, 2, 3, 1).contiguous()).reshape(B, F_, T, 2 * C)
+
+
+def unpack_inorm(out: Tensor, XrMM: Tensor) -> Tensor:
+    """SharedTrainer.py:121-128 + Norm.inorm (norm.py:97-108): [B,F,T,2S] -> complex [B,S,F,T] * XrMM."""
+    B, F_, T, S2 = out.shape
+    o = out if out.dtype == torch.float64 else out.float()
+    Y = torch.view_as_complex(o.reshape(B, F_, T, S2 // 2, 2).contiguous())
+    return Y.permute(0, 3, 1, 2) * XrMM
+
+
+def istft(X: Tensor, n_fft: int, n_hop: int, length: int) -> Tensor:
+    """STFT.istft (models/io/stft.py:68-97) == torch.istft per item: irfft of each frame, multiply by the window,
+    overlap-add, divide by the overlap-added squared window, drop n_fft//2 samples at the start, keep `length`.
+    X: complex [..., F, T] -> [..., length]."""
+    shape = X.shape
+    Fq, T = shape[-2:]
+    rdt = torch.float64 if X.dtype == torch.complex128 else torch.float32
+    w = hann_periodic(n_fft, rdt)
+    fr = torch.fft.irfft(X.reshape(-1, Fq, T).transpose(-1, -2), n=n_fft, dim=-1) * w  # [N, T, n_fft]
+    N = fr.shape[0]
+    total = n_fft + n_hop * (T - 1)
+    y = torch.zeros(N, total, dtype=rdt)
+    env = torch.zeros(total, dtype=rdt)
+    for t in range(T):
+        y[:, t * n_hop:t * n_hop + n_fft] += fr[:, t]
+        env[t * n_hop:t * n_hop + n_fft] += w * w
+    start = n_fft // 2
+    y = y[:, start:start + length] / env[start:start + length]
+    return y.reshape(*shape[:-2], length)
+
+
+def io_forward(P: Params, x: Tensor, cfg: dict, n_fft: int = 256, n_hop: int = 128, ref_channel: int = 0,
+               opround=_id, convround=_id) -> Tensor:
+    """TrainModule.forward (SharedTrainer.py:104-132) for loss.mask is None (si-sdr): wave [B,C,Ts] -> [B,S,Ts]."""
+    X = stft(x, n_fft, n_hop)
+    Xn, _Xr, XrMM = norm_frequency_online(X, ref_channel)
+    out = spatialnet_forward(P, pack(Xn), cfg, opround, convround)
+    Y = unpack_inorm(out, XrMM)
+    return istft(Y, n_fft, n_hop, x.shape[-1])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# helpers for precision budgeting
+# ----------------------------------------------------------------------------------------------------------------
+def round_bf16(t: Tensor) -> Tensor:
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+def round_f16(t: Tensor) -> Tensor:
+    return t.to(torch.float16).to(t.dtype)
+
+
+def round_tf32(t: Tensor) -> Tensor:
+    """Truncate fp32 mantissa to 10 bits (what the tf32 tensor-core path reads)."""
+    i = t.float().contiguous().view(torch.int32) & ~0x1FFF
+    return i.view(torch.float32).to(t.dtype)
+
+
+def rel_l2(a: Tensor, b: Tensor) -> float:
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))

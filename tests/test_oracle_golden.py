@@ -1,0 +1,113 @@
+"""CPU: pins oracle/spatialnet_oracle.py against fixtures generated from the UNMODIFIED reference modules
+(tests/golden/make_golden.py), and against the live reference when /root/reference is importable."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import spatialnet_oracle as O
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TINY = dict(dim_input=4, dim_output=4, dim_squeeze=4, num_layers=2, num_freqs=17, encoder_kernel_size=5,
+            dim_hidden=32, dim_ffn=64, num_heads=4, kernel_size=(5, 3), conv_groups=(8, 8))
+CFG1 = dict(dim_input=4, dim_output=4, dim_squeeze=8, num_layers=8, num_freqs=65, encoder_kernel_size=5,
+            dim_hidden=96, dim_ffn=192, num_heads=4, kernel_size=(5, 3), conv_groups=(8, 8))
+
+
+def _leaf_params(P):
+    """requires_grad leaves; the shared full.* tensor stays ONE leaf under all its keys."""
+    seen, out = {}, {}
+    for k, v in P.items():
+        if id(v) not in seen:
+            seen[id(v)] = v.clone().requires_grad_(True)
+        out[k] = seen[id(v)]
+    return out
+
+
+def test_tiny_forward_backward_matches_reference():
+    z = np.load(os.path.join(G, "tiny_fwd_bwd.npz"))
+    P = _leaf_params(O.synth_params(TINY, seed=101))
+    x = torch.from_numpy(z["x"]).requires_grad_(True)
+    y = O.spatialnet_forward(P, x, TINY)
+    assert O.rel_l2(y.detach(), torch.from_numpy(z["y"])) < 2e-6
+    y.backward(torch.from_numpy(z["dy"]))
+    assert O.rel_l2(x.grad, torch.from_numpy(z["dx"])) < 1e-5
+    checked = 0
+    for k in z.files:
+        if not k.startswith("grad."):
+            continue
+        name = k[5:]
+        assert O.rel_l2(P[name].grad, torch.from_numpy(z[k])) < 2e-5, name
+        checked += 1
+    assert checked >= 60
+
+
+def test_cfg1_small_2ch_forward_and_grad_norms():
+    """BASELINE.json configs[0]: SpatialNet-small 2ch F=65 T=64 forward on CPU, batch=1."""
+    z = np.load(os.path.join(G, "cfg1_small_2ch_f65_t64.npz"))
+    P = _leaf_params(O.synth_params(CFG1, seed=102))
+    y = O.spatialnet_forward(P, torch.from_numpy(z["x"]), CFG1)
+    assert tuple(y.shape) == (1, 65, 64, 4)
+    assert O.rel_l2(y.detach(), torch.from_numpy(z["y"])) < 5e-6
+    y.backward(torch.from_numpy(z["dy"]))
+    for k in z.files:
+        if k.startswith("gnorm."):
+            got = float(P[k[6:]].grad.double().norm())
+            assert abs(got - float(z[k])) <= 1e-4 * float(z[k]) + 1e-12, k
+
+
+def test_small_6ch_f129_forward():
+    z = np.load(os.path.join(G, "small_6ch_f129_t12.npz"))
+    P = O.synth_params(O.SMALL_CFG, seed=103)
+    with torch.no_grad():
+        y = O.spatialnet_forward(P, torch.from_numpy(z["x"]), O.SMALL_CFG)
+    assert O.rel_l2(y, torch.from_numpy(z["y"])) < 5e-6
+
+
+def test_param_count_matches_published():
+    """1.2 M parameters for SpatialNet-small (images/model_size_and_flops.png; SURVEY.md §2.2: 1,191,092)."""
+    P = O.synth_params(O.SMALL_CFG, seed=0)
+    n = sum(v.numel() for v in {id(v): v for v in P.values()}.values())
+    assert n == 1_191_092
+
+
+def test_framing_matches_reference():
+    z = np.load(os.path.join(G, "framing.npz"))
+    wave = torch.from_numpy(z["wave"])
+    X = O.stft(wave, 32, 16)
+    Xg = torch.complex(torch.from_numpy(z["X_re"]), torch.from_numpy(z["X_im"]))
+    assert O.rel_l2(torch.view_as_real(X), torch.view_as_real(Xg)) < 2e-6
+    P = O.synth_params(TINY, seed=101)
+    with torch.no_grad():
+        yw = O.io_forward(P, wave, TINY, n_fft=32, n_hop=16)
+    assert O.rel_l2(yw, torch.from_numpy(z["y_wave"])) < 1e-5
+    # 8 kHz framing of configs/SpatialNet.yaml (n_fft 256, hop 128)
+    w8 = torch.from_numpy(z["wave8"])
+    X8 = O.stft(w8, 256, 128)
+    X8g = torch.complex(torch.from_numpy(z["X8_re"]), torch.from_numpy(z["X8_im"]))
+    assert O.rel_l2(torch.view_as_real(X8), torch.view_as_real(X8g)) < 2e-6
+    Xn, Xr, XrMM = O.norm_frequency_online(X8g, 0)  # norm applied to the reference's own STFT output
+    Xng = torch.complex(torch.from_numpy(z["Xn8_re"]), torch.from_numpy(z["Xn8_im"]))
+    assert O.rel_l2(torch.view_as_real(Xn), torch.view_as_real(Xng)) < 2e-6
+    assert O.rel_l2(XrMM, torch.from_numpy(z["XrMM8"])) < 1e-6
+    rt = O.istft(X8, 256, 128, w8.shape[-1])
+    assert O.rel_l2(rt, torch.from_numpy(z["rt8"])) < 2e-6
+    assert O.rel_l2(rt, w8) < 1e-5  # STFT -> iSTFT round trip (models/io/stft.py:106-113)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="live reference only in the build container")
+def test_live_reference_layer_taps():
+    sys.path.insert(0, "/root/reference")
+    from models.arch.SpatialNet import SpatialNet
+    P = O.synth_params(TINY, seed=7)
+    m = SpatialNet(**TINY)
+    m.load_state_dict({k: v.clone() for k, v in P.items()}, strict=True)
+    x = torch.randn(1, 17, 9, 4, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        assert O.rel_l2(O.spatialnet_forward(P, x, TINY), m(x)) < 2e-6
+        h = O.encoder(x, P)
+        ref_layer = m.layers[1]
+        setattr(ref_layer, "need_weights", False)
+        assert O.rel_l2(O.layer_forward(h, P, 1, TINY), ref_layer(h)[0]) < 2e-6

@@ -1,0 +1,111 @@
+/* nbss_b200.h — C ABI of libnbss_b200.so: the B200 (sm_100a) SpatialNet hot path of Audio-WestlakeU/NBSS.
+ *
+ * The reference has no FFI: its hot path is a Python nn.Module injection point (TrainModule.__init__(arch, stft, norm),
+ * SharedTrainer.py:38-63, populated from configs/SpatialNet.yaml:11-43).  This library is what the drop-in modules in
+ * nbss_b200/{spatialnet,io}.py bind with ctypes; INTEGRATION.md shows the reference-side change (three class_path lines).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller (PyTorch's allocator); the library never allocates, frees or
+ *     synchronises; `stream` is a cudaStream_t passed as void*; every call only enqueues work on that stream.
+ *   - return value: 0 ok; < 0 argument error (-1 shape, -2 null pointer, -3 unsupported configuration, -4 workspace);
+ *     > 0 the cudaError_t of the launch.  Nothing throws.
+ *   - tensor-core kernels take `int* err`: a device int that is set to 0x7001 if an mbarrier wait timed out (bug guard).
+ *   - stream tensor: fp32 [B,F,T,96] (H contiguous); "slab" = one (b,f) pair = T x 96 contiguous floats; nslab = B*F.
+ *   - fmt / fmt_g / fmt_a: 16-bit tensor-core operand format, 0 = fp16, 1 = bf16.
+ *   - parameter pointers use the reference's state_dict tensors unchanged, fp32 contiguous.
+ *   - every *_bwd / *_wgrad entry ACCUMULATES (+=, fp32 atomics) into the parameter-gradient buffers it is given.
+ */
+#ifndef NBSS_B200_H
+#define NBSS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- weight images (pack.cu): UMMA B-operand tiles of one SpatialNetLayer's narrow-band weights ------------------- */
+unsigned int nbss_layer_image_bytes(void);
+/* w1 = tconvffn.1.weight [192,96,1], wc{1,2,3} = tconvffn.{3,5,8}.weight [192,24,3], w2 = tconvffn.10.weight [96,192,1],
+ * w_in = mhsa.in_proj_weight [288,96], w_out = mhsa.out_proj.weight [96,96]  (models/arch/SpatialNet.py:58,61-73) */
+int nbss_pack_layer_weights(const float* w1, const float* wc1, const float* wc2, const float* wc3, const float* w2,
+                            const float* w_in, const float* w_out, void* img, int fwd_fmt, int bwd_fmt, void* stream);
+
+/* ---- narrow-band block, forward (tcgen05) -------------------------------------------------------------------------- */
+/* y = x + MHSA(LN(x)) over T per (b,f): SpatialNetLayer._tsa + residual, models/arch/SpatialNet.py:88-89,93-100.
+ * save_* (nullable): fp16 (scaled q|k|v) [n,288], fp16 O [n,96], log2-domain logsumexp [nslab,4,T], LN (mean,rstd) [n,2]. */
+int nbss_mhsa_fwd(const float* x, float* y, int nslab, int T, const float* ln_w, const float* ln_b, const float* b_in,
+                  const float* b_out, const void* layer_img, void* save_qkv, void* save_o, float* save_lse,
+                  float* ln_stats, int fmt, int* err, void* stream);
+/* y = x + tconvffn(x): SpatialNetLayer._tconvffn + residual, models/arch/SpatialNet.py:90,102-114 (modules :61-73).
+ * save_* (nullable): fp16 pre-activations a1,c1,c2,c3 [n,192]; gn_stats [nslab,8,2]; ln_stats [n,2]. */
+int nbss_ffn_fwd(const float* x, float* y, int nslab, int T, const float* ln_w, const float* ln_b, const float* b1,
+                 const float* bc1, const float* bc2, const float* bc3, const float* gn_w, const float* gn_b,
+                 const float* b2, const void* layer_img, void* save_a1, void* save_c1, void* save_c2, void* save_c3,
+                 float* gn_stats, float* ln_stats, int fmt, int* err, void* stream);
+
+/* ---- narrow-band block, backward (tcgen05); autograd of the above -------------------------------- */
+int nbss_ffn_bwd(const float* x, const float* dy, float* dx, int nslab, int T, const float* ln_w, const float* gn_w,
+                 const float* gn_b, const float* ln_stats, const float* gn_stats, const void* layer_img, const void* a1,
+                 const void* c1, const void* c2, const void* c3, void* g_a1, void* g_c1, void* g_c2, void* g_c3, void* s1,
+                 void* s2, void* s3, void* s4, float* d_lnw, float* d_lnb, float* d_gnw, float* d_gnb, int fmt, int* err,
+                 void* stream);
+int nbss_ffn_wgrad(const float* x, const float* dy, int nslab, int T, const float* ln_w, const float* ln_b,
+                   const void* g_a1, const void* g_c1, const void* g_c2, const void* g_c3, const void* s1, const void* s2,
+                   const void* s3, const void* s4, float* dW1, float* db1, float* dWc1, float* dbc1, float* dWc2,
+                   float* dbc2, float* dWc3, float* dbc3, float* dW2, float* db2, int fmt_g, int fmt_a, int* err,
+                   void* stream);
+int nbss_mhsa_bwd(const float* x, const float* dy, float* dx, int nslab, int T, const float* ln_w, const float* ln_stats,
+                  const void* layer_img, const void* qkv, const void* o, const float* lse, void* dqkv, float* d_lnw,
+                  float* d_lnb, int fmt_g, int* err, void* stream);
+int nbss_mhsa_wgrad(const float* x, const float* dy, int nslab, int T, const float* ln_w, const float* ln_b,
+                    const void* dqkv, const void* o, float* dWin, float* dbin, float* dWo, float* dbo, int fmt_g,
+                    int fmt_a, int* err, void* stream);
+
+/* ---- cross-band block, fp32 (models/arch/SpatialNet.py:85-87,116-146; base/linear_group.py:29-34) ------------------ */
+/* y = x + PReLU(gconv_F(LN(x))): _fconv with modules :36-40 / :49-53.  W [96,12,5]. */
+int nbss_fconv_fwd(const float* x, float* y, int B, int F, int T, const float* lnw, const float* lnb, const float* W,
+                   const float* bias, const float* slope, void* stream);
+int nbss_fconv_bwd(const float* x, const float* dy, float* dx, int B, int F, int T, const float* lnw, const float* lnb,
+                   const float* W, const float* bias, const float* slope, float* dW, float* dbias, float* dslope,
+                   float* dlnw, float* dlnb, void* stream);
+/* y = x + unsqueeze(full(squeeze(LN(x)))): _full :129-146.  s_out,u_out: [B,T,8,F] (kept for backward). */
+int nbss_full_fwd(const float* x, float* y, float* s_out, float* u_out, int B, int F, int T, const float* lnw,
+                  const float* lnb, const float* Wsq, const float* bsq, const float* Wf, const float* bf, const float* Wun,
+                  const float* bun, void* stream);
+/* ws: workspace of 2*B*T*8*F floats. */
+int nbss_full_bwd(const float* x, const float* dy, float* dx, const float* s, const float* u, float* ws, int B, int F, int T,
+                  const float* lnw, const float* lnb, const float* Wsq, const float* bsq, const float* Wf, const float* Wun,
+                  const float* bun, float* dlnw, float* dlnb, float* dWsq, float* dbsq, float* dWf, float* dbf, float* dWun,
+                  float* dbun, void* stream);
+
+/* ---- encoder / decoder, fp32 (models/arch/SpatialNet.py:175,205 and :200,216) --------------------------------------- */
+int nbss_encoder_fwd(const float* x, float* y, int nslab, int T, int cin, const float* W, const float* bias, void* stream);
+int nbss_encoder_wgrad(const float* x, const float* dy, int nslab, int T, int cin, float* dW, float* dbias, void* stream);
+int nbss_decoder_fwd(const float* x, float* y, long long n, int cout, const float* W, const float* bias, void* stream);
+int nbss_decoder_bwd(const float* x, const float* dy, float* dx, long long n, int cout, const float* W, float* dW,
+                     float* dbias, void* stream);
+
+/* ---- framing (models/io/stft.py:49-97, models/io/norm.py:61-108, SharedTrainer.py:113-131) ------------------------- */
+/* STFT of x [B,C,Ts] (center, reflect, periodic Hann, onesided).  Output element (b,c,f,t): re at out + b*ob + c*oc +
+ * f*of + t*ot (floats), im at +1 — so the same kernel writes complex [B,C,F,T] or the packed network input [B,F,T,2C].
+ * normalize != 0 fuses Norm(mode='frequency', online=True): XrMM = |X[ref]| + eps -> xrmm [B,F,T]; xr (nullable). */
+int nbss_stft(const float* x, int B, int C, int Ts, int n_fft, int hop, int normalize, int ref_channel, float eps,
+              float* out, long long ob, long long oc, long long of, long long ot, float* xrmm, float* xr, void* stream);
+/* iSTFT (window, overlap-add, envelope division, centre trim) of a complex tensor given by float strides (b,s,f,t);
+ * scale (nullable) [B,F,T] multiplies every speaker's bin first (Norm.inorm).  y [B,S,Ts]. */
+int nbss_istft(const float* in, long long ib, long long is, long long if_, long long it, const float* scale, float* y,
+               int B, int S, int Ts, int T, int n_fft, int hop, void* stream);
+int nbss_istft_bwd(const float* dy, const float* scale, float* din, long long ib, long long is, long long if_, long long it,
+                   int B, int S, int Ts, int T, int n_fft, int hop, void* stream);
+int nbss_norm_freq_online(float* X, int B, int C, long long FT, int ref_channel, float eps, float* xrmm, float* xr,
+                          void* stream);
+int nbss_inorm(const float* X, float* Y, int B, int S, long long FT, const float* xrmm, void* stream);
+
+/* ---- test hook: one-CTA tcgen05 GEMM that pins the descriptor conventions (tests/test_umma_selftest.py) ------------- */
+int nbss_umma_selftest(const float* A, int a_rows, int a_feats, const float* B, int b_rows, int b_feats, float* D, int N,
+                       int Kdim, int a_mn, int b_mn, int fmt, int a_shift, int b_shift, int a_off, int b_off, int passes,
+                       int tmem_col, int fmt_b, int* err, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBSS_B200_H */

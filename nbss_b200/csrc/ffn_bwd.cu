@@ -1,0 +1,374 @@
+// ffn_bwd.cu — backward (data gradient) of the narrow-band T-ConvFFN sub-block, one CTA per (b,f) slab, tcgen05.
+//
+// Mirrors ffn_fwd.cu in reverse with transposed weight images (layout.cuh: W2T, WC{3,2,1}T, W1T).  Inputs: block input
+// x, upstream gradient dy, the fp16 pre-activations a1,c1,c2,c3 saved by ffn_fwd, GroupNorm / LayerNorm statistics.
+//   B0 stage dy -> 16-bit tile G                      E1 g(c3) = D * SiLU'(c3)              -> G
+//   B1 d s4 = dy  W2        (K=96,  N=192)            E2 GroupNorm backward (block sums)    -> G
+//   B2 d s3 = conv3^T(g c3) (row-shifted views)       E3 g(c1) = D * SiLU'(c1)              -> G
+//   B3 d s2 = conv2^T(g c2)                           E4 g(a1) = D * SiLU'(a1)              -> G
+//   B4 d s1 = conv1^T(g c1)                           E5 LayerNorm backward, dx = dy + ...
+//   B5 d ln = g(a1) W1      (K=192, N=96)
+// Every E-phase also streams out, for the weight-gradient kernels (wgrad.cu), the gradient operand g(.) and the
+// recomputed activation operand s(.) = SiLU(.) as 16-bit [n,192] tensors.  Column sums needed for the affine
+// parameters of LN / GN are formed with warp transposing reductions and accumulated in shared memory.
+#include "slab.cuh"
+
+namespace nbss {
+
+struct FfnBwdArgs {
+    const float* x;
+    const float* dy;
+    float* dx;
+    int nslab, T;
+    const float *ln_w, *gn_w, *gn_b;
+    const float* ln_stats;  // [n,2]
+    const float* gn_stats;  // [nslab,8,2]
+    const unsigned char* img;
+    const unsigned char *a1, *c1, *c2, *c3;   // fp16 [n,192]
+    unsigned char *g_a1, *g_c1, *g_c2, *g_c3;  // 16-bit (FMT) [n,192] gradients wrt the pre-activations
+    unsigned char *s1, *s2, *s3, *s4;          // 16-bit (FMT) [n,192] activations SiLU(.) (wgrad operands)
+    float *d_lnw, *d_lnb, *d_gnw, *d_gnb;      // accumulated with atomics
+    int* err;
+};
+
+constexpr uint32_t FB_HBUF = 0;
+constexpr uint32_t FB_WS0 = 24 * kCS;
+constexpr uint32_t FB_WS1 = FB_WS0 + IMG_WC_BYTES;
+constexpr uint32_t FB_CST = FB_WS1 + IMG_WC_BYTES;  // ln_w 96, gn_w 192, gn_b 192
+constexpr uint32_t FB_ACC = FB_CST + 480 * 4;       // column-sum accumulators: d_gnw 192, d_gnb 192, d_lnw 96, d_lnb 96
+constexpr uint32_t FB_RED = FB_ACC + 576 * 4;       // [8 warps][8 groups][2] + group totals [8][2]
+constexpr uint32_t FB_BAR = FB_RED + (128 + 16) * 4;
+constexpr uint32_t FB_SMEM = FB_BAR + 64;
+
+__device__ __forceinline__ void load_h16x32(const unsigned char* base, size_t row, int c0, float* v) {
+    const uint4* p = reinterpret_cast<const uint4*>(base + (row * kHF + c0) * 2);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const uint4 q = __ldg(p + cc);
+        unpack_f16x2(q.x, v[8 * cc + 0], v[8 * cc + 1]);
+        unpack_f16x2(q.y, v[8 * cc + 2], v[8 * cc + 3]);
+        unpack_f16x2(q.z, v[8 * cc + 4], v[8 * cc + 5]);
+        unpack_f16x2(q.w, v[8 * cc + 6], v[8 * cc + 7]);
+    }
+}
+__device__ __forceinline__ void load_h16x8(const unsigned char* base, size_t row, int c, float* v) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(base + (row * kHF + c) * 2));
+    unpack_f16x2(q.x, v[0], v[1]);
+    unpack_f16x2(q.y, v[2], v[3]);
+    unpack_f16x2(q.z, v[4], v[5]);
+    unpack_f16x2(q.w, v[6], v[7]);
+}
+template <int FMT>
+__device__ __forceinline__ void store16x32(unsigned char* base, size_t row, int c0, const float* v) {
+    uint4* p = reinterpret_cast<uint4*>(base + (row * kHF + c0) * 2);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) p[cc] = pack8<FMT>(v + 8 * cc);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* hbuf = smem + FB_HBUF;
+    unsigned char* ws0 = smem + FB_WS0;
+    unsigned char* ws1 = smem + FB_WS1;
+    float* cst = reinterpret_cast<float*>(smem + FB_CST);
+    float *s_lng = cst, *s_gng = cst + 96, *s_gnb = cst + 288;
+    float* acc = reinterpret_cast<float*>(smem + FB_ACC);  // [0,192) d_gnw, [192,384) d_gnb, [384,480) d_lnw, [480,576) d_lnb
+    float* red = reinterpret_cast<float*>(smem + FB_RED);
+    float* gtot = red + 128;  // [8][2] group totals S1, S2
+    uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + FB_BAR);
+    uint64_t* bar_w0 = bar_mma + 1;
+    uint64_t* bar_w1 = bar_mma + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 3);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = a.T;
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_w0, 1);
+        mbar_init(bar_w1, 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < 96; i += 256) s_lng[i] = a.ln_w[i];
+    for (int i = tid; i < 192; i += 256) { s_gng[i] = a.gn_w[i]; s_gnb[i] = a.gn_b[i]; }
+    for (int i = tid; i < 576; i += 256) acc[i] = 0.f;
+    for (int i = tid; i < (int)(24 * kCS / 16); i += 256) reinterpret_cast<uint4*>(hbuf)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int m = warp >> 2, q = warp & 3;
+    const int t = 128 * m + 32 * q + lane;
+    const bool valid = t < T;
+    const uint32_t tacc = tmem + ((uint32_t)(32 * q) << 16) + m * 192;
+    unsigned char* hrow = hbuf + (t + 1) * 16;
+    const uint32_t hb = smem_u32(hbuf), w0a = smem_u32(ws0), w1a = smem_u32(ws1);
+    const uint32_t id192 = make_idesc(FMT, 128, 192, 0, 0), id48 = make_idesc(FMT, 128, 48, 0, 0),
+                   id96 = make_idesc(FMT, 128, 96, 0, 0);
+    uint32_t ph_mma = 0, ph_w0 = 0, ph_w1 = 0;
+    const float inv_n = 1.f / (float)(kGC * T);
+
+    auto wait_mma = [&]() {
+        __syncwarp();
+        mbar_wait(bar_mma, ph_mma, a.err);
+        ph_mma ^= 1;
+        tc_fence_after();
+    };
+    // transposed conv: d_in[t] = sum_tap g[t - (tap-1)] Wt_tap  ->  A rows start at 128*mm + 2 - tap (frame t = row t+1)
+    auto convT_phase = [&](uint32_t wsa, uint64_t* bar_w, uint32_t& ph_w) {
+        if (tid == 0) {
+            tc_fence_after();
+            mbar_wait(bar_w, ph_w, a.err);
+            for (int mm = 0; mm < 2; ++mm)
+                for (int p = 0; p < kPairs; ++p)
+                    for (int tap = 0; tap < 3; ++tap)
+                        mma_kk(tmem + mm * 192 + p * 48, hb + 6 * p * kCS + (128 * mm + 2 - tap) * 16, kCS,
+                               wsa + (p * 3 + tap) * 6 * 768, 768, 3, id48, tap > 0);
+            umma_commit(bar_mma);
+        }
+        ph_w ^= 1;
+        wait_mma();
+    };
+    auto end_epilogue = [&]() {
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+    };
+    // g = D * SiLU'(c), s = SiLU(c): the three plain activation epilogues
+    auto silu_epilogue = [&](const unsigned char* csave, unsigned char* gout, unsigned char* sout, size_t grow) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < kHF; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tacc + c0, r);
+            tmem_ld_wait();
+            float c[32], g[32];
+            if (valid) load_h16x32(csave, grow, c0, c);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float cv = valid ? c[j] : 0.f;
+                const float sg = sigmoidf_(cv);
+                g[j] = valid ? __uint_as_float(r[j]) * sg * (1.f + cv * (1.f - sg)) : 0.f;
+                c[j] = cv * sg;
+            }
+            if (valid) {
+                store16x32<FMT>(sout, grow, c0, c);
+                store16x32<FMT>(gout, grow, c0, g);
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(hrow + (c0 / 8 + cc) * kCS) = pack8<FMT>(g + 8 * cc);
+        }
+    };
+
+    for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
+        const size_t grow = (size_t)slab * T + t;
+        const float* dys = a.dy + (size_t)slab * T * kH;
+        if (tid == 0) {
+            load_image(ws0, a.img + IMG_W2T, IMG_W1_BYTES, bar_w0);
+            load_image(ws1, a.img + IMG_WC3T, IMG_WC_BYTES, bar_w1);
+        }
+        // ---- B0: dy -> G (chunks 0..11)
+        stage_rows96<FMT, false>(dys, T, hbuf, 1, nullptr, nullptr, warp, lane);
+        end_epilogue();
+        // ---- B1: d s4 = dy W2
+        if (tid == 0) {
+            tc_fence_after();
+            mbar_wait(bar_w0, ph_w0, a.err);
+            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 192 * 16, 6, id192, 0);
+            umma_commit(bar_mma);
+        }
+        ph_w0 ^= 1;
+        wait_mma();
+        if (tid == 0) load_image(ws0, a.img + IMG_WC2T, IMG_WC_BYTES, bar_w0);
+        silu_epilogue(a.c3, a.g_c3, a.s4, grow);
+        end_epilogue();
+        // ---- B2: d s3 = conv3^T(g c3) ; E2: GroupNorm + SiLU backward
+        convT_phase(w1a, bar_w1, ph_w1);
+        if (tid == 0) load_image(ws1, a.img + IMG_WC1T, IMG_WC_BYTES, bar_w1);
+        {
+            const float* gst = a.gn_stats + (size_t)slab * 16;
+            // pass A: s3 out, dn -> G tile, group sums S1 = sum dn*gamma, S2 = sum dn*gamma*xhat
+#pragma unroll 1
+            for (int g = 0; g < kGroups; ++g) {
+                const float mean = gst[2 * g], rstd = gst[2 * g + 1];
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int c = kGC * g + 8 * k;
+                    uint32_t r[8];
+                    tmem_ld8(tacc + c, r);
+                    tmem_ld_wait();
+                    float cv[8], dn[8];
+                    if (valid) load_h16x8(a.c2, grow, c, cv);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float xh = valid ? (cv[j] - mean) * rstd : 0.f;
+                        const float n = xh * s_gng[c + j] + s_gnb[c + j];
+                        const float sg = sigmoidf_(n);
+                        dn[j] = valid ? __uint_as_float(r[j]) * sg * (1.f + n * (1.f - sg)) : 0.f;
+                        cv[j] = n * sg;  // s3
+                        const float dxh = dn[j] * s_gng[c + j];
+                        s1 += dxh;
+                        s2 += dxh * xh;
+                    }
+                    if (valid) *reinterpret_cast<uint4*>(a.s3 + (grow * kHF + c) * 2) = pack8<FMT>(cv);
+                    *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = pack8<FMT>(dn);
+                }
+                s1 = warp_sum(s1);
+                s2 = warp_sum(s2);
+                if (lane == 0) { red[(warp * 8 + g) * 2] = s1; red[(warp * 8 + g) * 2 + 1] = s2; }
+            }
+            __syncthreads();
+            if (tid < 16) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) s += red[(w * 8 + (tid >> 1)) * 2 + (tid & 1)];
+                gtot[tid] = s * inv_n;
+            }
+            __syncthreads();
+            // pass B: g(c2) = rstd * (dn*gamma - S1/N - xhat*S2/N) -> G tile + global; column sums for d_gnw, d_gnb
+#pragma unroll 1
+            for (int c0 = 0; c0 < kHF; c0 += 32) {
+                float dnv[32], dnx[32], gv[32];
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c = c0 + 8 * cc, g = c / kGC;
+                    const float mean = gst[2 * g], rstd = gst[2 * g + 1], m1 = gtot[2 * g], m2 = gtot[2 * g + 1];
+                    float cv[8];
+                    if (valid) load_h16x8(a.c2, grow, c, cv);
+                    const uint4 pk = *reinterpret_cast<const uint4*>(hrow + (c / 8) * kCS);
+                    float dn[8];
+                    unpack16<FMT>(pk.x, dn[0], dn[1]);
+                    unpack16<FMT>(pk.y, dn[2], dn[3]);
+                    unpack16<FMT>(pk.z, dn[4], dn[5]);
+                    unpack16<FMT>(pk.w, dn[6], dn[7]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float xh = valid ? (cv[j] - mean) * rstd : 0.f;
+                        dnv[8 * cc + j] = dn[j];
+                        dnx[8 * cc + j] = dn[j] * xh;
+                        gv[8 * cc + j] = valid ? rstd * (dn[j] * s_gng[c + j] - m1 - xh * m2) : 0.f;
+                    }
+                }
+                if (valid) store16x32<FMT>(a.g_c2, grow, c0, gv);
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(hrow + (c0 / 8 + cc) * kCS) = pack8<FMT>(gv + 8 * cc);
+                const float sw = warp_colsum32(dnx, lane), sb = warp_colsum32(dnv, lane);
+                atomicAdd(acc + c0 + lane, sw);
+                atomicAdd(acc + 192 + c0 + lane, sb);
+            }
+        }
+        end_epilogue();
+        // ---- B3: d s2 = conv2^T(g c2)
+        convT_phase(w0a, bar_w0, ph_w0);
+        if (tid == 0) load_image(ws0, a.img + IMG_W1T, IMG_W2_BYTES, bar_w0);
+        silu_epilogue(a.c1, a.g_c1, a.s2, grow);
+        end_epilogue();
+        // ---- B4: d s1 = conv1^T(g c1)
+        convT_phase(w1a, bar_w1, ph_w1);
+        silu_epilogue(a.a1, a.g_a1, a.s1, grow);
+        end_epilogue();
+        // ---- B5: d ln = g(a1) W1 ; E5: LayerNorm backward + residual
+        if (tid == 0) {
+            tc_fence_after();
+            mbar_wait(bar_w0, ph_w0, a.err);
+            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 96 * 16, 12, id96, 0);
+            umma_commit(bar_mma);
+        }
+        ph_w0 ^= 1;
+        wait_mma();
+        {
+            const float2 st = valid ? __ldg(reinterpret_cast<const float2*>(a.ln_stats + 2 * grow)) : make_float2(0.f, 0.f);
+            const float* xr = a.x + grow * kH;
+            float m1 = 0.f, m2 = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kH; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tacc + c0, r);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 xv = __ldg(reinterpret_cast<const float4*>(xr + c0) + j4);
+                        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float dzg = __uint_as_float(r[4 * j4 + e]) * s_lng[c0 + 4 * j4 + e];
+                            m1 += dzg;
+                            m2 += dzg * (xs[e] - st.x) * st.y;
+                        }
+                    }
+                }
+            }
+            m1 *= (1.f / kH);
+            m2 *= (1.f / kH);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kH; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tacc + c0, r);
+                tmem_ld_wait();
+                float dzv[32], dzx[32];
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    float4 xv = make_float4(0, 0, 0, 0), dv = xv;
+                    if (valid) {
+                        xv = __ldg(reinterpret_cast<const float4*>(xr + c0) + j4);
+                        dv = __ldg(reinterpret_cast<const float4*>(a.dy + grow * kH + c0) + j4);
+                    }
+                    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                    const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float dz = valid ? __uint_as_float(r[4 * j4 + e]) : 0.f;
+                        const float xh = (xs[e] - st.x) * st.y;
+                        dzv[4 * j4 + e] = dz;
+                        dzx[4 * j4 + e] = dz * xh;
+                        o[e] = ds[e] + st.y * (dz * s_lng[c0 + 4 * j4 + e] - m1 - xh * m2);
+                    }
+                    if (valid) reinterpret_cast<float4*>(a.dx + grow * kH + c0)[j4] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                const float sw = warp_colsum32(dzx, lane), sb = warp_colsum32(dzv, lane);
+                atomicAdd(acc + 384 + c0 + lane, sw);
+                atomicAdd(acc + 480 + c0 + lane, sb);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    // flush the affine-parameter gradients
+    for (int i = tid; i < 192; i += 256) { atomicAdd(a.d_gnw + i, acc[i]); atomicAdd(a.d_gnb + i, acc[192 + i]); }
+    for (int i = tid; i < 96; i += 256) { atomicAdd(a.d_lnw + i, acc[384 + i]); atomicAdd(a.d_lnb + i, acc[480 + i]); }
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace nbss
+
+extern "C" int nbss_ffn_bwd(const float* x, const float* dy, float* dx, int nslab, int T, const float* ln_w,
+                            const float* gn_w, const float* gn_b, const float* ln_stats, const float* gn_stats,
+                            const void* layer_img, const void* a1, const void* c1, const void* c2, const void* c3,
+                            void* g_a1, void* g_c1, void* g_c2, void* g_c3, void* s1, void* s2, void* s3, void* s4,
+                            float* d_lnw, float* d_lnb, float* d_gnw, float* d_gnb, int fmt, int* err, void* stream) {
+    using namespace nbss;
+    if (!x || !dy || !dx || !ln_w || !gn_w || !gn_b || !ln_stats || !gn_stats || !layer_img || !a1 || !c1 || !c2 || !c3 ||
+        !g_a1 || !g_c1 || !g_c2 || !g_c3 || !s1 || !s2 || !s3 || !s4 || !d_lnw || !d_lnb || !d_gnw || !d_gnb)
+        return NBSS_ERR_NULL;
+    if (T < 1 || T > kTMax || nslab < 1) return NBSS_ERR_SHAPE;
+    if (fmt != FMT_F16 && fmt != FMT_BF16) return NBSS_ERR_UNSUPPORTED;
+    FfnBwdArgs a{x, dy, dx, nslab, T, ln_w, gn_w, gn_b, ln_stats, gn_stats, (const unsigned char*)layer_img,
+                 (const unsigned char*)a1, (const unsigned char*)c1, (const unsigned char*)c2, (const unsigned char*)c3,
+                 (unsigned char*)g_a1, (unsigned char*)g_c1, (unsigned char*)g_c2, (unsigned char*)g_c3,
+                 (unsigned char*)s1, (unsigned char*)s2, (unsigned char*)s3, (unsigned char*)s4, d_lnw, d_lnb, d_gnw, d_gnb, err};
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = nslab < sms ? nslab : sms;
+    auto kern = (fmt == FMT_F16) ? ffn_bwd_kernel<FMT_F16> : ffn_bwd_kernel<FMT_BF16>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, 256, FB_SMEM, (cudaStream_t)stream>>>(a);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}

@@ -1,0 +1,329 @@
+// ffn_fwd.cu — narrow-band T-ConvFFN sub-block, forward, one CTA per (b,f) slab, tcgen05 + TMEM.
+//
+// Replaces SpatialNetLayer._tconvffn + residual (models/arch/SpatialNet.py:90,102-114; modules :61-73):
+//   y = x + pw2( SiLU(conv3( SiLU(GN( conv2( SiLU(conv1( SiLU(pw1(LN(x))) )) )) )) ) )
+// Phases per slab (all operands stay in shared memory / TMEM; HBM sees x in, y out, + optional saves for backward):
+//   P0 stage x -> LN -> fp16 tile A0            E1 +b1, SiLU            -> H   (H aliases A0)
+//   P1 pw1:  D[256x192] = A0 W1^T (6 k-steps)   E2 +bc1, SiLU           -> H
+//   P2..P4 conv k=3, groups 8: 3 row-shifted    E3 +bc2, GroupNorm(8) over (24 ch x T), SiLU -> H
+//      views of H x block-diagonal 48x48 tiles   E4 +bc3, SiLU           -> H
+//   P5 pw2:  D[256x96] = H W2^T (12 k-steps)    E5 +b2 + x -> y
+// Weights arrive as prepacked UMMA images (pack.cu) by TMA bulk copies into two ping-pong slots, overlapped with
+// the epilogues.  Epilogue thread = one frame (TMEM lane), so GroupNorm needs one block reduction per statistic.
+#include "slab.cuh"
+
+namespace nbss {
+
+struct FfnFwdArgs {
+    const float* x;
+    float* y;
+    int nslab, T;
+    const float *ln_w, *ln_b, *b1, *bc1, *bc2, *bc3, *gn_w, *gn_b, *b2;
+    const unsigned char* img;  // layer image base
+    unsigned char *save_a1, *save_c1, *save_c2, *save_c3;  // fp16 [nslab*T, 192] or null
+    float* gn_stats;                                       // [nslab, 8, 2] (mean, rstd) or null
+    float* ln_stats;                                       // [nslab*T, 2] (mean, rstd) of the LayerNorm or null
+    int* err;
+};
+
+constexpr uint32_t FF_HBUF = 0;
+constexpr uint32_t FF_WS0 = 24 * kCS;               // 101760
+constexpr uint32_t FF_WS1 = FF_WS0 + IMG_WC_BYTES;  // 157056
+constexpr uint32_t FF_CST = FF_WS1 + IMG_WC_BYTES;  // 212352
+constexpr uint32_t FF_NCST = 1440;                  // floats
+constexpr uint32_t FF_RED = FF_CST + FF_NCST * 4;   // 8*16 floats
+constexpr uint32_t FF_BAR = FF_RED + 512;
+constexpr uint32_t FF_SMEM = FF_BAR + 64;
+
+template <int FMT>
+__device__ __forceinline__ void store_h(unsigned char* hrow, int c0, const float* s) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(hrow + (c0 / 8 + cc) * kCS) = pack8<FMT>(s + 8 * cc);
+}
+__device__ __forceinline__ void save_f16(unsigned char* base, size_t row, int c0, const float* v) {
+    uint4* p = reinterpret_cast<uint4*>(base + (row * kHF + c0) * 2);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) p[cc] = pack8<FMT_F16>(v + 8 * cc);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* hbuf = smem + FF_HBUF;
+    unsigned char* ws0 = smem + FF_WS0;
+    unsigned char* ws1 = smem + FF_WS1;
+    float* cst = reinterpret_cast<float*>(smem + FF_CST);
+    float *s_lng = cst, *s_lnb = cst + 96, *s_b1 = cst + 192, *s_bc = cst + 384, *s_gng = cst + 960, *s_gnb = cst + 1152,
+          *s_b2 = cst + 1344;
+    float* red = reinterpret_cast<float*>(smem + FF_RED);
+    uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + FF_BAR);
+    uint64_t* bar_w0 = bar_mma + 1;
+    uint64_t* bar_w1 = bar_mma + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 3);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = a.T;
+
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_w0, 1);
+        mbar_init(bar_w1, 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < 96; i += 256) { s_lng[i] = a.ln_w[i]; s_lnb[i] = a.ln_b[i]; s_b2[i] = a.b2[i]; }
+    for (int i = tid; i < 192; i += 256) {
+        s_b1[i] = a.b1[i]; s_bc[i] = a.bc1[i]; s_bc[192 + i] = a.bc2[i]; s_bc[384 + i] = a.bc3[i];
+        s_gng[i] = a.gn_w[i]; s_gnb[i] = a.gn_b[i];
+    }
+    for (int i = tid; i < (int)(24 * kCS / 16); i += 256) reinterpret_cast<uint4*>(hbuf)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int m = warp >> 2, q = warp & 3;
+    const int t = 128 * m + 32 * q + lane;
+    const bool valid = t < T;
+    const uint32_t tacc = tmem + ((uint32_t)(32 * q) << 16) + m * 192;
+    unsigned char* hrow = hbuf + (t + 1) * 16;
+    const uint32_t hb = smem_u32(hbuf), w0a = smem_u32(ws0), w1a = smem_u32(ws1);
+    const uint32_t id192 = make_idesc(FMT, 128, 192, 0, 0), id48 = make_idesc(FMT, 128, 48, 0, 0),
+                   id96 = make_idesc(FMT, 128, 96, 0, 0);
+    uint32_t ph_mma = 0, ph_w0 = 0, ph_w1 = 0;
+    const float inv_n = 1.f / (float)(kGC * T);
+
+    auto conv_phase = [&](uint32_t wsa, uint64_t* bar_w, uint32_t& ph_w) {
+        if (tid == 0) {
+            tc_fence_after();
+            mbar_wait(bar_w, ph_w, a.err);
+            for (int mm = 0; mm < 2; ++mm)
+                for (int p = 0; p < kPairs; ++p)
+                    for (int tap = 0; tap < 3; ++tap)
+                        mma_kk(tmem + mm * 192 + p * 48, hb + 6 * p * kCS + (128 * mm + tap) * 16, kCS,
+                               wsa + (p * 3 + tap) * 6 * 768, 768, 3, id48, tap > 0);
+            umma_commit(bar_mma);
+        }
+        __syncwarp();
+        ph_w ^= 1;
+        mbar_wait(bar_mma, ph_mma, a.err);
+        ph_mma ^= 1;
+        tc_fence_after();
+    };
+    auto end_epilogue = [&]() {
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+    };
+
+    for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
+        const float* xs = a.x + (size_t)slab * T * kH;
+        const size_t grow = (size_t)slab * T + t;
+        if (tid == 0) {
+            load_image(ws0, a.img + IMG_W1, IMG_W1_BYTES, bar_w0);
+            load_image(ws1, a.img + IMG_WC1, IMG_WC_BYTES, bar_w1);
+        }
+        // ---- P0: LN(x) -> A0 (chunks 0..11 of H)
+        stage_rows96<FMT, true>(xs, T, hbuf, 1, s_lng, s_lnb, warp, lane, a.ln_stats ? a.ln_stats + (size_t)slab * T * 2 : nullptr);
+        end_epilogue();
+        // ---- P1: pw1
+        if (tid == 0) {
+            tc_fence_after();
+            mbar_wait(bar_w0, ph_w0, a.err);
+            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 192 * 16, 6, id192, 0);
+            umma_commit(bar_mma);
+        }
+        __syncwarp();
+        ph_w0 ^= 1;
+        mbar_wait(bar_mma, ph_mma, a.err);
+        ph_mma ^= 1;
+        tc_fence_after();
+        if (tid == 0) load_image(ws0, a.img + IMG_WC2, IMG_WC_BYTES, bar_w0);
+        // ---- E1: a1 = D + b1; H = SiLU(a1)
+#pragma unroll 1
+        for (int c0 = 0; c0 < kHF; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tacc + c0, r);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_b1[c0 + j];
+            if (a.save_a1 && valid) save_f16(a.save_a1, grow, c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = valid ? silu(v[j]) : 0.f;
+            store_h<FMT>(hrow, c0, v);
+        }
+        end_epilogue();
+        // ---- P2: conv1 ; E2: c1 = D + bc1; H = SiLU(c1)
+        conv_phase(w1a, bar_w1, ph_w1);
+        if (tid == 0) load_image(ws1, a.img + IMG_WC3, IMG_WC_BYTES, bar_w1);
+#pragma unroll 1
+        for (int c0 = 0; c0 < kHF; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tacc + c0, r);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bc[c0 + j];
+            if (a.save_c1 && valid) save_f16(a.save_c1, grow, c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = valid ? silu(v[j]) : 0.f;
+            store_h<FMT>(hrow, c0, v);
+        }
+        end_epilogue();
+        // ---- P3: conv2 ; E3: c2 = D + bc2; GroupNorm over (24 ch x T) per group; H = SiLU(GN(c2))
+        conv_phase(w0a, bar_w0, ph_w0);
+        if (tid == 0) load_image(ws0, a.img + IMG_W2, IMG_W2_BYTES, bar_w0);
+        {
+            float* red_sum = red;       // [8 warps][8 groups]
+            float* red_sq = red + 64;
+            const float* bc2 = s_bc + 192;
+            // pass A: per-group sums over valid frames
+#pragma unroll 1
+            for (int g = 0; g < kGroups; ++g) {
+                float s = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    uint32_t r[8];
+                    tmem_ld8(tacc + kGC * g + 8 * k, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) s += __uint_as_float(r[j]) + bc2[kGC * g + 8 * k + j];
+                }
+                s = warp_sum(valid ? s : 0.f);
+                if (lane == 0) red_sum[warp * 8 + g] = s;
+            }
+            __syncthreads();
+            // pass B: centred second moment
+#pragma unroll 1
+            for (int g = 0; g < kGroups; ++g) {
+                float mean = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) mean += red_sum[w * 8 + g];
+                mean *= inv_n;
+                float s = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    uint32_t r[8];
+                    tmem_ld8(tacc + kGC * g + 8 * k, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float d = __uint_as_float(r[j]) + bc2[kGC * g + 8 * k + j] - mean;
+                        s += d * d;
+                    }
+                }
+                s = warp_sum(valid ? s : 0.f);
+                if (lane == 0) red_sq[warp * 8 + g] = s;
+            }
+            __syncthreads();
+            // pass C: normalise, affine, SiLU -> H ; save c2
+#pragma unroll 1
+            for (int g = 0; g < kGroups; ++g) {
+                float mean = 0.f, var = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { mean += red_sum[w * 8 + g]; var += red_sq[w * 8 + g]; }
+                mean *= inv_n;
+                const float rstd = rsqrtf(var * inv_n + 1e-5f);
+                if (a.gn_stats && tid == g) {
+                    a.gn_stats[(size_t)slab * 16 + 2 * g] = mean;
+                    a.gn_stats[(size_t)slab * 16 + 2 * g + 1] = rstd;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int c = kGC * g + 8 * k;
+                    uint32_t r[8];
+                    tmem_ld8(tacc + c, r);
+                    tmem_ld_wait();
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + bc2[c + j];
+                    if (a.save_c2 && valid) *reinterpret_cast<uint4*>(a.save_c2 + (grow * kHF + c) * 2) = pack8<FMT_F16>(v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float n = (v[j] - mean) * rstd * s_gng[c + j] + s_gnb[c + j];
+                        v[j] = valid ? silu(n) : 0.f;
+                    }
+                    *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = pack8<FMT>(v);
+                }
+            }
+        }
+        end_epilogue();
+        // ---- P4: conv3 ; E4: c3 = D + bc3; H = SiLU(c3)
+        conv_phase(w1a, bar_w1, ph_w1);
+#pragma unroll 1
+        for (int c0 = 0; c0 < kHF; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tacc + c0, r);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bc[384 + c0 + j];
+            if (a.save_c3 && valid) save_f16(a.save_c3, grow, c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = valid ? silu(v[j]) : 0.f;
+            store_h<FMT>(hrow, c0, v);
+        }
+        end_epilogue();
+        // ---- P5: pw2 ; E5: y = x + D + b2
+        if (tid == 0) {
+            tc_fence_after();
+            mbar_wait(bar_w0, ph_w0, a.err);
+            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 96 * 16, 12, id96, 0);
+            umma_commit(bar_mma);
+        }
+        __syncwarp();
+        ph_w0 ^= 1;
+        mbar_wait(bar_mma, ph_mma, a.err);
+        ph_mma ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < kH; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tacc + c0, r);
+            tmem_ld_wait();
+            if (valid) {
+                const float4* xr = reinterpret_cast<const float4*>(xs + (size_t)t * kH + c0);
+                float4* yr = reinterpret_cast<float4*>(a.y + grow * kH + c0);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    float4 xv = __ldg(xr + j4);
+                    float4 o;
+                    o.x = xv.x + __uint_as_float(r[4 * j4 + 0]) + s_b2[c0 + 4 * j4 + 0];
+                    o.y = xv.y + __uint_as_float(r[4 * j4 + 1]) + s_b2[c0 + 4 * j4 + 1];
+                    o.z = xv.z + __uint_as_float(r[4 * j4 + 2]) + s_b2[c0 + 4 * j4 + 2];
+                    o.w = xv.w + __uint_as_float(r[4 * j4 + 3]) + s_b2[c0 + 4 * j4 + 3];
+                    yr[j4] = o;
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();  // TMEM + H are reused by the next slab
+    }
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace nbss
+
+extern "C" int nbss_ffn_fwd(const float* x, float* y, int nslab, int T, const float* ln_w, const float* ln_b,
+                            const float* b1, const float* bc1, const float* bc2, const float* bc3, const float* gn_w,
+                            const float* gn_b, const float* b2, const void* layer_img, void* save_a1, void* save_c1,
+                            void* save_c2, void* save_c3, float* gn_stats, float* ln_stats, int fmt, int* err, void* stream) {
+    using namespace nbss;
+    if (!x || !y || !layer_img || !ln_w || !ln_b || !b1 || !bc1 || !bc2 || !bc3 || !gn_w || !gn_b || !b2) return NBSS_ERR_NULL;
+    if (T < 1 || T > kTMax || nslab < 1) return NBSS_ERR_SHAPE;
+    if (fmt != FMT_F16 && fmt != FMT_BF16) return NBSS_ERR_UNSUPPORTED;
+    FfnFwdArgs a{x, y, nslab, T, ln_w, ln_b, b1, bc1, bc2, bc3, gn_w, gn_b, b2, (const unsigned char*)layer_img,
+                 (unsigned char*)save_a1, (unsigned char*)save_c1, (unsigned char*)save_c2, (unsigned char*)save_c3, gn_stats, ln_stats, err};
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = nslab < sms ? nslab : sms;
+    auto kern = (fmt == FMT_F16) ? ffn_fwd_kernel<FMT_F16> : ffn_fwd_kernel<FMT_BF16>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, 256, FF_SMEM, (cudaStream_t)stream>>>(a);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}

@@ -1,0 +1,503 @@
+// io.cu — framing and the thin ends of the network, fp32 CUDA-core kernels (all HBM-bound, SURVEY.md §8 a1-a4,a10,a11):
+//   stft (+ optional Norm 'frequency/online' + pack)   models/io/stft.py:49-66, models/io/norm.py:75-81,94,
+//                                                      SharedTrainer.py:116-117
+//   encoder  Conv1d(Cin->96, k=5, 'same') along T      models/arch/SpatialNet.py:175,205   (+ wgrad)
+//   decoder  Linear(96->Cout)                          models/arch/SpatialNet.py:200,216   (+ dgrad, wgrad)
+//   istft (+ optional inverse norm + unpack)           models/io/stft.py:68-97, models/io/norm.py:97-108,
+//                                                      SharedTrainer.py:121-128            (+ backward)
+// The reference loops torch.istft over B*S items in Python (stft.py:83-87); here it is one launch.
+#include "common.cuh"
+#include "layout.cuh"
+
+namespace nbss {
+
+constexpr int kFT = 8;  // frames per CTA in the framing kernels
+
+__device__ __forceinline__ float hann(int n, int N) { return 0.5f - 0.5f * cospif(2.f * (float)n / (float)N); }
+
+// ------------------------------------------------------------------------------------------------ STFT
+struct StftArgs {
+    const float* x;  // [B,C,Ts]
+    int B, C, Ts, T, F, N, hop;
+    int normalize, ref;  // Norm(mode='frequency', online=True) fused when normalize != 0
+    float eps;
+    float* out;  // re at out + b*ob + c*oc + f*of + t*ot, im at +1 (strides in floats)
+    long long ob, oc, of, ot;
+    float* xrmm;  // [B,F,T] or null
+    float* xr;    // [B,F,T,2] (reference-channel STFT before normalisation) or null
+};
+
+__global__ void __launch_bounds__(256) stft_kernel(StftArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int N = a.N, F = a.F, C = a.C;
+    float2* tw = reinterpret_cast<float2*>(sm);             // [N] (cos, sin)(2 pi k / N)
+    float* xw = sm + 2 * N;                                 // [kFT][C][N] windowed frames
+    float2* X = reinterpret_cast<float2*>(xw + kFT * C * N);  // [kFT][C][F]
+    const int tiles = (a.T + kFT - 1) / kFT, tid = threadIdx.x;
+    const int b = blockIdx.x / tiles, t0 = (blockIdx.x % tiles) * kFT;
+    for (int k = tid; k < N; k += 256) tw[k] = make_float2(cospif(2.f * k / N), sinpif(2.f * k / N));
+    for (int i = tid; i < kFT * C * N; i += 256) {
+        const int n = i % N, c = (i / N) % C, tt = i / (N * C), t = t0 + tt;
+        float v = 0.f;
+        if (t < a.T) {
+            int j = t * a.hop + n - N / 2;  // center=True, reflect padding
+            if (j < 0) j = -j;
+            if (j >= a.Ts) j = 2 * (a.Ts - 1) - j;
+            v = a.x[((size_t)b * C + c) * a.Ts + j] * hann(n, N);
+        }
+        xw[i] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < kFT * C * F; i += 256) {
+        const int f = i % F, tc = i / F;
+        const float* fr = xw + (size_t)tc * N;
+        float re = 0.f, im = 0.f;
+        for (int n = 0; n < N; ++n) {
+            const float2 w = tw[(f * n) & (N - 1)];
+            re = fmaf(fr[n], w.x, re);
+            im = fmaf(-fr[n], w.y, im);
+        }
+        X[i] = make_float2(re, im);
+    }
+    __syncthreads();
+    for (int i = tid; i < kFT * C * F; i += 256) {
+        // order (f, tt, c): consecutive threads write consecutive channels / frames of one frequency
+        const int c = i % C, tt = (i / C) % kFT, f = i / (C * kFT), t = t0 + tt;
+        if (t >= a.T) continue;
+        float2 v = X[((size_t)tt * C + c) * F + f];
+        if (a.normalize) {
+            const float2 r = X[((size_t)tt * C + a.ref) * F + f];
+            const float mm = sqrtf(r.x * r.x + r.y * r.y) + a.eps;
+            v.x /= mm;
+            v.y /= mm;
+            if (c == a.ref) {
+                const size_t o = ((size_t)b * F + f) * a.T + t;
+                if (a.xrmm) a.xrmm[o] = mm;
+                if (a.xr) { a.xr[2 * o] = r.x; a.xr[2 * o + 1] = r.y; }
+            }
+        }
+        float* o = a.out + b * a.ob + c * a.oc + f * a.of + t * a.ot;
+        o[0] = v.x;
+        o[1] = v.y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ iSTFT
+struct IstftArgs {
+    const float* in;  // re at in + b*ib + s*is + f*if_ + t*it, im at +1 (strides in floats)
+    long long ib, is, if_, it;
+    const float* scale;  // optional [B,F,T] multiplier (inverse normalisation), or null
+    float* y;            // [B,S,Ts]
+    int B, S, Ts, T, F, N, hop;
+};
+
+// squared-window envelope at padded position p (frames t with 0 <= p - t*hop < N, 0 <= t < T)
+__device__ __forceinline__ float ola_env(int p, int N, int hop, int T) {
+    float e = 0.f;
+    const int thi = min(T - 1, p / hop);
+    for (int t = thi; t >= 0 && p - t * hop < N; --t) {
+        const float w = hann(p - t * hop, N);
+        e += w * w;
+    }
+    return e;
+}
+
+__global__ void __launch_bounds__(256) istft_kernel(IstftArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int N = a.N, F = a.F, R = N / a.hop, NFR = kFT + R - 1;
+    float2* tw = reinterpret_cast<float2*>(sm);                 // [N]
+    float2* X = reinterpret_cast<float2*>(sm + 2 * N);          // [NFR][F]
+    float* fr = sm + 2 * N + 2 * NFR * F;                       // [NFR][N] windowed inverse DFT of each frame
+    const int nseg = a.T + R - 1, tiles = (nseg + kFT - 1) / kFT, tid = threadIdx.x;
+    const int bs = blockIdx.x / tiles, k0 = (blockIdx.x % tiles) * kFT;
+    const int b = bs / a.S, s = bs % a.S;
+    const int tfirst = k0 - (R - 1);
+    for (int k = tid; k < N; k += 256) tw[k] = make_float2(cospif(2.f * k / N), sinpif(2.f * k / N));
+    for (int i = tid; i < NFR * F; i += 256) {
+        const int f = i % F, t = tfirst + i / F;
+        float2 v = make_float2(0.f, 0.f);
+        if (t >= 0 && t < a.T) {
+            const float* p = a.in + b * a.ib + s * a.is + f * a.if_ + t * a.it;
+            const float sc = a.scale ? a.scale[((size_t)b * F + f) * a.T + t] : 1.f;
+            v = make_float2(p[0] * sc, p[1] * sc);
+        }
+        X[i] = v;
+    }
+    __syncthreads();
+    const float invN = 1.f / N;
+    for (int i = tid; i < NFR * N; i += 256) {
+        const int n = i % N, fi = i / N;
+        const float2* xf = X + (size_t)fi * F;
+        float acc = xf[0].x + ((n & 1) ? -xf[F - 1].x : xf[F - 1].x);  // DC + Nyquist (imaginary parts ignored)
+        float acc2 = 0.f;
+        for (int f = 1; f < F - 1; ++f) {
+            const float2 w = tw[(f * n) & (N - 1)];
+            acc2 = fmaf(xf[f].x, w.x, acc2);
+            acc2 = fmaf(-xf[f].y, w.y, acc2);
+        }
+        fr[i] = (acc + 2.f * acc2) * invN * hann(n, N);
+    }
+    __syncthreads();
+    for (int i = tid; i < kFT * a.hop; i += 256) {
+        const int k = k0 + i / a.hop, p = k * a.hop + i % a.hop, j = p - N / 2;
+        if (k >= nseg || j < 0 || j >= a.Ts) continue;
+        float v = 0.f;
+        for (int t = max(0, k - R + 1); t <= min(k, a.T - 1); ++t) v += fr[(size_t)(t - tfirst) * N + p - t * a.hop];
+        const float e = ola_env(p, N, a.hop, a.T);
+        a.y[((size_t)b * a.S + s) * a.Ts + j] = e > 1e-11f ? v / e : 0.f;
+    }
+}
+
+// Backward of iSTFT(+scale): d in[b,s,f,t] (re, im) from dy [B,S,Ts]:  a windowed, envelope-normalised DFT of dy.
+struct IstftBwdArgs {
+    const float* dy;  // [B,S,Ts]
+    const float* scale;
+    float* din;  // re at din + b*ib + s*is + f*if_ + t*it, im at +1
+    long long ib, is, if_, it;
+    int B, S, Ts, T, F, N, hop;
+};
+
+__global__ void __launch_bounds__(256) istft_bwd_kernel(IstftBwdArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int N = a.N, F = a.F;
+    float2* tw = reinterpret_cast<float2*>(sm);  // [N]
+    float* g = sm + 2 * N;                       // [kFT][N]  dy * w / env per frame
+    const int tiles = (a.T + kFT - 1) / kFT, tid = threadIdx.x;
+    const int bs = blockIdx.x / tiles, t0 = (blockIdx.x % tiles) * kFT;
+    const int b = bs / a.S, s = bs % a.S;
+    for (int k = tid; k < N; k += 256) tw[k] = make_float2(cospif(2.f * k / N), sinpif(2.f * k / N));
+    for (int i = tid; i < kFT * N; i += 256) {
+        const int n = i % N, t = t0 + i / N, p = t * a.hop + n, j = p - N / 2;
+        float v = 0.f;
+        if (t < a.T && j >= 0 && j < a.Ts) {
+            const float e = ola_env(p, N, a.hop, a.T);
+            if (e > 1e-11f) v = a.dy[((size_t)b * a.S + s) * a.Ts + j] * hann(n, N) / e;
+        }
+        g[i] = v;
+    }
+    __syncthreads();
+    const float invN = 1.f / N;
+    for (int i = tid; i < kFT * F; i += 256) {
+        const int tt = i % kFT, f = i / kFT, t = t0 + tt;
+        if (t >= a.T) continue;
+        const float* gr = g + (size_t)tt * N;
+        float re = 0.f, im = 0.f;
+        for (int n = 0; n < N; ++n) {
+            const float2 w = tw[(f * n) & (N - 1)];
+            re = fmaf(gr[n], w.x, re);
+            im = fmaf(-gr[n], w.y, im);
+        }
+        const bool edge = (f == 0 || f == F - 1);
+        const float c = (edge ? 1.f : 2.f) * invN * (a.scale ? a.scale[((size_t)b * F + f) * a.T + t] : 1.f);
+        float* o = a.din + b * a.ib + s * a.is + f * a.if_ + t * a.it;
+        o[0] = re * c;
+        o[1] = edge ? 0.f : im * c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ encoder
+// y[b,f,t,co] = bias[co] + sum_k sum_ci W[co,ci,k] * x[b,f,t+k-K/2,ci]     (K = 5, zero padding)
+template <int CIN>
+__global__ void __launch_bounds__(192) encoder_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int nslab, int T,
+                                                          const float* W, const float* bias) {
+    constexpr int K = 5, TT = 64;
+    __shared__ __align__(16) float xs[(TT + K - 1) * CIN];
+    const int tiles = (T + TT - 1) / TT, tid = threadIdx.x;
+    const int slab = blockIdx.x / tiles, t0 = (blockIdx.x % tiles) * TT;
+    for (int i = tid; i < (TT + K - 1) * CIN; i += 192) {
+        const int t = t0 + i / CIN - K / 2;
+        xs[i] = (t >= 0 && t < T) ? x[((size_t)slab * T + t) * CIN + i % CIN] : 0.f;
+    }
+    const int co = tid % kH, half = tid / kH;
+    float w[CIN * K];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+        for (int k = 0; k < K; ++k) w[k * CIN + ci] = W[(co * CIN + ci) * K + k];
+    const float bi = bias[co];
+    __syncthreads();
+    for (int r = half; r < TT; r += 2) {
+        if (t0 + r >= T) break;
+        float acc = bi;
+#pragma unroll
+        for (int i = 0; i < K * CIN; ++i) acc = fmaf(w[i], xs[r * CIN + i], acc);
+        y[((size_t)slab * T + t0 + r) * kH + co] = acc;
+    }
+}
+
+// dW[co,ci,k] += sum dy[.,t,co] x[.,t+k-2,ci];  dbias[co] += sum dy.   (the network input needs no gradient)
+template <int CIN>
+__global__ void __launch_bounds__(192) encoder_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, int nslab,
+                                                            int T, float* dW, float* dbias) {
+    constexpr int K = 5, TT = 64;
+    __shared__ __align__(16) float xs[(TT + K - 1) * CIN];
+    const int tiles = (T + TT - 1) / TT, tid = threadIdx.x;
+    const int co = tid % kH, half = tid / kH;
+    float dw[CIN * K];
+#pragma unroll
+    for (int i = 0; i < CIN * K; ++i) dw[i] = 0.f;
+    float db = 0.f;
+    for (int tile = blockIdx.x; tile < nslab * tiles; tile += gridDim.x) {
+        const int slab = tile / tiles, t0 = (tile % tiles) * TT;
+        __syncthreads();
+        for (int i = tid; i < (TT + K - 1) * CIN; i += 192) {
+            const int t = t0 + i / CIN - K / 2;
+            xs[i] = (t >= 0 && t < T) ? x[((size_t)slab * T + t) * CIN + i % CIN] : 0.f;
+        }
+        __syncthreads();
+        for (int r = half; r < TT; r += 2) {
+            if (t0 + r >= T) break;
+            const float g = dy[((size_t)slab * T + t0 + r) * kH + co];
+            db += g;
+#pragma unroll
+            for (int i = 0; i < K * CIN; ++i) dw[i] = fmaf(g, xs[r * CIN + i], dw[i]);
+        }
+    }
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+        for (int k = 0; k < K; ++k) atomicAdd(dW + (co * CIN + ci) * K + k, dw[k * CIN + ci]);
+    atomicAdd(dbias + co, db);
+}
+
+// ------------------------------------------------------------------------------------------------ decoder
+// y[n, o] = sum_c x[n,c] W[o,c] + b[o], o < COUT.  Warp per row.
+template <int COUT>
+__global__ void __launch_bounds__(256) decoder_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n,
+                                                          const float* W, const float* bias) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5, nw = ((size_t)gridDim.x * 256) >> 5;
+    const bool act = lane < 24;
+    float4 w[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) w[o] = act ? ld_f4(W + o * kH + 4 * lane) : make_float4(0, 0, 0, 0);
+    for (size_t r = warp; r < n; r += nw) {
+        const float4 v = act ? ld_f4(x + r * kH + 4 * lane) : make_float4(0, 0, 0, 0);
+        float outv = 0.f;
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+            const float p = warp_sum(v.x * w[o].x + v.y * w[o].y + v.z * w[o].z + v.w * w[o].w);
+            if (lane == o) outv = p + bias[o];
+        }
+        if (lane < COUT) y[r * COUT + lane] = outv;
+    }
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(256) decoder_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                          float* __restrict__ dx, size_t n, const float* W, float* dW,
+                                                          float* dbias) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5, nw = ((size_t)gridDim.x * 256) >> 5;
+    const bool act = lane < 24;
+    float4 w[COUT], dw[COUT];
+    float db = 0.f;
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+        w[o] = act ? ld_f4(W + o * kH + 4 * lane) : make_float4(0, 0, 0, 0);
+        dw[o] = make_float4(0, 0, 0, 0);
+    }
+    for (size_t r = warp; r < n; r += nw) {
+        const float4 v = act ? ld_f4(x + r * kH + 4 * lane) : make_float4(0, 0, 0, 0);
+        const float gl = lane < COUT ? dy[r * COUT + lane] : 0.f;
+        db += gl;
+        float4 d = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+            const float g = __shfl_sync(0xffffffffu, gl, o);
+            d = make_float4(fmaf(g, w[o].x, d.x), fmaf(g, w[o].y, d.y), fmaf(g, w[o].z, d.z), fmaf(g, w[o].w, d.w));
+            dw[o] = make_float4(fmaf(g, v.x, dw[o].x), fmaf(g, v.y, dw[o].y), fmaf(g, v.z, dw[o].z), fmaf(g, v.w, dw[o].w));
+        }
+        if (act) st_f4(dx + r * kH + 4 * lane, d);
+    }
+    if (act) {
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+            atomicAdd(dW + o * kH + 4 * lane + 0, dw[o].x); atomicAdd(dW + o * kH + 4 * lane + 1, dw[o].y);
+            atomicAdd(dW + o * kH + 4 * lane + 2, dw[o].z); atomicAdd(dW + o * kH + 4 * lane + 3, dw[o].w);
+        }
+    }
+    if (lane < COUT) atomicAdd(dbias + lane, db);
+}
+
+// ------------------------------------------------------------------------------------------------ Norm (standalone)
+// Norm.norm, mode='frequency', online=True (models/io/norm.py:75-81,94) on complex [B,C,F,T]: XrMM = |X[:,ref]| + eps,
+// X /= XrMM (in place, like the reference), Xr = copy of the reference channel before normalisation.
+__global__ void __launch_bounds__(256) norm_freq_kernel(float2* X, int B, int C, size_t FT, int ref, float eps, float* xrmm, float2* xr) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (size_t)B * FT) return;
+    const size_t b = i / FT, r = i % FT;
+    const float2 v = X[(b * C + ref) * FT + r];
+    const float mm = sqrtf(v.x * v.x + v.y * v.y) + eps;
+    xrmm[i] = mm;
+    xr[i] = v;
+    for (int c = 0; c < C; ++c) {
+        float2 w = X[(b * C + c) * FT + r];
+        w.x /= mm;
+        w.y /= mm;
+        X[(b * C + c) * FT + r] = w;
+    }
+}
+// Norm.inorm (models/io/norm.py:97-108): Y[b,s,:] = X[b,s,:] * XrMM[b,:]
+__global__ void __launch_bounds__(256) inorm_kernel(const float2* X, float2* Y, int B, int S, size_t FT, const float* xrmm) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (size_t)B * S * FT) return;
+    const size_t b = i / (S * FT), r = i % FT;
+    const float m = xrmm[b * FT + r];
+    const float2 v = X[i];
+    Y[i] = make_float2(v.x * m, v.y * m);
+}
+
+static int io_num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return sms;
+}
+
+}  // namespace nbss
+
+using namespace nbss;
+
+static bool pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+extern "C" int nbss_stft(const float* x, int B, int C, int Ts, int n_fft, int hop, int normalize, int ref_channel,
+                         float eps, float* out, long long ob, long long oc, long long of, long long ot, float* xrmm,
+                         float* xr, void* stream) {
+    if (!x || !out) return NBSS_ERR_NULL;
+    if (!pow2(n_fft) || n_fft > 1024 || hop < 1 || n_fft % hop || B < 1 || C < 1 || Ts <= n_fft / 2) return NBSS_ERR_SHAPE;
+    if (normalize && (ref_channel < 0 || ref_channel >= C)) return NBSS_ERR_SHAPE;
+    const int T = 1 + Ts / hop, F = n_fft / 2 + 1;
+    const size_t smem = (size_t)(2 * n_fft + kFT * C * n_fft + 2 * kFT * C * F) * 4;
+    if (smem > 227 * 1024) return NBSS_ERR_UNSUPPORTED;
+    StftArgs a{x, B, C, Ts, T, F, n_fft, hop, normalize, ref_channel, eps, out, ob, oc, of, ot, xrmm, xr};
+    cudaError_t e = cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    stft_kernel<<<B * ((T + kFT - 1) / kFT), 256, smem, (cudaStream_t)stream>>>(a);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+
+extern "C" int nbss_istft(const float* in, long long ib, long long is, long long if_, long long it, const float* scale,
+                          float* y, int B, int S, int Ts, int T, int n_fft, int hop, void* stream) {
+    if (!in || !y) return NBSS_ERR_NULL;
+    if (!pow2(n_fft) || n_fft > 1024 || hop < 1 || n_fft % hop || n_fft / hop > 8 || B < 1 || S < 1 || T < 1) return NBSS_ERR_SHAPE;
+    const int F = n_fft / 2 + 1, R = n_fft / hop, NFR = kFT + R - 1;
+    const size_t smem = (size_t)(2 * n_fft + 2 * NFR * F + NFR * n_fft) * 4;
+    if (smem > 227 * 1024) return NBSS_ERR_UNSUPPORTED;
+    IstftArgs a{in, ib, is, if_, it, scale, y, B, S, Ts, T, F, n_fft, hop};
+    cudaError_t e = cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(y, 0, (size_t)B * S * Ts * 4, (cudaStream_t)stream);  // samples no frame covers stay 0
+    if (e != cudaSuccess) return (int)e;
+    const int nseg = T + R - 1;
+    istft_kernel<<<B * S * ((nseg + kFT - 1) / kFT), 256, smem, (cudaStream_t)stream>>>(a);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+
+extern "C" int nbss_istft_bwd(const float* dy, const float* scale, float* din, long long ib, long long is, long long if_,
+                              long long it, int B, int S, int Ts, int T, int n_fft, int hop, void* stream) {
+    if (!dy || !din) return NBSS_ERR_NULL;
+    if (!pow2(n_fft) || n_fft > 1024 || hop < 1 || n_fft % hop || B < 1 || S < 1 || T < 1) return NBSS_ERR_SHAPE;
+    const int F = n_fft / 2 + 1;
+    const size_t smem = (size_t)(2 * n_fft + kFT * n_fft) * 4;
+    IstftBwdArgs a{dy, scale, din, ib, is, if_, it, B, S, Ts, T, F, n_fft, hop};
+    cudaError_t e = cudaFuncSetAttribute(istft_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    istft_bwd_kernel<<<B * S * ((T + kFT - 1) / kFT), 256, smem, (cudaStream_t)stream>>>(a);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+
+extern "C" int nbss_encoder_fwd(const float* x, float* y, int nslab, int T, int cin, const float* W, const float* bias,
+                                void* stream) {
+    if (!x || !y || !W || !bias) return NBSS_ERR_NULL;
+    if (nslab < 1 || T < 1) return NBSS_ERR_SHAPE;
+    const int grid = nslab * ((T + 63) / 64);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (cin) {
+        case 2: encoder_fwd_kernel<2><<<grid, 192, 0, st>>>(x, y, nslab, T, W, bias); break;
+        case 4: encoder_fwd_kernel<4><<<grid, 192, 0, st>>>(x, y, nslab, T, W, bias); break;
+        case 8: encoder_fwd_kernel<8><<<grid, 192, 0, st>>>(x, y, nslab, T, W, bias); break;
+        case 12: encoder_fwd_kernel<12><<<grid, 192, 0, st>>>(x, y, nslab, T, W, bias); break;
+        case 16: encoder_fwd_kernel<16><<<grid, 192, 0, st>>>(x, y, nslab, T, W, bias); break;
+        default: return NBSS_ERR_UNSUPPORTED;
+    }
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+
+extern "C" int nbss_encoder_wgrad(const float* x, const float* dy, int nslab, int T, int cin, float* dW, float* dbias,
+                                  void* stream) {
+    if (!x || !dy || !dW || !dbias) return NBSS_ERR_NULL;
+    if (nslab < 1 || T < 1) return NBSS_ERR_SHAPE;
+    const int tiles = nslab * ((T + 63) / 64), cap = 4 * io_num_sms(), grid = tiles < cap ? tiles : cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (cin) {
+        case 2: encoder_wgrad_kernel<2><<<grid, 192, 0, st>>>(x, dy, nslab, T, dW, dbias); break;
+        case 4: encoder_wgrad_kernel<4><<<grid, 192, 0, st>>>(x, dy, nslab, T, dW, dbias); break;
+        case 8: encoder_wgrad_kernel<8><<<grid, 192, 0, st>>>(x, dy, nslab, T, dW, dbias); break;
+        case 12: encoder_wgrad_kernel<12><<<grid, 192, 0, st>>>(x, dy, nslab, T, dW, dbias); break;
+        case 16: encoder_wgrad_kernel<16><<<grid, 192, 0, st>>>(x, dy, nslab, T, dW, dbias); break;
+        default: return NBSS_ERR_UNSUPPORTED;
+    }
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+
+extern "C" int nbss_decoder_fwd(const float* x, float* y, long long n, int cout, const float* W, const float* bias,
+                                void* stream) {
+    if (!x || !y || !W || !bias) return NBSS_ERR_NULL;
+    if (n < 1) return NBSS_ERR_SHAPE;
+    const int grid = 8 * io_num_sms();
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (cout) {
+        case 2: decoder_fwd_kernel<2><<<grid, 256, 0, st>>>(x, y, (size_t)n, W, bias); break;
+        case 4: decoder_fwd_kernel<4><<<grid, 256, 0, st>>>(x, y, (size_t)n, W, bias); break;
+        case 6: decoder_fwd_kernel<6><<<grid, 256, 0, st>>>(x, y, (size_t)n, W, bias); break;
+        case 8: decoder_fwd_kernel<8><<<grid, 256, 0, st>>>(x, y, (size_t)n, W, bias); break;
+        default: return NBSS_ERR_UNSUPPORTED;
+    }
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+
+extern "C" int nbss_decoder_bwd(const float* x, const float* dy, float* dx, long long n, int cout, const float* W, float* dW,
+                                float* dbias, void* stream) {
+    if (!x || !dy || !dx || !W || !dW || !dbias) return NBSS_ERR_NULL;
+    if (n < 1) return NBSS_ERR_SHAPE;
+    const int grid = 4 * io_num_sms();
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (cout) {
+        case 2: decoder_bwd_kernel<2><<<grid, 256, 0, st>>>(x, dy, dx, (size_t)n, W, dW, dbias); break;
+        case 4: decoder_bwd_kernel<4><<<grid, 256, 0, st>>>(x, dy, dx, (size_t)n, W, dW, dbias); break;
+        case 6: decoder_bwd_kernel<6><<<grid, 256, 0, st>>>(x, dy, dx, (size_t)n, W, dW, dbias); break;
+        case 8: decoder_bwd_kernel<8><<<grid, 256, 0, st>>>(x, dy, dx, (size_t)n, W, dW, dbias); break;
+        default: return NBSS_ERR_UNSUPPORTED;
+    }
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+
+extern "C" int nbss_norm_freq_online(float* X, int B, int C, long long FT, int ref_channel, float eps, float* xrmm, float* xr,
+                                     void* stream) {
+    if (!X || !xrmm || !xr) return NBSS_ERR_NULL;
+    if (B < 1 || C < 1 || FT < 1 || ref_channel < 0 || ref_channel >= C) return NBSS_ERR_SHAPE;
+    const size_t n = (size_t)B * FT;
+    norm_freq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((float2*)X, B, C, (size_t)FT, ref_channel, eps, xrmm, (float2*)xr);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+
+extern "C" int nbss_inorm(const float* X, float* Y, int B, int S, long long FT, const float* xrmm, void* stream) {
+    if (!X || !Y || !xrmm) return NBSS_ERR_NULL;
+    if (B < 1 || S < 1 || FT < 1) return NBSS_ERR_SHAPE;
+    const size_t n = (size_t)B * S * FT;
+    inorm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float2*)X, (float2*)Y, B, S, (size_t)FT, xrmm);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}

@@ -1,0 +1,420 @@
+// mhsa_bwd.cu — backward (data gradient) of the narrow-band MHSA sub-block, tcgen05 + TMEM, T <= 256.
+//
+//   mhsa_bwd_core : per (b,f) slab.  dO = dy Wo (tensor core), delta = rowsum(dO * O), then per head and per
+//                   (query tile, key tile) block of 128 x 128:  S = Qs K^T and dP = dO V^T (TMEM), P = exp2(S - lse),
+//                   dS = P (dP - delta) staged as 16-bit tiles, dQ += dS K, dK += dS^T Qs, dV += P^T dO with the
+//                   accumulators living in TMEM across the blocks.  Writes dQKV [n,288] (gradient wrt the in-proj
+//                   outputs) for the LN/in-proj backward and the weight-gradient kernel.
+//   mhsa_bwd_ln   : per slab.  d ln = dQKV Win (K = 288), LayerNorm backward, dx = dy + ..., d gamma / d beta.
+// Inputs saved by mhsa_fwd: fp16 (scaled q | k | v), fp16 O, log2-domain logsumexp, LN statistics.
+// FMT_G is the 16-bit format of gradient operands (bf16); q,k,v,O stay fp16 (mixed-format kind::f16 MMAs).
+#include "slab.cuh"
+
+namespace nbss {
+
+constexpr uint32_t kCSQ = 129 * 16;  // chunk stride of 128-row tiles (P, dS)
+
+struct MhsaBwdArgs {
+    const float* dy;
+    int nslab, T;
+    const unsigned char* img;
+    const unsigned char* qkv;  // fp16 [n,288] scaled q | k | v
+    const unsigned char* o;    // fp16 [n,96]
+    const float* lse;          // [nslab,4,T]
+    unsigned char* dqkv;       // FMT_G [n,288]
+    int* err;
+};
+
+// smem map (bytes)
+constexpr uint32_t MB_DO = 0;                       // dO tile, 13 chunks x kCS (chunk 12 = zeros); first holds dy (12 chunks)
+constexpr uint32_t MB_Q = 13 * kCS;                 // per-head Qs tile [256 x 32] fp16, 4 chunks
+constexpr uint32_t MB_K = MB_Q + 4 * kCS;
+constexpr uint32_t MB_V = MB_K + 4 * kCS;
+constexpr uint32_t MB_P = MB_V + 4 * kCS;           // P tile [128 q x 128 keys], 16 chunks x kCSQ; aliases the WoT image
+constexpr uint32_t MB_DS = MB_P + 16 * kCSQ;        // dS tile
+constexpr uint32_t MB_DELTA = MB_DS + 16 * kCSQ;    // delta [4][256] floats
+constexpr uint32_t MB_LSE = MB_DELTA + 4096;        // lse   [4][256] floats
+constexpr uint32_t MB_BAR = MB_LSE + 4096;
+constexpr uint32_t MB_SMEM = MB_BAR + 64;
+static_assert(IMG_WQ_BYTES <= 16 * kCSQ, "WoT image must fit the P region");
+
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int FMT_G>
+__global__ void __launch_bounds__(256, 1) mhsa_bwd_core_kernel(MhsaBwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* dot = smem + MB_DO;
+    unsigned char* qt = smem + MB_Q;
+    unsigned char* kt = smem + MB_K;
+    unsigned char* vt = smem + MB_V;
+    unsigned char* pt = smem + MB_P;
+    unsigned char* dst = smem + MB_DS;
+    float* s_delta = reinterpret_cast<float*>(smem + MB_DELTA);
+    float* s_lse = reinterpret_cast<float*>(smem + MB_LSE);
+    uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + MB_BAR);
+    uint64_t* bar_w = bar_mma + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = a.T;
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_w, 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < (int)(MB_DELTA / 16); i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int m = warp >> 2, q = warp & 3, rt = 32 * q + lane, t = 128 * m + rt;
+    const uint32_t lane_off = (uint32_t)(32 * q) << 16;
+    const uint32_t doa = smem_u32(dot), qa = smem_u32(qt), ka = smem_u32(kt), va = smem_u32(vt), pa = smem_u32(pt), dsa = smem_u32(dst);
+    // instruction descriptors: (A fmt, B fmt, A major, B major, N)
+    auto idesc = [](uint32_t fa, uint32_t fb, uint32_t amn, uint32_t bmn, uint32_t n) {
+        return (1u << 4) | (fa << 7) | (fb << 10) | (amn << 15) | (bmn << 16) | ((n >> 3) << 17) | (8u << 24);
+    };
+    const uint32_t id_do = idesc(FMT_G, FMT_G, 0, 0, 96);       // dO = dy WoT
+    const uint32_t id_s = idesc(FMT_F16, FMT_F16, 0, 0, 128);   // S = Qs K^T
+    const uint32_t id_dp = idesc(FMT_G, FMT_F16, 0, 0, 128);    // dP = dO V^T
+    const uint32_t id_dq = idesc(FMT_G, FMT_F16, 0, 1, 32);     // dQ = dS K      (B MN-major)
+    const uint32_t id_dk = idesc(FMT_G, FMT_F16, 1, 1, 32);     // dK = dS^T Qs   (A, B MN-major)
+    const uint32_t id_dv = idesc(FMT_G, FMT_G, 1, 1, 32);       // dV = P^T dO
+    // TMEM columns
+    constexpr uint32_t C_S = 0, C_DP = 128, C_DQ = 256, C_DK = 320, C_DV = 384;  // dO (M0) uses 0..191
+    const float kscale = 0.6931471805599453f;                   // dK was formed with log2e-scaled q
+    const float qscale = rsqrtf((float)kDH);
+    uint32_t ph_mma = 0, ph_w = 0;
+
+    auto wait_mma = [&]() {
+        __syncwarp();
+        mbar_wait(bar_mma, ph_mma, a.err);
+        ph_mma ^= 1;
+        tc_fence_after();
+    };
+    auto end_epilogue = [&]() {
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+    };
+
+    for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
+        const size_t row0 = (size_t)slab * T;
+        if (tid == 0) load_image(pt, a.img + IMG_WOT, IMG_WQ_BYTES, bar_w);
+        for (int i = tid; i < kNH * 256; i += 256) {
+            const int h = i >> 8, tt = i & 255;
+            s_lse[i] = tt < T ? a.lse[((size_t)slab * kNH + h) * T + tt] : 0.f;
+        }
+        stage_rows96<FMT_G, false>(a.dy + row0 * kH, T, dot, 0, nullptr, nullptr, warp, lane);
+        end_epilogue();
+        // ---- M0: dO = dy Wo
+        if (tid == 0) {
+            tc_fence_after();
+            mbar_wait(bar_w, ph_w, a.err);
+            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 96, doa + 128 * mm * 16, kCS, pa, 96 * 16, 6, id_do, 0);
+            umma_commit(bar_mma);
+        }
+        ph_w ^= 1;
+        wait_mma();
+        // ---- E0: dO -> 16-bit tile (in place of dy), delta_h = sum_c dO O
+        {
+            const bool valid = t < T;
+            const uint32_t tacc = tmem + lane_off + m * 96;
+#pragma unroll 1
+            for (int h = 0; h < kNH; ++h) {
+                float dl = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int c = kDH * h + 8 * k;
+                    uint32_t r[8];
+                    tmem_ld8(tacc + c, r);
+                    tmem_ld_wait();
+                    float v[8], ov[8];
+                    if (valid) {
+                        const uint4 oq = __ldg(reinterpret_cast<const uint4*>(a.o + ((row0 + t) * kH + c) * 2));
+                        unpack_f16x2(oq.x, ov[0], ov[1]);
+                        unpack_f16x2(oq.y, ov[2], ov[3]);
+                        unpack_f16x2(oq.z, ov[4], ov[5]);
+                        unpack_f16x2(oq.w, ov[6], ov[7]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v[j] = valid ? __uint_as_float(r[j]) : 0.f;
+                        dl += valid ? v[j] * ov[j] : 0.f;
+                    }
+                    *reinterpret_cast<uint4*>(dot + (c / 8) * kCS + t * 16) = pack8<FMT_G>(v);
+                }
+                s_delta[h * 256 + t] = dl;
+            }
+        }
+        end_epilogue();
+        // ---- heads
+#pragma unroll 1
+        for (int h = 0; h < kNH; ++h) {
+            // load the head's Qs, K, V (fp16, 24 -> 32 features: 4th chunk stays zero) from the saved projections
+            for (int i = tid; i < T * 9; i += 256) {
+                const int r = i / 9, j = i % 9, which = j / 3, c = j % 3;
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.qkv + ((row0 + r) * 288 + 96 * which + kDH * h + 8 * c) * 2));
+                unsigned char* base = which == 0 ? qt : (which == 1 ? kt : vt);
+                *reinterpret_cast<uint4*>(base + c * kCS + r * 16) = v;
+            }
+            end_epilogue();
+#pragma unroll 1
+            for (int blk = 0; blk < 4; ++blk) {
+                const int qb = blk >> 1, kb = blk & 1;
+                if (tid == 0) {
+                    tc_fence_after();
+                    mma_kk(tmem + C_S, qa + 128 * qb * 16, kCS, ka + 128 * kb * 16, kCS, 2, id_s, 0);
+                    mma_kk(tmem + C_DP, doa + 3 * h * kCS + 128 * qb * 16, kCS, va + 128 * kb * 16, kCS, 2, id_dp, 0);
+                    umma_commit(bar_mma);
+                }
+                wait_mma();
+                // P and dS for this block: thread = (query row rt, 64-key half m)
+                {
+                    const int tq = 128 * qb + rt;
+                    const float lse = s_lse[h * 256 + tq], dl = s_delta[h * 256 + tq];
+                    const bool qok = tq < T;
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        uint32_t rs[32], rp[32];
+                        tmem_ld32(tmem + lane_off + C_S + 64 * m + c0, rs);
+                        tmem_ld32(tmem + lane_off + C_DP + 64 * m + c0, rp);
+                        tmem_ld_wait();
+                        float p[32], ds[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int key = 128 * kb + 64 * m + c0 + j;
+                            const float pv = (qok && key < T) ? ex2f(__uint_as_float(rs[j]) - lse) : 0.f;
+                            p[j] = pv;
+                            ds[j] = pv * (__uint_as_float(rp[j]) - dl);
+                        }
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            const int chunk = (64 * m + c0) / 8 + cc;
+                            *reinterpret_cast<uint4*>(pt + chunk * kCSQ + rt * 16) = pack8<FMT_G>(p + 8 * cc);
+                            *reinterpret_cast<uint4*>(dst + chunk * kCSQ + rt * 16) = pack8<FMT_G>(ds + 8 * cc);
+                        }
+                    }
+                }
+                end_epilogue();
+                if (tid == 0) {
+                    tc_fence_after();
+                    for (int ks = 0; ks < 8; ++ks) {
+                        // dQ[qb] += dS K[kb]: A = dS (K-major, K = keys), B = K tile MN-major (K = key rows)
+                        umma_f16(tmem + C_DQ + 32 * qb, sdesc_kmajor(dsa + 2 * ks * kCSQ, kCSQ),
+                                 sdesc_mnmajor(ka + (128 * kb + 16 * ks) * 16, kCS), id_dq, (kb | ks) ? 1u : 0u);
+                        // dK[kb] += dS^T Qs[qb]: A = dS MN-major (M = keys, K = query rows), B = Qs MN-major
+                        umma_f16(tmem + C_DK + 32 * kb, sdesc_mnmajor(dsa + 16 * ks * 16, kCSQ),
+                                 sdesc_mnmajor(qa + (128 * qb + 16 * ks) * 16, kCS), id_dk, (qb | ks) ? 1u : 0u);
+                        // dV[kb] += P^T dO[qb]
+                        umma_f16(tmem + C_DV + 32 * kb, sdesc_mnmajor(pa + 16 * ks * 16, kCSQ),
+                                 sdesc_mnmajor(doa + 3 * h * kCS + (128 * qb + 16 * ks) * 16, kCS), id_dv, (qb | ks) ? 1u : 0u);
+                    }
+                    umma_commit(bar_mma);
+                }
+                wait_mma();
+            }
+            // read out dQ_h, dK_h, dV_h (thread = frame t of tile m) -> dQKV
+            {
+                // tcgen05.ld is warp-collective: every lane issues it, only valid frames store
+                const bool valid = t < T;
+                unsigned char* orow = a.dqkv + (row0 + (valid ? t : 0)) * 288 * 2;
+#pragma unroll
+                for (int which = 0; which < 3; ++which) {
+                    const uint32_t col = (which == 0 ? C_DQ : (which == 1 ? C_DK : C_DV)) + 32 * m;
+                    const float sc = which == 0 ? qscale : (which == 1 ? kscale : 1.f);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        uint32_t r[8];
+                        tmem_ld8(tmem + lane_off + col + 8 * k, r);
+                        tmem_ld_wait();
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) * sc;
+                        if (valid) *reinterpret_cast<uint4*>(orow + (96 * which + kDH * h + 8 * k) * 2) = pack8<FMT_G>(v);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncthreads();
+        }
+    }
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ LN / in-proj backward
+struct MhsaLnArgs {
+    const float* x;
+    const float* dy;
+    float* dx;
+    int nslab, T;
+    const float* ln_w;
+    const float* ln_stats;
+    const unsigned char* img;
+    const unsigned char* dqkv;  // FMT_G [n,288]
+    float *d_lnw, *d_lnb;
+    int* err;
+};
+constexpr uint32_t ML_A = 0;                        // dQKV tile 36 chunks
+constexpr uint32_t ML_W = 36 * kCS;                 // WinT image 55296
+constexpr uint32_t ML_CST = ML_W + IMG_WINT_BYTES;  // ln_w 96 + acc 192 floats
+constexpr uint32_t ML_BAR = ML_CST + 288 * 4;
+constexpr uint32_t ML_SMEM = ML_BAR + 64;
+
+template <int FMT_G>
+__global__ void __launch_bounds__(256, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* at = smem + ML_A;
+    unsigned char* wt = smem + ML_W;
+    float* s_lng = reinterpret_cast<float*>(smem + ML_CST);
+    float* acc = s_lng + 96;  // [0,96) d_lnw, [96,192) d_lnb
+    uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + ML_BAR);
+    uint64_t* bar_w = bar_mma + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = a.T;
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    if (tid == 0) {
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_w, 1);
+        fence_mbar_init();
+        load_image(wt, a.img + IMG_WINT, IMG_WINT_BYTES, bar_w);  // resident for the whole kernel
+    }
+    for (int i = tid; i < 96; i += 256) s_lng[i] = a.ln_w[i];
+    for (int i = tid; i < 192; i += 256) acc[i] = 0.f;
+    for (int i = tid; i < (int)(36 * kCS / 16); i += 256) reinterpret_cast<uint4*>(at)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int m = warp >> 2, q = warp & 3, t = 128 * m + 32 * q + lane;
+    const bool valid = t < T;
+    const uint32_t tacc = tmem + ((uint32_t)(32 * q) << 16) + m * 96;
+    const uint32_t ata = smem_u32(at), wta = smem_u32(wt);
+    const uint32_t id96 = make_idesc(FMT_G, 128, 96, 0, 0);
+    uint32_t ph = 0;
+    bool wready = false;
+    for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
+        const size_t row0 = (size_t)slab * T, grow = row0 + t;
+        const unsigned char* src = a.dqkv + row0 * 288 * 2;
+        for (int i = tid; i < T * 36; i += 256) {
+            const int r = i / 36, c = i % 36;
+            *reinterpret_cast<uint4*>(at + (size_t)c * kCS + r * 16) = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)r * 288 + 8 * c) * 2));
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            if (!wready) mbar_wait(bar_w, 0, a.err);
+            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 96, ata + 128 * mm * 16, kCS, wta, 96 * 16, 18, id96, 0);
+            umma_commit(bar_mma);
+        }
+        wready = true;
+        __syncwarp();
+        mbar_wait(bar_mma, ph, a.err);
+        ph ^= 1;
+        tc_fence_after();
+        // LayerNorm backward (same arithmetic as ffn_bwd E5)
+        const float2 st = valid ? __ldg(reinterpret_cast<const float2*>(a.ln_stats + 2 * grow)) : make_float2(0.f, 0.f);
+        const float* xr = a.x + grow * kH;
+        float m1 = 0.f, m2 = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kH; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tacc + c0, r);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 xv = __ldg(reinterpret_cast<const float4*>(xr + c0) + j4);
+                    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float dzg = __uint_as_float(r[4 * j4 + e]) * s_lng[c0 + 4 * j4 + e];
+                        m1 += dzg;
+                        m2 += dzg * (xs[e] - st.x) * st.y;
+                    }
+                }
+            }
+        }
+        m1 *= (1.f / kH);
+        m2 *= (1.f / kH);
+#pragma unroll 1
+        for (int c0 = 0; c0 < kH; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tacc + c0, r);
+            tmem_ld_wait();
+            float dzv[32], dzx[32];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                float4 xv = make_float4(0, 0, 0, 0), dv = xv;
+                if (valid) {
+                    xv = __ldg(reinterpret_cast<const float4*>(xr + c0) + j4);
+                    dv = __ldg(reinterpret_cast<const float4*>(a.dy + grow * kH + c0) + j4);
+                }
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float dz = valid ? __uint_as_float(r[4 * j4 + e]) : 0.f;
+                    const float xh = (xs[e] - st.x) * st.y;
+                    dzv[4 * j4 + e] = dz;
+                    dzx[4 * j4 + e] = dz * xh;
+                    o[e] = ds[e] + st.y * (dz * s_lng[c0 + 4 * j4 + e] - m1 - xh * m2);
+                }
+                if (valid) reinterpret_cast<float4*>(a.dx + grow * kH + c0)[j4] = make_float4(o[0], o[1], o[2], o[3]);
+            }
+            const float sw = warp_colsum32(dzx, lane), sb = warp_colsum32(dzv, lane);
+            atomicAdd(acc + c0 + lane, sw);
+            atomicAdd(acc + 96 + c0 + lane, sb);
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    for (int i = tid; i < 96; i += 256) { atomicAdd(a.d_lnw + i, acc[i]); atomicAdd(a.d_lnb + i, acc[96 + i]); }
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace nbss
+
+// Backward of y = x + MHSA(LN(x)).  Writes dqkv (scratch, fmt_g [n,288], also consumed by nbss_mhsa_wgrad) and dx;
+// accumulates d_lnw / d_lnb.
+extern "C" int nbss_mhsa_bwd(const float* x, const float* dy, float* dx, int nslab, int T, const float* ln_w,
+                             const float* ln_stats, const void* layer_img, const void* qkv, const void* o, const float* lse,
+                             void* dqkv, float* d_lnw, float* d_lnb, int fmt_g, int* err, void* stream) {
+    using namespace nbss;
+    if (!x || !dy || !dx || !ln_w || !ln_stats || !layer_img || !qkv || !o || !lse || !dqkv || !d_lnw || !d_lnb) return NBSS_ERR_NULL;
+    if (T < 1 || T > kTMax || nslab < 1) return NBSS_ERR_SHAPE;
+    if (fmt_g != FMT_BF16 && fmt_g != FMT_F16) return NBSS_ERR_UNSUPPORTED;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = nslab < sms ? nslab : sms;
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        MhsaBwdArgs a{dy, nslab, T, (const unsigned char*)layer_img, (const unsigned char*)qkv, (const unsigned char*)o, lse,
+                      (unsigned char*)dqkv, err};
+        auto kern = (fmt_g == FMT_BF16) ? mhsa_bwd_core_kernel<FMT_BF16> : mhsa_bwd_core_kernel<FMT_F16>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MB_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, 256, MB_SMEM, st>>>(a);
+        NBSS_LAUNCH_CHECK();
+    }
+    {
+        MhsaLnArgs a{x, dy, dx, nslab, T, ln_w, ln_stats, (const unsigned char*)layer_img, (const unsigned char*)dqkv, d_lnw, d_lnb, err};
+        auto kern = (fmt_g == FMT_BF16) ? mhsa_bwd_ln_kernel<FMT_BF16> : mhsa_bwd_ln_kernel<FMT_F16>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ML_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, 256, ML_SMEM, st>>>(a);
+        NBSS_LAUNCH_CHECK();
+    }
+    return NBSS_OK;
+}

@@ -1,0 +1,135 @@
+// slab.cuh — building blocks of the narrow-band "slab" kernels (one CTA = one (b,f) slab = all T frames x channels).
+//
+// A slab [T<=256, C] lives in shared memory as a 16-bit UMMA operand tile in the chunk-column layout (umma.cuh):
+// 8 channels per 16-byte chunk, rows linear at 16 B, chunk stride kCS.  The T axis is split in two M-tiles of 128
+// rows; rows >= T are zero.  Accumulators: TMEM lane = row within the M-tile, column = output channel.
+// Thread mapping of every epilogue: 256 threads, warp w -> M-tile (w>>2), TMEM lane quarter (w&3), thread = one
+// frame: t = 128*(w>>2) + 32*(w&3) + lane.  Row reductions (LayerNorm, softmax) are therefore thread-local.
+#pragma once
+#include "common.cuh"
+#include "layout.cuh"
+#include "umma.cuh"
+
+namespace nbss {
+
+// ---------------------------------------------------------------- TMA bulk copy (global -> smem) of weight images
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// Call from ONE thread. The barrier must have been initialised with count 1.
+__device__ __forceinline__ void load_image(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(dst_smem, src, bytes, bar);
+}
+
+// ---------------------------------------------------------------- MMA issue helpers (call from ONE thread)
+// D[128 x N] (+)= A[128 x 16*ksteps] * B[N x 16*ksteps]^T, both K-major chunk-column tiles.
+__device__ __forceinline__ void mma_kk(uint32_t tmem_d, uint32_t a_addr, uint32_t a_cs, uint32_t b_addr, uint32_t b_cs,
+                                       int ksteps, uint32_t idesc, uint32_t acc) {
+    for (int ks = 0; ks < ksteps; ++ks) {
+        umma_f16(tmem_d, sdesc_kmajor(a_addr + 2 * ks * a_cs, a_cs), sdesc_kmajor(b_addr + 2 * ks * b_cs, b_cs), idesc, acc);
+        acc = 1;
+    }
+}
+
+// ---------------------------------------------------------------- packing
+template <int FMT>
+__device__ __forceinline__ uint4 pack8(const float* v) {
+    return make_uint4(pack16<FMT>(v[0], v[1]), pack16<FMT>(v[2], v[3]), pack16<FMT>(v[4], v[5]), pack16<FMT>(v[6], v[7]));
+}
+__device__ __forceinline__ void unpack_f16x2(uint32_t p, float& lo, float& hi) {
+    asm("{\n.reg .b16 l, h;\nmov.b32 {l, h}, %2;\ncvt.f32.f16 %0, l;\ncvt.f32.f16 %1, h;\n}" : "=f"(lo), "=f"(hi) : "r"(p));
+}
+template <int FMT>
+__device__ __forceinline__ void unpack16(uint32_t p, float& lo, float& hi) {
+    if constexpr (FMT == FMT_F16) unpack_f16x2(p, lo, hi);
+    else { lo = bf16lo_to_f32(p); hi = bf16hi_to_f32(p); }
+}
+
+// ---------------------------------------------------------------- staging: fp32 rows -> (LayerNorm) -> 16-bit tile
+// Warp-per-row, coalesced float4 loads (24 lanes x 16 B = one 96-channel row).  Writes rows [row_off, row_off+256)
+// of the tile; rows t >= T are written as zeros.  gamma/beta in shared memory.
+template <int FMT, bool LN>
+__device__ __forceinline__ void stage_rows96(const float* __restrict__ xslab, int T, unsigned char* tile, int row_off,
+                                             const float* s_gamma, const float* s_beta, int warp, int lane,
+                                             float* stats_out = nullptr /* [T,2] (mean, rstd) of this slab */) {
+    const bool act = lane < 24;
+    float4 g = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (LN && act) {
+        g = *reinterpret_cast<const float4*>(s_gamma + 4 * lane);
+        be = *reinterpret_cast<const float4*>(s_beta + 4 * lane);
+    }
+#pragma unroll 1
+    for (int i = 0; i < 32; i += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = warp + 8 * (i + j);
+            v[j] = (act && r < T) ? __ldg(reinterpret_cast<const float4*>(xslab + (size_t)r * kH) + lane)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = warp + 8 * (i + j);
+            float4 y = v[j];
+            if (LN) {
+                float s = warp_sum(y.x + y.y + y.z + y.w);
+                const float mean = s * (1.f / kH);
+                float4 d = act ? make_float4(y.x - mean, y.y - mean, y.z - mean, y.w - mean) : make_float4(0, 0, 0, 0);
+                float q = warp_sum(d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w);
+                const float rstd = rsqrtf(q * (1.f / kH) + 1e-5f);
+                y = make_float4(d.x * rstd * g.x + be.x, d.y * rstd * g.y + be.y, d.z * rstd * g.z + be.z,
+                                d.w * rstd * g.w + be.w);
+                if (stats_out && lane == 0 && r < T) *reinterpret_cast<float2*>(stats_out + 2 * r) = make_float2(mean, rstd);
+            }
+            if (act) {
+                uint2 p = (r < T) ? make_uint2(pack16<FMT>(y.x, y.y), pack16<FMT>(y.z, y.w)) : make_uint2(0u, 0u);
+                *reinterpret_cast<uint2*>(tile + (lane >> 1) * kCS + (r + row_off) * 16 + (lane & 1) * 8) = p;
+            }
+        }
+    }
+}
+
+// Column sums across the 32 lanes of a warp: on entry lane l holds v[0..31] = one row of a 32-column block; on return
+// lane l gets the sum over all 32 rows of column l.  31 shuffles (recursive halving) instead of 32 x 5.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float a = v[i], b = v[i + s];
+            const float send = up ? a : b, keep = up ? b : a;
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+// Block-wide sum of NV per-thread values (256 threads). `red` is smem scratch of 8*NV floats. Result broadcast.
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* red, int warp, int lane) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();  // protect `red` from the previous use
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) red[warp * NV + i] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w * NV + i];
+        v[i] = s;
+    }
+}
+
+}  // namespace nbss

@@ -48,16 +48,30 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
         : "memory");
     return ok;
 }
-#ifndef NBSS_SPIN_LIMIT
-#define NBSS_SPIN_LIMIT (1u << 24)
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#ifndef NBSS_WAIT_TIMEOUT_NS
+#define NBSS_WAIT_TIMEOUT_NS 200000000ull  // 0.2 s: far beyond any legitimate wait in these kernels
 #endif
-// Bounded wait. Returns false (and sets *err_flag if non-null) when the barrier never completed.
+// Bounded wait. Returns false (and sets *err_flag) when the barrier did not complete within the timeout; once the
+// flag is set every later wait in the grid bails out immediately, so a protocol bug cannot hang the GPU.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag = nullptr) {
-    for (uint32_t i = 0; i < NBSS_SPIN_LIMIT; ++i) {
-        if (mbar_try_wait(bar, parity)) return true;
+    if (mbar_try_wait(bar, parity)) return true;
+    const uint64_t t0 = global_timer_ns();
+    uint32_t polls = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++polls & 255u) == 0) {
+            if (err_flag && *reinterpret_cast<volatile int*>(err_flag) != 0) return false;
+            if (global_timer_ns() - t0 > NBSS_WAIT_TIMEOUT_NS) {
+                if (err_flag) atomicExch(err_flag, 0x7001);
+                return false;
+            }
+        }
     }
-    if (err_flag) atomicExch(err_flag, 0x7001);
-    return false;
+    return true;
 }
 
 // ---------------------------------------------------------------- fences

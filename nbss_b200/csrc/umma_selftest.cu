@@ -13,7 +13,8 @@ struct SelfTestArgs {
     int a_rows, a_feats, b_rows, b_feats;
     int N, Kdim;
     int a_mn, b_mn;      // 1 = MN-major view
-    int fmt;             // FMT_F16 / FMT_BF16 / FMT_TF32
+    int fmt;             // FMT_F16 / FMT_BF16 / FMT_TF32 (A operand)
+    int fmt_b;           // B operand format (may differ from A for the 16-bit kinds)
     int a_shift, b_shift;  // row shift of the view (rows)
     int a_off, b_off;      // feature offset of the MN index (MN-major) or of the K index (K-major)
     int passes;            // issue the whole K loop `passes` times (accumulating)
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(SelfTestArgs a) {
         fence_mbar_init();
     }
     fill_tile(sA, a.A, a.a_rows, a.a_feats, a_rtot, a.fmt, tid, blockDim.x);
-    fill_tile(sB, a.B, a.b_rows, a.b_feats, b_rtot, a.fmt, tid, blockDim.x);
+    fill_tile(sB, a.B, a.b_rows, a.b_feats, b_rtot, a.fmt_b, tid, blockDim.x);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(SelfTestArgs a) {
     const uint32_t tbase = tmem_base_s + a.tmem_col;
 
     if (tid == 0) {
-        const uint32_t idesc = make_idesc(a.fmt, 128, a.N, a.a_mn, a.b_mn);
+        const uint32_t idesc = (make_idesc(a.fmt, 128, a.N, a.a_mn, a.b_mn) & ~(7u << 10)) | ((uint32_t)a.fmt_b << 10);
         const int kstep = (a.fmt == FMT_TF32) ? 8 : 16;
         const int nk = a.Kdim / kstep;
         uint32_t acc = 0;
@@ -126,14 +127,14 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(SelfTestArgs a) {
 
 extern "C" int nbss_umma_selftest(const float* A, int a_rows, int a_feats, const float* B, int b_rows, int b_feats,
                                   float* D, int N, int Kdim, int a_mn, int b_mn, int fmt, int a_shift, int b_shift,
-                                  int a_off, int b_off, int passes, int tmem_col, int* err, void* stream) {
+                                  int a_off, int b_off, int passes, int tmem_col, int fmt_b, int* err, void* stream) {
     using namespace nbss;
     if (N % 16 || N < 16 || N > 256) return NBSS_ERR_SHAPE;
     if (tmem_col + N > 512) return NBSS_ERR_SHAPE;
     const int es = (fmt == FMT_TF32) ? 4 : 2, ce = 16 / es;
     size_t bytes = (size_t)((a_feats + ce - 1) / ce) * (a_rows + 8) * 16 + (size_t)((b_feats + ce - 1) / ce) * (b_rows + 8) * 16;
     if (bytes > 200 * 1024) return NBSS_ERR_SHAPE;
-    SelfTestArgs a{A, B, D, a_rows, a_feats, b_rows, b_feats, N, Kdim, a_mn, b_mn, fmt, a_shift, b_shift, a_off, b_off, passes, tmem_col, err};
+    SelfTestArgs a{A, B, D, a_rows, a_feats, b_rows, b_feats, N, Kdim, a_mn, b_mn, fmt, fmt_b < 0 ? fmt : fmt_b, a_shift, b_shift, a_off, b_off, passes, tmem_col, err};
     cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
     umma_selftest_kernel<<<1, 128, bytes, (cudaStream_t)stream>>>(a);

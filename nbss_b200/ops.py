@@ -1,0 +1,320 @@
+"""Thin Python wrappers over the C-ABI entry points of libnbss_b200.so (include/nbss_b200.h).
+
+Each wrapper takes torch CUDA tensors, passes raw device pointers + sizes + the current CUDA stream, and raises
+``NbssError`` on a non-zero status.  No arithmetic happens here and there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+FMT_F16, FMT_BF16, FMT_TF32 = 0, 1, 2
+Tensor = torch.Tensor
+
+
+def _f32c(t: Tensor) -> Tensor:
+    assert t.is_cuda and t.dtype == torch.float32, (t.device, t.dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def device_err_flag(device) -> Tensor:
+    return torch.zeros(1, dtype=torch.int32, device=device)
+
+
+def check_err_flag(flag: Tensor, what: str) -> None:
+    v = int(flag.item())
+    if v != 0:
+        raise _lib.NbssError(f"{what}: device-side error flag {v:#x} (mbarrier wait timed out)")
+
+
+def layer_image_bytes() -> int:
+    L = _lib.lib()
+    L.nbss_layer_image_bytes.restype = ctypes.c_uint
+    return int(L.nbss_layer_image_bytes())
+
+
+def pack_layer_weights(P: Dict[str, Tensor], pre: str, img: Optional[Tensor] = None, fwd_fmt: int = FMT_F16,
+                       bwd_fmt: int = FMT_BF16) -> Tensor:
+    """Builds the UMMA weight images of one SpatialNet layer (pack.cu) from its fp32 parameters."""
+    L = _lib.lib()
+    dev = P[pre + "tconvffn.1.weight"].device
+    if img is None:
+        img = torch.empty(layer_image_bytes(), dtype=torch.uint8, device=dev)
+    t = pre + "tconvffn."
+    st = L.nbss_pack_layer_weights(
+        ptr(_f32c(P[t + "1.weight"])), ptr(_f32c(P[t + "3.weight"])), ptr(_f32c(P[t + "5.weight"])),
+        ptr(_f32c(P[t + "8.weight"])), ptr(_f32c(P[t + "10.weight"])), ptr(_f32c(P[pre + "mhsa.in_proj_weight"])),
+        ptr(_f32c(P[pre + "mhsa.out_proj.weight"])), ptr(img), fwd_fmt, bwd_fmt, stream_ptr())
+    check(st, "nbss_pack_layer_weights")
+    return img
+
+
+def ffn_fwd(x: Tensor, P: Dict[str, Tensor], pre: str, img: Tensor, save: bool = False, fmt: int = FMT_F16,
+            out: Optional[Tensor] = None):
+    """x: [B,F,T,96] fp32 -> y = x + tconvffn(x).  With save=True also returns the fp16 pre-activations
+    (a1, c1, c2, c3) [B*F*T,192] and GroupNorm stats [B*F,8,2] needed by the backward kernels."""
+    L = _lib.lib()
+    x = _f32c(x)
+    B, F, T, H = x.shape
+    assert H == 96
+    y = torch.empty_like(x) if out is None else out
+    n = B * F * T
+    saves = [torch.empty(n, 192, dtype=torch.float16, device=x.device) for _ in range(4)] if save else [None] * 4
+    stats = torch.empty(B * F, 8, 2, dtype=torch.float32, device=x.device) if save else None
+    ln_stats = torch.empty(n, 2, dtype=torch.float32, device=x.device) if save else None
+    err = device_err_flag(x.device)
+    t = pre + "tconvffn."
+    st = L.nbss_ffn_fwd(
+        ptr(x), ptr(y), B * F, T, ptr(_f32c(P[t + "0.weight"])), ptr(_f32c(P[t + "0.bias"])), ptr(_f32c(P[t + "1.bias"])),
+        ptr(_f32c(P[t + "3.bias"])), ptr(_f32c(P[t + "5.bias"])), ptr(_f32c(P[t + "8.bias"])), ptr(_f32c(P[t + "6.weight"])),
+        ptr(_f32c(P[t + "6.bias"])), ptr(_f32c(P[t + "10.bias"])), ptr(img), ptr(saves[0]), ptr(saves[1]), ptr(saves[2]),
+        ptr(saves[3]), ptr(stats), ptr(ln_stats), fmt, ptr(err), stream_ptr())
+    check(st, "nbss_ffn_fwd")
+    if save:
+        return y, saves + [ln_stats], stats, err
+    return y, err
+
+
+def mhsa_fwd(x: Tensor, P: Dict[str, Tensor], pre: str, img: Tensor, save: bool = False, fmt: int = FMT_F16,
+             out: Optional[Tensor] = None):
+    """x: [B,F,T,96] fp32 -> y = x + MHSA(LN(x)) over T per (b,f).  With save=True also returns fp16 (scaled q|k|v)
+    [n,288], O [n,96] and the log2-domain logsumexp [B*F,4,T]."""
+    L = _lib.lib()
+    x = _f32c(x)
+    B, F, T, H = x.shape
+    assert H == 96
+    y = torch.empty_like(x) if out is None else out
+    n = B * F * T
+    qkv = torch.empty(n, 288, dtype=torch.float16, device=x.device) if save else None
+    o = torch.empty(n, 96, dtype=torch.float16, device=x.device) if save else None
+    lse = torch.empty(B * F, 4, T, dtype=torch.float32, device=x.device) if save else None
+    ln_stats = torch.empty(n, 2, dtype=torch.float32, device=x.device) if save else None
+    err = device_err_flag(x.device)
+    st = L.nbss_mhsa_fwd(
+        ptr(x), ptr(y), B * F, T, ptr(_f32c(P[pre + "norm_mhsa.weight"])), ptr(_f32c(P[pre + "norm_mhsa.bias"])),
+        ptr(_f32c(P[pre + "mhsa.in_proj_bias"])), ptr(_f32c(P[pre + "mhsa.out_proj.bias"])), ptr(img), ptr(qkv), ptr(o),
+        ptr(lse), ptr(ln_stats), fmt, ptr(err), stream_ptr())
+    check(st, "nbss_mhsa_fwd")
+    if save:
+        return y, (qkv, o, lse, ln_stats), err
+    return y, err
+
+
+# ------------------------------------------------------------------------------------------------ cross-band (fp32)
+def fconv_fwd(x: Tensor, P, pre: str, out: Optional[Tensor] = None) -> Tensor:
+    """y = x + PReLU(gconv_F(LN(x))); pre = 'layers.i.fconv1' / '...fconv2'."""
+    L = _lib.lib()
+    x = _f32c(x)
+    B, F, T, H = x.shape
+    assert H == 96
+    y = torch.empty_like(x) if out is None else out
+    st = L.nbss_fconv_fwd(ptr(x), ptr(y), B, F, T, ptr(_f32c(P[pre + ".0.weight"])), ptr(_f32c(P[pre + ".0.bias"])),
+                          ptr(_f32c(P[pre + ".1.weight"])), ptr(_f32c(P[pre + ".1.bias"])), ptr(_f32c(P[pre + ".2.weight"])),
+                          stream_ptr())
+    check(st, "nbss_fconv_fwd")
+    return y
+
+
+def fconv_bwd(x: Tensor, dy: Tensor, P, pre: str, G) -> Tensor:
+    """Returns dx; accumulates parameter gradients into the fp32 tensors G[name] (same keys as P)."""
+    L = _lib.lib()
+    x, dy = _f32c(x), _f32c(dy)
+    B, F, T, H = x.shape
+    dx = torch.empty_like(x)
+    st = L.nbss_fconv_bwd(ptr(x), ptr(dy), ptr(dx), B, F, T, ptr(_f32c(P[pre + ".0.weight"])), ptr(_f32c(P[pre + ".0.bias"])),
+                          ptr(_f32c(P[pre + ".1.weight"])), ptr(_f32c(P[pre + ".1.bias"])), ptr(_f32c(P[pre + ".2.weight"])),
+                          ptr(G[pre + ".1.weight"]), ptr(G[pre + ".1.bias"]), ptr(G[pre + ".2.weight"]),
+                          ptr(G[pre + ".0.weight"]), ptr(G[pre + ".0.bias"]), stream_ptr())
+    check(st, "nbss_fconv_bwd")
+    return dx
+
+
+def full_fwd(x: Tensor, P, pre: str, out: Optional[Tensor] = None):
+    """y = x + full-band branch; returns (y, s, u) with s,u [B,T,8,F] kept for backward."""
+    L = _lib.lib()
+    x = _f32c(x)
+    B, F, T, H = x.shape
+    y = torch.empty_like(x) if out is None else out
+    s = torch.empty(B, T, 8, F, dtype=torch.float32, device=x.device)
+    u = torch.empty_like(s)
+    st = L.nbss_full_fwd(ptr(x), ptr(y), ptr(s), ptr(u), B, F, T, ptr(_f32c(P[pre + "norm_full.weight"])),
+                         ptr(_f32c(P[pre + "norm_full.bias"])), ptr(_f32c(P[pre + "squeeze.0.weight"])),
+                         ptr(_f32c(P[pre + "squeeze.0.bias"])), ptr(_f32c(P[pre + "full.weight"])),
+                         ptr(_f32c(P[pre + "full.bias"])), ptr(_f32c(P[pre + "unsqueeze.0.weight"])),
+                         ptr(_f32c(P[pre + "unsqueeze.0.bias"])), stream_ptr())
+    check(st, "nbss_full_fwd")
+    return y, s, u
+
+
+def full_bwd(x: Tensor, dy: Tensor, s: Tensor, u: Tensor, P, pre: str, G) -> Tensor:
+    L = _lib.lib()
+    x, dy = _f32c(x), _f32c(dy)
+    B, F, T, H = x.shape
+    dx = torch.empty_like(x)
+    ws = torch.empty(2 * s.numel(), dtype=torch.float32, device=x.device)
+    st = L.nbss_full_bwd(ptr(x), ptr(dy), ptr(dx), ptr(s), ptr(u), ptr(ws), B, F, T, ptr(_f32c(P[pre + "norm_full.weight"])),
+                         ptr(_f32c(P[pre + "norm_full.bias"])), ptr(_f32c(P[pre + "squeeze.0.weight"])),
+                         ptr(_f32c(P[pre + "squeeze.0.bias"])), ptr(_f32c(P[pre + "full.weight"])),
+                         ptr(_f32c(P[pre + "unsqueeze.0.weight"])), ptr(_f32c(P[pre + "unsqueeze.0.bias"])),
+                         ptr(G[pre + "norm_full.weight"]), ptr(G[pre + "norm_full.bias"]), ptr(G[pre + "squeeze.0.weight"]),
+                         ptr(G[pre + "squeeze.0.bias"]), ptr(G[pre + "full.weight"]), ptr(G[pre + "full.bias"]),
+                         ptr(G[pre + "unsqueeze.0.weight"]), ptr(G[pre + "unsqueeze.0.bias"]), stream_ptr())
+    check(st, "nbss_full_bwd")
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------ encoder / decoder
+def encoder_fwd(x: Tensor, P) -> Tensor:
+    L = _lib.lib()
+    x = _f32c(x)
+    B, F, T, Cin = x.shape
+    y = torch.empty(B, F, T, 96, dtype=torch.float32, device=x.device)
+    st = L.nbss_encoder_fwd(ptr(x), ptr(y), B * F, T, Cin, ptr(_f32c(P["encoder.weight"])), ptr(_f32c(P["encoder.bias"])), stream_ptr())
+    check(st, "nbss_encoder_fwd")
+    return y
+
+
+def encoder_wgrad(x: Tensor, dy: Tensor, G) -> None:
+    L = _lib.lib()
+    x, dy = _f32c(x), _f32c(dy)
+    B, F, T, Cin = x.shape
+    st = L.nbss_encoder_wgrad(ptr(x), ptr(dy), B * F, T, Cin, ptr(G["encoder.weight"]), ptr(G["encoder.bias"]), stream_ptr())
+    check(st, "nbss_encoder_wgrad")
+
+
+def decoder_fwd(x: Tensor, P) -> Tensor:
+    L = _lib.lib()
+    x = _f32c(x)
+    B, F, T, H = x.shape
+    cout = P["decoder.weight"].shape[0]
+    y = torch.empty(B, F, T, cout, dtype=torch.float32, device=x.device)
+    st = L.nbss_decoder_fwd(ptr(x), ptr(y), ctypes.c_longlong(B * F * T), cout, ptr(_f32c(P["decoder.weight"])),
+                            ptr(_f32c(P["decoder.bias"])), stream_ptr())
+    check(st, "nbss_decoder_fwd")
+    return y
+
+
+def decoder_bwd(x: Tensor, dy: Tensor, P, G) -> Tensor:
+    L = _lib.lib()
+    x, dy = _f32c(x), _f32c(dy)
+    B, F, T, H = x.shape
+    cout = P["decoder.weight"].shape[0]
+    dx = torch.empty_like(x)
+    st = L.nbss_decoder_bwd(ptr(x), ptr(dy), ptr(dx), ctypes.c_longlong(B * F * T), cout, ptr(_f32c(P["decoder.weight"])),
+                            ptr(G["decoder.weight"]), ptr(G["decoder.bias"]), stream_ptr())
+    check(st, "nbss_decoder_bwd")
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------ framing
+def _ll(v):
+    return ctypes.c_longlong(int(v))
+
+
+def stft(x: Tensor, n_fft: int, hop: int) -> Tensor:
+    """STFT.stft: [B,C,Ts] fp32 -> complex64 [B,C,F,T] (center, reflect, periodic Hann, onesided)."""
+    L = _lib.lib()
+    x = _f32c(x)
+    B, C, Ts = x.shape
+    F, T = n_fft // 2 + 1, 1 + Ts // hop
+    out = torch.empty(B, C, F, T, 2, dtype=torch.float32, device=x.device)
+    st = L.nbss_stft(ptr(x), B, C, Ts, n_fft, hop, 0, 0, ctypes.c_float(0.0), ptr(out), _ll(C * F * T * 2), _ll(F * T * 2),
+                     _ll(T * 2), _ll(2), ptr(None), ptr(None), stream_ptr())
+    check(st, "nbss_stft")
+    return torch.view_as_complex(out)
+
+
+def stft_norm_pack(x: Tensor, n_fft: int, hop: int, ref_channel: int, eps: float = 1e-6, want_xr: bool = False):
+    """Fused stft + Norm(frequency, online) + pack: [B,C,Ts] -> (X [B,F,T,2C], XrMM [B,F,T], Xr [B,F,T] complex|None)."""
+    L = _lib.lib()
+    x = _f32c(x)
+    B, C, Ts = x.shape
+    F, T = n_fft // 2 + 1, 1 + Ts // hop
+    out = torch.empty(B, F, T, 2 * C, dtype=torch.float32, device=x.device)
+    xrmm = torch.empty(B, F, T, dtype=torch.float32, device=x.device)
+    xr = torch.empty(B, F, T, 2, dtype=torch.float32, device=x.device) if want_xr else None
+    st = L.nbss_stft(ptr(x), B, C, Ts, n_fft, hop, 1, ref_channel, ctypes.c_float(eps), ptr(out), _ll(F * T * 2 * C), _ll(2),
+                     _ll(T * 2 * C), _ll(2 * C), ptr(xrmm), ptr(xr), stream_ptr())
+    check(st, "nbss_stft")
+    return out, xrmm, (torch.view_as_complex(xr) if want_xr else None)
+
+
+def istft_strided(real_view: Tensor, strides_bsft, scale: Optional[Tensor], B: int, S: int, F: int, T: int, n_fft: int,
+                  hop: int, length: int) -> Tensor:
+    """iSTFT of a complex tensor given as a float32 storage + (b,s,f,t) strides in floats (imag at +1)."""
+    L = _lib.lib()
+    y = torch.empty(B, S, length, dtype=torch.float32, device=real_view.device)
+    ib, is_, if_, it = strides_bsft
+    st = L.nbss_istft(ptr(real_view), _ll(ib), _ll(is_), _ll(if_), _ll(it), ptr(scale), ptr(y), B, S, length, T, n_fft, hop,
+                      stream_ptr())
+    check(st, "nbss_istft")
+    return y
+
+
+def istft_bwd_strided(dy: Tensor, scale: Optional[Tensor], out: Tensor, strides_bsft, B, S, F, T, n_fft, hop) -> Tensor:
+    L = _lib.lib()
+    dy = _f32c(dy)
+    ib, is_, if_, it = strides_bsft
+    st = L.nbss_istft_bwd(ptr(dy), ptr(scale), ptr(out), _ll(ib), _ll(is_), _ll(if_), _ll(it), B, S, dy.shape[-1], T, n_fft, hop,
+                          stream_ptr())
+    check(st, "nbss_istft_bwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ narrow-band backward
+def ffn_bwd(x: Tensor, dy: Tensor, saves, gn_stats: Tensor, P, pre: str, img: Tensor, G, fmt_g: int = FMT_BF16):
+    """Backward of y = x + tconvffn(x).  saves = [a1, c1, c2, c3, ln_stats] from ffn_fwd(save=True).
+    Returns dx; accumulates every tconvffn.* parameter gradient into G (fp32)."""
+    L = _lib.lib()
+    x, dy = _f32c(x), _f32c(dy)
+    B, F, T, H = x.shape
+    n = B * F * T
+    a1, c1, c2, c3, ln_stats = saves
+    dt = torch.bfloat16 if fmt_g == FMT_BF16 else torch.float16
+    gbuf = [torch.empty(n, 192, dtype=dt, device=x.device) for _ in range(4)]  # g_a1, g_c1, g_c2, g_c3
+    sbuf = [torch.empty(n, 192, dtype=dt, device=x.device) for _ in range(4)]  # s1..s4
+    dx = torch.empty_like(x)
+    err = device_err_flag(x.device)
+    t = pre + "tconvffn."
+    st = L.nbss_ffn_bwd(
+        ptr(x), ptr(dy), ptr(dx), B * F, T, ptr(_f32c(P[t + "0.weight"])), ptr(_f32c(P[t + "6.weight"])), ptr(_f32c(P[t + "6.bias"])),
+        ptr(ln_stats), ptr(gn_stats), ptr(img), ptr(a1), ptr(c1), ptr(c2), ptr(c3), ptr(gbuf[0]), ptr(gbuf[1]), ptr(gbuf[2]),
+        ptr(gbuf[3]), ptr(sbuf[0]), ptr(sbuf[1]), ptr(sbuf[2]), ptr(sbuf[3]), ptr(G[t + "0.weight"]), ptr(G[t + "0.bias"]),
+        ptr(G[t + "6.weight"]), ptr(G[t + "6.bias"]), fmt_g, ptr(err), stream_ptr())
+    check(st, "nbss_ffn_bwd")
+    st = L.nbss_ffn_wgrad(
+        ptr(x), ptr(dy), B * F, T, ptr(_f32c(P[t + "0.weight"])), ptr(_f32c(P[t + "0.bias"])), ptr(gbuf[0]), ptr(gbuf[1]),
+        ptr(gbuf[2]), ptr(gbuf[3]), ptr(sbuf[0]), ptr(sbuf[1]), ptr(sbuf[2]), ptr(sbuf[3]), ptr(G[t + "1.weight"]),
+        ptr(G[t + "1.bias"]), ptr(G[t + "3.weight"]), ptr(G[t + "3.bias"]), ptr(G[t + "5.weight"]), ptr(G[t + "5.bias"]),
+        ptr(G[t + "8.weight"]), ptr(G[t + "8.bias"]), ptr(G[t + "10.weight"]), ptr(G[t + "10.bias"]), fmt_g, fmt_g, ptr(err),
+        stream_ptr())
+    check(st, "nbss_ffn_wgrad")
+    return dx, err
+
+
+def mhsa_bwd(x: Tensor, dy: Tensor, msave, P, pre: str, img: Tensor, G, fmt_g: int = FMT_BF16):
+    """Backward of y = x + MHSA(LN(x)).  msave = (qkv, o, lse, ln_stats) from mhsa_fwd(save=True)."""
+    L = _lib.lib()
+    x, dy = _f32c(x), _f32c(dy)
+    B, F, T, H = x.shape
+    n = B * F * T
+    qkv, o, lse, ln_stats = msave
+    dt = torch.bfloat16 if fmt_g == FMT_BF16 else torch.float16
+    dqkv = torch.empty(n, 288, dtype=dt, device=x.device)
+    dx = torch.empty_like(x)
+    err = device_err_flag(x.device)
+    st = L.nbss_mhsa_bwd(ptr(x), ptr(dy), ptr(dx), B * F, T, ptr(_f32c(P[pre + "norm_mhsa.weight"])), ptr(ln_stats), ptr(img),
+                         ptr(qkv), ptr(o), ptr(lse), ptr(dqkv), ptr(G[pre + "norm_mhsa.weight"]), ptr(G[pre + "norm_mhsa.bias"]),
+                         fmt_g, ptr(err), stream_ptr())
+    check(st, "nbss_mhsa_bwd")
+    st = L.nbss_mhsa_wgrad(ptr(x), ptr(dy), B * F, T, ptr(_f32c(P[pre + "norm_mhsa.weight"])), ptr(_f32c(P[pre + "norm_mhsa.bias"])),
+                           ptr(dqkv), ptr(o), ptr(G[pre + "mhsa.in_proj_weight"]), ptr(G[pre + "mhsa.in_proj_bias"]),
+                           ptr(G[pre + "mhsa.out_proj.weight"]), ptr(G[pre + "mhsa.out_proj.bias"]), fmt_g, FMT_F16, ptr(err),
+                           stream_ptr())
+    check(st, "nbss_mhsa_wgrad")
+    return dx, err

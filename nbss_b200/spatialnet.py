@@ -1,0 +1,234 @@
+"""Drop-in ``SpatialNet`` for the reference's ``models.arch.SpatialNet.SpatialNet`` (models/arch/SpatialNet.py:152-220).
+
+Same constructor signature, same parameter names / shapes / creation order (so ``seed_everything`` gives the same
+initial weights and reference checkpoints load), same ``forward(x[B,F,T,dim_input]) -> [B,F,T,dim_output]``
+contract.  The torch submodules created here are ONLY parameter containers — their ``forward`` is never called; all
+arithmetic runs in the sm_100a kernels of ``libnbss_b200.so`` through ``nbss_b200.ops``.  There is no fallback: without
+the library, or on CPU tensors, ``forward`` raises.
+
+Precision policy: fp32 residual stream, norms, activations, cross-band block, encoder/decoder; 16-bit
+tensor-core operands (fp16 forward, bf16 gradient operands) with fp32 accumulation in the narrow-band block.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import ops
+
+
+class LinearGroup(nn.Module):
+    """Parameter container for the full-band linear (models/arch/base/linear_group.py:7-37): weight [G,out,in]."""
+
+    def __init__(self, in_features: int, out_features: int, num_groups: int) -> None:
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(num_groups, out_features, in_features))
+        self.bias = nn.Parameter(torch.empty(num_groups, out_features))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        fan_in, _ = nn.init._calculate_fan_in_and_fan_out(self.weight)
+        bound = 1 / math.sqrt(fan_in) if fan_in > 0 else 0
+        nn.init.uniform_(self.bias, -bound, bound)
+
+
+class SpatialNetLayer(nn.Module):
+    """Parameters of one layer, registered in the reference's order (models/arch/SpatialNet.py:33-74)."""
+
+    def __init__(self, dim_hidden, dim_ffn, dim_squeeze, num_freqs, num_heads, kernel_size, conv_groups, full=None):
+        super().__init__()
+        fk, tk = kernel_size
+        fg, tg = conv_groups
+        self.fconv1 = nn.ModuleList([nn.LayerNorm(dim_hidden),
+                                     nn.Conv1d(dim_hidden, dim_hidden, fk, groups=fg, padding="same"), nn.PReLU(dim_hidden)])
+        self.norm_full = nn.LayerNorm(dim_hidden)
+        self.full_share = full is not None
+        self.squeeze = nn.Sequential(nn.Conv1d(dim_hidden, dim_squeeze, 1), nn.SiLU())
+        self.full = LinearGroup(num_freqs, num_freqs, dim_squeeze) if full is None else full
+        self.unsqueeze = nn.Sequential(nn.Conv1d(dim_squeeze, dim_hidden, 1), nn.SiLU())
+        self.fconv2 = nn.ModuleList([nn.LayerNorm(dim_hidden),
+                                     nn.Conv1d(dim_hidden, dim_hidden, fk, groups=fg, padding="same"), nn.PReLU(dim_hidden)])
+        self.norm_mhsa = nn.LayerNorm(dim_hidden)
+        self.mhsa = nn.MultiheadAttention(embed_dim=dim_hidden, num_heads=num_heads, batch_first=True)
+        self.tconvffn = nn.ModuleList([
+            nn.LayerNorm(dim_hidden), nn.Conv1d(dim_hidden, dim_ffn, 1), nn.SiLU(),
+            nn.Conv1d(dim_ffn, dim_ffn, tk, padding="same", groups=tg), nn.SiLU(),
+            nn.Conv1d(dim_ffn, dim_ffn, tk, padding="same", groups=tg), nn.GroupNorm(tg, dim_ffn), nn.SiLU(),
+            nn.Conv1d(dim_ffn, dim_ffn, tk, padding="same", groups=tg), nn.SiLU(), nn.Conv1d(dim_ffn, dim_hidden, 1)])
+
+    def extra_repr(self) -> str:
+        return f"full_share={self.full_share}"
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# functional engine: forward (optionally saving for backward) and backward over a flat dict of parameter tensors
+# ----------------------------------------------------------------------------------------------------------------------
+class Engine:
+    """Runs the network on CUDA tensors given a name -> tensor dict P (reference state_dict keys)."""
+
+    def __init__(self, num_layers: int, fwd_fmt: int = ops.FMT_F16, grad_fmt: int = ops.FMT_BF16):
+        self.L = num_layers
+        self.fwd_fmt = fwd_fmt
+        self.grad_fmt = grad_fmt
+        self._imgs: Optional[List[Tensor]] = None
+        self._img_key = None
+
+    def images(self, P: Dict[str, Tensor]) -> List[Tensor]:
+        """Per-layer UMMA weight images; rebuilt whenever a narrow-band weight changed (tensor version counters)."""
+        names = []
+        for i in range(self.L):
+            pre = f"layers.{i}."
+            names += [pre + "tconvffn.1.weight", pre + "tconvffn.3.weight", pre + "tconvffn.5.weight", pre + "tconvffn.8.weight",
+                      pre + "tconvffn.10.weight", pre + "mhsa.in_proj_weight", pre + "mhsa.out_proj.weight"]
+        key = tuple((P[n].data_ptr(), P[n]._version) for n in names)
+        if self._imgs is None or key != self._img_key:
+            old = self._imgs
+            self._imgs = [ops.pack_layer_weights(P, f"layers.{i}.", old[i] if old else None, self.fwd_fmt, self.grad_fmt)
+                          for i in range(self.L)]
+            self._img_key = key
+        return self._imgs
+
+    def forward(self, P: Dict[str, Tensor], x: Tensor, save: bool):
+        if not x.is_cuda:
+            raise ops._lib.NbssError("nbss_b200.SpatialNet runs on CUDA tensors only (there is no CPU path)")
+        imgs = self.images(P)
+        ctx = {"x_in": x, "layers": []} if save else None
+        errs = []
+        h = ops.encoder_fwd(x, P)
+        for i in range(self.L):
+            pre = f"layers.{i}."
+            if save:
+                lc = {"x0": h}
+                h1 = ops.fconv_fwd(h, P, pre + "fconv1")
+                h2, s, u = ops.full_fwd(h1, P, pre)
+                h3 = ops.fconv_fwd(h2, P, pre + "fconv2")
+                h4, msave, e1 = ops.mhsa_fwd(h3, P, pre, imgs[i], save=True, fmt=self.fwd_fmt)
+                h5, fsave, gstats, e2 = ops.ffn_fwd(h4, P, pre, imgs[i], save=True, fmt=self.fwd_fmt)
+                lc.update(x1=h1, s=s, u=u, x2=h2, x3=h3, msave=msave, x4=h4, fsave=fsave, gstats=gstats)
+                ctx["layers"].append(lc)
+                h = h5
+            else:
+                # inference: every sub-block updates the stream in place (each kernel reads a row before writing it)
+                h = ops.fconv_fwd(h, P, pre + "fconv1", out=h)
+                h, _, _ = ops.full_fwd(h, P, pre, out=h)
+                h = ops.fconv_fwd(h, P, pre + "fconv2", out=h)
+                h, e1 = ops.mhsa_fwd(h, P, pre, imgs[i], fmt=self.fwd_fmt, out=h)
+                h, e2 = ops.ffn_fwd(h, P, pre, imgs[i], fmt=self.fwd_fmt, out=h)
+            errs += [e1, e2]
+        y = ops.decoder_fwd(h, P)
+        if save:
+            ctx["x_last"] = h
+        return y, ctx, errs
+
+    def backward(self, P: Dict[str, Tensor], ctx, dy: Tensor, G: Dict[str, Tensor]):
+        """Accumulates parameter gradients into G (fp32 tensors keyed like P).  The network input needs no gradient
+        (SharedTrainer.py:113-120: X comes from the STFT of the data)."""
+        imgs = self.images(P)
+        errs = []
+        d = ops.decoder_bwd(ctx["x_last"], dy, P, G)
+        for i in reversed(range(self.L)):
+            pre = f"layers.{i}."
+            lc = ctx["layers"][i]
+            d, e1 = ops.ffn_bwd(lc["x4"], d, lc["fsave"], lc["gstats"], P, pre, imgs[i], G, fmt_g=self.grad_fmt)
+            d, e2 = ops.mhsa_bwd(lc["x3"], d, lc["msave"], P, pre, imgs[i], G, fmt_g=self.grad_fmt)
+            d = ops.fconv_bwd(lc["x2"], d, P, pre + "fconv2", G)
+            d = ops.full_bwd(lc["x1"], d, lc["s"], lc["u"], P, pre, G)
+            d = ops.fconv_bwd(lc["x0"], d, P, pre + "fconv1", G)
+            errs += [e1, e2]
+            ctx["layers"][i] = None  # free this layer's saved activations
+        ops.encoder_wgrad(ctx["x_in"], d, G)
+        return errs
+
+
+class _SpatialNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(fctx, module: "SpatialNet", x: Tensor, *params: Tensor):
+        P = module._param_dict()
+        y, ctx, errs = module.engine.forward(P, x.detach().float(), save=True)
+        fctx.module, fctx.ctx, fctx.errs = module, ctx, errs
+        return y
+
+    @staticmethod
+    def backward(fctx, dy: Tensor):
+        module = fctx.module
+        P = module._param_dict()
+        uniq = module._unique_params()
+        flat = torch.zeros(sum(p.numel() for _, p in uniq), dtype=torch.float32, device=dy.device)
+        G, off, views = {}, 0, []
+        for name, p in uniq:
+            v = flat[off:off + p.numel()].view_as(p)
+            views.append(v)
+            off += p.numel()
+            for alias in module._aliases[name]:
+                G[alias] = v
+        errs = module.engine.backward(P, fctx.ctx, dy.contiguous().float(), G)
+        for e in fctx.errs + errs:
+            ops.check_err_flag(e, "nbss_b200 kernel")
+        fctx.ctx = None
+        return (None, None) + tuple(views)
+
+
+class SpatialNet(nn.Module):
+    """See module docstring.  Tensor-core path supports the reference's small configuration (dim_hidden 96, dim_ffn
+    192, 4 heads, conv_groups (8,8), kernel_size (5,3), LN/GN norms, zero padding, no dropout) and T <= 256 frames."""
+
+    def __init__(self, dim_input: int, dim_output: int, dim_squeeze: int, num_layers: int, num_freqs: int,
+                 encoder_kernel_size: int = 5, dim_hidden: int = 192, dim_ffn: int = 384, num_heads: int = 2,
+                 dropout: Tuple[float, float, float] = (0, 0, 0), kernel_size: Tuple[int, int] = (5, 3),
+                 conv_groups: Tuple[int, int] = (8, 8), norms: List[str] = ("LN", "LN", "GN", "LN", "LN", "LN"),
+                 padding: str = "zeros", full_share: int = 0):
+        super().__init__()
+        unsupported = []
+        if (dim_hidden, dim_ffn, num_heads) != (96, 192, 4): unsupported.append("dim_hidden/dim_ffn/num_heads != 96/192/4")
+        if tuple(kernel_size) != (5, 3) or tuple(conv_groups) != (8, 8) or encoder_kernel_size != 5: unsupported.append("kernel sizes / groups")
+        if [n.upper() for n in norms] != ["LN", "LN", "GN", "LN", "LN", "LN"]: unsupported.append("norms")
+        if any(d > 0 for d in dropout): unsupported.append("dropout > 0")
+        if padding != "zeros": unsupported.append("padding")
+        if dim_squeeze != 8: unsupported.append("dim_squeeze != 8")
+        if unsupported:
+            raise NotImplementedError("nbss_b200.SpatialNet (round 1) supports the SpatialNet-small configuration only: " + ", ".join(unsupported))
+        self.encoder = nn.Conv1d(dim_input, dim_hidden, encoder_kernel_size, stride=1, padding="same")
+        full, layers = None, []
+        for l in range(num_layers):
+            layer = SpatialNetLayer(dim_hidden, dim_ffn, dim_squeeze, num_freqs, num_heads, kernel_size, conv_groups,
+                                    full=full if l > full_share else None)
+            full = layer.full
+            layers.append(layer)
+        self.layers = nn.ModuleList(layers)
+        self.decoder = nn.Linear(dim_hidden, dim_output)
+        self.engine = Engine(num_layers)
+        self._aliases: Dict[str, List[str]] = {}
+        self._build_aliases()
+
+    def _build_aliases(self) -> None:
+        """state_dict repeats the shared ``full.*`` tensor under every layer; map unique parameter -> all its keys."""
+        first: Dict[int, str] = {}
+        self._aliases = {}
+        for name, p in self.named_parameters(remove_duplicate=False):
+            if id(p) not in first:
+                first[id(p)] = name
+                self._aliases[name] = []
+            self._aliases[first[id(p)]].append(name)
+
+    def _unique_params(self):
+        return list(self.named_parameters())  # duplicates removed, registration order
+
+    def _param_dict(self) -> Dict[str, Tensor]:
+        return {n: p.data for n, p in self.named_parameters(remove_duplicate=False)}
+
+    def forward(self, x: Tensor, return_attn_score: bool = False):
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if needs_grad:
+            y = _SpatialNetFn.apply(self, x, *[p for _, p in self._unique_params()])
+        else:
+            y, _, errs = self.engine.forward(self._param_dict(), x.detach().float().contiguous(), save=False)
+            self._last_errs = errs
+        if return_attn_score:
+            return y, [None] * len(self.layers)  # the reference also returns None here (SpatialNet.py:97 quirk)
+        return y
+
+    def check_device_errors(self) -> None:
+        for e in getattr(self, "_last_errs", []):
+            ops.check_err_flag(e, "nbss_b200 kernel")

@@ -1,0 +1,247 @@
+"""GPU parity of each CUDA sub-block kernel against the oracle sub-function on the same seeded inputs.
+Tolerances: fp16-operand tensor-core kernels <= 1e-3 rel-L2 of the BRANCH output (bf16: 8e-3); fp32 SIMT kernels
+<= 1e-5."""
+import pytest
+import torch
+
+from nbss_b200 import ops
+from oracle import spatialnet_oracle as O
+
+CFG = O.SMALL_CFG
+
+
+def _params(seed=5):
+    P = O.synth_params(CFG, seed)
+    return P, {k: v.cuda() for k, v in P.items()}
+
+
+def _branch_err(y_gpu, x, branch_ref):
+    """rel-L2 of the branch (y - x) — the residual would otherwise hide the error."""
+    return O.rel_l2(y_gpu.cpu() - x, branch_ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T", [250, 251, 256, 37])
+@pytest.mark.parametrize("fmt", [ops.FMT_F16, ops.FMT_BF16])
+def test_ffn_fwd(T, fmt):
+    P, Pd = _params()
+    pre = "layers.3."
+    x = torch.randn(2, 5, T, 96, generator=torch.Generator().manual_seed(T))
+    with torch.no_grad():
+        ref = O.tconvffn(x, P, pre, 8)
+    img = ops.pack_layer_weights(Pd, pre, fwd_fmt=fmt)
+    y, saves, stats, err = ops.ffn_fwd(x.cuda(), Pd, pre, img, save=True, fmt=fmt)
+    torch.cuda.synchronize()
+    ops.check_err_flag(err, "ffn_fwd")
+    e = _branch_err(y, x, ref)
+    assert e < (1e-3 if fmt == ops.FMT_F16 else 8e-3), f"branch rel-L2 {e:.3e}"
+    # saved pre-activations must match the oracle's intermediates (a1 = pw1(LN(x)) + b1)
+    t = pre + "tconvffn."
+    with torch.no_grad():
+        a1 = O.layer_norm(x, P[t + "0.weight"], P[t + "0.bias"]) @ P[t + "1.weight"][:, :, 0].t() + P[t + "1.bias"]
+    assert O.rel_l2(saves[0].float().cpu().reshape(a1.shape), a1) < (1e-3 if fmt == ops.FMT_F16 else 8e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T", [250, 251, 256, 37, 128])
+@pytest.mark.parametrize("fmt", [ops.FMT_F16, ops.FMT_BF16])
+def test_mhsa_fwd(T, fmt):
+    P, Pd = _params()
+    pre = "layers.2."
+    x = torch.randn(2, 3, T, 96, generator=torch.Generator().manual_seed(100 + T))
+    with torch.no_grad():
+        ref = O.mhsa(x, P, pre, 4)
+    img = ops.pack_layer_weights(Pd, pre, fwd_fmt=fmt)
+    y, (qkv, o, lse, _lnst), err = ops.mhsa_fwd(x.cuda(), Pd, pre, img, save=True, fmt=fmt)
+    torch.cuda.synchronize()
+    ops.check_err_flag(err, "mhsa_fwd")
+    e = _branch_err(y, x, ref)
+    assert e < (1e-3 if fmt == ops.FMT_F16 else 8e-3), f"branch rel-L2 {e:.3e}"
+    # saved k|v against the oracle's projections
+    with torch.no_grad():
+        h = O.layer_norm(x, P[pre + "norm_mhsa.weight"], P[pre + "norm_mhsa.bias"]).reshape(-1, 96)
+        qkv_ref = h @ P[pre + "mhsa.in_proj_weight"].t() + P[pre + "mhsa.in_proj_bias"]
+    assert O.rel_l2(qkv.float().cpu()[:, 96:], qkv_ref[:, 96:]) < (1e-3 if fmt == ops.FMT_F16 else 8e-3)
+
+
+def _grads_like(Pd):
+    return {k: torch.zeros_like(v) for k, v in Pd.items()}
+
+
+def _leaf(P):
+    seen, out = {}, {}
+    for k, v in P.items():
+        if id(v) not in seen:
+            seen[id(v)] = v.clone().requires_grad_(True)
+        out[k] = seen[id(v)]
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 129, 7), (1, 129, 6), (1, 65, 5)])
+def test_fconv_fwd_bwd(shape):
+    B, F, T = shape
+    P, Pd = _params()
+    Pl = _leaf(P)
+    pre = "layers.1.fconv2"
+    g = torch.Generator().manual_seed(F * T)
+    x = torch.randn(B, F, T, 96, generator=g, requires_grad=True)
+    dy = torch.randn(B, F, T, 96, generator=g)
+    y_ref = x + O.fconv(x, Pl, pre, 8)
+    y_ref.backward(dy)
+    y = ops.fconv_fwd(x.detach().cuda(), Pd, pre)
+    assert O.rel_l2(y.cpu() - x.detach(), (y_ref - x).detach()) < 1e-5
+    G = _grads_like(Pd)
+    dx = ops.fconv_bwd(x.detach().cuda(), dy.cuda(), Pd, pre, G)
+    torch.cuda.synchronize()
+    assert O.rel_l2(dx.cpu(), x.grad) < 1e-5
+    for k in (".0.weight", ".0.bias", ".1.weight", ".1.bias", ".2.weight"):
+        assert O.rel_l2(G[pre + k].cpu(), Pl[pre + k].grad) < 2e-5, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 129, 7), (1, 129, 250), (1, 65, 5)])
+def test_full_fwd_bwd(shape):
+    B, F, T = shape
+    cfg = dict(CFG, num_freqs=F)
+    P = O.synth_params(cfg, 5)
+    Pd = {k: v.cuda() for k, v in P.items()}
+    Pl = _leaf(P)
+    pre = "layers.1."
+    g = torch.Generator().manual_seed(F + T)
+    x = torch.randn(B, F, T, 96, generator=g, requires_grad=True)
+    dy = torch.randn(B, F, T, 96, generator=g)
+    y_ref = x + O.full(x, Pl, pre)
+    y_ref.backward(dy)
+    y, s, u = ops.full_fwd(x.detach().cuda(), Pd, pre)
+    assert O.rel_l2(y.cpu() - x.detach(), (y_ref - x).detach()) < 1e-5
+    G = _grads_like(Pd)
+    dx = ops.full_bwd(x.detach().cuda(), dy.cuda(), s, u, Pd, pre, G)
+    torch.cuda.synchronize()
+    assert O.rel_l2(dx.cpu(), x.grad) < 1e-5
+    for k in ("norm_full.weight", "norm_full.bias", "squeeze.0.weight", "squeeze.0.bias", "full.weight", "full.bias",
+              "unsqueeze.0.weight", "unsqueeze.0.bias"):
+        assert O.rel_l2(G[pre + k].cpu().reshape(-1), Pl[pre + k].grad.reshape(-1)) < 3e-5, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,T", [(12, 250), (4, 64), (12, 37)])
+def test_encoder_decoder(cin, T):
+    cfg = dict(CFG, dim_input=cin)
+    P = O.synth_params(cfg, 9)
+    Pd = {k: v.cuda() for k, v in P.items()}
+    Pl = _leaf(P)
+    g = torch.Generator().manual_seed(cin + T)
+    x = torch.randn(2, 5, T, cin, generator=g)
+    dy = torch.randn(2, 5, T, 96, generator=g)
+    y_ref = O.encoder(x, Pl)
+    y_ref.backward(dy)
+    y = ops.encoder_fwd(x.cuda(), Pd)
+    assert O.rel_l2(y.cpu(), y_ref.detach()) < 1e-5
+    G = _grads_like(Pd)
+    ops.encoder_wgrad(x.cuda(), dy.cuda(), G)
+    assert O.rel_l2(G["encoder.weight"].cpu(), Pl["encoder.weight"].grad) < 2e-5
+    assert O.rel_l2(G["encoder.bias"].cpu(), Pl["encoder.bias"].grad) < 2e-5
+    # decoder
+    h = torch.randn(2, 5, T, 96, generator=g, requires_grad=True)
+    dz = torch.randn(2, 5, T, 4, generator=g)
+    z_ref = O.decoder(h, Pl)
+    z_ref.backward(dz)
+    z = ops.decoder_fwd(h.detach().cuda(), Pd)
+    assert O.rel_l2(z.cpu(), z_ref.detach()) < 1e-5
+    dh = ops.decoder_bwd(h.detach().cuda(), dz.cuda(), Pd, G)
+    assert O.rel_l2(dh.cpu(), h.grad) < 1e-5
+    assert O.rel_l2(G["decoder.weight"].cpu(), Pl["decoder.weight"].grad) < 2e-5
+    assert O.rel_l2(G["decoder.bias"].cpu(), Pl["decoder.bias"].grad) < 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_fft,hop,Ts", [(256, 128, 128 * 249), (256, 128, 32000), (32, 16, 16 * 19), (512, 256, 256 * 20)])
+def test_stft_istft(n_fft, hop, Ts):
+    g = torch.Generator().manual_seed(Ts)
+    wave = 0.1 * torch.randn(2, 3, Ts, generator=g)
+    X_ref = O.stft(wave, n_fft, hop)
+    X = ops.stft(wave.cuda(), n_fft, hop)
+    assert X.shape == X_ref.shape
+    assert O.rel_l2(torch.view_as_real(X.cpu()), torch.view_as_real(X_ref)) < 2e-5
+    # fused stft + norm + pack
+    Xn_ref, Xr_ref, XrMM_ref = O.norm_frequency_online(X_ref, 1)
+    Xp, xrmm, xr = ops.stft_norm_pack(wave.cuda(), n_fft, hop, ref_channel=1, want_xr=True)
+    assert O.rel_l2(xrmm.cpu(), XrMM_ref[:, 0]) < 2e-5
+    assert O.rel_l2(torch.view_as_real(xr.cpu()), torch.view_as_real(Xr_ref[:, 0].contiguous())) < 2e-5
+    # the normalised values are ill-conditioned where |Xr| ~ eps: compare after multiplying back
+    Xp_c = torch.view_as_complex(Xp.cpu().reshape(*Xp.shape[:3], -1, 2).contiguous())  # [B,F,T,C]
+    assert O.rel_l2(torch.view_as_real(Xp_c * xrmm.cpu()[..., None]), torch.view_as_real(X_ref.permute(0, 2, 3, 1).contiguous())) < 2e-5
+    # istft (+ scale) forward and backward
+    B, S, F, T = 2, 2, n_fft // 2 + 1, X_ref.shape[-1]
+    out = torch.randn(B, F, T, 2 * S, generator=g, requires_grad=True)
+    scale = torch.rand(B, F, T, generator=g) + 0.5
+    dyw = torch.randn(B, S, Ts, generator=g)
+    Y = O.unpack_inorm(out, scale[:, None])
+    w_ref = O.istft(Y, n_fft, hop, Ts)
+    w_ref.backward(dyw)
+    strides = (F * T * 2 * S, 2, T * 2 * S, 2 * S)
+    w = ops.istft_strided(out.detach().cuda(), strides, scale.cuda(), B, S, F, T, n_fft, hop, Ts)
+    assert O.rel_l2(w.cpu(), w_ref.detach()) < 2e-5
+    dout = torch.zeros(B, F, T, 2 * S, device="cuda")
+    ops.istft_bwd_strided(dyw.cuda(), scale.cuda(), dout, strides, B, S, F, T, n_fft, hop)
+    assert O.rel_l2(dout.cpu(), out.grad) < 2e-5
+
+
+GRAD_TOL = 2e-2  # bf16 gradient operands (precision policy)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T", [250, 64])
+def test_ffn_bwd(T):
+    P, Pd = _params()
+    Pl = _leaf(P)
+    pre = "layers.3."
+    g = torch.Generator().manual_seed(7 + T)
+    x = torch.randn(2, 4, T, 96, generator=g, requires_grad=True)
+    dy = torch.randn(2, 4, T, 96, generator=g)
+    y_ref = x + O.tconvffn(x, Pl, pre, 8)
+    y_ref.backward(dy)
+    img = ops.pack_layer_weights(Pd, pre)
+    xd = x.detach().cuda()
+    y, saves, stats, err = ops.ffn_fwd(xd, Pd, pre, img, save=True)
+    G = _grads_like(Pd)
+    dx, err2 = ops.ffn_bwd(xd, dy.cuda(), saves, stats, Pd, pre, img, G)
+    torch.cuda.synchronize()
+    ops.check_err_flag(err, "ffn_fwd")
+    ops.check_err_flag(err2, "ffn_bwd")
+    e = O.rel_l2(dx.cpu() - dy, x.grad - dy)
+    assert e < GRAD_TOL, f"dx branch rel-L2 {e:.3e}"
+    t = pre + "tconvffn."
+    errs = {k: O.rel_l2(G[t + k].cpu().reshape(-1), Pl[t + k].grad.reshape(-1)) for k in
+            ("0.weight", "0.bias", "1.weight", "1.bias", "3.weight", "3.bias", "5.weight", "5.bias", "6.weight", "6.bias",
+             "8.weight", "8.bias", "10.weight", "10.bias")}
+    bad = {k: f"{v:.2e}" for k, v in errs.items() if not v < GRAD_TOL}
+    assert not bad, f"parameter-gradient rel-L2 over tolerance: {bad}; all: { {k: f'{v:.1e}' for k, v in errs.items()} }"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T", [250, 64])
+def test_mhsa_bwd(T):
+    P, Pd = _params()
+    Pl = _leaf(P)
+    pre = "layers.2."
+    g = torch.Generator().manual_seed(17 + T)
+    x = torch.randn(2, 3, T, 96, generator=g, requires_grad=True)
+    dy = torch.randn(2, 3, T, 96, generator=g)
+    y_ref = x + O.mhsa(x, Pl, pre, 4)
+    y_ref.backward(dy)
+    img = ops.pack_layer_weights(Pd, pre)
+    xd = x.detach().cuda()
+    y, msave, err = ops.mhsa_fwd(xd, Pd, pre, img, save=True)
+    G = _grads_like(Pd)
+    dx, err2 = ops.mhsa_bwd(xd, dy.cuda(), msave, Pd, pre, img, G)
+    torch.cuda.synchronize()
+    ops.check_err_flag(err, "mhsa_fwd")
+    ops.check_err_flag(err2, "mhsa_bwd")
+    e = O.rel_l2(dx.cpu() - dy, x.grad - dy)
+    assert e < GRAD_TOL, f"dx branch rel-L2 {e:.3e}"
+    errs = {k: O.rel_l2(G[pre + k].cpu().reshape(-1), Pl[pre + k].grad.reshape(-1)) for k in
+            ("norm_mhsa.weight", "norm_mhsa.bias", "mhsa.in_proj_weight", "mhsa.in_proj_bias", "mhsa.out_proj.weight", "mhsa.out_proj.bias")}
+    bad = {k: f"{v:.2e}" for k, v in errs.items() if not v < GRAD_TOL}
+    assert not bad, f"parameter-gradient rel-L2 over tolerance: {bad}; all: { {k: f'{v:.1e}' for k, v in errs.items()} }"

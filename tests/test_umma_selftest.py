@@ -48,10 +48,11 @@ CASES = [
     ("mm_bf16_wgrad", "bf16", (256, 192), (256, 96), 96, 256, 1, 1, 0, 0, 64, 0, 1, 0),
     ("mm_bf16_wgrad_bshift1", "bf16", (248, 128), (250, 96), 96, 240, 1, 1, 0, 1, 0, 0, 1, 0),
     ("mm_bf16_wgrad_ashift2", "bf16", (250, 128), (250, 96), 96, 240, 1, 1, 2, 0, 0, 0, 1, 0),
-    ("mm_tf32_wgrad", "tf32", (128, 128), (128, 96), 96, 128, 1, 1, 0, 0, 0, 0, 1, 0),
     ("km_bf16_pv", "bf16", (128, 256), (256, 104), 32, 256, 0, 1, 0, 0, 0, 24, 1, 0),
     ("km_f16_pv", "f16", (128, 128), (128, 104), 32, 128, 0, 1, 0, 0, 0, 72, 1, 0),
     ("mk_bf16", "bf16", (64, 128), (96, 64), 96, 64, 1, 0, 0, 0, 0, 0, 1, 0),
+    ("mm_mixed_bf16_f16", "bf16:f16", (256, 128), (256, 96), 96, 256, 1, 1, 0, 1, 0, 0, 1, 0),
+    ("kk_mixed_f16_bf16", "f16:bf16", (128, 96), (192, 96), 192, 96, 0, 0, 0, 0, 0, 0, 1, 0),
 ]
 
 
@@ -63,7 +64,10 @@ def test_umma_selftest(case):
     g = torch.Generator().manual_seed(hash(name) % (2**31))
     A = torch.randn(*ash, generator=g)
     B = torch.randn(*bsh, generator=g)
-    Ar, Br = _round(A, fmt), _round(B, fmt)
+    fmt_b = fmt
+    if ":" in fmt:
+        fmt, fmt_b = fmt.split(":")
+    Ar, Br = _round(A, fmt), _round(B, fmt_b)
     Av = _view(Ar, a_mn, a_shift, a_off, 128, K).double()
     Bv = _view(Br, b_mn, b_shift, b_off, N, K).double()
     # zero-pad views that run off the end of the array (the kernel reads zero rows / features there)
@@ -78,7 +82,7 @@ def test_umma_selftest(case):
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
     st = L.nbss_umma_selftest(
         _lib.ptr(dA), ash[0], ash[1], _lib.ptr(dB), bsh[0], bsh[1], _lib.ptr(dD), N, K, a_mn, b_mn, FMT[fmt],
-        a_shift, b_shift, a_off, b_off, passes, tmem_col, _lib.ptr(err), _lib.stream_ptr())
+        a_shift, b_shift, a_off, b_off, passes, tmem_col, FMT[fmt_b], _lib.ptr(err), _lib.stream_ptr())
     _lib.check(st, "nbss_umma_selftest")
     torch.cuda.synchronize()
     assert int(err.item()) == 0, f"device error flag {int(err.item()):#x} (mbarrier timeout?)"

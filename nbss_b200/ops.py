@@ -16,6 +16,30 @@ from ._lib import check, ptr, stream_ptr
 FMT_F16, FMT_BF16, FMT_TF32 = 0, 1, 2
 Tensor = torch.Tensor
 
+# Instrumentation used by bench.py: LAUNCHES counts kernel launches issued through this module; when TIMING is a dict,
+# every C-ABI call is bracketed by CUDA events on the launching (current) stream.
+LAUNCHES = 0
+TIMING = None
+_NLAUNCH = {"nbss_full_fwd": 3, "nbss_full_bwd": 4, "nbss_ffn_wgrad": 3, "nbss_mhsa_bwd": 2, "nbss_istft": 2}
+
+
+def _K(name: str):
+    fn = getattr(_lib.lib(), name)
+
+    def call(*args):
+        global LAUNCHES
+        LAUNCHES += _NLAUNCH.get(name, 1)
+        if TIMING is None:
+            return fn(*args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st = fn(*args)
+        e1.record()
+        TIMING.setdefault(name[5:], []).append((e0, e1))
+        return st
+
+    return call
+
 
 def _f32c(t: Tensor) -> Tensor:
     assert t.is_cuda and t.dtype == torch.float32, (t.device, t.dtype)
@@ -35,18 +59,18 @@ def check_err_flag(flag: Tensor, what: str) -> None:
 def layer_image_bytes() -> int:
     L = _lib.lib()
     L.nbss_layer_image_bytes.restype = ctypes.c_uint
-    return int(L.nbss_layer_image_bytes())
+    return int(_K("nbss_layer_image_bytes")())
 
 
 def pack_layer_weights(P: Dict[str, Tensor], pre: str, img: Optional[Tensor] = None, fwd_fmt: int = FMT_F16,
-                       bwd_fmt: int = FMT_BF16) -> Tensor:
+                       bwd_fmt: int = FMT_F16) -> Tensor:
     """Builds the UMMA weight images of one SpatialNet layer (pack.cu) from its fp32 parameters."""
     L = _lib.lib()
     dev = P[pre + "tconvffn.1.weight"].device
     if img is None:
         img = torch.empty(layer_image_bytes(), dtype=torch.uint8, device=dev)
     t = pre + "tconvffn."
-    st = L.nbss_pack_layer_weights(
+    st = _K("nbss_pack_layer_weights")(
         ptr(_f32c(P[t + "1.weight"])), ptr(_f32c(P[t + "3.weight"])), ptr(_f32c(P[t + "5.weight"])),
         ptr(_f32c(P[t + "8.weight"])), ptr(_f32c(P[t + "10.weight"])), ptr(_f32c(P[pre + "mhsa.in_proj_weight"])),
         ptr(_f32c(P[pre + "mhsa.out_proj.weight"])), ptr(img), fwd_fmt, bwd_fmt, stream_ptr())
@@ -69,7 +93,7 @@ def ffn_fwd(x: Tensor, P: Dict[str, Tensor], pre: str, img: Tensor, save: bool =
     ln_stats = torch.empty(n, 2, dtype=torch.float32, device=x.device) if save else None
     err = device_err_flag(x.device)
     t = pre + "tconvffn."
-    st = L.nbss_ffn_fwd(
+    st = _K("nbss_ffn_fwd")(
         ptr(x), ptr(y), B * F, T, ptr(_f32c(P[t + "0.weight"])), ptr(_f32c(P[t + "0.bias"])), ptr(_f32c(P[t + "1.bias"])),
         ptr(_f32c(P[t + "3.bias"])), ptr(_f32c(P[t + "5.bias"])), ptr(_f32c(P[t + "8.bias"])), ptr(_f32c(P[t + "6.weight"])),
         ptr(_f32c(P[t + "6.bias"])), ptr(_f32c(P[t + "10.bias"])), ptr(img), ptr(saves[0]), ptr(saves[1]), ptr(saves[2]),
@@ -95,7 +119,7 @@ def mhsa_fwd(x: Tensor, P: Dict[str, Tensor], pre: str, img: Tensor, save: bool 
     lse = torch.empty(B * F, 4, T, dtype=torch.float32, device=x.device) if save else None
     ln_stats = torch.empty(n, 2, dtype=torch.float32, device=x.device) if save else None
     err = device_err_flag(x.device)
-    st = L.nbss_mhsa_fwd(
+    st = _K("nbss_mhsa_fwd")(
         ptr(x), ptr(y), B * F, T, ptr(_f32c(P[pre + "norm_mhsa.weight"])), ptr(_f32c(P[pre + "norm_mhsa.bias"])),
         ptr(_f32c(P[pre + "mhsa.in_proj_bias"])), ptr(_f32c(P[pre + "mhsa.out_proj.bias"])), ptr(img), ptr(qkv), ptr(o),
         ptr(lse), ptr(ln_stats), fmt, ptr(err), stream_ptr())
@@ -113,7 +137,7 @@ def fconv_fwd(x: Tensor, P, pre: str, out: Optional[Tensor] = None) -> Tensor:
     B, F, T, H = x.shape
     assert H == 96
     y = torch.empty_like(x) if out is None else out
-    st = L.nbss_fconv_fwd(ptr(x), ptr(y), B, F, T, ptr(_f32c(P[pre + ".0.weight"])), ptr(_f32c(P[pre + ".0.bias"])),
+    st = _K("nbss_fconv_fwd")(ptr(x), ptr(y), B, F, T, ptr(_f32c(P[pre + ".0.weight"])), ptr(_f32c(P[pre + ".0.bias"])),
                           ptr(_f32c(P[pre + ".1.weight"])), ptr(_f32c(P[pre + ".1.bias"])), ptr(_f32c(P[pre + ".2.weight"])),
                           stream_ptr())
     check(st, "nbss_fconv_fwd")
@@ -126,7 +150,7 @@ def fconv_bwd(x: Tensor, dy: Tensor, P, pre: str, G) -> Tensor:
     x, dy = _f32c(x), _f32c(dy)
     B, F, T, H = x.shape
     dx = torch.empty_like(x)
-    st = L.nbss_fconv_bwd(ptr(x), ptr(dy), ptr(dx), B, F, T, ptr(_f32c(P[pre + ".0.weight"])), ptr(_f32c(P[pre + ".0.bias"])),
+    st = _K("nbss_fconv_bwd")(ptr(x), ptr(dy), ptr(dx), B, F, T, ptr(_f32c(P[pre + ".0.weight"])), ptr(_f32c(P[pre + ".0.bias"])),
                           ptr(_f32c(P[pre + ".1.weight"])), ptr(_f32c(P[pre + ".1.bias"])), ptr(_f32c(P[pre + ".2.weight"])),
                           ptr(G[pre + ".1.weight"]), ptr(G[pre + ".1.bias"]), ptr(G[pre + ".2.weight"]),
                           ptr(G[pre + ".0.weight"]), ptr(G[pre + ".0.bias"]), stream_ptr())
@@ -142,7 +166,7 @@ def full_fwd(x: Tensor, P, pre: str, out: Optional[Tensor] = None):
     y = torch.empty_like(x) if out is None else out
     s = torch.empty(B, T, 8, F, dtype=torch.float32, device=x.device)
     u = torch.empty_like(s)
-    st = L.nbss_full_fwd(ptr(x), ptr(y), ptr(s), ptr(u), B, F, T, ptr(_f32c(P[pre + "norm_full.weight"])),
+    st = _K("nbss_full_fwd")(ptr(x), ptr(y), ptr(s), ptr(u), B, F, T, ptr(_f32c(P[pre + "norm_full.weight"])),
                          ptr(_f32c(P[pre + "norm_full.bias"])), ptr(_f32c(P[pre + "squeeze.0.weight"])),
                          ptr(_f32c(P[pre + "squeeze.0.bias"])), ptr(_f32c(P[pre + "full.weight"])),
                          ptr(_f32c(P[pre + "full.bias"])), ptr(_f32c(P[pre + "unsqueeze.0.weight"])),
@@ -157,7 +181,7 @@ def full_bwd(x: Tensor, dy: Tensor, s: Tensor, u: Tensor, P, pre: str, G) -> Ten
     B, F, T, H = x.shape
     dx = torch.empty_like(x)
     ws = torch.empty(2 * s.numel(), dtype=torch.float32, device=x.device)
-    st = L.nbss_full_bwd(ptr(x), ptr(dy), ptr(dx), ptr(s), ptr(u), ptr(ws), B, F, T, ptr(_f32c(P[pre + "norm_full.weight"])),
+    st = _K("nbss_full_bwd")(ptr(x), ptr(dy), ptr(dx), ptr(s), ptr(u), ptr(ws), B, F, T, ptr(_f32c(P[pre + "norm_full.weight"])),
                          ptr(_f32c(P[pre + "norm_full.bias"])), ptr(_f32c(P[pre + "squeeze.0.weight"])),
                          ptr(_f32c(P[pre + "squeeze.0.bias"])), ptr(_f32c(P[pre + "full.weight"])),
                          ptr(_f32c(P[pre + "unsqueeze.0.weight"])), ptr(_f32c(P[pre + "unsqueeze.0.bias"])),
@@ -174,7 +198,7 @@ def encoder_fwd(x: Tensor, P) -> Tensor:
     x = _f32c(x)
     B, F, T, Cin = x.shape
     y = torch.empty(B, F, T, 96, dtype=torch.float32, device=x.device)
-    st = L.nbss_encoder_fwd(ptr(x), ptr(y), B * F, T, Cin, ptr(_f32c(P["encoder.weight"])), ptr(_f32c(P["encoder.bias"])), stream_ptr())
+    st = _K("nbss_encoder_fwd")(ptr(x), ptr(y), B * F, T, Cin, ptr(_f32c(P["encoder.weight"])), ptr(_f32c(P["encoder.bias"])), stream_ptr())
     check(st, "nbss_encoder_fwd")
     return y
 
@@ -183,7 +207,7 @@ def encoder_wgrad(x: Tensor, dy: Tensor, G) -> None:
     L = _lib.lib()
     x, dy = _f32c(x), _f32c(dy)
     B, F, T, Cin = x.shape
-    st = L.nbss_encoder_wgrad(ptr(x), ptr(dy), B * F, T, Cin, ptr(G["encoder.weight"]), ptr(G["encoder.bias"]), stream_ptr())
+    st = _K("nbss_encoder_wgrad")(ptr(x), ptr(dy), B * F, T, Cin, ptr(G["encoder.weight"]), ptr(G["encoder.bias"]), stream_ptr())
     check(st, "nbss_encoder_wgrad")
 
 
@@ -193,7 +217,7 @@ def decoder_fwd(x: Tensor, P) -> Tensor:
     B, F, T, H = x.shape
     cout = P["decoder.weight"].shape[0]
     y = torch.empty(B, F, T, cout, dtype=torch.float32, device=x.device)
-    st = L.nbss_decoder_fwd(ptr(x), ptr(y), ctypes.c_longlong(B * F * T), cout, ptr(_f32c(P["decoder.weight"])),
+    st = _K("nbss_decoder_fwd")(ptr(x), ptr(y), ctypes.c_longlong(B * F * T), cout, ptr(_f32c(P["decoder.weight"])),
                             ptr(_f32c(P["decoder.bias"])), stream_ptr())
     check(st, "nbss_decoder_fwd")
     return y
@@ -205,7 +229,7 @@ def decoder_bwd(x: Tensor, dy: Tensor, P, G) -> Tensor:
     B, F, T, H = x.shape
     cout = P["decoder.weight"].shape[0]
     dx = torch.empty_like(x)
-    st = L.nbss_decoder_bwd(ptr(x), ptr(dy), ptr(dx), ctypes.c_longlong(B * F * T), cout, ptr(_f32c(P["decoder.weight"])),
+    st = _K("nbss_decoder_bwd")(ptr(x), ptr(dy), ptr(dx), ctypes.c_longlong(B * F * T), cout, ptr(_f32c(P["decoder.weight"])),
                             ptr(G["decoder.weight"]), ptr(G["decoder.bias"]), stream_ptr())
     check(st, "nbss_decoder_bwd")
     return dx
@@ -223,7 +247,7 @@ def stft(x: Tensor, n_fft: int, hop: int) -> Tensor:
     B, C, Ts = x.shape
     F, T = n_fft // 2 + 1, 1 + Ts // hop
     out = torch.empty(B, C, F, T, 2, dtype=torch.float32, device=x.device)
-    st = L.nbss_stft(ptr(x), B, C, Ts, n_fft, hop, 0, 0, ctypes.c_float(0.0), ptr(out), _ll(C * F * T * 2), _ll(F * T * 2),
+    st = _K("nbss_stft")(ptr(x), B, C, Ts, n_fft, hop, 0, 0, ctypes.c_float(0.0), ptr(out), _ll(C * F * T * 2), _ll(F * T * 2),
                      _ll(T * 2), _ll(2), ptr(None), ptr(None), stream_ptr())
     check(st, "nbss_stft")
     return torch.view_as_complex(out)
@@ -238,7 +262,7 @@ def stft_norm_pack(x: Tensor, n_fft: int, hop: int, ref_channel: int, eps: float
     out = torch.empty(B, F, T, 2 * C, dtype=torch.float32, device=x.device)
     xrmm = torch.empty(B, F, T, dtype=torch.float32, device=x.device)
     xr = torch.empty(B, F, T, 2, dtype=torch.float32, device=x.device) if want_xr else None
-    st = L.nbss_stft(ptr(x), B, C, Ts, n_fft, hop, 1, ref_channel, ctypes.c_float(eps), ptr(out), _ll(F * T * 2 * C), _ll(2),
+    st = _K("nbss_stft")(ptr(x), B, C, Ts, n_fft, hop, 1, ref_channel, ctypes.c_float(eps), ptr(out), _ll(F * T * 2 * C), _ll(2),
                      _ll(T * 2 * C), _ll(2 * C), ptr(xrmm), ptr(xr), stream_ptr())
     check(st, "nbss_stft")
     return out, xrmm, (torch.view_as_complex(xr) if want_xr else None)
@@ -250,7 +274,7 @@ def istft_strided(real_view: Tensor, strides_bsft, scale: Optional[Tensor], B: i
     L = _lib.lib()
     y = torch.empty(B, S, length, dtype=torch.float32, device=real_view.device)
     ib, is_, if_, it = strides_bsft
-    st = L.nbss_istft(ptr(real_view), _ll(ib), _ll(is_), _ll(if_), _ll(it), ptr(scale), ptr(y), B, S, length, T, n_fft, hop,
+    st = _K("nbss_istft")(ptr(real_view), _ll(ib), _ll(is_), _ll(if_), _ll(it), ptr(scale), ptr(y), B, S, length, T, n_fft, hop,
                       stream_ptr())
     check(st, "nbss_istft")
     return y
@@ -260,14 +284,14 @@ def istft_bwd_strided(dy: Tensor, scale: Optional[Tensor], out: Tensor, strides_
     L = _lib.lib()
     dy = _f32c(dy)
     ib, is_, if_, it = strides_bsft
-    st = L.nbss_istft_bwd(ptr(dy), ptr(scale), ptr(out), _ll(ib), _ll(is_), _ll(if_), _ll(it), B, S, dy.shape[-1], T, n_fft, hop,
+    st = _K("nbss_istft_bwd")(ptr(dy), ptr(scale), ptr(out), _ll(ib), _ll(is_), _ll(if_), _ll(it), B, S, dy.shape[-1], T, n_fft, hop,
                           stream_ptr())
     check(st, "nbss_istft_bwd")
     return out
 
 
 # ------------------------------------------------------------------------------------------------ narrow-band backward
-def ffn_bwd(x: Tensor, dy: Tensor, saves, gn_stats: Tensor, P, pre: str, img: Tensor, G, fmt_g: int = FMT_BF16):
+def ffn_bwd(x: Tensor, dy: Tensor, saves, gn_stats: Tensor, P, pre: str, img: Tensor, G, fmt_g: int = FMT_F16):
     """Backward of y = x + tconvffn(x).  saves = [a1, c1, c2, c3, ln_stats] from ffn_fwd(save=True).
     Returns dx; accumulates every tconvffn.* parameter gradient into G (fp32)."""
     L = _lib.lib()
@@ -281,13 +305,13 @@ def ffn_bwd(x: Tensor, dy: Tensor, saves, gn_stats: Tensor, P, pre: str, img: Te
     dx = torch.empty_like(x)
     err = device_err_flag(x.device)
     t = pre + "tconvffn."
-    st = L.nbss_ffn_bwd(
+    st = _K("nbss_ffn_bwd")(
         ptr(x), ptr(dy), ptr(dx), B * F, T, ptr(_f32c(P[t + "0.weight"])), ptr(_f32c(P[t + "6.weight"])), ptr(_f32c(P[t + "6.bias"])),
         ptr(ln_stats), ptr(gn_stats), ptr(img), ptr(a1), ptr(c1), ptr(c2), ptr(c3), ptr(gbuf[0]), ptr(gbuf[1]), ptr(gbuf[2]),
         ptr(gbuf[3]), ptr(sbuf[0]), ptr(sbuf[1]), ptr(sbuf[2]), ptr(sbuf[3]), ptr(G[t + "0.weight"]), ptr(G[t + "0.bias"]),
         ptr(G[t + "6.weight"]), ptr(G[t + "6.bias"]), fmt_g, ptr(err), stream_ptr())
     check(st, "nbss_ffn_bwd")
-    st = L.nbss_ffn_wgrad(
+    st = _K("nbss_ffn_wgrad")(
         ptr(x), ptr(dy), B * F, T, ptr(_f32c(P[t + "0.weight"])), ptr(_f32c(P[t + "0.bias"])), ptr(gbuf[0]), ptr(gbuf[1]),
         ptr(gbuf[2]), ptr(gbuf[3]), ptr(sbuf[0]), ptr(sbuf[1]), ptr(sbuf[2]), ptr(sbuf[3]), ptr(G[t + "1.weight"]),
         ptr(G[t + "1.bias"]), ptr(G[t + "3.weight"]), ptr(G[t + "3.bias"]), ptr(G[t + "5.weight"]), ptr(G[t + "5.bias"]),
@@ -297,7 +321,7 @@ def ffn_bwd(x: Tensor, dy: Tensor, saves, gn_stats: Tensor, P, pre: str, img: Te
     return dx, err
 
 
-def mhsa_bwd(x: Tensor, dy: Tensor, msave, P, pre: str, img: Tensor, G, fmt_g: int = FMT_BF16):
+def mhsa_bwd(x: Tensor, dy: Tensor, msave, P, pre: str, img: Tensor, G, fmt_g: int = FMT_F16):
     """Backward of y = x + MHSA(LN(x)).  msave = (qkv, o, lse, ln_stats) from mhsa_fwd(save=True)."""
     L = _lib.lib()
     x, dy = _f32c(x), _f32c(dy)
@@ -308,11 +332,11 @@ def mhsa_bwd(x: Tensor, dy: Tensor, msave, P, pre: str, img: Tensor, G, fmt_g: i
     dqkv = torch.empty(n, 288, dtype=dt, device=x.device)
     dx = torch.empty_like(x)
     err = device_err_flag(x.device)
-    st = L.nbss_mhsa_bwd(ptr(x), ptr(dy), ptr(dx), B * F, T, ptr(_f32c(P[pre + "norm_mhsa.weight"])), ptr(ln_stats), ptr(img),
+    st = _K("nbss_mhsa_bwd")(ptr(x), ptr(dy), ptr(dx), B * F, T, ptr(_f32c(P[pre + "norm_mhsa.weight"])), ptr(ln_stats), ptr(img),
                          ptr(qkv), ptr(o), ptr(lse), ptr(dqkv), ptr(G[pre + "norm_mhsa.weight"]), ptr(G[pre + "norm_mhsa.bias"]),
                          fmt_g, ptr(err), stream_ptr())
     check(st, "nbss_mhsa_bwd")
-    st = L.nbss_mhsa_wgrad(ptr(x), ptr(dy), B * F, T, ptr(_f32c(P[pre + "norm_mhsa.weight"])), ptr(_f32c(P[pre + "norm_mhsa.bias"])),
+    st = _K("nbss_mhsa_wgrad")(ptr(x), ptr(dy), B * F, T, ptr(_f32c(P[pre + "norm_mhsa.weight"])), ptr(_f32c(P[pre + "norm_mhsa.bias"])),
                            ptr(dqkv), ptr(o), ptr(G[pre + "mhsa.in_proj_weight"]), ptr(G[pre + "mhsa.in_proj_bias"]),
                            ptr(G[pre + "mhsa.out_proj.weight"]), ptr(G[pre + "mhsa.out_proj.bias"]), fmt_g, FMT_F16, ptr(err),
                            stream_ptr())

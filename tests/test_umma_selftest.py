@@ -51,8 +51,8 @@ CASES = [
     ("km_bf16_pv", "bf16", (128, 256), (256, 104), 32, 256, 0, 1, 0, 0, 0, 24, 1, 0),
     ("km_f16_pv", "f16", (128, 128), (128, 104), 32, 128, 0, 1, 0, 0, 0, 72, 1, 0),
     ("mk_bf16", "bf16", (64, 128), (96, 64), 96, 64, 1, 0, 0, 0, 0, 0, 1, 0),
-    ("mm_mixed_bf16_f16", "bf16:f16", (256, 128), (256, 96), 96, 256, 1, 1, 0, 1, 0, 0, 1, 0),
-    ("kk_mixed_f16_bf16", "f16:bf16", (128, 96), (192, 96), 192, 96, 0, 0, 0, 0, 0, 0, 1, 0),
+    ("mm_f16_wgrad_bshift1", "f16", (248, 128), (250, 96), 96, 240, 1, 1, 0, 1, 0, 0, 1, 0),
+    # NOTE: mixing fp16 and bf16 operands in one kind::f16 MMA raises cudaErrorIllegalInstruction on sm_100a (measured)
 ]
 
 

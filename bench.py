@@ -99,6 +99,22 @@ class ClockSampler:
                 "samples": len(rows), "reasons": reasons}
 
 
+def log(msg):
+    sys.stderr.write(f"[bench {time.strftime('%H:%M:%S')}] {msg}\n")
+    sys.stderr.flush()
+
+
+def cpu_oracle_subprocess(threads, reps, timeout_s=240):
+    """Runs cpu_oracle_step in a child process under a timeout so a slow host cannot stall the GPU bench line."""
+    code = (f"import sys, json; sys.path.insert(0, {ROOT!r}); import bench; "
+            f"print(json.dumps(bench.cpu_oracle_step({threads}, 1, {reps})))")
+    try:
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=timeout_s)
+        return tuple(json.loads(r.stdout.strip().splitlines()[-1]))
+    except Exception as e:  # timeout / parse error
+        return None, None, f"cpu baseline unavailable: {type(e).__name__}"
+
+
 def cpu_oracle_step(threads, b=1, reps=2):
     """One training pass of the same path through the oracle on the host cores (forward + autograd backward)."""
     from oracle import spatialnet_oracle as O
@@ -125,7 +141,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 64)
     steps = max(1, min(args.steps, 3))
     fps, t, sample = cpu_oracle_step(cores, b=1, reps=steps)
     print(json.dumps({
@@ -225,17 +241,21 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
-    for _ in range(max(args.warmup, 3)):
+    log("setup done; warm-up")
+    for i in range(max(args.warmup, 3)):
         step(x_dev, y_dev)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        log(f"warm-up step {i} done")
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ops.LAUNCHES = 0
     ms_dev, loss_v = timed(args.steps, host_io=False)
+    log(f"device-resident: {ms_dev:.2f} ms/step")
     launches = ops.LAUNCHES // args.steps
     ms_e2e, _ = timed(args.steps, host_io=True)
+    log(f"e2e: {ms_e2e:.2f} ms/step")
     clocks = sampler.stop() if rank == 0 else None
 
     # per-kernel live timing (CUDA events around every C-ABI call on the launching stream) for the roofline
@@ -292,8 +312,9 @@ def main():
         "roofline": roof, "kernels": kernels, "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        fps, t, sample = cpu_oracle_step(cores, b=1, reps=2)
+        cores = min(os.cpu_count() or 1, 64)
+        log(f"cpu baseline on {cores} threads")
+        fps, t, sample = cpu_oracle_subprocess(cores, reps=2)
         out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(out))
     if world > 1:

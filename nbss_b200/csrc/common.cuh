@@ -31,7 +31,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // SiLU and its derivative (fp32, accurate exp: the parity budget is spent on 16-bit MMA operands, not here).
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float silu(float x) { return x * sigmoidf_(x); }
 __device__ __forceinline__ float silu_grad(float x) {
     float s = sigmoidf_(x);

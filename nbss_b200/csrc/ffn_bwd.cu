@@ -40,29 +40,22 @@ constexpr uint32_t FB_RED = FB_ACC + 576 * 4;       // [8 warps][8 groups][2] + 
 constexpr uint32_t FB_BAR = FB_RED + (128 + 16) * 4;
 constexpr uint32_t FB_SMEM = FB_BAR + 64;
 
-__device__ __forceinline__ void load_h16x32(const unsigned char* base, size_t row, int c0, float* v) {
-    const uint4* p = reinterpret_cast<const uint4*>(base + (row * kHF + c0) * 2);
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-        const uint4 q = __ldg(p + cc);
-        unpack_f16x2(q.x, v[8 * cc + 0], v[8 * cc + 1]);
-        unpack_f16x2(q.y, v[8 * cc + 2], v[8 * cc + 3]);
-        unpack_f16x2(q.z, v[8 * cc + 4], v[8 * cc + 5]);
-        unpack_f16x2(q.w, v[8 * cc + 6], v[8 * cc + 7]);
-    }
-}
-__device__ __forceinline__ void load_h16x8(const unsigned char* base, size_t row, int c, float* v) {
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(base + (row * kHF + c) * 2));
+// all 16-bit tensors here use the slab-tile layout [slab][24 chunks][T][8] (slab.cuh)
+__device__ __forceinline__ void load_h16x8(const unsigned char* base, int slab, int T, int t, int c, float* v) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(base + tile_off(slab, 24, T, c / 8, t)));
     unpack_f16x2(q.x, v[0], v[1]);
     unpack_f16x2(q.y, v[2], v[3]);
     unpack_f16x2(q.z, v[4], v[5]);
     unpack_f16x2(q.w, v[6], v[7]);
 }
-template <int FMT>
-__device__ __forceinline__ void store16x32(unsigned char* base, size_t row, int c0, const float* v) {
-    uint4* p = reinterpret_cast<uint4*>(base + (row * kHF + c0) * 2);
+__device__ __forceinline__ void load_h16x32(const unsigned char* base, int slab, int T, int t, int c0, float* v) {
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) p[cc] = pack8<FMT>(v + 8 * cc);
+    for (int cc = 0; cc < 4; ++cc) load_h16x8(base, slab, T, t, c0 + 8 * cc, v + 8 * cc);
+}
+template <int FMT>
+__device__ __forceinline__ void store16x32(unsigned char* base, int slab, int T, int t, int c0, const float* v) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(base + tile_off(slab, 24, T, c0 / 8 + cc, t)) = pack8<FMT>(v + 8 * cc);
 }
 
 template <int FMT>
@@ -138,14 +131,14 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
         __syncthreads();
     };
     // g = D * SiLU'(c), s = SiLU(c): the three plain activation epilogues
-    auto silu_epilogue = [&](const unsigned char* csave, unsigned char* gout, unsigned char* sout, size_t grow) {
+    auto silu_epilogue = [&](const unsigned char* csave, unsigned char* gout, unsigned char* sout, int slab) {
 #pragma unroll 1
         for (int c0 = 0; c0 < kHF; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(tacc + c0, r);
             tmem_ld_wait();
             float c[32], g[32];
-            if (valid) load_h16x32(csave, grow, c0, c);
+            if (valid) load_h16x32(csave, slab, T, t, c0, c);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const float cv = valid ? c[j] : 0.f;
@@ -154,8 +147,8 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
                 c[j] = cv * sg;
             }
             if (valid) {
-                store16x32<FMT>(sout, grow, c0, c);
-                store16x32<FMT>(gout, grow, c0, g);
+                store16x32<FMT>(sout, slab, T, t, c0, c);
+                store16x32<FMT>(gout, slab, T, t, c0, g);
             }
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(hrow + (c0 / 8 + cc) * kCS) = pack8<FMT>(g + 8 * cc);
@@ -182,7 +175,7 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
         ph_w0 ^= 1;
         wait_mma();
         if (tid == 0) load_image(ws0, a.img + IMG_WC2T, IMG_WC_BYTES, bar_w0);
-        silu_epilogue(a.c3, a.g_c3, a.s4, grow);
+        silu_epilogue(a.c3, a.g_c3, a.s4, slab);
         end_epilogue();
         // ---- B2: d s3 = conv3^T(g c3) ; E2: GroupNorm + SiLU backward
         convT_phase(w1a, bar_w1, ph_w1);
@@ -201,7 +194,7 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
                     tmem_ld8(tacc + c, r);
                     tmem_ld_wait();
                     float cv[8], dn[8];
-                    if (valid) load_h16x8(a.c2, grow, c, cv);
+                    if (valid) load_h16x8(a.c2, slab, T, t, c, cv);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float xh = valid ? (cv[j] - mean) * rstd : 0.f;
@@ -213,7 +206,7 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
                         s1 += dxh;
                         s2 += dxh * xh;
                     }
-                    if (valid) *reinterpret_cast<uint4*>(a.s3 + (grow * kHF + c) * 2) = pack8<FMT>(cv);
+                    if (valid) *reinterpret_cast<uint4*>(a.s3 + tile_off(slab, 24, T, c / 8, t)) = pack8<FMT>(cv);
                     *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = pack8<FMT>(dn);
                 }
                 s1 = warp_sum(s1);
@@ -237,7 +230,7 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
                     const int c = c0 + 8 * cc, g = c / kGC;
                     const float mean = gst[2 * g], rstd = gst[2 * g + 1], m1 = gtot[2 * g], m2 = gtot[2 * g + 1];
                     float cv[8];
-                    if (valid) load_h16x8(a.c2, grow, c, cv);
+                    if (valid) load_h16x8(a.c2, slab, T, t, c, cv);
                     const uint4 pk = *reinterpret_cast<const uint4*>(hrow + (c / 8) * kCS);
                     float dn[8];
                     unpack16<FMT>(pk.x, dn[0], dn[1]);
@@ -252,7 +245,7 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
                         gv[8 * cc + j] = valid ? rstd * (dn[j] * s_gng[c + j] - m1 - xh * m2) : 0.f;
                     }
                 }
-                if (valid) store16x32<FMT>(a.g_c2, grow, c0, gv);
+                if (valid) store16x32<FMT>(a.g_c2, slab, T, t, c0, gv);
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(hrow + (c0 / 8 + cc) * kCS) = pack8<FMT>(gv + 8 * cc);
                 const float sw = warp_colsum32(dnx, lane), sb = warp_colsum32(dnv, lane);
@@ -264,11 +257,11 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
         // ---- B3: d s2 = conv2^T(g c2)
         convT_phase(w0a, bar_w0, ph_w0);
         if (tid == 0) load_image(ws0, a.img + IMG_W1T, IMG_W2_BYTES, bar_w0);
-        silu_epilogue(a.c1, a.g_c1, a.s2, grow);
+        silu_epilogue(a.c1, a.g_c1, a.s2, slab);
         end_epilogue();
         // ---- B4: d s1 = conv1^T(g c1)
         convT_phase(w1a, bar_w1, ph_w1);
-        silu_epilogue(a.a1, a.g_a1, a.s1, grow);
+        silu_epilogue(a.a1, a.g_a1, a.s1, slab);
         end_epilogue();
         // ---- B5: d ln = g(a1) W1 ; E5: LayerNorm backward + residual
         if (tid == 0) {

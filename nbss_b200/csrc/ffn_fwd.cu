@@ -20,7 +20,7 @@ struct FfnFwdArgs {
     int nslab, T;
     const float *ln_w, *ln_b, *b1, *bc1, *bc2, *bc3, *gn_w, *gn_b, *b2;
     const unsigned char* img;  // layer image base
-    unsigned char *save_a1, *save_c1, *save_c2, *save_c3;  // fp16 [nslab*T, 192] or null
+    unsigned char *save_a1, *save_c1, *save_c2, *save_c3;  // fp16 slab-tile [nslab][24][T][8] or null
     float* gn_stats;                                       // [nslab, 8, 2] (mean, rstd) or null
     float* ln_stats;                                       // [nslab*T, 2] (mean, rstd) of the LayerNorm or null
     int* err;
@@ -40,10 +40,10 @@ __device__ __forceinline__ void store_h(unsigned char* hrow, int c0, const float
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(hrow + (c0 / 8 + cc) * kCS) = pack8<FMT>(s + 8 * cc);
 }
-__device__ __forceinline__ void save_f16(unsigned char* base, size_t row, int c0, const float* v) {
-    uint4* p = reinterpret_cast<uint4*>(base + (row * kHF + c0) * 2);
+// saved pre-activations use the slab-tile layout [slab][24 chunks][T][8] (slab.cuh): coalesced 16-byte pieces per frame
+__device__ __forceinline__ void save_f16(unsigned char* base, int slab, int T, int t, int c0, const float* v) {
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) p[cc] = pack8<FMT_F16>(v + 8 * cc);
+    for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(base + tile_off(slab, 24, T, c0 / 8 + cc, t)) = pack8<FMT_F16>(v + 8 * cc);
 }
 
 template <int FMT>
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_b1[c0 + j];
-            if (a.save_a1 && valid) save_f16(a.save_a1, grow, c0, v);
+            if (a.save_a1 && valid) save_f16(a.save_a1, slab, T, t, c0, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = valid ? silu(v[j]) : 0.f;
             store_h<FMT>(hrow, c0, v);
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bc[c0 + j];
-            if (a.save_c1 && valid) save_f16(a.save_c1, grow, c0, v);
+            if (a.save_c1 && valid) save_f16(a.save_c1, slab, T, t, c0, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = valid ? silu(v[j]) : 0.f;
             store_h<FMT>(hrow, c0, v);
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
                     float v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + bc2[c + j];
-                    if (a.save_c2 && valid) *reinterpret_cast<uint4*>(a.save_c2 + (grow * kHF + c) * 2) = pack8<FMT_F16>(v);
+                    if (a.save_c2 && valid) *reinterpret_cast<uint4*>(a.save_c2 + tile_off(slab, 24, T, c / 8, t)) = pack8<FMT_F16>(v);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float n = (v[j] - mean) * rstd * s_gng[c + j] + s_gnb[c + j];
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bc[384 + c0 + j];
-            if (a.save_c3 && valid) save_f16(a.save_c3, grow, c0, v);
+            if (a.save_c3 && valid) save_f16(a.save_c3, slab, T, t, c0, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = valid ? silu(v[j]) : 0.f;
             store_h<FMT>(hrow, c0, v);

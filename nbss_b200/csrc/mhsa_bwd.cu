@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256, 1) mhsa_bwd_core_kernel(MhsaBwdArgs a) {
                     tmem_ld_wait();
                     float v[8], ov[8];
                     if (valid) {
-                        const uint4 oq = __ldg(reinterpret_cast<const uint4*>(a.o + ((row0 + t) * kH + c) * 2));
+                        const uint4 oq = __ldg(reinterpret_cast<const uint4*>(a.o + tile_off(slab, 12, T, c / 8, t)));
                         unpack_f16x2(oq.x, ov[0], ov[1]);
                         unpack_f16x2(oq.y, ov[2], ov[3]);
                         unpack_f16x2(oq.z, ov[4], ov[5]);
@@ -157,13 +157,18 @@ __global__ void __launch_bounds__(256, 1) mhsa_bwd_core_kernel(MhsaBwdArgs a) {
         // ---- heads
 #pragma unroll 1
         for (int h = 0; h < kNH; ++h) {
-            // load the head's Qs, K, V (fp16, 24 -> 32 features: 4th chunk stays zero) from the saved projections
-            for (int i = tid; i < T * 9; i += 256) {
-                const int r = i / 9, j = i % 9, which = j / 3, c = j % 3;
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.qkv + ((row0 + r) * 288 + 96 * which + kDH * h + 8 * c) * 2));
-                unsigned char* base = which == 0 ? qt : (which == 1 ? kt : vt);
-                *reinterpret_cast<uint4*>(base + c * kCS + r * 16) = v;
+            // the head's Qs, K, V (fp16, 24 -> 32 features: the 4th chunk stays zero): three chunk columns each, straight
+            // TMA bulk copies out of the slab-tile tensor written by mhsa_fwd
+            if (tid == 0) {
+                mbar_expect_tx(bar_w, (uint32_t)(9 * T * 16));
+                for (int which = 0; which < 3; ++which) {
+                    unsigned char* base = which == 0 ? qt : (which == 1 ? kt : vt);
+                    for (int c = 0; c < 3; ++c)
+                        bulk_g2s(base + c * kCS, a.qkv + tile_off(slab, 36, T, 12 * which + 3 * h + c, 0), (uint32_t)(T * 16), bar_w);
+                }
+                mbar_wait(bar_w, ph_w, a.err);
             }
+            ph_w ^= 1;
             end_epilogue();
 #pragma unroll 1
             for (int blk = 0; blk < 4; ++blk) {
@@ -224,7 +229,6 @@ __global__ void __launch_bounds__(256, 1) mhsa_bwd_core_kernel(MhsaBwdArgs a) {
             {
                 // tcgen05.ld is warp-collective: every lane issues it, only valid frames store
                 const bool valid = t < T;
-                unsigned char* orow = a.dqkv + (row0 + (valid ? t : 0)) * 288 * 2;
 #pragma unroll
                 for (int which = 0; which < 3; ++which) {
                     const uint32_t col = (which == 0 ? C_DQ : (which == 1 ? C_DK : C_DV)) + 32 * m;
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(256, 1) mhsa_bwd_core_kernel(MhsaBwdArgs a) {
                         float v[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) * sc;
-                        if (valid) *reinterpret_cast<uint4*>(orow + (96 * which + kDH * h + 8 * k) * 2) = pack8<FMT_G>(v);
+                        if (valid) *reinterpret_cast<uint4*>(a.dqkv + tile_off(slab, 36, T, 12 * which + 3 * h + k, t)) = pack8<FMT_G>(v);
                     }
                 }
             }
@@ -276,12 +280,14 @@ __global__ void __launch_bounds__(256, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a) {
     float* acc = s_lng + 96;  // [0,96) d_lnw, [96,192) d_lnb
     uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + ML_BAR);
     uint64_t* bar_w = bar_mma + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
+    uint64_t* bar_ld = bar_mma + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 3);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = a.T;
     if (warp == 0) tmem_alloc(tmem_slot, 256);
     if (tid == 0) {
         mbar_init(bar_mma, 1);
         mbar_init(bar_w, 1);
+        mbar_init(bar_ld, 1);
         fence_mbar_init();
         load_image(wt, a.img + IMG_WINT, IMG_WINT_BYTES, bar_w);  // resident for the whole kernel
     }
@@ -298,25 +304,23 @@ __global__ void __launch_bounds__(256, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a) {
     const uint32_t tacc = tmem + ((uint32_t)(32 * q) << 16) + m * 96;
     const uint32_t ata = smem_u32(at), wta = smem_u32(wt);
     const uint32_t id96 = make_idesc(FMT_G, 128, 96, 0, 0);
-    uint32_t ph = 0;
+    uint32_t ph = 0, ph_ld = 0;
     bool wready = false;
     for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
         const size_t row0 = (size_t)slab * T, grow = row0 + t;
-        const unsigned char* src = a.dqkv + row0 * 288 * 2;
-        for (int i = tid; i < T * 36; i += 256) {
-            const int r = i / 36, c = i % 36;
-            *reinterpret_cast<uint4*>(at + (size_t)c * kCS + r * 16) = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)r * 288 + 8 * c) * 2));
-        }
+        if (tid == 0) bulk_load_chunks(at, kCS, 0, a.dqkv + tile_off(slab, 36, T, 0, 0), 36, T, bar_ld);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
             if (!wready) mbar_wait(bar_w, 0, a.err);
+            mbar_wait(bar_ld, ph_ld, a.err);
             for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 96, ata + 128 * mm * 16, kCS, wta, 96 * 16, 18, id96, 0);
             umma_commit(bar_mma);
         }
         wready = true;
+        ph_ld ^= 1;
         __syncwarp();
         mbar_wait(bar_mma, ph, a.err);
         ph ^= 1;

@@ -20,8 +20,8 @@ struct MhsaFwdArgs {
     int nslab, T;
     const float *ln_w, *ln_b, *b_in, *b_out;
     const unsigned char* img;
-    unsigned char* save_qkv;  // fp16 [nslab*T, 288]: (scaled q | k | v) or null
-    unsigned char* save_o;    // fp16 [nslab*T, 96] or null
+    unsigned char* save_qkv;  // fp16 slab-tile [nslab][36][T][8]: (scaled q | k | v) or null
+    unsigned char* save_o;    // fp16 slab-tile [nslab][12][T][8] or null
     float* save_lse;          // [nslab, 4, T] log2-domain logsumexp or null
     float* ln_stats;          // [nslab*T, 2] (mean, rstd) of the LayerNorm or null
     int* err;
@@ -121,7 +121,6 @@ __global__ void __launch_bounds__(256, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
         {
             const bool valid = t < T;
             const uint32_t tacc = tmem + lane_off + m * 192;
-            const size_t grow = (size_t)slab * T + t;
             // K: cols 0..95 -> per-head padded chunks 4h..4h+2
 #pragma unroll 1
             for (int h = 0; h < kNH; ++h) {
@@ -135,7 +134,7 @@ __global__ void __launch_bounds__(256, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
                     for (int j = 0; j < 8; ++j) v[j] = valid ? __uint_as_float(r[j]) + s_bin[96 + kDH * h + 8 * k + j] : 0.f;
                     uint4 p = pack8<FMT>(v);
                     *reinterpret_cast<uint4*>(kt + (4 * h + k) * kCS + t * 16) = p;
-                    if (a.save_qkv && valid) *reinterpret_cast<uint4*>(a.save_qkv + (grow * 288 + 96 + kDH * h + 8 * k) * 2) = pack8<FMT_F16>(v);
+                    if (a.save_qkv && valid) *reinterpret_cast<uint4*>(a.save_qkv + tile_off(slab, 36, T, 12 + 3 * h + k, t)) = pack8<FMT_F16>(v);
                 }
             }
             // V: cols 96..191 -> compact chunks 0..11
@@ -148,7 +147,7 @@ __global__ void __launch_bounds__(256, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = valid ? __uint_as_float(r[j]) + s_bin[192 + 8 * c + j] : 0.f;
                 *reinterpret_cast<uint4*>(vt + c * kCS + t * 16) = pack8<FMT>(v);
-                if (a.save_qkv && valid) *reinterpret_cast<uint4*>(a.save_qkv + (grow * 288 + 192 + 8 * c) * 2) = pack8<FMT_F16>(v);
+                if (a.save_qkv && valid) *reinterpret_cast<uint4*>(a.save_qkv + tile_off(slab, 36, T, 24 + c, t)) = pack8<FMT_F16>(v);
             }
         }
         end_epilogue();
@@ -180,7 +179,7 @@ __global__ void __launch_bounds__(256, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
                     for (int j = 0; j < 8; ++j) v[j] = valid ? (__uint_as_float(r[j]) + s_bin[kDH * h + 8 * k + j]) * qscale : 0.f;
                     *reinterpret_cast<uint4*>(qs + k * kCSP + rt * 16) = pack8<FMT>(v);
                     if (a.save_qkv && valid)
-                        *reinterpret_cast<uint4*>(a.save_qkv + (((size_t)slab * T + tq) * 288 + kDH * h + 8 * k) * 2) = pack8<FMT_F16>(v);
+                        *reinterpret_cast<uint4*>(a.save_qkv + tile_off(slab, 36, T, 3 * h + k, tq)) = pack8<FMT_F16>(v);
                 }
                 *reinterpret_cast<uint4*>(qs + 3 * kCSP + rt * 16) = make_uint4(0, 0, 0, 0);
             }
@@ -258,7 +257,7 @@ __global__ void __launch_bounds__(256, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
                     for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) * inv;
                     *reinterpret_cast<uint4*>(ao + (3 * h + k) * kCS + tq * 16) = pack8<FMT>(v);
                     if (a.save_o && tq < T)
-                        *reinterpret_cast<uint4*>(a.save_o + (((size_t)slab * T + tq) * kH + kDH * h + 8 * k) * 2) = pack8<FMT_F16>(v);
+                        *reinterpret_cast<uint4*>(a.save_o + tile_off(slab, 12, T, 3 * h + k, tq)) = pack8<FMT_F16>(v);
                 }
             }
             tc_fence_before();

@@ -28,12 +28,33 @@ __device__ __forceinline__ void load_image(void* dst_smem, const void* src, uint
     bulk_g2s(dst_smem, src, bytes, bar);
 }
 
+// ---------------------------------------------------------------- 16-bit intermediates in HBM: "slab tile" layout
+// Every 16-bit tensor that only travels between these kernels (saved pre-activations, q|k|v, O, gradient operands) is
+// stored as [slab][C/8 chunks][T rows][8 elements]: the byte image of the smem operand tile.  A thread-per-frame
+// epilogue then writes 32 consecutive 16-byte pieces per warp instruction (fully coalesced), and a consumer brings a
+// chunk column into shared memory with one TMA bulk copy of T*16 bytes.
+__device__ __forceinline__ size_t tile_off(size_t slab, int nchunks, int T, int chunk, int t) {
+    return (((size_t)slab * nchunks + chunk) * T + t) * 16;
+}
+// ONE thread: copy `nch` chunk columns (T rows each) of a slab-tile tensor into a smem tile; completion on `bar`.
+__device__ __forceinline__ void bulk_load_chunks(unsigned char* tile, uint32_t cs, int row_off, const unsigned char* src,
+                                                 int nch, int T, uint64_t* bar) {
+    mbar_expect_tx(bar, (uint32_t)(nch * T * 16));
+    for (int c = 0; c < nch; ++c) bulk_g2s(tile + (size_t)c * cs + row_off * 16, src + (size_t)c * T * 16, (uint32_t)(T * 16), bar);
+}
+
 // ---------------------------------------------------------------- MMA issue helpers (call from ONE thread)
 // D[128 x N] (+)= A[128 x 16*ksteps] * B[N x 16*ksteps]^T, both K-major chunk-column tiles.
 __device__ __forceinline__ void mma_kk(uint32_t tmem_d, uint32_t a_addr, uint32_t a_cs, uint32_t b_addr, uint32_t b_cs,
                                        int ksteps, uint32_t idesc, uint32_t acc) {
+    // the start-address field is the low 14 bits of the descriptor: advancing K is a plain add of (bytes >> 4)
+    uint64_t da = sdesc_kmajor(a_addr, a_cs), db = sdesc_kmajor(b_addr, b_cs);
+    const uint64_t sa = (uint64_t)((2 * a_cs) >> 4), sb = (uint64_t)((2 * b_cs) >> 4);
+#pragma unroll 1
     for (int ks = 0; ks < ksteps; ++ks) {
-        umma_f16(tmem_d, sdesc_kmajor(a_addr + 2 * ks * a_cs, a_cs), sdesc_kmajor(b_addr + 2 * ks * b_cs, b_cs), idesc, acc);
+        umma_f16(tmem_d, da, db, idesc, acc);
+        da += sa;
+        db += sb;
         acc = 1;
     }
 }

@@ -35,7 +35,7 @@ struct WgArgs {
 template <int FMT_G, int FMT_A>
 __global__ void __launch_bounds__(256, 1) wgrad_kernel(WgArgs args) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar_mma;
+    __shared__ uint64_t bar_mma, bar_ld;
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float s_ln[192];
     const WgJob& J = args.job[blockIdx.y];
@@ -43,10 +43,12 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(WgArgs args) {
     unsigned char* gt = smem;
     unsigned char* at = smem + (size_t)J.g_alloc * kCS;
     const int a_alloc = J.a_chunks + 2;
+    const int n_bulk = (J.g_fp32 ? 0 : 1) + (J.a_ln ? 0 : 1);  // operands arriving by TMA bulk copy (one arrive each)
 
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
     if (tid == 0) {
         mbar_init(&bar_mma, 1);
+        mbar_init(&bar_ld, n_bulk > 0 ? n_bulk : 1);
         fence_mbar_init();
     }
     if (J.a_ln) for (int i = tid; i < 96; i += 256) { s_ln[i] = J.ln_w[i]; s_ln[96 + i] = J.ln_b[i]; }
@@ -62,41 +64,30 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(WgArgs args) {
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const uint32_t gta = smem_u32(gt), ata = smem_u32(at);
-    uint32_t ph = 0;
+    uint32_t ph = 0, ph_ld = 0;
     bool first = true;
     (void)a_alloc;
 
     for (int slab = blockIdx.x; slab < args.nslab; slab += gridDim.x) {
         const size_t row0 = (size_t)slab * T;
-        // ---- stage G
-        if (J.g_fp32) {
-            stage_rows96<FMT_G, false>(reinterpret_cast<const float*>(J.g) + row0 * kH, T, gt, 0, nullptr, nullptr, warp, lane);
-        } else {
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(J.g) + (row0 * J.g_cols + J.g_c0) * 2;
-            const int nch = J.g_chunks;
-            for (int i = tid; i < T * nch; i += 256) {
-                const int r = i / nch, c = i % nch;
-                *reinterpret_cast<uint4*>(gt + (size_t)c * kCS + r * 16) =
-                    __ldg(reinterpret_cast<const uint4*>(src + ((size_t)r * J.g_cols + 8 * c) * 2));
-            }
+        // ---- stage G and ACT: 16-bit slab-tile tensors come in by TMA bulk copies (one per chunk column), fp32
+        //      sources (upstream gradient, x through LayerNorm) are converted by the warps
+        if (tid == 0) {
+            if (!J.g_fp32)
+                bulk_load_chunks(gt, kCS, 0, reinterpret_cast<const unsigned char*>(J.g) + tile_off(slab, J.g_cols / 8, T, J.g_c0 / 8, 0),
+                                 J.g_chunks, T, &bar_ld);
+            if (!J.a_ln)
+                bulk_load_chunks(at, kCS, J.a_row_off, reinterpret_cast<const unsigned char*>(J.act) + tile_off(slab, J.a_cols / 8, T, J.a_c0 / 8, 0),
+                                 J.a_chunks, T, &bar_ld);
         }
-        // ---- stage ACT
-        if (J.a_ln) {
-            stage_rows96<FMT_A, true>(reinterpret_cast<const float*>(J.act) + row0 * kH, T, at, J.a_row_off, s_ln, s_ln + 96, warp, lane);
-        } else {
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(J.act) + (row0 * J.a_cols + J.a_c0) * 2;
-            const int nch = J.a_chunks;
-            for (int i = tid; i < T * nch; i += 256) {
-                const int r = i / nch, c = i % nch;
-                *reinterpret_cast<uint4*>(at + (size_t)c * kCS + (r + J.a_row_off) * 16) =
-                    __ldg(reinterpret_cast<const uint4*>(src + ((size_t)r * J.a_cols + 8 * c) * 2));
-            }
-        }
+        if (J.g_fp32) stage_rows96<FMT_G, false>(reinterpret_cast<const float*>(J.g) + row0 * kH, T, gt, 0, nullptr, nullptr, warp, lane);
+        if (J.a_ln) stage_rows96<FMT_A, true>(reinterpret_cast<const float*>(J.act) + row0 * kH, T, at, J.a_row_off, s_ln, s_ln + 96, warp, lane);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
+            if (n_bulk > 0) { mbar_wait(&bar_ld, ph_ld, args.err); ph_ld ^= 1; }
             for (int i = 0; i < J.nmma; ++i) {
                 const WgMma mm = J.mma[i];
                 const uint32_t idesc = (1u << 4) | ((uint32_t)FMT_G << 7) | ((uint32_t)FMT_A << 10) | (1u << 15) | (1u << 16) |

@@ -56,6 +56,12 @@ def check_err_flag(flag: Tensor, what: str) -> None:
         raise _lib.NbssError(f"{what}: device-side error flag {v:#x} (mbarrier wait timed out)")
 
 
+def untile(t: Tensor, nslab: int, T: int) -> Tensor:
+    """16-bit intermediates are stored in the slab-tile layout [slab][C/8][T][8] (csrc/slab.cuh); returns [nslab*T, C]."""
+    C = t.numel() // (nslab * T)
+    return t.reshape(nslab, C // 8, T, 8).permute(0, 2, 1, 3).reshape(nslab * T, C)
+
+
 def layer_image_bytes() -> int:
     L = _lib.lib()
     L.nbss_layer_image_bytes.restype = ctypes.c_uint

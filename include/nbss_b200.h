@@ -67,6 +67,15 @@ int nbss_fconv_fwd(const float* x, float* y, int B, int F, int T, const float* l
 int nbss_fconv_bwd(const float* x, const float* dy, float* dx, int B, int F, int T, const float* lnw, const float* lnb,
                    const float* W, const float* bias, const float* slope, float* dW, float* dbias, float* dslope,
                    float* dlnw, float* dlnb, void* stream);
+/* The same sub-block on tensor cores (fconv_tc.cu): frames stacked into one UMMA tile with zero gap rows, taps as
+ * row-shifted views, block-diagonal 48x48 weight tiles; img from nbss_fconv_pack (nbss_fconv_image_bytes() bytes). */
+unsigned int nbss_fconv_image_bytes(void);
+int nbss_fconv_pack(const float* W, void* img, int fmt, void* stream);
+int nbss_fconv_tc_fwd(const float* x, float* y, int B, int F, int T, const float* lnw, const float* lnb, const float* bias,
+                      const float* slope, const void* img, int fmt, int* err, void* stream);
+int nbss_fconv_tc_bwd(const float* x, const float* dy, float* dx, int B, int F, int T, const float* lnw, const float* lnb,
+                      const float* bias, const float* slope, const void* img, float* dW, float* dbias, float* dslope,
+                      float* dlnw, float* dlnb, int fmt, int* err, void* stream);
 /* y = x + unsqueeze(full(squeeze(LN(x)))): _full :129-146.  s_out,u_out: [B,T,8,F] (kept for backward). */
 int nbss_full_fwd(const float* x, float* y, float* s_out, float* u_out, int B, int F, int T, const float* lnw,
                   const float* lnb, const float* Wsq, const float* bsq, const float* Wf, const float* bf, const float* Wun,

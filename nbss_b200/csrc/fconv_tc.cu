@@ -1,0 +1,500 @@
+// fconv_tc.cu — cross-band frequency-convolution sub-block on tensor cores (tcgen05), forward and backward.
+//
+// Replaces SpatialNetLayer._fconv + residual (models/arch/SpatialNet.py:85,87,116-127; modules :36-40,:49-53):
+//     y = x + PReLU( Conv1d_F(k=5, groups=8, zero 'same' padding)( LayerNorm_H(x) ) )
+// The convolution runs along F for a fixed frame (b,t).  A CTA stacks the F rows of a few consecutive frames into ONE
+// UMMA operand tile with two zero rows between frames (row p = 2 + slot*(F+2) + f): a conv tap is then a row-shifted
+// view of the tile (descriptor start + 16 B * tap) and the zero gaps ARE the zero padding.  Weights are block-diagonal
+// 48x48 tiles (4 groups of 12 channels), one per (channel half, tap).  fp16 operands, fp32 accumulation in TMEM.
+//   forward : stage LN(x) -> 5 taps x 2 halves MMAs per 128-row tile -> epilogue (+bias, PReLU, +x) thread = (frame,f) row
+//   backward: recompute conv; dc = dy * PReLU'(c) -> 16-bit tile; weight grad = dc^T x shifted LN(x) (MN-major MMAs,
+//             accumulated per thread in registers across the CTA's frame groups); data grad = transposed conv of dc;
+//             LayerNorm backward + residual in the epilogue; d(bias), d(slope), d(gamma), d(beta) by warp column sums.
+#include "slab.cuh"
+
+namespace nbss {
+
+constexpr int kFQ = 2;                                   // channel halves (48 channels = 4 groups)
+constexpr int kFTaps = 5;
+constexpr uint32_t FC_IMG_TILE = 6 * 48 * 16;            // one [48 x 48] 16-bit tile, chunk-column, 4608 B
+constexpr uint32_t FC_IMG_BYTES = kFQ * kFTaps * FC_IMG_TILE;  // 46080: forward image; the transposed image follows
+
+// ------------------------------------------------------------------------------------------------ weight images
+// fwd tile (half q, tap k): elem(n, kk) = W[48q+n][kk%12][k] if n/12 == kk/12 (N index = out channel, K = in channel)
+// bwd tile              : elem(n, kk) = W[48q+kk][n%12][k] if n/12 == kk/12 (N index = in channel,  K = out channel)
+__global__ void fconv_pack_kernel(const float* __restrict__ W, unsigned char* img, int fmt) {
+    const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chunk * 16 >= 2 * FC_IMG_BYTES) return;
+    const bool bwd = chunk * 16 >= FC_IMG_BYTES;
+    const uint32_t i = (chunk * 16 - (bwd ? FC_IMG_BYTES : 0)) / 16;
+    const int tile = i / (6 * 48), r = i % (6 * 48), c = r / 48, n = r % 48, q = tile / kFTaps, k = tile % kFTaps;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int kk = 8 * c + j;
+        const bool same = (n / 12) == (kk / 12);
+        v[j] = !same ? 0.f : (bwd ? W[((48 * q + kk) * 12 + n % 12) * 5 + k] : W[((48 * q + n) * 12 + kk % 12) * 5 + k]);
+    }
+    uint4 o = (fmt == FMT_F16) ? make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]))
+                               : make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    *reinterpret_cast<uint4*>(img + (size_t)chunk * 16) = o;
+}
+
+struct FcGeom {
+    int B, F, T, FP;   // FP = F + 2 (frame period in tile rows)
+    int nfr, nt;       // frames per group, 128-row M-tiles per group
+    int rows;          // tile rows (128*nt + 9)
+    uint32_t cs;       // chunk stride = rows * 16
+    int groups_per_b, ngroups;
+};
+
+// ------------------------------------------------------------------------------------------------ staging
+// LN(x) of the group's frames into the tile (fp16); rows of frames beyond T are zero; optional (mean, rstd) per tile row.
+template <int FMT>
+__device__ __forceinline__ void fc_stage(const FcGeom& g, const float* __restrict__ x, int b, int t0, unsigned char* tile,
+                                         const float* s_lnw, const float* s_lnb, float2* s_stats, int warp, int lane) {
+    const bool act = lane < 24;
+    float4 gw = make_float4(0, 0, 0, 0), gb = gw;
+    if (act) { gw = *reinterpret_cast<const float4*>(s_lnw + 4 * lane); gb = *reinterpret_cast<const float4*>(s_lnb + 4 * lane); }
+    const int nrows = g.nfr * g.F;
+#pragma unroll 1
+    for (int i0 = warp; i0 < nrows; i0 += 32) {
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = i0 + 8 * j;
+            const int tt = i / g.F, f = i % g.F, t = t0 + tt;
+            v[j] = (act && i < nrows && t < g.T) ? __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * g.F + f) * g.T + t) * kH) + lane)
+                                                 : make_float4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = i0 + 8 * j;
+            if (i >= nrows) continue;
+            const int tt = i / g.F, f = i % g.F, t = t0 + tt, p = 2 + tt * g.FP + f;
+            const float s = warp_sum(v[j].x + v[j].y + v[j].z + v[j].w);
+            const float mean = s * (1.f / kH);
+            const float4 d = act ? make_float4(v[j].x - mean, v[j].y - mean, v[j].z - mean, v[j].w - mean) : make_float4(0, 0, 0, 0);
+            const float qv = warp_sum(d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w);
+            const float rstd = rsqrtf(qv * (1.f / kH) + 1e-5f);
+            if (s_stats && lane == 0) s_stats[p] = make_float2(mean, rstd);
+            if (act) {
+                uint2 pk = make_uint2(0u, 0u);
+                if (t < g.T)
+                    pk = make_uint2(pack16<FMT>(d.x * rstd * gw.x + gb.x, d.y * rstd * gw.y + gb.y),
+                                    pack16<FMT>(d.z * rstd * gw.z + gb.z, d.w * rstd * gw.w + gb.w));
+                *reinterpret_cast<uint2*>(tile + (size_t)(lane >> 1) * g.cs + p * 16 + (lane & 1) * 8) = pk;
+            }
+        }
+    }
+}
+
+// conv (or transposed conv) MMAs of one group: D[tile m][half q] = sum_tap A(rows shifted) * Wimg(q, tap)
+__device__ __forceinline__ void fc_conv_mmas(const FcGeom& g, uint32_t tmem, uint32_t tile_addr, uint32_t w_addr, uint32_t idesc,
+                                             bool transposed) {
+    for (int m = 0; m < g.nt; ++m)
+        for (int q = 0; q < kFQ; ++q)
+            for (int tap = 0; tap < kFTaps; ++tap) {
+                const int row = 128 * m + (transposed ? 4 - tap : tap);  // tile row of output q0: 2 + q0 + (tap-2) resp. 2 + q0 - (tap-2)
+                mma_kk(tmem + m * 96 + q * 48, tile_addr + 6 * q * g.cs + row * 16, g.cs, w_addr + (q * kFTaps + tap) * FC_IMG_TILE, 768, 3,
+                       idesc, tap > 0);
+            }
+}
+
+struct FcFwdArgs {
+    const float* x;
+    float* y;
+    FcGeom g;
+    const float *lnw, *lnb, *bias, *slope;
+    const unsigned char* img;
+    int* err;
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(256, 1) fconv_tc_fwd_kernel(FcFwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const FcGeom g = a.g;
+    unsigned char* tile = smem;
+    unsigned char* wimg = smem + (size_t)12 * g.cs;
+    float* cst = reinterpret_cast<float*>(wimg + FC_IMG_BYTES);  // lnw, lnb, bias, slope
+    uint64_t* bar_mma = reinterpret_cast<uint64_t*>(cst + 384);
+    uint64_t* bar_w = bar_mma + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_w, 1);
+        fence_mbar_init();
+        load_image(wimg, a.img, FC_IMG_BYTES, bar_w);
+    }
+    for (int i = tid; i < 96; i += 256) { cst[i] = a.lnw[i]; cst[96 + i] = a.lnb[i]; cst[192 + i] = a.bias[i]; cst[288 + i] = a.slope[i]; }
+    for (int i = tid; i < (int)(12 * g.cs / 16); i += 256) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t ta = smem_u32(tile), wa = smem_u32(wimg);
+    const uint32_t id48 = make_idesc(FMT, 128, 48, 0, 0);
+    const uint32_t lane_off = (uint32_t)(32 * (warp & 3)) << 16;
+    uint32_t ph = 0;
+    bool wready = false;
+    for (int grp = blockIdx.x; grp < g.ngroups; grp += gridDim.x) {
+        const int b = grp / g.groups_per_b, t0 = (grp % g.groups_per_b) * g.nfr;
+        fc_stage<FMT>(g, a.x, b, t0, tile, cst, cst + 96, nullptr, warp, lane);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            if (!wready) mbar_wait(bar_w, 0, a.err);
+            fc_conv_mmas(g, tmem, ta, wa, id48, false);
+            umma_commit(bar_mma);
+        }
+        wready = true;
+        __syncwarp();
+        mbar_wait(bar_mma, ph, a.err);
+        ph ^= 1;
+        tc_fence_after();
+        // epilogue: warps 0-3 take even tiles, warps 4-7 odd tiles; thread = one (frame, f) row
+        for (int m = warp >> 2; m < g.nt; m += 2) {
+            const int q = 128 * m + 32 * (warp & 3) + lane;
+            const int tt = q / g.FP, f = q % g.FP, t = t0 + tt;
+            const bool valid = tt < g.nfr && f < g.F && t < g.T;
+            const size_t base = valid ? (((size_t)b * g.F + f) * g.T + t) * kH : 0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kH; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem + lane_off + m * 96 + c0, r);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 xv = __ldg(reinterpret_cast<const float4*>(a.x + base + c0) + j4);
+                        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                        float o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int c = c0 + 4 * j4 + e;
+                            const float v = __uint_as_float(r[4 * j4 + e]) + cst[192 + c];
+                            o[e] = xs[e] + (v >= 0.f ? v : cst[288 + c] * v);
+                        }
+                        reinterpret_cast<float4*>(a.y + base + c0)[j4] = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+struct FcBwdArgs {
+    const float* x;
+    const float* dy;
+    float* dx;
+    FcGeom g;
+    const float *lnw, *lnb, *bias, *slope;
+    const unsigned char* img;  // forward image followed by the transposed image
+    float *dW, *dbias, *dslope, *dlnw, *dlnb;
+    int* err;
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const FcGeom g = a.g;
+    unsigned char* htile = smem;                           // LN(x)
+    unsigned char* gtile = smem + (size_t)12 * g.cs;       // dc
+    unsigned char* wimg = gtile + (size_t)12 * g.cs;       // weight slot (fwd image, then transposed image); also the
+                                                           // over-read area of the 128-feature MN-major window of gtile
+    float* cst = reinterpret_cast<float*>(wimg + FC_IMG_BYTES);  // lnw, lnb, bias, slope (384) + acc (384): dbias, dslope, dlnw, dlnb
+    float* acc = cst + 384;
+    float2* stats = reinterpret_cast<float2*>(acc + 384);  // [rows] (mean, rstd)
+    uint64_t* bar_mma = reinterpret_cast<uint64_t*>(stats + g.rows);
+    uint64_t* bar_w = bar_mma + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_w, 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < 96; i += 256) { cst[i] = a.lnw[i]; cst[96 + i] = a.lnb[i]; cst[192 + i] = a.bias[i]; cst[288 + i] = a.slope[i]; }
+    for (int i = tid; i < 384; i += 256) acc[i] = 0.f;
+    for (int i = tid; i < (int)(24 * g.cs / 16); i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t ha = smem_u32(htile), ga = smem_u32(gtile), wa = smem_u32(wimg);
+    const uint32_t id48 = make_idesc(FMT, 128, 48, 0, 0);
+    const uint32_t id_wg = make_idesc(FMT, 128, 96, 1, 1);
+    const uint32_t lane_off = (uint32_t)(32 * (warp & 3)) << 16;
+    uint32_t ph = 0, ph_w = 0;
+    // weight-gradient accumulators: thread = output channel co (warps 0-2), 5 taps x 12 in-channels of its group
+    const int co = 32 * warp + lane;
+    float dw[60];
+#pragma unroll
+    for (int i = 0; i < 60; ++i) dw[i] = 0.f;
+
+    auto wait_mma = [&]() {
+        __syncwarp();
+        mbar_wait(bar_mma, ph, a.err);
+        ph ^= 1;
+        tc_fence_after();
+    };
+    for (int grp = blockIdx.x; grp < g.ngroups; grp += gridDim.x) {
+        const int b = grp / g.groups_per_b, t0 = (grp % g.groups_per_b) * g.nfr;
+        if (tid == 0) load_image(wimg, a.img, FC_IMG_BYTES, bar_w);
+        fc_stage<FMT>(g, a.x, b, t0, htile, cst, cst + 96, stats, warp, lane);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- P1: recompute the conv
+        if (tid == 0) {
+            tc_fence_after();
+            mbar_wait(bar_w, ph_w, a.err);
+            fc_conv_mmas(g, tmem, ha, wa, id48, false);
+            umma_commit(bar_mma);
+        }
+        ph_w ^= 1;
+        wait_mma();
+        if (tid == 0) load_image(wimg, a.img + FC_IMG_BYTES, FC_IMG_BYTES, bar_w);  // transposed image for the data gradient
+        // ---- E-A: dc = dy * PReLU'(c) -> gtile; column sums for dbias / dslope
+        for (int m = warp >> 2; m < g.nt + (g.nt & 1); m += 2) {  // every warp runs the same trip count (warp-collective loads)
+            const bool mt = m < g.nt;
+            const int q = 128 * m + 32 * (warp & 3) + lane;
+            const int tt = q / g.FP, f = q % g.FP, t = t0 + tt;
+            const bool valid = mt && tt < g.nfr && f < g.F && t < g.T;
+            const size_t base = valid ? (((size_t)b * g.F + f) * g.T + t) * kH : 0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kH; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem + lane_off + (mt ? m : 0) * 96 + c0, r);
+                tmem_ld_wait();
+                float dc[32], ds[32];
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    float4 dv = make_float4(0, 0, 0, 0);
+                    if (valid) dv = __ldg(reinterpret_cast<const float4*>(a.dy + base + c0) + j4);
+                    const float dys[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = c0 + 4 * j4 + e;
+                        const float cv = __uint_as_float(r[4 * j4 + e]) + cst[192 + c];
+                        dc[4 * j4 + e] = valid ? dys[e] * (cv >= 0.f ? 1.f : cst[288 + c]) : 0.f;
+                        ds[4 * j4 + e] = (valid && cv < 0.f) ? dys[e] * cv : 0.f;
+                    }
+                }
+                if (mt) {
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc)
+                        *reinterpret_cast<uint4*>(gtile + (size_t)(c0 / 8 + cc) * g.cs + (2 + q) * 16) = pack8<FMT>(dc + 8 * cc);
+                }
+                const float sb = warp_colsum32(dc, lane), ss = warp_colsum32(ds, lane);
+                atomicAdd(acc + c0 + lane, sb);
+                atomicAdd(acc + 96 + c0 + lane, ss);
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- P2: weight gradient  dW[co, ci, tap] += sum_q dc[q, co] * h[q + tap - 2, ci]   (MN-major x MN-major)
+        if (tid == 0) {
+            tc_fence_after();
+            const int nks = 8 * g.nt;  // 16 rows per k-step
+            for (int tap = 0; tap < kFTaps; ++tap)
+                for (int ks = 0; ks < nks; ++ks)
+                    umma_f16(tmem + 96 * tap, sdesc_mnmajor(ga + (2 + 16 * ks) * 16, g.cs), sdesc_mnmajor(ha + (tap + 16 * ks) * 16, g.cs),
+                             id_wg, ks ? 1u : 0u);
+            umma_commit(bar_mma);
+        }
+        wait_mma();
+        if (warp < 3) {  // thread = out channel co (TMEM lane): keep the 12 in-channel columns of its own group, 5 taps
+            const int cbase = 12 * (co / 12);   // first column of the group: 0, 12, ..., 84
+            const int cb8 = cbase & ~7;         // aligned 16-column window [cb8, cb8+16) contains [cbase, cbase+12)
+            const bool sh4 = (cbase & 7) != 0;  // window offset is 0 or 4
+#pragma unroll
+            for (int tap = 0; tap < kFTaps; ++tap) {
+                uint32_t r0[8], r1[8];
+                tmem_ld8(tmem + lane_off + 96 * tap + cb8, r0);
+                tmem_ld8(tmem + lane_off + 96 * tap + cb8 + 8, r1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int ci = 0; ci < 12; ++ci) {
+                    const uint32_t lo = ci < 8 ? r0[ci] : r1[ci - 8];
+                    const uint32_t hi = ci + 4 < 8 ? r0[ci + 4] : r1[ci + 4 - 8];
+                    dw[ci * 5 + tap] += __uint_as_float(sh4 ? hi : lo);
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        // ---- P3: data gradient of the conv
+        if (tid == 0) {
+            tc_fence_after();
+            mbar_wait(bar_w, ph_w, a.err);
+            fc_conv_mmas(g, tmem, ga, wa, id48, true);
+            umma_commit(bar_mma);
+        }
+        ph_w ^= 1;
+        wait_mma();
+        // ---- E-B: LayerNorm backward + residual; column sums for dlnw / dlnb
+        for (int m = warp >> 2; m < g.nt + (g.nt & 1); m += 2) {
+            const bool mt = m < g.nt;
+            const int q = 128 * m + 32 * (warp & 3) + lane;
+            const int tt = q / g.FP, f = q % g.FP, t = t0 + tt;
+            const bool valid = mt && tt < g.nfr && f < g.F && t < g.T;
+            const size_t base = valid ? (((size_t)b * g.F + f) * g.T + t) * kH : 0;
+            const float2 st = valid ? stats[2 + q] : make_float2(0.f, 0.f);
+            const uint32_t tacc = tmem + lane_off + (mt ? m : 0) * 96;
+            float m1 = 0.f, m2 = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kH; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tacc + c0, r);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 xv = __ldg(reinterpret_cast<const float4*>(a.x + base + c0) + j4);
+                        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float dzg = __uint_as_float(r[4 * j4 + e]) * cst[c0 + 4 * j4 + e];
+                            m1 += dzg;
+                            m2 += dzg * (xs[e] - st.x) * st.y;
+                        }
+                    }
+                }
+            }
+            m1 *= (1.f / kH);
+            m2 *= (1.f / kH);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kH; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tacc + c0, r);
+                tmem_ld_wait();
+                float dzv[32], dzx[32];
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    float4 xv = make_float4(0, 0, 0, 0), dv = xv;
+                    if (valid) {
+                        xv = __ldg(reinterpret_cast<const float4*>(a.x + base + c0) + j4);
+                        dv = __ldg(reinterpret_cast<const float4*>(a.dy + base + c0) + j4);
+                    }
+                    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                    const float dys[4] = {dv.x, dv.y, dv.z, dv.w};
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float dz = valid ? __uint_as_float(r[4 * j4 + e]) : 0.f;
+                        const float xh = (xs[e] - st.x) * st.y;
+                        dzv[4 * j4 + e] = dz;
+                        dzx[4 * j4 + e] = dz * xh;
+                        o[e] = dys[e] + st.y * (dz * cst[c0 + 4 * j4 + e] - m1 - xh * m2);
+                    }
+                    if (valid) reinterpret_cast<float4*>(a.dx + base + c0)[j4] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                const float sw = warp_colsum32(dzx, lane), sb = warp_colsum32(dzv, lane);
+                atomicAdd(acc + 192 + c0 + lane, sw);
+                atomicAdd(acc + 288 + c0 + lane, sb);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    // ---- flush parameter gradients
+    if (warp < 3) {
+#pragma unroll
+        for (int i = 0; i < 60; ++i) atomicAdd(a.dW + co * 60 + i, dw[i]);
+    }
+    for (int i = tid; i < 96; i += 256) {
+        atomicAdd(a.dbias + i, acc[i]);
+        atomicAdd(a.dslope + i, acc[96 + i]);
+        atomicAdd(a.dlnw + i, acc[192 + i]);
+        atomicAdd(a.dlnb + i, acc[288 + i]);
+    }
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static int fc_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return sms;
+}
+
+static bool fc_geom(FcGeom& g, int B, int F, int T, int max_tiles, int max_frames) {
+    g.B = B; g.F = F; g.T = T; g.FP = F + 2;
+    int nfr = (128 * max_tiles) / g.FP;
+    if (nfr > max_frames) nfr = max_frames;
+    if (nfr < 1) return false;
+    g.nfr = nfr;
+    g.nt = (nfr * g.FP + 127) / 128;
+    g.rows = 128 * g.nt + 9;
+    g.cs = (uint32_t)g.rows * 16;
+    g.groups_per_b = (T + nfr - 1) / nfr;
+    g.ngroups = B * g.groups_per_b;
+    return true;
+}
+
+}  // namespace nbss
+
+using namespace nbss;
+
+extern "C" unsigned int nbss_fconv_image_bytes() { return 2 * FC_IMG_BYTES; }
+
+// W: fconv{1,2}.1.weight [96,12,5] -> forward + transposed UMMA images (nbss_fconv_image_bytes() bytes)
+extern "C" int nbss_fconv_pack(const float* W, void* img, int fmt, void* stream) {
+    if (!W || !img) return NBSS_ERR_NULL;
+    const int n = 2 * FC_IMG_BYTES / 16;
+    fconv_pack_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, (unsigned char*)img, fmt);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+
+extern "C" int nbss_fconv_tc_fwd(const float* x, float* y, int B, int F, int T, const float* lnw, const float* lnb,
+                                 const float* bias, const float* slope, const void* img, int fmt, int* err, void* stream) {
+    if (!x || !y || !lnw || !lnb || !bias || !slope || !img) return NBSS_ERR_NULL;
+    if (B < 1 || F < 1 || T < 1) return NBSS_ERR_SHAPE;
+    if (fmt != FMT_F16 && fmt != FMT_BF16) return NBSS_ERR_UNSUPPORTED;
+    FcFwdArgs a{x, y, {}, lnw, lnb, bias, slope, (const unsigned char*)img, err};
+    if (!fc_geom(a.g, B, F, T, 5, 4)) return NBSS_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)12 * a.g.cs + FC_IMG_BYTES + 384 * 4 + 64;
+    if (smem > 227 * 1024) return NBSS_ERR_UNSUPPORTED;
+    auto kern = (fmt == FMT_F16) ? fconv_tc_fwd_kernel<FMT_F16> : fconv_tc_fwd_kernel<FMT_BF16>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int grid = a.g.ngroups < fc_sms() ? a.g.ngroups : fc_sms();
+    kern<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+
+extern "C" int nbss_fconv_tc_bwd(const float* x, const float* dy, float* dx, int B, int F, int T, const float* lnw,
+                                 const float* lnb, const float* bias, const float* slope, const void* img, float* dW,
+                                 float* dbias, float* dslope, float* dlnw, float* dlnb, int fmt, int* err, void* stream) {
+    if (!x || !dy || !dx || !lnw || !lnb || !bias || !slope || !img || !dW || !dbias || !dslope || !dlnw || !dlnb) return NBSS_ERR_NULL;
+    if (B < 1 || F < 1 || T < 1) return NBSS_ERR_SHAPE;
+    if (fmt != FMT_F16 && fmt != FMT_BF16) return NBSS_ERR_UNSUPPORTED;
+    FcBwdArgs a{x, dy, dx, {}, lnw, lnb, bias, slope, (const unsigned char*)img, dW, dbias, dslope, dlnw, dlnb, err};
+    if (!fc_geom(a.g, B, F, T, 3, 2)) return NBSS_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)24 * a.g.cs + FC_IMG_BYTES + 768 * 4 + (size_t)a.g.rows * 8 + 64;
+    if (smem > 227 * 1024) return NBSS_ERR_UNSUPPORTED;
+    auto kern = (fmt == FMT_F16) ? fconv_tc_bwd_kernel<FMT_F16> : fconv_tc_bwd_kernel<FMT_BF16>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int grid = a.g.ngroups < fc_sms() ? a.g.ngroups : fc_sms();
+    kern<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}

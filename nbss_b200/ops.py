@@ -348,3 +348,44 @@ def mhsa_bwd(x: Tensor, dy: Tensor, msave, P, pre: str, img: Tensor, G, fmt_g: i
                            stream_ptr())
     check(st, "nbss_mhsa_wgrad")
     return dx, err
+
+
+# ------------------------------------------------------------------------------------------------ F-conv on tensor cores
+def fconv_image_bytes() -> int:
+    L = _lib.lib()
+    L.nbss_fconv_image_bytes.restype = ctypes.c_uint
+    return int(L.nbss_fconv_image_bytes())
+
+
+def fconv_pack(W: Tensor, img: Optional[Tensor] = None, fmt: int = FMT_F16) -> Tensor:
+    """UMMA weight images (forward + transposed) of one F-conv weight [96,12,5]."""
+    if img is None:
+        img = torch.empty(fconv_image_bytes(), dtype=torch.uint8, device=W.device)
+    check(_K("nbss_fconv_pack")(ptr(_f32c(W)), ptr(img), fmt, stream_ptr()), "nbss_fconv_pack")
+    return img
+
+
+def fconv_tc_fwd(x: Tensor, P, pre: str, img: Tensor, out: Optional[Tensor] = None, fmt: int = FMT_F16):
+    """y = x + PReLU(gconv_F(LN(x))) on tensor cores (fconv_tc.cu); pre = 'layers.i.fconv1' / '...fconv2'."""
+    x = _f32c(x)
+    B, F, T, H = x.shape
+    assert H == 96
+    y = torch.empty_like(x) if out is None else out
+    err = device_err_flag(x.device)
+    st = _K("nbss_fconv_tc_fwd")(ptr(x), ptr(y), B, F, T, ptr(_f32c(P[pre + ".0.weight"])), ptr(_f32c(P[pre + ".0.bias"])),
+                                 ptr(_f32c(P[pre + ".1.bias"])), ptr(_f32c(P[pre + ".2.weight"])), ptr(img), fmt, ptr(err), stream_ptr())
+    check(st, "nbss_fconv_tc_fwd")
+    return y, err
+
+
+def fconv_tc_bwd(x: Tensor, dy: Tensor, P, pre: str, img: Tensor, G, fmt: int = FMT_F16):
+    x, dy = _f32c(x), _f32c(dy)
+    B, F, T, H = x.shape
+    dx = torch.empty_like(x)
+    err = device_err_flag(x.device)
+    st = _K("nbss_fconv_tc_bwd")(ptr(x), ptr(dy), ptr(dx), B, F, T, ptr(_f32c(P[pre + ".0.weight"])), ptr(_f32c(P[pre + ".0.bias"])),
+                                 ptr(_f32c(P[pre + ".1.bias"])), ptr(_f32c(P[pre + ".2.weight"])), ptr(img), ptr(G[pre + ".1.weight"]),
+                                 ptr(G[pre + ".1.bias"]), ptr(G[pre + ".2.weight"]), ptr(G[pre + ".0.weight"]), ptr(G[pre + ".0.bias"]),
+                                 fmt, ptr(err), stream_ptr())
+    check(st, "nbss_fconv_tc_bwd")
+    return dx, err

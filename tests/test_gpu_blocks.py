@@ -277,3 +277,32 @@ def test_persistent_loop_many_slabs():
     assert O.rel_l2(dx.cpu() - dy, x.grad - dy) < 4e-3
     for k in ("tconvffn.5.weight", "tconvffn.1.weight", "mhsa.in_proj_weight", "mhsa.out_proj.bias", "norm_mhsa.weight"):
         assert O.rel_l2(G[pre + k].cpu().reshape(-1), Pl[pre + k].grad.reshape(-1)) < 4e-3, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 129, 7), (1, 129, 250), (1, 65, 5), (2, 129, 1)])
+def test_fconv_tc_fwd_bwd(shape):
+    """Tensor-core F-conv (fp16 operands) against the oracle; includes many frame groups per CTA (T=250)."""
+    B, F, T = shape
+    cfg = dict(CFG, num_freqs=F)
+    P = O.synth_params(cfg, 5)
+    Pd = {k: v.cuda() for k, v in P.items()}
+    Pl = _leaf(P)
+    pre = "layers.1.fconv1"
+    g = torch.Generator().manual_seed(F * T + 1)
+    x = torch.randn(B, F, T, 96, generator=g, requires_grad=True)
+    dy = torch.randn(B, F, T, 96, generator=g)
+    y_ref = x + O.fconv(x, Pl, pre, 8)
+    y_ref.backward(dy)
+    img = ops.fconv_pack(Pd[pre + ".1.weight"])
+    y, e1 = ops.fconv_tc_fwd(x.detach().cuda(), Pd, pre, img)
+    G = _grads_like(Pd)
+    dx, e2 = ops.fconv_tc_bwd(x.detach().cuda(), dy.cuda(), Pd, pre, img, G)
+    torch.cuda.synchronize()
+    ops.check_err_flag(e1, "fconv_tc_fwd")
+    ops.check_err_flag(e2, "fconv_tc_bwd")
+    assert O.rel_l2(y.cpu() - x.detach(), (y_ref - x).detach()) < 1e-3
+    assert O.rel_l2(dx.cpu() - dy, x.grad - dy) < 4e-3
+    errs = {k: O.rel_l2(G[pre + k].cpu().reshape(-1), Pl[pre + k].grad.reshape(-1)) for k in (".0.weight", ".0.bias", ".1.weight", ".1.bias", ".2.weight")}
+    bad = {k: f"{v:.2e}" for k, v in errs.items() if not v < 4e-3}
+    assert not bad, f"{bad}; all { {k: f'{v:.1e}' for k, v in errs.items()} }"

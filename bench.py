@@ -32,7 +32,7 @@ CFG = dict(B=32, C=6, F=129, T=250, n_fft=256, hop=128, S=2, L=8)
 TS = CFG["hop"] * (CFG["T"] - 1)  # 31872 samples -> T = 250 frames
 FLOP_PER_POINT = {  # algorithmic FLOPs per T-F point
     "ffn_fwd": 156_672, "mhsa_fwd": 169_728, "ffn_bwd": 156_672, "ffn_wgrad": 156_672, "mhsa_bwd": 265_728,
-    "mhsa_wgrad": 73_728, "fconv_fwd": 11_520, "fconv_bwd": 34_560, "full_fwd": 5_136, "full_bwd": 10_272,
+    "mhsa_wgrad": 73_728, "fconv_fwd": 11_520, "fconv_bwd": 34_560, "fconv_tc_fwd": 11_520, "fconv_tc_bwd": 34_560, "full_fwd": 5_136, "full_bwd": 10_272,
 }
 STREAM_BYTES_PER_POINT = 96 * 4  # one fp32 pass over the stream
 
@@ -288,7 +288,7 @@ def main():
             ent["tflops"] = round(FLOP_PER_POINT[k] * npts / (ms * 1e-3) / 1e12, 2)
         kernels[k] = ent
     top = max((k for k in kernels if k in FLOP_PER_POINT), key=lambda k: kernels[k]["ms_per_step"])
-    tensor_kernel = top in ("ffn_fwd", "mhsa_fwd", "ffn_bwd", "ffn_wgrad", "mhsa_bwd", "mhsa_wgrad")
+    tensor_kernel = top in ("ffn_fwd", "mhsa_fwd", "ffn_bwd", "ffn_wgrad", "mhsa_bwd", "mhsa_wgrad", "fconv_tc_fwd", "fconv_tc_bwd")
     if tensor_kernel:
         ach = FLOP_PER_POINT[top] * npts / (kernels[top]["ms_per_launch"] * 1e-3) / 1e12
         roof = {"kernel": top, "bound": "tensor", "achieved": round(ach, 2), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),

@@ -29,6 +29,35 @@ __device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float f4_sum(float4 a) { return a.x + a.y + a.z + a.w; }
 
+// Sum 8 per-lane values across the warp with 9 shuffles (recursive halving on lane bits 16, 8, 4, then 2 plain steps).
+// On return every lane holds the total of value index g = lane >> 2.
+__device__ __forceinline__ float warp_reduce8(float (&v)[8], int lane) {
+    {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float a = v[i], b = v[i + 4];
+            v[i] = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, 16);
+        }
+    }
+    {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float a = v[i], b = v[i + 2];
+            v[i] = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, 8);
+        }
+    }
+    {
+        const bool up = (lane & 4) != 0;
+        const float a = v[0], b = v[1];
+        v[0] = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, 4);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    return v[0];
+}
+
 // conv window dot product: 5 taps x 12 input channels of group g at frame slot tt
 __device__ __forceinline__ float fconv_dot(const float* h, int f, int tt, int TT, int g, const float (&w)[60], float acc) {
 #pragma unroll
@@ -225,12 +254,11 @@ __global__ void __launch_bounds__(256) squeeze_fwd_kernel(const float* __restric
         float4 xh;
         ln_row(v, act, mean, rstd, xh);
         const float4 ln = f4_fma(xh, g4, b4);
+        float p[kHS];
 #pragma unroll
-        for (int g = 0; g < kHS; ++g) {
-            float p = act ? f4_sum(f4_mul(ln, ld_f4(wsq + g * kH + 4 * lane))) : 0.f;
-            p = warp_sum(p);
-            if (lane == g) st[(tt * kHS + g) * F + f] = silu(p + bsq[g]);
-        }
+        for (int g = 0; g < kHS; ++g) p[g] = act ? f4_sum(f4_mul(ln, ld_f4(wsq + g * kH + 4 * lane))) : 0.f;
+        const float tot = warp_reduce8(p, lane);  // lane holds group lane >> 2
+        if ((lane & 3) == 0) st[(tt * kHS + (lane >> 2)) * F + f] = silu(tot + bsq[lane >> 2]);
     }
     __syncthreads();
     for (int i = tid; i < kSQT * kHS * F; i += 256) {
@@ -276,11 +304,16 @@ __global__ void __launch_bounds__(256) squeeze_bwd_kernel(const float* __restric
             ln_row(v, act, mean, rstd, xh);
             const float4 ln = f4_fma(xh, g4, b4);
             float4 dln = make_float4(0, 0, 0, 0);
+            float pz[kHS];
+#pragma unroll
+            for (int g = 0; g < kHS; ++g) pz[g] = act ? f4_sum(f4_mul(ln, ld_f4(wsq + g * kH + 4 * lane))) : 0.f;
+            const int gown = lane >> 2;
+            const float zown = warp_reduce8(pz, lane) + bsq[gown];
+            const float dz_own = st[(tt * kHS + gown) * F + f] * silu_grad(zown);
 #pragma unroll
             for (int g = 0; g < kHS; ++g) {
                 const float4 wv = act ? ld_f4(wsq + g * kH + 4 * lane) : make_float4(0, 0, 0, 0);
-                const float z = warp_sum(f4_sum(f4_mul(ln, wv))) + bsq[g];
-                const float dz = st[(tt * kHS + g) * F + f] * silu_grad(z);
+                const float dz = __shfl_sync(0xffffffffu, dz_own, 4 * g);
                 dln = make_float4(fmaf(dz, wv.x, dln.x), fmaf(dz, wv.y, dln.y), fmaf(dz, wv.z, dln.z), fmaf(dz, wv.w, dln.w));
                 dwq[g] = make_float4(fmaf(dz, ln.x, dwq[g].x), fmaf(dz, ln.y, dwq[g].y), fmaf(dz, ln.z, dwq[g].z), fmaf(dz, ln.w, dwq[g].w));
                 if (lane == g) dbq += dz;

@@ -315,21 +315,27 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
             umma_commit(bar_mma);
         }
         wait_mma();
-        if (warp < 3) {  // thread = out channel co (TMEM lane): keep the 12 in-channel columns of its own group, 5 taps
-            const int cbase = 12 * (co / 12);   // first column of the group: 0, 12, ..., 84
-            const int cb8 = cbase & ~7;         // aligned 16-column window [cb8, cb8+16) contains [cbase, cbase+12)
-            const bool sh4 = (cbase & 7) != 0;  // window offset is 0 or 4
+        if (warp < 3) {
+            // thread = out channel co (TMEM lane); it keeps the 12 in-channel columns [12*(co/12), +12) of each tap.
+            // tcgen05.ld takes ONE column address per warp, so every warp loads a uniform 48-column window
+            // [24*warp, 24*warp+48) that contains the groups of its 32 channels and each lane selects its slice.
+            const int ws = 24 * warp;
+            const int off = 12 * (co / 12) - ws;  // 0, 12, 24 or 36
 #pragma unroll
             for (int tap = 0; tap < kFTaps; ++tap) {
-                uint32_t r0[8], r1[8];
-                tmem_ld8(tmem + lane_off + 96 * tap + cb8, r0);
-                tmem_ld8(tmem + lane_off + 96 * tap + cb8 + 8, r1);
+                uint32_t r[48];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    uint32_t t8[8];
+                    tmem_ld8(tmem + lane_off + 96 * tap + ws + 8 * k, t8);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[8 * k + j] = t8[j];
+                }
                 tmem_ld_wait();
 #pragma unroll
                 for (int ci = 0; ci < 12; ++ci) {
-                    const uint32_t lo = ci < 8 ? r0[ci] : r1[ci - 8];
-                    const uint32_t hi = ci + 4 < 8 ? r0[ci + 4] : r1[ci + 4 - 8];
-                    dw[ci * 5 + tap] += __uint_as_float(sh4 ? hi : lo);
+                    const uint32_t v = off == 0 ? r[ci] : (off == 12 ? r[12 + ci] : (off == 24 ? r[24 + ci] : r[36 + ci]));
+                    dw[ci * 5 + tap] += __uint_as_float(v);
                 }
             }
         }

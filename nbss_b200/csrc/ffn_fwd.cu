@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
     const int m = warp >> 2, q = warp & 3;
     const int t = 128 * m + 32 * q + lane;
     const bool valid = t < T;
+    const float vmask = valid ? 1.f : 0.f;  // frames >= T are written as zeros (conv zero padding) without branching
     const uint32_t tacc = tmem + ((uint32_t)(32 * q) << 16) + m * 192;
     unsigned char* hrow = hbuf + (t + 1) * 16;
     const uint32_t hb = smem_u32(hbuf), w0a = smem_u32(ws0), w1a = smem_u32(ws1);
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_b1[c0 + j];
             if (a.save_a1 && valid) save_f16(a.save_a1, slab, T, t, c0, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = valid ? silu(v[j]) : 0.f;
+            for (int j = 0; j < 32; ++j) v[j] = silu(v[j]) * vmask;  // branch-free: keeps the 32 chains interleaved
             store_h<FMT>(hrow, c0, v);
         }
         end_epilogue();
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bc[c0 + j];
             if (a.save_c1 && valid) save_f16(a.save_c1, slab, T, t, c0, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = valid ? silu(v[j]) : 0.f;
+            for (int j = 0; j < 32; ++j) v[j] = silu(v[j]) * vmask;  // branch-free: keeps the 32 chains interleaved
             store_h<FMT>(hrow, c0, v);
         }
         end_epilogue();
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float n = (v[j] - mean) * rstd * s_gng[c + j] + s_gnb[c + j];
-                        v[j] = valid ? silu(n) : 0.f;
+                        v[j] = silu(n) * vmask;
                     }
                     *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = pack8<FMT>(v);
                 }
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bc[384 + c0 + j];
             if (a.save_c3 && valid) save_f16(a.save_c3, slab, T, t, c0, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = valid ? silu(v[j]) : 0.f;
+            for (int j = 0; j < 32; ++j) v[j] = silu(v[j]) * vmask;  // branch-free: keeps the 32 chains interleaved
             store_h<FMT>(hrow, c0, v);
         }
         end_epilogue();

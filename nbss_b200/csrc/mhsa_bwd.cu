@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256, 1) mhsa_bwd_core_kernel(MhsaBwdArgs a) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int key = 128 * kb + 64 * m + c0 + j;
-                            const float pv = (qok && key < T) ? ex2f(__uint_as_float(rs[j]) - lse) : 0.f;
+                            const float pv = ex2f((qok && key < T) ? __uint_as_float(rs[j]) - lse : -INFINITY);
                             p[j] = pv;
                             ds[j] = pv * (__uint_as_float(rp[j]) - dl);
                         }

@@ -216,8 +216,9 @@ __global__ void __launch_bounds__(256, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
                     const int key = 128 * m + c0 + j;
-                    float p0 = key < T ? ex2(__uint_as_float(r[j]) - rowmax) : 0.f;
-                    float p1 = key + 1 < T ? ex2(__uint_as_float(r[j + 1]) - rowmax) : 0.f;
+                    // masked keys get exponent -inf (ex2 -> 0): a select on the argument, no branch around the MUFU
+                    float p0 = ex2(key < T ? __uint_as_float(r[j]) - rowmax : -INFINITY);
+                    float p1 = ex2(key + 1 < T ? __uint_as_float(r[j + 1]) - rowmax : -INFINITY);
                     sum += p0 + p1;
                     pk[(c0 + j) >> 1] = pack16<FMT>(p0, p1);
                 }

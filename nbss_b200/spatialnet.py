@@ -75,6 +75,8 @@ class Engine:
         self.grad_fmt = grad_fmt
         self._imgs: Optional[List[Tensor]] = None
         self._img_key = None
+        self._fimgs: Optional[List[List[Tensor]]] = None
+        self._fimg_key = None
 
     def images(self, P: Dict[str, Tensor]) -> List[Tensor]:
         """Per-layer UMMA weight images; rebuilt whenever a narrow-band weight changed (tensor version counters)."""
@@ -91,10 +93,22 @@ class Engine:
             self._img_key = key
         return self._imgs
 
+    def fconv_images(self, P: Dict[str, Tensor]) -> List[List[Tensor]]:
+        """Per-layer UMMA images of the two F-conv weights (fconv_tc.cu), rebuilt when a weight changed."""
+        names = [f"layers.{i}.fconv{j}.1.weight" for i in range(self.L) for j in (1, 2)]
+        key = tuple((P[n].data_ptr(), P[n]._version) for n in names)
+        if self._fimgs is None or key != self._fimg_key:
+            old = self._fimgs
+            self._fimgs = [[ops.fconv_pack(P[f"layers.{i}.fconv{j}.1.weight"], old[i][j - 1] if old else None, self.fwd_fmt)
+                            for j in (1, 2)] for i in range(self.L)]
+            self._fimg_key = key
+        return self._fimgs
+
     def forward(self, P: Dict[str, Tensor], x: Tensor, save: bool):
         if not x.is_cuda:
             raise ops._lib.NbssError("nbss_b200.SpatialNet runs on CUDA tensors only (there is no CPU path)")
         imgs = self.images(P)
+        fimgs = self.fconv_images(P)
         ctx = {"x_in": x, "layers": []} if save else None
         errs = []
         h = ops.encoder_fwd(x, P)
@@ -102,9 +116,9 @@ class Engine:
             pre = f"layers.{i}."
             if save:
                 lc = {"x0": h}
-                h1 = ops.fconv_fwd(h, P, pre + "fconv1")
+                h1, e3 = ops.fconv_tc_fwd(h, P, pre + "fconv1", fimgs[i][0], fmt=self.fwd_fmt)
                 h2, s, u = ops.full_fwd(h1, P, pre)
-                h3 = ops.fconv_fwd(h2, P, pre + "fconv2")
+                h3, e4 = ops.fconv_tc_fwd(h2, P, pre + "fconv2", fimgs[i][1], fmt=self.fwd_fmt)
                 h4, msave, e1 = ops.mhsa_fwd(h3, P, pre, imgs[i], save=True, fmt=self.fwd_fmt)
                 h5, fsave, gstats, e2 = ops.ffn_fwd(h4, P, pre, imgs[i], save=True, fmt=self.fwd_fmt)
                 lc.update(x1=h1, s=s, u=u, x2=h2, x3=h3, msave=msave, x4=h4, fsave=fsave, gstats=gstats)
@@ -112,12 +126,12 @@ class Engine:
                 h = h5
             else:
                 # inference: every sub-block updates the stream in place (each kernel reads a row before writing it)
-                h = ops.fconv_fwd(h, P, pre + "fconv1", out=h)
+                h, e3 = ops.fconv_tc_fwd(h, P, pre + "fconv1", fimgs[i][0], out=h, fmt=self.fwd_fmt)
                 h, _, _ = ops.full_fwd(h, P, pre, out=h)
-                h = ops.fconv_fwd(h, P, pre + "fconv2", out=h)
+                h, e4 = ops.fconv_tc_fwd(h, P, pre + "fconv2", fimgs[i][1], out=h, fmt=self.fwd_fmt)
                 h, e1 = ops.mhsa_fwd(h, P, pre, imgs[i], fmt=self.fwd_fmt, out=h)
                 h, e2 = ops.ffn_fwd(h, P, pre, imgs[i], fmt=self.fwd_fmt, out=h)
-            errs += [e1, e2]
+            errs += [e1, e2, e3, e4]
         y = ops.decoder_fwd(h, P)
         if save:
             ctx["x_last"] = h
@@ -127,6 +141,7 @@ class Engine:
         """Accumulates parameter gradients into G (fp32 tensors keyed like P).  The network input needs no gradient
         (SharedTrainer.py:113-120: X comes from the STFT of the data)."""
         imgs = self.images(P)
+        fimgs = self.fconv_images(P)
         errs = []
         d = ops.decoder_bwd(ctx["x_last"], dy, P, G)
         for i in reversed(range(self.L)):
@@ -134,10 +149,10 @@ class Engine:
             lc = ctx["layers"][i]
             d, e1 = ops.ffn_bwd(lc["x4"], d, lc["fsave"], lc["gstats"], P, pre, imgs[i], G, fmt_g=self.grad_fmt)
             d, e2 = ops.mhsa_bwd(lc["x3"], d, lc["msave"], P, pre, imgs[i], G, fmt_g=self.grad_fmt)
-            d = ops.fconv_bwd(lc["x2"], d, P, pre + "fconv2", G)
+            d, e3 = ops.fconv_tc_bwd(lc["x2"], d, P, pre + "fconv2", fimgs[i][1], G, fmt=self.grad_fmt)
             d = ops.full_bwd(lc["x1"], d, lc["s"], lc["u"], P, pre, G)
-            d = ops.fconv_bwd(lc["x0"], d, P, pre + "fconv1", G)
-            errs += [e1, e2]
+            d, e4 = ops.fconv_tc_bwd(lc["x0"], d, P, pre + "fconv1", fimgs[i][0], G, fmt=self.grad_fmt)
+            errs += [e1, e2, e3, e4]
             ctx["layers"][i] = None  # free this layer's saved activations
         ops.encoder_wgrad(ctx["x_in"], d, G)
         return errs

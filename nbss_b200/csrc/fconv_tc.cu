@@ -52,20 +52,23 @@ struct FcGeom {
 // LN(x) of the group's frames into the tile (fp16); rows of frames beyond T are zero; optional (mean, rstd) per tile row.
 template <int FMT>
 __device__ __forceinline__ void fc_stage(const FcGeom& g, const float* __restrict__ x, int b, int t0, unsigned char* tile,
-                                         const float* s_lnw, const float* s_lnb, float2* s_stats, int warp, int lane) {
+                                         const float* s_lnw, const float* s_lnb, float2* s_stats, int warp, int lane,
+                                         const float* __restrict__ dy = nullptr, unsigned char* dytile = nullptr) {
     const bool act = lane < 24;
     float4 gw = make_float4(0, 0, 0, 0), gb = gw;
     if (act) { gw = *reinterpret_cast<const float4*>(s_lnw + 4 * lane); gb = *reinterpret_cast<const float4*>(s_lnb + 4 * lane); }
     const int nrows = g.nfr * g.F;
 #pragma unroll 1
     for (int i0 = warp; i0 < nrows; i0 += 32) {
-        float4 v[4];
+        float4 v[4], w[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int i = i0 + 8 * j;
             const int tt = i / g.F, f = i % g.F, t = t0 + tt;
-            v[j] = (act && i < nrows && t < g.T) ? __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * g.F + f) * g.T + t) * kH) + lane)
-                                                 : make_float4(0, 0, 0, 0);
+            const bool ok = act && i < nrows && t < g.T;
+            const size_t off = (((size_t)b * g.F + f) * g.T + t) * kH;
+            v[j] = ok ? __ldg(reinterpret_cast<const float4*>(x + off) + lane) : make_float4(0, 0, 0, 0);
+            w[j] = (ok && dy) ? __ldg(reinterpret_cast<const float4*>(dy + off) + lane) : make_float4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -84,6 +87,9 @@ __device__ __forceinline__ void fc_stage(const FcGeom& g, const float* __restric
                     pk = make_uint2(pack16<FMT>(d.x * rstd * gw.x + gb.x, d.y * rstd * gw.y + gb.y),
                                     pack16<FMT>(d.z * rstd * gw.z + gb.z, d.w * rstd * gw.w + gb.w));
                 *reinterpret_cast<uint2*>(tile + (size_t)(lane >> 1) * g.cs + p * 16 + (lane & 1) * 8) = pk;
+                if (dytile)  // upstream gradient of the same row, 16-bit, same slot of the second tile
+                    *reinterpret_cast<uint2*>(dytile + (size_t)(lane >> 1) * g.cs + p * 16 + (lane & 1) * 8) =
+                        make_uint2(pack16<FMT>(w[j].x, w[j].y), pack16<FMT>(w[j].z, w[j].w));
             }
         }
     }
@@ -157,31 +163,55 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_fwd_kernel(FcFwdArgs a) {
         mbar_wait(bar_mma, ph, a.err);
         ph ^= 1;
         tc_fence_after();
-        // epilogue: warps 0-3 take even tiles, warps 4-7 odd tiles; thread = one (frame, f) row
+        // epilogue 1: thread = one tile row (TMEM lane): PReLU(D + bias) -> 16-bit, written over the operand tile (dead
+        // once every MMA of the group has completed) at the row's own slot.  warps 0-3 even tiles, warps 4-7 odd tiles.
         for (int m = warp >> 2; m < g.nt; m += 2) {
             const int q = 128 * m + 32 * (warp & 3) + lane;
-            const int tt = q / g.FP, f = q % g.FP, t = t0 + tt;
-            const bool valid = tt < g.nfr && f < g.F && t < g.T;
-            const size_t base = valid ? (((size_t)b * g.F + f) * g.T + t) * kH : 0;
+            // gap rows between frames (and rows past the last frame) must stay zero: they are the conv's zero padding
+            const float rmask = ((q % g.FP) < g.F && (q / g.FP) < g.nfr) ? 1.f : 0.f;
 #pragma unroll 1
             for (int c0 = 0; c0 < kH; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem + lane_off + m * 96 + c0, r);
                 tmem_ld_wait();
-                if (valid) {
+                float v[32];
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 xv = __ldg(reinterpret_cast<const float4*>(a.x + base + c0) + j4);
-                        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-                        float o[4];
+                for (int j = 0; j < 32; ++j) {
+                    const float u = __uint_as_float(r[j]) + cst[192 + c0 + j];
+                    v[j] = (u >= 0.f ? u : cst[288 + c0 + j] * u) * rmask;
+                }
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int c = c0 + 4 * j4 + e;
-                            const float v = __uint_as_float(r[4 * j4 + e]) + cst[192 + c];
-                            o[e] = xs[e] + (v >= 0.f ? v : cst[288 + c] * v);
-                        }
-                        reinterpret_cast<float4*>(a.y + base + c0)[j4] = make_float4(o[0], o[1], o[2], o[3]);
-                    }
+                for (int cc = 0; cc < 4; ++cc)
+                    *reinterpret_cast<uint4*>(tile + (size_t)(c0 / 8 + cc) * g.cs + (2 + q) * 16) = pack8<FMT>(v + 8 * cc);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        // epilogue 2: warp per (frame, f) row, coalesced: y = x + branch
+        {
+            const bool act = lane < 24;
+            const int nrows = g.nfr * g.F;
+#pragma unroll 1
+            for (int i0 = warp; i0 < nrows; i0 += 32) {
+                float4 xv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + 8 * j;
+                    const int tt = i / g.F, f = i % g.F, t = t0 + tt;
+                    xv[j] = (act && i < nrows && t < g.T) ? __ldg(reinterpret_cast<const float4*>(a.x + (((size_t)b * g.F + f) * g.T + t) * kH) + lane)
+                                                          : make_float4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + 8 * j;
+                    const int tt = i / g.F, f = i % g.F, t = t0 + tt;
+                    if (!(act && i < nrows && t < g.T)) continue;
+                    const uint2 pk = *reinterpret_cast<const uint2*>(tile + (size_t)(lane >> 1) * g.cs + (2 + tt * g.FP + f) * 16 + (lane & 1) * 8);
+                    float b0, b1, b2, b3;
+                    unpack16<FMT>(pk.x, b0, b1);
+                    unpack16<FMT>(pk.y, b2, b3);
+                    reinterpret_cast<float4*>(a.y + (((size_t)b * g.F + f) * g.T + t) * kH)[lane] =
+                        make_float4(xv[j].x + b0, xv[j].y + b1, xv[j].z + b2, xv[j].w + b3);
                 }
             }
         }
@@ -241,6 +271,10 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
     float dw[60];
 #pragma unroll
     for (int i = 0; i < 60; ++i) dw[i] = 0.f;
+    // LayerNorm affine gradients: lane l < 24 owns channels 4l..4l+3 in the warp-per-row phase
+    const bool act24 = lane < 24;
+    float4 gw4 = make_float4(0, 0, 0, 0), dg4 = gw4, db4 = gw4;
+    if (act24) gw4 = *reinterpret_cast<const float4*>(cst + 4 * lane);
 
     auto wait_mma = [&]() {
         __syncwarp();
@@ -251,7 +285,7 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
     for (int grp = blockIdx.x; grp < g.ngroups; grp += gridDim.x) {
         const int b = grp / g.groups_per_b, t0 = (grp % g.groups_per_b) * g.nfr;
         if (tid == 0) load_image(wimg, a.img, FC_IMG_BYTES, bar_w);
-        fc_stage<FMT>(g, a.x, b, t0, htile, cst, cst + 96, stats, warp, lane);
+        fc_stage<FMT>(g, a.x, b, t0, htile, cst, cst + 96, stats, warp, lane, a.dy, gtile);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -265,13 +299,11 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
         ph_w ^= 1;
         wait_mma();
         if (tid == 0) load_image(wimg, a.img + FC_IMG_BYTES, FC_IMG_BYTES, bar_w);  // transposed image for the data gradient
-        // ---- E-A: dc = dy * PReLU'(c) -> gtile; column sums for dbias / dslope
-        for (int m = warp >> 2; m < g.nt + (g.nt & 1); m += 2) {  // every warp runs the same trip count (warp-collective loads)
+        // ---- E-A: dc = dy * PReLU'(c), in place over the staged dy in gtile; column sums for dbias / dslope
+        for (int m = warp >> 2; m < g.nt + (g.nt & 1); m += 2) {  // equal trip counts: the column sums are warp-collective
             const bool mt = m < g.nt;
-            const int q = 128 * m + 32 * (warp & 3) + lane;
-            const int tt = q / g.FP, f = q % g.FP, t = t0 + tt;
-            const bool valid = mt && tt < g.nfr && f < g.F && t < g.T;
-            const size_t base = valid ? (((size_t)b * g.F + f) * g.T + t) * kH : 0;
+            const int q = 128 * (mt ? m : 0) + 32 * (warp & 3) + lane;
+            unsigned char* grow_ = gtile + (size_t)(2 + q) * 16;
 #pragma unroll 1
             for (int c0 = 0; c0 < kH; c0 += 32) {
                 uint32_t r[32];
@@ -279,22 +311,25 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
                 tmem_ld_wait();
                 float dc[32], ds[32];
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    float4 dv = make_float4(0, 0, 0, 0);
-                    if (valid) dv = __ldg(reinterpret_cast<const float4*>(a.dy + base + c0) + j4);
-                    const float dys[4] = {dv.x, dv.y, dv.z, dv.w};
+                for (int cc = 0; cc < 4; ++cc) {
+                    const uint4 pk = *reinterpret_cast<const uint4*>(grow_ + (size_t)(c0 / 8 + cc) * g.cs);
+                    float dys[8];
+                    unpack16<FMT>(pk.x, dys[0], dys[1]);
+                    unpack16<FMT>(pk.y, dys[2], dys[3]);
+                    unpack16<FMT>(pk.z, dys[4], dys[5]);
+                    unpack16<FMT>(pk.w, dys[6], dys[7]);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int c = c0 + 4 * j4 + e;
-                        const float cv = __uint_as_float(r[4 * j4 + e]) + cst[192 + c];
-                        dc[4 * j4 + e] = valid ? dys[e] * (cv >= 0.f ? 1.f : cst[288 + c]) : 0.f;
-                        ds[4 * j4 + e] = (valid && cv < 0.f) ? dys[e] * cv : 0.f;
+                    for (int e = 0; e < 8; ++e) {
+                        const int c = c0 + 8 * cc + e;
+                        const float cv = __uint_as_float(r[8 * cc + e]) + cst[192 + c];
+                        const float dyv = mt ? dys[e] : 0.f;  // gap / invalid rows hold zeros in gtile
+                        dc[8 * cc + e] = dyv * (cv >= 0.f ? 1.f : cst[288 + c]);
+                        ds[8 * cc + e] = cv < 0.f ? dyv * cv : 0.f;
                     }
                 }
                 if (mt) {
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc)
-                        *reinterpret_cast<uint4*>(gtile + (size_t)(c0 / 8 + cc) * g.cs + (2 + q) * 16) = pack8<FMT>(dc + 8 * cc);
+                    for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(grow_ + (size_t)(c0 / 8 + cc) * g.cs) = pack8<FMT>(dc + 8 * cc);
                 }
                 const float sb = warp_colsum32(dc, lane), ss = warp_colsum32(ds, lane);
                 atomicAdd(acc + c0 + lane, sb);
@@ -350,66 +385,65 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
         }
         ph_w ^= 1;
         wait_mma();
-        // ---- E-B: LayerNorm backward + residual; column sums for dlnw / dlnb
-        for (int m = warp >> 2; m < g.nt + (g.nt & 1); m += 2) {
-            const bool mt = m < g.nt;
+        // ---- E-B1: thread = tile row: d h (data gradient of the conv) -> 16-bit, over htile (dead after the weight
+        //      gradient MMAs); gap rows are written as zeros so they keep acting as the next group's zero padding
+        for (int m = warp >> 2; m < g.nt; m += 2) {
             const int q = 128 * m + 32 * (warp & 3) + lane;
-            const int tt = q / g.FP, f = q % g.FP, t = t0 + tt;
-            const bool valid = mt && tt < g.nfr && f < g.F && t < g.T;
-            const size_t base = valid ? (((size_t)b * g.F + f) * g.T + t) * kH : 0;
-            const float2 st = valid ? stats[2 + q] : make_float2(0.f, 0.f);
-            const uint32_t tacc = tmem + lane_off + (mt ? m : 0) * 96;
-            float m1 = 0.f, m2 = 0.f;
+            const float rmask = ((q % g.FP) < g.F && (q / g.FP) < g.nfr) ? 1.f : 0.f;
 #pragma unroll 1
             for (int c0 = 0; c0 < kH; c0 += 32) {
                 uint32_t r[32];
-                tmem_ld32(tacc + c0, r);
+                tmem_ld32(tmem + lane_off + m * 96 + c0, r);
                 tmem_ld_wait();
-                if (valid) {
+                float v[32];
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 xv = __ldg(reinterpret_cast<const float4*>(a.x + base + c0) + j4);
-                        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * rmask;
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float dzg = __uint_as_float(r[4 * j4 + e]) * cst[c0 + 4 * j4 + e];
-                            m1 += dzg;
-                            m2 += dzg * (xs[e] - st.x) * st.y;
-                        }
-                    }
-                }
+                for (int cc = 0; cc < 4; ++cc)
+                    *reinterpret_cast<uint4*>(htile + (size_t)(c0 / 8 + cc) * g.cs + (2 + q) * 16) = pack8<FMT>(v + 8 * cc);
             }
-            m1 *= (1.f / kH);
-            m2 *= (1.f / kH);
+        }
+        tc_fence_before();
+        __syncthreads();
+        // ---- E-B2: warp per (frame, f) row, coalesced: LayerNorm backward + residual; d gamma / d beta per lane
+        {
+            const int nrows = g.nfr * g.F;
 #pragma unroll 1
-            for (int c0 = 0; c0 < kH; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tacc + c0, r);
-                tmem_ld_wait();
-                float dzv[32], dzx[32];
+            for (int i0 = warp; i0 < nrows; i0 += 32) {
+                float4 xv[4], dv[4];
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    float4 xv = make_float4(0, 0, 0, 0), dv = xv;
-                    if (valid) {
-                        xv = __ldg(reinterpret_cast<const float4*>(a.x + base + c0) + j4);
-                        dv = __ldg(reinterpret_cast<const float4*>(a.dy + base + c0) + j4);
-                    }
-                    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-                    const float dys[4] = {dv.x, dv.y, dv.z, dv.w};
-                    float o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float dz = valid ? __uint_as_float(r[4 * j4 + e]) : 0.f;
-                        const float xh = (xs[e] - st.x) * st.y;
-                        dzv[4 * j4 + e] = dz;
-                        dzx[4 * j4 + e] = dz * xh;
-                        o[e] = dys[e] + st.y * (dz * cst[c0 + 4 * j4 + e] - m1 - xh * m2);
-                    }
-                    if (valid) reinterpret_cast<float4*>(a.dx + base + c0)[j4] = make_float4(o[0], o[1], o[2], o[3]);
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + 8 * j;
+                    const int tt = i / g.F, f = i % g.F, t = t0 + tt;
+                    const bool ok = act24 && i < nrows && t < g.T;
+                    const size_t off = (((size_t)b * g.F + f) * g.T + t) * kH;
+                    xv[j] = ok ? __ldg(reinterpret_cast<const float4*>(a.x + off) + lane) : make_float4(0, 0, 0, 0);
+                    dv[j] = ok ? __ldg(reinterpret_cast<const float4*>(a.dy + off) + lane) : make_float4(0, 0, 0, 0);
                 }
-                const float sw = warp_colsum32(dzx, lane), sb = warp_colsum32(dzv, lane);
-                atomicAdd(acc + 192 + c0 + lane, sw);
-                atomicAdd(acc + 288 + c0 + lane, sb);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + 8 * j;
+                    const int tt = i / g.F, f = i % g.F, t = t0 + tt;
+                    if (i >= nrows || t >= g.T) continue;  // warp-uniform
+                    const int p = 2 + tt * g.FP + f;
+                    const float2 st = stats[p];
+                    float4 dh = make_float4(0, 0, 0, 0), xh = dh;
+                    if (act24) {
+                        const uint2 pk = *reinterpret_cast<const uint2*>(htile + (size_t)(lane >> 1) * g.cs + p * 16 + (lane & 1) * 8);
+                        unpack16<FMT>(pk.x, dh.x, dh.y);
+                        unpack16<FMT>(pk.y, dh.z, dh.w);
+                        xh = make_float4((xv[j].x - st.x) * st.y, (xv[j].y - st.x) * st.y, (xv[j].z - st.x) * st.y, (xv[j].w - st.x) * st.y);
+                    }
+                    const float4 dxh = make_float4(dh.x * gw4.x, dh.y * gw4.y, dh.z * gw4.z, dh.w * gw4.w);
+                    const float m1 = warp_sum(dxh.x + dxh.y + dxh.z + dxh.w) * (1.f / kH);
+                    const float m2 = warp_sum(dxh.x * xh.x + dxh.y * xh.y + dxh.z * xh.z + dxh.w * xh.w) * (1.f / kH);
+                    dg4 = make_float4(dg4.x + dh.x * xh.x, dg4.y + dh.y * xh.y, dg4.z + dh.z * xh.z, dg4.w + dh.w * xh.w);
+                    db4 = make_float4(db4.x + dh.x, db4.y + dh.y, db4.z + dh.z, db4.w + dh.w);
+                    if (act24)
+                        reinterpret_cast<float4*>(a.dx + (((size_t)b * g.F + f) * g.T + t) * kH)[lane] =
+                            make_float4(dv[j].x + st.y * (dxh.x - m1 - xh.x * m2), dv[j].y + st.y * (dxh.y - m1 - xh.y * m2),
+                                        dv[j].z + st.y * (dxh.z - m1 - xh.z * m2), dv[j].w + st.y * (dxh.w - m1 - xh.w * m2));
+                }
             }
         }
         tc_fence_before();
@@ -423,8 +457,12 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
     for (int i = tid; i < 96; i += 256) {
         atomicAdd(a.dbias + i, acc[i]);
         atomicAdd(a.dslope + i, acc[96 + i]);
-        atomicAdd(a.dlnw + i, acc[192 + i]);
-        atomicAdd(a.dlnb + i, acc[288 + i]);
+    }
+    if (act24) {
+        atomicAdd(a.dlnw + 4 * lane + 0, dg4.x); atomicAdd(a.dlnw + 4 * lane + 1, dg4.y);
+        atomicAdd(a.dlnw + 4 * lane + 2, dg4.z); atomicAdd(a.dlnw + 4 * lane + 3, dg4.w);
+        atomicAdd(a.dlnb + 4 * lane + 0, db4.x); atomicAdd(a.dlnb + 4 * lane + 1, db4.y);
+        atomicAdd(a.dlnb + 4 * lane + 2, db4.z); atomicAdd(a.dlnb + 4 * lane + 3, db4.w);
     }
     if (warp == 0) tmem_dealloc(tmem, 512);
 }

@@ -36,8 +36,10 @@ constexpr uint32_t FB_WS0 = 24 * kCS;
 constexpr uint32_t FB_WS1 = FB_WS0 + IMG_WC_BYTES;
 constexpr uint32_t FB_CST = FB_WS1 + IMG_WC_BYTES;  // ln_w 96, gn_w 192, gn_b 192
 constexpr uint32_t FB_ACC = FB_CST + 480 * 4;       // column-sum accumulators: d_gnw 192, d_gnb 192, d_lnw 96, d_lnb 96
-constexpr uint32_t FB_RED = FB_ACC + 576 * 4;       // [8 warps][8 groups][2] + group totals [8][2]
-constexpr uint32_t FB_BAR = FB_RED + (128 + 16) * 4;
+constexpr uint32_t FB_RED = FB_ACC + 576 * 4;       // [16 warps][8 groups][2] + group totals [8][2]
+constexpr uint32_t FB_XCH = FB_RED + (256 + 16) * 4;  // LayerNorm partial sums of the two channel halves [512][2]
+constexpr uint32_t FB_BAR = FB_XCH + 512 * 8;
+constexpr int kFfnBwdThreads = 512;  // warp w -> M-tile (w>>2)&1, TMEM lane quarter w&3, channel half w>>3
 constexpr uint32_t FB_SMEM = FB_BAR + 64;
 
 // all 16-bit tensors here use the slab-tile layout [slab][24 chunks][T][8] (slab.cuh)
@@ -59,7 +61,7 @@ __device__ __forceinline__ void store16x32(unsigned char* base, int slab, int T,
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
+__global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* hbuf = smem + FB_HBUF;
     unsigned char* ws0 = smem + FB_WS0;
@@ -68,7 +70,8 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
     float *s_lng = cst, *s_gng = cst + 96, *s_gnb = cst + 288;
     float* acc = reinterpret_cast<float*>(smem + FB_ACC);  // [0,192) d_gnw, [192,384) d_gnb, [384,480) d_lnw, [480,576) d_lnb
     float* red = reinterpret_cast<float*>(smem + FB_RED);
-    float* gtot = red + 128;  // [8][2] group totals S1, S2
+    float* gtot = red + 256;  // [8][2] group totals S1, S2
+    float2* xch = reinterpret_cast<float2*>(smem + FB_XCH);
     uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + FB_BAR);
     uint64_t* bar_w0 = bar_mma + 1;
     uint64_t* bar_w1 = bar_mma + 2;
@@ -83,19 +86,21 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
         mbar_init(bar_w1, 1);
         fence_mbar_init();
     }
-    for (int i = tid; i < 96; i += 256) s_lng[i] = a.ln_w[i];
-    for (int i = tid; i < 192; i += 256) { s_gng[i] = a.gn_w[i]; s_gnb[i] = a.gn_b[i]; }
-    for (int i = tid; i < 576; i += 256) acc[i] = 0.f;
-    for (int i = tid; i < (int)(24 * kCS / 16); i += 256) reinterpret_cast<uint4*>(hbuf)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 96; i += kFfnBwdThreads) s_lng[i] = a.ln_w[i];
+    for (int i = tid; i < 192; i += kFfnBwdThreads) { s_gng[i] = a.gn_w[i]; s_gnb[i] = a.gn_b[i]; }
+    for (int i = tid; i < 576; i += kFfnBwdThreads) acc[i] = 0.f;
+    for (int i = tid; i < (int)(24 * kCS / 16); i += kFfnBwdThreads) reinterpret_cast<uint4*>(hbuf)[i] = make_uint4(0, 0, 0, 0);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    const int m = warp >> 2, q = warp & 3;
+    const int m = (warp >> 2) & 1, q = warp & 3, hf = warp >> 3;  // two threads per frame: channel halves
+    const int cb = 96 * hf;
     const int t = 128 * m + 32 * q + lane;
     const bool valid = t < T;
+    const float vmask = valid ? 1.f : 0.f;
     const uint32_t tacc = tmem + ((uint32_t)(32 * q) << 16) + m * 192;
     unsigned char* hrow = hbuf + (t + 1) * 16;
     const uint32_t hb = smem_u32(hbuf), w0a = smem_u32(ws0), w1a = smem_u32(ws1);
@@ -133,25 +138,31 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
     // g = D * SiLU'(c), s = SiLU(c): the three plain activation epilogues
     auto silu_epilogue = [&](const unsigned char* csave, unsigned char* gout, unsigned char* sout, int slab) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < kHF; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tacc + c0, r);
+        for (int c0 = cb; c0 < cb + 96; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tacc + c0, r);
             tmem_ld_wait();
-            float c[32], g[32];
-            if (valid) load_h16x32(csave, slab, T, t, c0, c);
+            float c[16], g[16];
+            if (valid) {
+                load_h16x8(csave, slab, T, t, c0, c);
+                load_h16x8(csave, slab, T, t, c0 + 8, c + 8);
+            }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 const float cv = valid ? c[j] : 0.f;
                 const float sg = sigmoidf_(cv);
-                g[j] = valid ? __uint_as_float(r[j]) * sg * (1.f + cv * (1.f - sg)) : 0.f;
+                g[j] = __uint_as_float(r[j]) * sg * (1.f + cv * (1.f - sg)) * vmask;
                 c[j] = cv * sg;
             }
-            if (valid) {
-                store16x32<FMT>(sout, slab, T, t, c0, c);
-                store16x32<FMT>(gout, slab, T, t, c0, g);
-            }
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(hrow + (c0 / 8 + cc) * kCS) = pack8<FMT>(g + 8 * cc);
+            for (int cc = 0; cc < 2; ++cc) {
+                const uint4 gp = pack8<FMT>(g + 8 * cc);
+                if (valid) {
+                    *reinterpret_cast<uint4*>(sout + tile_off(slab, 24, T, c0 / 8 + cc, t)) = pack8<FMT>(c + 8 * cc);
+                    *reinterpret_cast<uint4*>(gout + tile_off(slab, 24, T, c0 / 8 + cc, t)) = gp;
+                }
+                *reinterpret_cast<uint4*>(hrow + (c0 / 8 + cc) * kCS) = gp;
+            }
         }
     };
 
@@ -163,7 +174,7 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
             load_image(ws1, a.img + IMG_WC3T, IMG_WC_BYTES, bar_w1);
         }
         // ---- B0: dy -> G (chunks 0..11)
-        stage_rows96<FMT, false>(dys, T, hbuf, 1, nullptr, nullptr, warp, lane);
+        stage_rows96<FMT, false>(dys, T, hbuf, 1, nullptr, nullptr, warp, lane, nullptr, kFfnBwdThreads / 32);
         end_epilogue();
         // ---- B1: d s4 = dy W2
         if (tid == 0) {
@@ -184,7 +195,7 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
             const float* gst = a.gn_stats + (size_t)slab * 16;
             // pass A: s3 out, dn -> G tile, group sums S1 = sum dn*gamma, S2 = sum dn*gamma*xhat
 #pragma unroll 1
-            for (int g = 0; g < kGroups; ++g) {
+            for (int g = 4 * hf; g < 4 * hf + 4; ++g) {
                 const float mean = gst[2 * g], rstd = gst[2 * g + 1];
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -217,19 +228,19 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
             if (tid < 16) {
                 float s = 0.f;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) s += red[(w * 8 + (tid >> 1)) * 2 + (tid & 1)];
+                for (int w = 0; w < 8; ++w) s += red[((8 * ((tid >> 1) >> 2) + w) * 8 + (tid >> 1)) * 2 + (tid & 1)];
                 gtot[tid] = s * inv_n;
             }
             __syncthreads();
             // pass B: g(c2) = rstd * (dn*gamma - S1/N - xhat*S2/N) -> G tile + global; column sums for d_gnw, d_gnb
 #pragma unroll 1
-            for (int c0 = 0; c0 < kHF; c0 += 32) {
-                float dnv[32], dnx[32], gv[32];
+            for (int c0 = cb; c0 < cb + 96; c0 += 16) {
+                float dnv[16], dnx[16];
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
+                for (int cc = 0; cc < 2; ++cc) {
                     const int c = c0 + 8 * cc, g = c / kGC;
                     const float mean = gst[2 * g], rstd = gst[2 * g + 1], m1 = gtot[2 * g], m2 = gtot[2 * g + 1];
-                    float cv[8];
+                    float cv[8], gv[8];
                     if (valid) load_h16x8(a.c2, slab, T, t, c, cv);
                     const uint4 pk = *reinterpret_cast<const uint4*>(hrow + (c / 8) * kCS);
                     float dn[8];
@@ -242,15 +253,17 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
                         const float xh = valid ? (cv[j] - mean) * rstd : 0.f;
                         dnv[8 * cc + j] = dn[j];
                         dnx[8 * cc + j] = dn[j] * xh;
-                        gv[8 * cc + j] = valid ? rstd * (dn[j] * s_gng[c + j] - m1 - xh * m2) : 0.f;
+                        gv[j] = valid ? rstd * (dn[j] * s_gng[c + j] - m1 - xh * m2) : 0.f;
                     }
+                    const uint4 gp = pack8<FMT>(gv);
+                    if (valid) *reinterpret_cast<uint4*>(a.g_c2 + tile_off(slab, 24, T, c / 8, t)) = gp;
+                    *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = gp;
                 }
-                if (valid) store16x32<FMT>(a.g_c2, slab, T, t, c0, gv);
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(hrow + (c0 / 8 + cc) * kCS) = pack8<FMT>(gv + 8 * cc);
-                const float sw = warp_colsum32(dnx, lane), sb = warp_colsum32(dnv, lane);
-                atomicAdd(acc + c0 + lane, sw);
-                atomicAdd(acc + 192 + c0 + lane, sb);
+                const float sw = warp_colsum16(dnx, lane), sb = warp_colsum16(dnv, lane);
+                if (!(lane & 1)) {
+                    atomicAdd(acc + c0 + (lane >> 1), sw);
+                    atomicAdd(acc + 192 + c0 + (lane >> 1), sb);
+                }
             }
         }
         end_epilogue();
@@ -273,17 +286,19 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
         ph_w0 ^= 1;
         wait_mma();
         {
+            // this thread owns 48 of the 96 channels of its frame; the two halves exchange their partial row sums
             const float2 st = valid ? __ldg(reinterpret_cast<const float2*>(a.ln_stats + 2 * grow)) : make_float2(0.f, 0.f);
             const float* xr = a.x + grow * kH;
+            const int c48 = 48 * hf;
             float m1 = 0.f, m2 = 0.f;
 #pragma unroll 1
-            for (int c0 = 0; c0 < kH; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tacc + c0, r);
+            for (int c0 = c48; c0 < c48 + 48; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tacc + c0, r);
                 tmem_ld_wait();
                 if (valid) {
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
+                    for (int j4 = 0; j4 < 4; ++j4) {
                         const float4 xv = __ldg(reinterpret_cast<const float4*>(xr + c0) + j4);
                         const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
@@ -295,16 +310,21 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
                     }
                 }
             }
-            m1 *= (1.f / kH);
-            m2 *= (1.f / kH);
+            xch[tid] = make_float2(m1, m2);
+            __syncthreads();
+            {
+                const float2 o = xch[tid ^ 256];
+                m1 = (m1 + o.x) * (1.f / kH);
+                m2 = (m2 + o.y) * (1.f / kH);
+            }
 #pragma unroll 1
-            for (int c0 = 0; c0 < kH; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tacc + c0, r);
+            for (int c0 = c48; c0 < c48 + 48; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tacc + c0, r);
                 tmem_ld_wait();
-                float dzv[32], dzx[32];
+                float dzv[16], dzx[16];
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
+                for (int j4 = 0; j4 < 4; ++j4) {
                     float4 xv = make_float4(0, 0, 0, 0), dv = xv;
                     if (valid) {
                         xv = __ldg(reinterpret_cast<const float4*>(xr + c0) + j4);
@@ -323,17 +343,19 @@ __global__ void __launch_bounds__(256, 1) ffn_bwd_kernel(FfnBwdArgs a) {
                     }
                     if (valid) reinterpret_cast<float4*>(a.dx + grow * kH + c0)[j4] = make_float4(o[0], o[1], o[2], o[3]);
                 }
-                const float sw = warp_colsum32(dzx, lane), sb = warp_colsum32(dzv, lane);
-                atomicAdd(acc + 384 + c0 + lane, sw);
-                atomicAdd(acc + 480 + c0 + lane, sb);
+                const float sw = warp_colsum16(dzx, lane), sb = warp_colsum16(dzv, lane);
+                if (!(lane & 1)) {
+                    atomicAdd(acc + 384 + c0 + (lane >> 1), sw);
+                    atomicAdd(acc + 480 + c0 + (lane >> 1), sb);
+                }
             }
         }
         tc_fence_before();
         __syncthreads();
     }
     // flush the affine-parameter gradients
-    for (int i = tid; i < 192; i += 256) { atomicAdd(a.d_gnw + i, acc[i]); atomicAdd(a.d_gnb + i, acc[192 + i]); }
-    for (int i = tid; i < 96; i += 256) { atomicAdd(a.d_lnw + i, acc[384 + i]); atomicAdd(a.d_lnb + i, acc[480 + i]); }
+    for (int i = tid; i < 192; i += kFfnBwdThreads) { atomicAdd(a.d_gnw + i, acc[i]); atomicAdd(a.d_gnb + i, acc[192 + i]); }
+    for (int i = tid; i < 96; i += kFfnBwdThreads) { atomicAdd(a.d_lnw + i, acc[384 + i]); atomicAdd(a.d_lnb + i, acc[480 + i]); }
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -361,7 +383,7 @@ extern "C" int nbss_ffn_bwd(const float* x, const float* dy, float* dx, int nsla
     auto kern = (fmt == FMT_F16) ? ffn_bwd_kernel<FMT_F16> : ffn_bwd_kernel<FMT_BF16>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_SMEM);
     if (e != cudaSuccess) return (int)e;
-    kern<<<grid, 256, FB_SMEM, (cudaStream_t)stream>>>(a);
+    kern<<<grid, kFfnBwdThreads, FB_SMEM, (cudaStream_t)stream>>>(a);
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
 }

@@ -9,7 +9,8 @@
 //      views of H x block-diagonal 48x48 tiles   E4 +bc3, SiLU           -> H
 //   P5 pw2:  D[256x96] = H W2^T (12 k-steps)    E5 +b2 + x -> y
 // Weights arrive as prepacked UMMA images (pack.cu) by TMA bulk copies into two ping-pong slots, overlapped with
-// the epilogues.  Epilogue thread = one frame (TMEM lane), so GroupNorm needs one block reduction per statistic.
+// the epilogues.  512 threads: two threads per frame (TMEM lane), each owning half of the channels, so 16 warps hide
+// the TMEM / MUFU / shared-memory latencies of the epilogues; GroupNorm needs one block reduction per statistic.
 #include "slab.cuh"
 
 namespace nbss {
@@ -31,8 +32,9 @@ constexpr uint32_t FF_WS0 = 24 * kCS;               // 101760
 constexpr uint32_t FF_WS1 = FF_WS0 + IMG_WC_BYTES;  // 157056
 constexpr uint32_t FF_CST = FF_WS1 + IMG_WC_BYTES;  // 212352
 constexpr uint32_t FF_NCST = 1440;                  // floats
-constexpr uint32_t FF_RED = FF_CST + FF_NCST * 4;   // 8*16 floats
-constexpr uint32_t FF_BAR = FF_RED + 512;
+constexpr uint32_t FF_RED = FF_CST + FF_NCST * 4;   // 2 x [16 warps][8 groups] floats
+constexpr uint32_t FF_BAR = FF_RED + 1024;
+constexpr int kFfnThreads = 512;  // 16 warps: warp w -> M-tile (w>>2)&1, TMEM lane quarter w&3, channel half w>>3
 constexpr uint32_t FF_SMEM = FF_BAR + 64;
 
 template <int FMT>
@@ -47,7 +49,7 @@ __device__ __forceinline__ void save_f16(unsigned char* base, int slab, int T, i
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
+__global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* hbuf = smem + FF_HBUF;
     unsigned char* ws0 = smem + FF_WS0;
@@ -71,19 +73,20 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         mbar_init(bar_w1, 1);
         fence_mbar_init();
     }
-    for (int i = tid; i < 96; i += 256) { s_lng[i] = a.ln_w[i]; s_lnb[i] = a.ln_b[i]; s_b2[i] = a.b2[i]; }
-    for (int i = tid; i < 192; i += 256) {
+    for (int i = tid; i < 96; i += kFfnThreads) { s_lng[i] = a.ln_w[i]; s_lnb[i] = a.ln_b[i]; s_b2[i] = a.b2[i]; }
+    for (int i = tid; i < 192; i += kFfnThreads) {
         s_b1[i] = a.b1[i]; s_bc[i] = a.bc1[i]; s_bc[192 + i] = a.bc2[i]; s_bc[384 + i] = a.bc3[i];
         s_gng[i] = a.gn_w[i]; s_gnb[i] = a.gn_b[i];
     }
-    for (int i = tid; i < (int)(24 * kCS / 16); i += 256) reinterpret_cast<uint4*>(hbuf)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (int)(24 * kCS / 16); i += kFfnThreads) reinterpret_cast<uint4*>(hbuf)[i] = make_uint4(0, 0, 0, 0);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    const int m = warp >> 2, q = warp & 3;
+    const int m = (warp >> 2) & 1, q = warp & 3, hf = warp >> 3;  // two threads per frame: channel halves
+    const int cb = 96 * hf;                                     // first of this thread's 96 (of 192) channels
     const int t = 128 * m + 32 * q + lane;
     const bool valid = t < T;
     const float vmask = valid ? 1.f : 0.f;  // frames >= T are written as zeros (conv zero padding) without branching
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
             load_image(ws1, a.img + IMG_WC1, IMG_WC_BYTES, bar_w1);
         }
         // ---- P0: LN(x) -> A0 (chunks 0..11 of H)
-        stage_rows96<FMT, true>(xs, T, hbuf, 1, s_lng, s_lnb, warp, lane, a.ln_stats ? a.ln_stats + (size_t)slab * T * 2 : nullptr);
+        stage_rows96<FMT, true>(xs, T, hbuf, 1, s_lng, s_lnb, warp, lane, a.ln_stats ? a.ln_stats + (size_t)slab * T * 2 : nullptr, kFfnThreads / 32);
         end_epilogue();
         // ---- P1: pw1
         if (tid == 0) {
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         if (tid == 0) load_image(ws0, a.img + IMG_WC2, IMG_WC_BYTES, bar_w0);
         // ---- E1: a1 = D + b1; H = SiLU(a1)
 #pragma unroll 1
-        for (int c0 = 0; c0 < kHF; c0 += 32) {
+        for (int c0 = cb; c0 < cb + 96; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(tacc + c0, r);
             tmem_ld_wait();
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         conv_phase(w1a, bar_w1, ph_w1);
         if (tid == 0) load_image(ws1, a.img + IMG_WC3, IMG_WC_BYTES, bar_w1);
 #pragma unroll 1
-        for (int c0 = 0; c0 < kHF; c0 += 32) {
+        for (int c0 = cb; c0 < cb + 96; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(tacc + c0, r);
             tmem_ld_wait();
@@ -177,12 +180,12 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         conv_phase(w0a, bar_w0, ph_w0);
         if (tid == 0) load_image(ws0, a.img + IMG_W2, IMG_W2_BYTES, bar_w0);
         {
-            float* red_sum = red;       // [8 warps][8 groups]
-            float* red_sq = red + 64;
+            float* red_sum = red;       // [16 warps][8 groups] (a warp fills the 4 groups of its channel half)
+            float* red_sq = red + 128;
             const float* bc2 = s_bc + 192;
             // pass A: per-group sums over valid frames
 #pragma unroll 1
-            for (int g = 0; g < kGroups; ++g) {
+            for (int g = 4 * hf; g < 4 * hf + 4; ++g) {
                 float s = 0.f;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
@@ -198,10 +201,10 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
             __syncthreads();
             // pass B: centred second moment
 #pragma unroll 1
-            for (int g = 0; g < kGroups; ++g) {
+            for (int g = 4 * hf; g < 4 * hf + 4; ++g) {
                 float mean = 0.f;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) mean += red_sum[w * 8 + g];
+                for (int w = 0; w < 8; ++w) mean += red_sum[(8 * hf + w) * 8 + g];
                 mean *= inv_n;
                 float s = 0.f;
 #pragma unroll
@@ -221,13 +224,13 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
             __syncthreads();
             // pass C: normalise, affine, SiLU -> H ; save c2
 #pragma unroll 1
-            for (int g = 0; g < kGroups; ++g) {
+            for (int g = 4 * hf; g < 4 * hf + 4; ++g) {
                 float mean = 0.f, var = 0.f;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) { mean += red_sum[w * 8 + g]; var += red_sq[w * 8 + g]; }
+                for (int w = 0; w < 8; ++w) { mean += red_sum[(8 * hf + w) * 8 + g]; var += red_sq[(8 * hf + w) * 8 + g]; }
                 mean *= inv_n;
                 const float rstd = rsqrtf(var * inv_n + 1e-5f);
-                if (a.gn_stats && tid == g) {
+                if (a.gn_stats && m == 0 && q == 0 && lane == (g & 3)) {
                     a.gn_stats[(size_t)slab * 16 + 2 * g] = mean;
                     a.gn_stats[(size_t)slab * 16 + 2 * g + 1] = rstd;
                 }
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         // ---- P4: conv3 ; E4: c3 = D + bc3; H = SiLU(c3)
         conv_phase(w1a, bar_w1, ph_w1);
 #pragma unroll 1
-        for (int c0 = 0; c0 < kHF; c0 += 32) {
+        for (int c0 = cb; c0 < cb + 96; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(tacc + c0, r);
             tmem_ld_wait();
@@ -279,24 +282,32 @@ __global__ void __launch_bounds__(256, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         mbar_wait(bar_mma, ph_mma, a.err);
         ph_mma ^= 1;
         tc_fence_after();
+        // E5a: thread = (frame, channel half): D + b2 -> fp32, staged into the (now dead) H tile with 4-float chunks at
+        // the frame's row slot, so that E5b can do the residual add with coalesced warp-per-row global traffic
 #pragma unroll 1
-        for (int c0 = 0; c0 < kH; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tacc + c0, r);
+        for (int c0 = 48 * hf; c0 < 48 * hf + 48; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tacc + c0, r);
             tmem_ld_wait();
-            if (valid) {
-                const float4* xr = reinterpret_cast<const float4*>(xs + (size_t)t * kH + c0);
-                float4* yr = reinterpret_cast<float4*>(a.y + grow * kH + c0);
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    float4 xv = __ldg(xr + j4);
-                    float4 o;
-                    o.x = xv.x + __uint_as_float(r[4 * j4 + 0]) + s_b2[c0 + 4 * j4 + 0];
-                    o.y = xv.y + __uint_as_float(r[4 * j4 + 1]) + s_b2[c0 + 4 * j4 + 1];
-                    o.z = xv.z + __uint_as_float(r[4 * j4 + 2]) + s_b2[c0 + 4 * j4 + 2];
-                    o.w = xv.w + __uint_as_float(r[4 * j4 + 3]) + s_b2[c0 + 4 * j4 + 3];
-                    yr[j4] = o;
-                }
+            for (int j4 = 0; j4 < 4; ++j4) {
+                float4 o;
+                o.x = __uint_as_float(r[4 * j4 + 0]) + s_b2[c0 + 4 * j4 + 0];
+                o.y = __uint_as_float(r[4 * j4 + 1]) + s_b2[c0 + 4 * j4 + 1];
+                o.z = __uint_as_float(r[4 * j4 + 2]) + s_b2[c0 + 4 * j4 + 2];
+                o.w = __uint_as_float(r[4 * j4 + 3]) + s_b2[c0 + 4 * j4 + 3];
+                *reinterpret_cast<float4*>(hrow + (c0 / 4 + j4) * kCS) = o;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        // E5b: warp per frame: y = x + branch (24 lanes x float4 = one 384-byte row)
+        if (lane < 24) {
+#pragma unroll 4
+            for (int r = warp; r < T; r += kFfnThreads / 32) {
+                const float4 v = *reinterpret_cast<const float4*>(hbuf + lane * kCS + (r + 1) * 16);
+                const float4 xv = __ldg(reinterpret_cast<const float4*>(xs + (size_t)r * kH) + lane);
+                reinterpret_cast<float4*>(a.y + ((size_t)slab * T + r) * kH)[lane] = make_float4(xv.x + v.x, xv.y + v.y, xv.z + v.z, xv.w + v.w);
             }
         }
         tc_fence_before();
@@ -324,7 +335,7 @@ extern "C" int nbss_ffn_fwd(const float* x, float* y, int nslab, int T, const fl
     auto kern = (fmt == FMT_F16) ? ffn_fwd_kernel<FMT_F16> : ffn_fwd_kernel<FMT_BF16>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM);
     if (e != cudaSuccess) return (int)e;
-    kern<<<grid, 256, FF_SMEM, (cudaStream_t)stream>>>(a);
+    kern<<<grid, kFfnThreads, FF_SMEM, (cudaStream_t)stream>>>(a);
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
 }

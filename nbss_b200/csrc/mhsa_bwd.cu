@@ -13,6 +13,7 @@
 namespace nbss {
 
 constexpr uint32_t kCSQ = 129 * 16;  // chunk stride of 128-row tiles (P, dS)
+constexpr int kMbThreads = 512;      // 16 warps: M-tile (w>>2)&1, TMEM lane quarter w&3, half w>>3 / key quarter w>>2
 
 struct MhsaBwdArgs {
     const float* dy;
@@ -45,7 +46,7 @@ __device__ __forceinline__ float ex2f(float x) {
 }
 
 template <int FMT_G>
-__global__ void __launch_bounds__(256, 1) mhsa_bwd_core_kernel(MhsaBwdArgs a) {
+__global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* dot = smem + MB_DO;
     unsigned char* qt = smem + MB_Q;
@@ -66,14 +67,14 @@ __global__ void __launch_bounds__(256, 1) mhsa_bwd_core_kernel(MhsaBwdArgs a) {
         mbar_init(bar_w, 1);
         fence_mbar_init();
     }
-    for (int i = tid; i < (int)(MB_DELTA / 16); i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (int)(MB_DELTA / 16); i += kMbThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    const int m = warp >> 2, q = warp & 3, rt = 32 * q + lane, t = 128 * m + rt;
+    const int m = (warp >> 2) & 1, q = warp & 3, hf = warp >> 3, kq = warp >> 2, rt = 32 * q + lane, t = 128 * m + rt;
     const uint32_t lane_off = (uint32_t)(32 * q) << 16;
     const uint32_t doa = smem_u32(dot), qa = smem_u32(qt), ka = smem_u32(kt), va = smem_u32(vt), pa = smem_u32(pt), dsa = smem_u32(dst);
     // instruction descriptors: (A fmt, B fmt, A major, B major, N)
@@ -107,11 +108,11 @@ __global__ void __launch_bounds__(256, 1) mhsa_bwd_core_kernel(MhsaBwdArgs a) {
     for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
         const size_t row0 = (size_t)slab * T;
         if (tid == 0) load_image(pt, a.img + IMG_WOT, IMG_WQ_BYTES, bar_w);
-        for (int i = tid; i < kNH * 256; i += 256) {
+        for (int i = tid; i < kNH * 256; i += kMbThreads) {
             const int h = i >> 8, tt = i & 255;
             s_lse[i] = tt < T ? a.lse[((size_t)slab * kNH + h) * T + tt] : 0.f;
         }
-        stage_rows96<FMT_G, false>(a.dy + row0 * kH, T, dot, 0, nullptr, nullptr, warp, lane);
+        stage_rows96<FMT_G, false>(a.dy + row0 * kH, T, dot, 0, nullptr, nullptr, warp, lane, nullptr, kMbThreads / 32);
         end_epilogue();
         // ---- M0: dO = dy Wo
         if (tid == 0) {
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256, 1) mhsa_bwd_core_kernel(MhsaBwdArgs a) {
             const bool valid = t < T;
             const uint32_t tacc = tmem + lane_off + m * 96;
 #pragma unroll 1
-            for (int h = 0; h < kNH; ++h) {
+            for (int h = 2 * hf; h < 2 * hf + 2; ++h) {  // each channel half owns two heads
                 float dl = 0.f;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
@@ -180,31 +181,28 @@ __global__ void __launch_bounds__(256, 1) mhsa_bwd_core_kernel(MhsaBwdArgs a) {
                     umma_commit(bar_mma);
                 }
                 wait_mma();
-                // P and dS for this block: thread = (query row rt, 64-key half m)
+                // P and dS for this block: thread = (query row rt, key quarter kq: 32 of the 128 keys)
                 {
                     const int tq = 128 * qb + rt;
                     const float lse = s_lse[h * 256 + tq], dl = s_delta[h * 256 + tq];
                     const bool qok = tq < T;
+                    uint32_t rs[32], rp[32];
+                    tmem_ld32(tmem + lane_off + C_S + 32 * kq, rs);
+                    tmem_ld32(tmem + lane_off + C_DP + 32 * kq, rp);
+                    tmem_ld_wait();
+                    float p[32], ds[32];
 #pragma unroll
-                    for (int c0 = 0; c0 < 64; c0 += 32) {
-                        uint32_t rs[32], rp[32];
-                        tmem_ld32(tmem + lane_off + C_S + 64 * m + c0, rs);
-                        tmem_ld32(tmem + lane_off + C_DP + 64 * m + c0, rp);
-                        tmem_ld_wait();
-                        float p[32], ds[32];
+                    for (int j = 0; j < 32; ++j) {
+                        const int key = 128 * kb + 32 * kq + j;
+                        const float pv = ex2f((qok && key < T) ? __uint_as_float(rs[j]) - lse : -INFINITY);
+                        p[j] = pv;
+                        ds[j] = pv * (__uint_as_float(rp[j]) - dl);
+                    }
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int key = 128 * kb + 64 * m + c0 + j;
-                            const float pv = ex2f((qok && key < T) ? __uint_as_float(rs[j]) - lse : -INFINITY);
-                            p[j] = pv;
-                            ds[j] = pv * (__uint_as_float(rp[j]) - dl);
-                        }
-#pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) {
-                            const int chunk = (64 * m + c0) / 8 + cc;
-                            *reinterpret_cast<uint4*>(pt + chunk * kCSQ + rt * 16) = pack8<FMT_G>(p + 8 * cc);
-                            *reinterpret_cast<uint4*>(dst + chunk * kCSQ + rt * 16) = pack8<FMT_G>(ds + 8 * cc);
-                        }
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int chunk = 4 * kq + cc;
+                        *reinterpret_cast<uint4*>(pt + chunk * kCSQ + rt * 16) = pack8<FMT_G>(p + 8 * cc);
+                        *reinterpret_cast<uint4*>(dst + chunk * kCSQ + rt * 16) = pack8<FMT_G>(ds + 8 * cc);
                     }
                 }
                 end_epilogue();
@@ -231,6 +229,7 @@ __global__ void __launch_bounds__(256, 1) mhsa_bwd_core_kernel(MhsaBwdArgs a) {
                 const bool valid = t < T;
 #pragma unroll
                 for (int which = 0; which < 3; ++which) {
+                    if ((which == 2) != (hf == 1)) continue;  // half 0 writes dQ and dK, half 1 writes dV (warp-uniform)
                     const uint32_t col = (which == 0 ? C_DQ : (which == 1 ? C_DK : C_DV)) + 32 * m;
                     const float sc = which == 0 ? qscale : (which == 1 ? kscale : 1.f);
 #pragma unroll
@@ -268,11 +267,12 @@ struct MhsaLnArgs {
 constexpr uint32_t ML_A = 0;                        // dQKV tile 36 chunks
 constexpr uint32_t ML_W = 36 * kCS;                 // WinT image 55296
 constexpr uint32_t ML_CST = ML_W + IMG_WINT_BYTES;  // ln_w 96 + acc 192 floats
-constexpr uint32_t ML_BAR = ML_CST + 288 * 4;
+constexpr uint32_t ML_XCH = ML_CST + 288 * 4;      // partial LayerNorm row sums of the two channel halves
+constexpr uint32_t ML_BAR = ML_XCH + 512 * 8;
 constexpr uint32_t ML_SMEM = ML_BAR + 64;
 
 template <int FMT_G>
-__global__ void __launch_bounds__(256, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a) {
+__global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* at = smem + ML_A;
     unsigned char* wt = smem + ML_W;
@@ -291,15 +291,16 @@ __global__ void __launch_bounds__(256, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a) {
         fence_mbar_init();
         load_image(wt, a.img + IMG_WINT, IMG_WINT_BYTES, bar_w);  // resident for the whole kernel
     }
-    for (int i = tid; i < 96; i += 256) s_lng[i] = a.ln_w[i];
-    for (int i = tid; i < 192; i += 256) acc[i] = 0.f;
-    for (int i = tid; i < (int)(36 * kCS / 16); i += 256) reinterpret_cast<uint4*>(at)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 96; i += kMbThreads) s_lng[i] = a.ln_w[i];
+    for (int i = tid; i < 192; i += kMbThreads) acc[i] = 0.f;
+    for (int i = tid; i < (int)(36 * kCS / 16); i += kMbThreads) reinterpret_cast<uint4*>(at)[i] = make_uint4(0, 0, 0, 0);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const int m = warp >> 2, q = warp & 3, t = 128 * m + 32 * q + lane;
+    const int m = (warp >> 2) & 1, q = warp & 3, hf = warp >> 3, t = 128 * m + 32 * q + lane;
+    float2* xch = reinterpret_cast<float2*>(smem + ML_XCH);
     const bool valid = t < T;
     const uint32_t tacc = tmem + ((uint32_t)(32 * q) << 16) + m * 96;
     const uint32_t ata = smem_u32(at), wta = smem_u32(wt);
@@ -325,18 +326,19 @@ __global__ void __launch_bounds__(256, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a) {
         mbar_wait(bar_mma, ph, a.err);
         ph ^= 1;
         tc_fence_after();
-        // LayerNorm backward (same arithmetic as ffn_bwd E5)
+        // LayerNorm backward (same arithmetic as ffn_bwd E5): this thread owns 48 of the 96 channels of its frame
         const float2 st = valid ? __ldg(reinterpret_cast<const float2*>(a.ln_stats + 2 * grow)) : make_float2(0.f, 0.f);
         const float* xr = a.x + grow * kH;
+        const int c48 = 48 * hf;
         float m1 = 0.f, m2 = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < kH; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tacc + c0, r);
+        for (int c0 = c48; c0 < c48 + 48; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tacc + c0, r);
             tmem_ld_wait();
             if (valid) {
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
+                for (int j4 = 0; j4 < 4; ++j4) {
                     const float4 xv = __ldg(reinterpret_cast<const float4*>(xr + c0) + j4);
                     const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
@@ -348,16 +350,21 @@ __global__ void __launch_bounds__(256, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a) {
                 }
             }
         }
-        m1 *= (1.f / kH);
-        m2 *= (1.f / kH);
+        xch[tid] = make_float2(m1, m2);
+        __syncthreads();
+        {
+            const float2 o = xch[tid ^ 256];
+            m1 = (m1 + o.x) * (1.f / kH);
+            m2 = (m2 + o.y) * (1.f / kH);
+        }
 #pragma unroll 1
-        for (int c0 = 0; c0 < kH; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tacc + c0, r);
+        for (int c0 = c48; c0 < c48 + 48; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tacc + c0, r);
             tmem_ld_wait();
-            float dzv[32], dzx[32];
+            float dzv[16], dzx[16];
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
+            for (int j4 = 0; j4 < 4; ++j4) {
                 float4 xv = make_float4(0, 0, 0, 0), dv = xv;
                 if (valid) {
                     xv = __ldg(reinterpret_cast<const float4*>(xr + c0) + j4);
@@ -376,14 +383,16 @@ __global__ void __launch_bounds__(256, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a) {
                 }
                 if (valid) reinterpret_cast<float4*>(a.dx + grow * kH + c0)[j4] = make_float4(o[0], o[1], o[2], o[3]);
             }
-            const float sw = warp_colsum32(dzx, lane), sb = warp_colsum32(dzv, lane);
-            atomicAdd(acc + c0 + lane, sw);
-            atomicAdd(acc + 96 + c0 + lane, sb);
+            const float sw = warp_colsum16(dzx, lane), sb = warp_colsum16(dzv, lane);
+            if (!(lane & 1)) {
+                atomicAdd(acc + c0 + (lane >> 1), sw);
+                atomicAdd(acc + 96 + c0 + (lane >> 1), sb);
+            }
         }
         tc_fence_before();
         __syncthreads();
     }
-    for (int i = tid; i < 96; i += 256) { atomicAdd(a.d_lnw + i, acc[i]); atomicAdd(a.d_lnb + i, acc[96 + i]); }
+    for (int i = tid; i < 96; i += kMbThreads) { atomicAdd(a.d_lnw + i, acc[i]); atomicAdd(a.d_lnb + i, acc[96 + i]); }
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
@@ -409,7 +418,7 @@ extern "C" int nbss_mhsa_bwd(const float* x, const float* dy, float* dx, int nsl
         auto kern = (fmt_g == FMT_BF16) ? mhsa_bwd_core_kernel<FMT_BF16> : mhsa_bwd_core_kernel<FMT_F16>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MB_SMEM);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, 256, MB_SMEM, st>>>(a);
+        kern<<<grid, kMbThreads, MB_SMEM, st>>>(a);
         NBSS_LAUNCH_CHECK();
     }
     {
@@ -417,7 +426,7 @@ extern "C" int nbss_mhsa_bwd(const float* x, const float* dy, float* dx, int nsl
         auto kern = (fmt_g == FMT_BF16) ? mhsa_bwd_ln_kernel<FMT_BF16> : mhsa_bwd_ln_kernel<FMT_F16>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ML_SMEM);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, 256, ML_SMEM, st>>>(a);
+        kern<<<grid, kMbThreads, ML_SMEM, st>>>(a);
         NBSS_LAUNCH_CHECK();
     }
     return NBSS_OK;

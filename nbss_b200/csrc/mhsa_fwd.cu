@@ -35,7 +35,8 @@ constexpr uint32_t MH_W = MH_V + 13 * kCS;      // 178080
 constexpr uint32_t MH_W_BYTES = 20 * kCSP;      // 41280: P (16 chunks) + Qs (4 chunks), or one weight image
 constexpr uint32_t MH_CST = MH_W + MH_W_BYTES;  // 219360
 constexpr uint32_t MH_XCH = MH_CST + 576 * 4;
-constexpr uint32_t MH_BAR = MH_XCH + 2048;
+constexpr uint32_t MH_BAR = MH_XCH + 4096;
+constexpr int kMhThreads = 512;  // 16 warps
 constexpr uint32_t MH_SMEM = MH_BAR + 64;
 static_assert(IMG_W1_BYTES <= MH_W_BYTES, "weight image must fit the W region");
 
@@ -46,7 +47,7 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(256, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
+__global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* ao = smem + MH_AO;
     unsigned char* kt = smem + MH_K;
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(256, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
     float* cst = reinterpret_cast<float*>(smem + MH_CST);
     float *s_lng = cst, *s_lnb = cst + 96, *s_bin = cst + 192, *s_bout = cst + 480;
     float* xmax = reinterpret_cast<float*>(smem + MH_XCH);
-    float* xsum = xmax + 256;
+    float* xsum = xmax + 512;  // [4 key quarters][128 rows] each
     uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + MH_BAR);
     uint64_t* bar_w = bar_mma + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
@@ -70,17 +71,18 @@ __global__ void __launch_bounds__(256, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
         mbar_init(bar_w, 1);
         fence_mbar_init();
     }
-    for (int i = tid; i < 96; i += 256) { s_lng[i] = a.ln_w[i]; s_lnb[i] = a.ln_b[i]; s_bout[i] = a.b_out[i]; }
-    for (int i = tid; i < 288; i += 256) s_bin[i] = a.b_in[i];
+    for (int i = tid; i < 96; i += kMhThreads) { s_lng[i] = a.ln_w[i]; s_lnb[i] = a.ln_b[i]; s_bout[i] = a.b_out[i]; }
+    for (int i = tid; i < 288; i += kMhThreads) s_bin[i] = a.b_in[i];
     // zero everything that is read as padding: AO, K (pad chunks), V (13th chunk)
-    for (int i = tid; i < (int)(MH_W / 16); i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (int)(MH_W / 16); i += kMhThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    const int m = warp >> 2, q = warp & 3;
+    // 16 warps.  'Both tiles' epilogues: M-tile m, lane quarter q, column half hf.  Softmax: key quarter kq.
+    const int m = (warp >> 2) & 1, q = warp & 3, hf = warp >> 3, kq = warp >> 2;
     const int rt = 32 * q + lane;       // row within an M-tile (TMEM lane)
     const int t = 128 * m + rt;         // frame handled in "both tiles" epilogues
     const uint32_t lane_off = (uint32_t)(32 * q) << 16;
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(256, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
     for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
         const float* xs = a.x + (size_t)slab * T * kH;
         if (tid == 0) load_image(wr, a.img + IMG_WKV, IMG_W1_BYTES, bar_w);
-        stage_rows96<FMT, true>(xs, T, ao, 0, s_lng, s_lnb, warp, lane, a.ln_stats ? a.ln_stats + (size_t)slab * T * 2 : nullptr);
+        stage_rows96<FMT, true>(xs, T, ao, 0, s_lng, s_lnb, warp, lane, a.ln_stats ? a.ln_stats + (size_t)slab * T * 2 : nullptr, kMhThreads / 32);
         end_epilogue();
         // ---- P1: K|V
         if (tid == 0) {
@@ -121,9 +123,9 @@ __global__ void __launch_bounds__(256, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
         {
             const bool valid = t < T;
             const uint32_t tacc = tmem + lane_off + m * 192;
-            // K: cols 0..95 -> per-head padded chunks 4h..4h+2
+            // K: cols 0..95 -> per-head padded chunks 4h..4h+2   (channel half 0 does K, half 1 does V)
 #pragma unroll 1
-            for (int h = 0; h < kNH; ++h) {
+            for (int h = 0; h < (hf == 0 ? kNH : 0); ++h) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     uint32_t r[8];
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(256, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
             }
             // V: cols 96..191 -> compact chunks 0..11
 #pragma unroll 1
-            for (int c = 0; c < 12; ++c) {
+            for (int c = 0; c < (hf == 1 ? 12 : 0); ++c) {
                 uint32_t r[8];
                 tmem_ld8(tacc + 96 + 8 * c, r);
                 tmem_ld_wait();
@@ -191,31 +193,31 @@ __global__ void __launch_bounds__(256, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
                 umma_commit(bar_mma);
             }
             wait_mma();
-            // softmax: thread = (row rt, key half m)
-            const uint32_t ts = tmem + lane_off + 192 + 128 * m;
+            // softmax: thread = (query row rt, key quarter kq): 64 of the 256 score columns
+            const uint32_t ts = tmem + lane_off + 192 + 64 * kq;
             float mx = -INFINITY;
 #pragma unroll
-            for (int c0 = 0; c0 < 128; c0 += 32) {
+            for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(ts + c0, r);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (128 * m + c0 + j < T) mx = fmaxf(mx, __uint_as_float(r[j]));
+                    mx = fmaxf(mx, (64 * kq + c0 + j < T) ? __uint_as_float(r[j]) : -INFINITY);
             }
-            xmax[m * 128 + rt] = mx;
+            xmax[kq * 128 + rt] = mx;
             __syncthreads();
-            const float rowmax = fmaxf(xmax[rt], xmax[128 + rt]);
-            uint32_t pk[64];
+            const float rowmax = fmaxf(fmaxf(xmax[rt], xmax[128 + rt]), fmaxf(xmax[256 + rt], xmax[384 + rt]));
+            uint32_t pk[32];
             float sum = 0.f;
 #pragma unroll
-            for (int c0 = 0; c0 < 128; c0 += 32) {
+            for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(ts + c0, r);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                    const int key = 128 * m + c0 + j;
+                    const int key = 64 * kq + c0 + j;
                     // masked keys get exponent -inf (ex2 -> 0): a select on the argument, no branch around the MUFU
                     float p0 = ex2(key < T ? __uint_as_float(r[j]) - rowmax : -INFINITY);
                     float p1 = ex2(key + 1 < T ? __uint_as_float(r[j + 1]) - rowmax : -INFINITY);
@@ -223,14 +225,14 @@ __global__ void __launch_bounds__(256, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
                     pk[(c0 + j) >> 1] = pack16<FMT>(p0, p1);
                 }
             }
-            xsum[m * 128 + rt] = sum;
-            // O_h = P V_h, one key half at a time (P tile holds 128 keys)
+            xsum[kq * 128 + rt] = sum;
+            // O_h = P V_h, one key half at a time (the P tile holds 128 keys = two key quarters)
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                if (m == half) {
+                if ((kq >> 1) == half) {
 #pragma unroll
-                    for (int c = 0; c < 16; ++c)
-                        *reinterpret_cast<uint4*>(pt + c * kCSP + rt * 16) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<uint4*>(pt + (8 * (kq & 1) + c) * kCSP + rt * 16) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
                 }
                 end_epilogue();
                 if (tid == 0) {
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(256, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
             // EO: normalise and place O_h into the O tile (aliases A0, dead after P2)
             if (warp < 4) {
                 const int tq = 128 * mq + rt;
-                const float l = xsum[rt] + xsum[128 + rt];
+                const float l = xsum[rt] + xsum[128 + rt] + xsum[256 + rt] + xsum[384 + rt];
                 const float inv = 1.f / l;
                 if (a.save_lse && tq < T) a.save_lse[((size_t)slab * kNH + h) * T + tq] = rowmax + log2f(l);
 #pragma unroll
@@ -282,13 +284,13 @@ __global__ void __launch_bounds__(256, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
             const float4* xr = reinterpret_cast<const float4*>(xs + (size_t)(valid ? t : 0) * kH);
             float4* yr = reinterpret_cast<float4*>(a.y + ((size_t)slab * T + (valid ? t : 0)) * kH);
 #pragma unroll 1
-            for (int c0 = 0; c0 < kH; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tacc + c0, r);
+            for (int c0 = 48 * hf; c0 < 48 * hf + 48; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tacc + c0, r);
                 tmem_ld_wait();
                 if (valid) {
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
+                    for (int j4 = 0; j4 < 4; ++j4) {
                         float4 xv = __ldg(xr + c0 / 4 + j4);
                         float4 o;
                         o.x = xv.x + __uint_as_float(r[4 * j4 + 0]) + s_bout[c0 + 4 * j4 + 0];
@@ -324,7 +326,7 @@ extern "C" int nbss_mhsa_fwd(const float* x, float* y, int nslab, int T, const f
     auto kern = (fmt == FMT_F16) ? mhsa_fwd_kernel<FMT_F16> : mhsa_fwd_kernel<FMT_BF16>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MH_SMEM);
     if (e != cudaSuccess) return (int)e;
-    kern<<<grid, 256, MH_SMEM, (cudaStream_t)stream>>>(a);
+    kern<<<grid, kMhThreads, MH_SMEM, (cudaStream_t)stream>>>(a);
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
 }

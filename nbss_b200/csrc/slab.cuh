@@ -79,25 +79,27 @@ __device__ __forceinline__ void unpack16(uint32_t p, float& lo, float& hi) {
 template <int FMT, bool LN>
 __device__ __forceinline__ void stage_rows96(const float* __restrict__ xslab, int T, unsigned char* tile, int row_off,
                                              const float* s_gamma, const float* s_beta, int warp, int lane,
-                                             float* stats_out = nullptr /* [T,2] (mean, rstd) of this slab */) {
+                                             float* stats_out = nullptr /* [T,2] (mean, rstd) of this slab */,
+                                             int nwarps = 8) {
     const bool act = lane < 24;
     float4 g = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
     if (LN && act) {
         g = *reinterpret_cast<const float4*>(s_gamma + 4 * lane);
         be = *reinterpret_cast<const float4*>(s_beta + 4 * lane);
     }
+    const int iters = 256 / nwarps;
 #pragma unroll 1
-    for (int i = 0; i < 32; i += 4) {
+    for (int i = 0; i < iters; i += 4) {
         float4 v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int r = warp + 8 * (i + j);
+            const int r = warp + nwarps * (i + j);
             v[j] = (act && r < T) ? __ldg(reinterpret_cast<const float4*>(xslab + (size_t)r * kH) + lane)
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int r = warp + 8 * (i + j);
+            const int r = warp + nwarps * (i + j);
             float4 y = v[j];
             if (LN) {
                 float s = warp_sum(y.x + y.y + y.z + y.w);
@@ -130,6 +132,25 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
         }
     }
+    return v[0];
+}
+
+// 16-column variant (15 shuffles): on return lane l holds the column sum of column (l >> 1) (both lanes of a pair).
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#define NBSS_HALVE(S, N)                                                          \
+    {                                                                             \
+        const bool up = (lane & S) != 0;                                          \
+        _Pragma("unroll") for (int i = 0; i < N; ++i) {                           \
+            const float a = v[i], b = v[i + N];                                   \
+            v[i] = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, S);    \
+        }                                                                         \
+    }
+    NBSS_HALVE(16, 8)
+    NBSS_HALVE(8, 4)
+    NBSS_HALVE(4, 2)
+    NBSS_HALVE(2, 1)
+#undef NBSS_HALVE
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
     return v[0];
 }
 

@@ -34,7 +34,12 @@ FLOP_PER_POINT = {  # algorithmic FLOPs per T-F point
     "ffn_fwd": 156_672, "mhsa_fwd": 169_728, "ffn_bwd": 156_672, "ffn_wgrad": 156_672, "mhsa_bwd": 265_728,
     "mhsa_wgrad": 73_728, "fconv_fwd": 11_520, "fconv_bwd": 34_560, "fconv_tc_fwd": 11_520, "fconv_tc_bwd": 34_560, "full_fwd": 5_136, "full_bwd": 10_272,
 }
-STREAM_BYTES_PER_POINT = 96 * 4  # one fp32 pass over the stream
+# algorithmic HBM bytes per T-F point with one fused kernel per sub-block and an fp32 stream:
+# forward = x in + y out; data-gradient = x, dy in + dx out; weight-gradient = x, dy in.  (What the kernels move on top
+# of this — 16-bit saves and gradient operands — is design overhead and shows up as a lower fraction.)
+BYTES_PER_POINT = {"ffn_fwd": 768, "mhsa_fwd": 768, "fconv_tc_fwd": 768, "full_fwd": 768, "ffn_bwd": 1152, "mhsa_bwd": 1152,
+                   "fconv_tc_bwd": 1152, "full_bwd": 1152, "ffn_wgrad": 768, "mhsa_wgrad": 768}
+TENSOR_BOUND = ("ffn_fwd", "mhsa_fwd", "ffn_bwd", "ffn_wgrad", "mhsa_bwd", "mhsa_wgrad")  # AI >= ~200 FLOP/B: narrow-band block
 
 
 def neg_si_sdr_pit(est, ref):
@@ -287,29 +292,31 @@ def main():
         if k in FLOP_PER_POINT:
             ent["tflops"] = round(FLOP_PER_POINT[k] * npts / (ms * 1e-3) / 1e12, 2)
         kernels[k] = ent
-    top = max((k for k in kernels if k in FLOP_PER_POINT), key=lambda k: kernels[k]["ms_per_step"])
-    tensor_kernel = top in ("ffn_fwd", "mhsa_fwd", "ffn_bwd", "ffn_wgrad", "mhsa_bwd", "mhsa_wgrad", "fconv_tc_fwd", "fconv_tc_bwd")
-    if tensor_kernel:
-        ach = FLOP_PER_POINT[top] * npts / (kernels[top]["ms_per_launch"] * 1e-3) / 1e12
-        roof = {"kernel": top, "bound": "tensor", "achieved": round(ach, 2), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
-                "traffic": None, "peak_source": peak_src}
-    else:
-        nbytes = {"fconv_fwd": 2, "fconv_bwd": 3, "full_fwd": 2, "full_bwd": 3}[top] * STREAM_BYTES_PER_POINT * npts
-        ach = nbytes / (kernels[top]["ms_per_launch"] * 1e-3) / 1e9
-        roof = {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": peak_bw, "unit": "GB/s", "frac": round(ach / peak_bw, 4),
-                "traffic": None, "peak_source": peak_src}
+    def roof(k):
+        sec = kernels[k]["ms_per_launch"] * 1e-3
+        tf = FLOP_PER_POINT[k] * npts / sec / 1e12
+        gb = BYTES_PER_POINT[k] * npts / sec / 1e9
+        if k in TENSOR_BOUND:
+            return {"kernel": k, "bound": "tensor", "achieved": round(tf, 2), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(tf / peak_tf, 4),
+                    "traffic": None, "also_hbm_gbs": round(gb, 1), "peak_source": peak_src}
+        return {"kernel": k, "bound": "hbm", "achieved": round(gb, 1), "peak": peak_bw, "unit": "GB/s", "frac": round(gb / peak_bw, 4),
+                "traffic": None, "also_tflops": round(tf, 2), "peak_source": peak_src}
+    cands = [k for k in kernels if k in FLOP_PER_POINT and k in BYTES_PER_POINT]
+    top = max(cands, key=lambda k: kernels[k]["ms_per_step"])
+    rooflines = sorted((dict(roof(k), ms_per_step=kernels[k]["ms_per_step"]) for k in cands), key=lambda r: -r["ms_per_step"])
+    roof = dict(roof(top), share_of_step=round(kernels[top]["ms_per_step"] / ms_dev, 3))
     out = {
         "metric": "T-F frames/sec (SpatialNet-small 6ch F=129, training step fwd+bwd incl. STFT/iSTFT)",
         "value": frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "fp16/bf16 tensor-core operands, fp32 accumulate + fp32 stream", "data": "synthetic",
+        "dtype": "fp16 tensor-core operands (fwd + loss-scaled bwd), fp32 accumulate, fp32 stream", "data": "synthetic",
         "config": {"workload": "SpatialNet-small 6ch F=129 T=250 fwd+bwd, batch=32 (BASELINE configs[1])", "global_batch": args.batch,
                    "per_gpu_batch": b_local, "frames_per_utt": CFG["T"], "parallelism": f"dp{world}",
                    "l2": "activations per step (>10 GB) far exceed the 126 MB L2; no explicit flush"},
         "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4) * world, "d2h_bytes_per_step": 4 * world},
         "gpu_launches": launches, "loss": loss_v, "rtf": ms_dev * 1e-3 / (args.batch * TS / 8000.0),
-        "roofline": roof, "kernels": kernels, "clocks": clocks,
+        "roofline": roof, "rooflines": rooflines, "kernels": kernels, "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = min(os.cpu_count() or 1, 64)

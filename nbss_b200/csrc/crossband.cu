@@ -635,7 +635,7 @@ extern "C" int nbss_full_bwd(const float* x, const float* dy, float* dx, const f
     const int tiles = B * ((T + kSQT - 1) / kSQT), M = B * T;
     float* du = ws;
     float* ds = ws + (size_t)M * kHS * F;
-    const int pg = tiles < 2 * sms ? tiles : 2 * sms;
+    const int pg = tiles < 6 * sms ? tiles : 6 * sms;  // persistent row kernels: 6 CTAs (48 warps) per SM hide the load latency
     cudaFuncSetAttribute(unsqueeze_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * kSQT * kHS * F * 4));
     unsqueeze_bwd_kernel<<<pg, 256, (size_t)2 * kSQT * kHS * F * 4, st>>>(dy, u, du, B, F, T, Wun, bun, dWun, dbun);
     NBSS_LAUNCH_CHECK();

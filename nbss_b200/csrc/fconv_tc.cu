@@ -117,7 +117,7 @@ struct FcFwdArgs {
 };
 
 template <int FMT>
-__global__ void __launch_bounds__(256, 1) fconv_tc_fwd_kernel(FcFwdArgs a) {
+__global__ void __launch_bounds__(256, 2) fconv_tc_fwd_kernel(FcFwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const FcGeom g = a.g;
     unsigned char* tile = smem;
@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_fwd_kernel(FcFwdArgs a) {
     uint64_t* bar_w = bar_mma + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    const uint32_t ncols = g.nt * 96 <= 256 ? 256u : 512u;  // 256 columns let two CTAs share an SM (one frame per group)
+    if (warp == 0) tmem_alloc(tmem_slot, ncols);
     if (tid == 0) {
         mbar_init(bar_mma, 1);
         mbar_init(bar_w, 1);
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_fwd_kernel(FcFwdArgs a) {
         tc_fence_before();
         __syncthreads();
     }
-    if (warp == 0) tmem_dealloc(tmem, 512);
+    if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
 struct FcBwdArgs {
@@ -512,13 +513,16 @@ extern "C" int nbss_fconv_tc_fwd(const float* x, float* y, int B, int F, int T, 
     if (B < 1 || F < 1 || T < 1) return NBSS_ERR_SHAPE;
     if (fmt != FMT_F16 && fmt != FMT_BF16) return NBSS_ERR_UNSUPPORTED;
     FcFwdArgs a{x, y, {}, lnw, lnb, bias, slope, (const unsigned char*)img, err};
-    if (!fc_geom(a.g, B, F, T, 5, 4)) return NBSS_ERR_UNSUPPORTED;
+    // one frame (2 M-tiles) per group: 98 KB of shared memory and 256 TMEM columns, so two CTAs are resident per SM and
+    // one stages / stores while the other issues MMAs
+    if (!fc_geom(a.g, B, F, T, 2, 1) && !fc_geom(a.g, B, F, T, 5, 4)) return NBSS_ERR_UNSUPPORTED;
     const size_t smem = (size_t)12 * a.g.cs + FC_IMG_BYTES + 384 * 4 + 64;
     if (smem > 227 * 1024) return NBSS_ERR_UNSUPPORTED;
     auto kern = (fmt == FMT_F16) ? fconv_tc_fwd_kernel<FMT_F16> : fconv_tc_fwd_kernel<FMT_BF16>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    const int grid = a.g.ngroups < fc_sms() ? a.g.ngroups : fc_sms();
+    const int per_sm = (smem <= 110 * 1024 && a.g.nt * 96 <= 256) ? 2 : 1;
+    const int grid = a.g.ngroups < per_sm * fc_sms() ? a.g.ngroups : per_sm * fc_sms();
     kern<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;

@@ -108,6 +108,9 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
                    id96 = make_idesc(FMT, 128, 96, 0, 0);
     uint32_t ph_mma = 0, ph_w0 = 0, ph_w1 = 0;
     const float inv_n = 1.f / (float)(kGC * T);
+    // LayerNorm affine gradients: lane l < 24 owns channels 4l..4l+3 in the warp-per-frame phase
+    float4 lng4 = make_float4(0, 0, 0, 0), dlng4 = lng4, dlnb4 = lng4;
+    if (lane < 24) lng4 = *reinterpret_cast<const float4*>(s_lng + 4 * lane);
 
     auto wait_mma = [&]() {
         __syncwarp();
@@ -286,76 +289,35 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         ph_w0 ^= 1;
         wait_mma();
         {
-            // this thread owns 48 of the 96 channels of its frame; the two halves exchange their partial row sums
-            const float2 st = valid ? __ldg(reinterpret_cast<const float2*>(a.ln_stats + 2 * grow)) : make_float2(0.f, 0.f);
-            const float* xr = a.x + grow * kH;
-            const int c48 = 48 * hf;
-            float m1 = 0.f, m2 = 0.f;
+            // E5a: thread = (frame, channel half): d ln (fp32) staged into the dead G tile with 4-float chunks
 #pragma unroll 1
-            for (int c0 = c48; c0 < c48 + 48; c0 += 16) {
+            for (int c0 = 48 * hf; c0 < 48 * hf + 48; c0 += 16) {
                 uint32_t r[16];
                 tmem_ld16(tacc + c0, r);
                 tmem_ld_wait();
-                if (valid) {
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        const float4 xv = __ldg(reinterpret_cast<const float4*>(xr + c0) + j4);
-                        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float dzg = __uint_as_float(r[4 * j4 + e]) * s_lng[c0 + 4 * j4 + e];
-                            m1 += dzg;
-                            m2 += dzg * (xs[e] - st.x) * st.y;
-                        }
-                    }
-                }
+                for (int j4 = 0; j4 < 4; ++j4)
+                    *reinterpret_cast<float4*>(hrow + (c0 / 4 + j4) * kCS) =
+                        make_float4(__uint_as_float(r[4 * j4 + 0]), __uint_as_float(r[4 * j4 + 1]), __uint_as_float(r[4 * j4 + 2]),
+                                    __uint_as_float(r[4 * j4 + 3]));
             }
-            xch[tid] = make_float2(m1, m2);
+            tc_fence_before();
             __syncthreads();
-            {
-                const float2 o = xch[tid ^ 256];
-                m1 = (m1 + o.x) * (1.f / kH);
-                m2 = (m2 + o.y) * (1.f / kH);
-            }
-#pragma unroll 1
-            for (int c0 = c48; c0 < c48 + 48; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(tacc + c0, r);
-                tmem_ld_wait();
-                float dzv[16], dzx[16];
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    float4 xv = make_float4(0, 0, 0, 0), dv = xv;
-                    if (valid) {
-                        xv = __ldg(reinterpret_cast<const float4*>(xr + c0) + j4);
-                        dv = __ldg(reinterpret_cast<const float4*>(a.dy + grow * kH + c0) + j4);
-                    }
-                    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-                    const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
-                    float o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float dz = valid ? __uint_as_float(r[4 * j4 + e]) : 0.f;
-                        const float xh = (xs[e] - st.x) * st.y;
-                        dzv[4 * j4 + e] = dz;
-                        dzx[4 * j4 + e] = dz * xh;
-                        o[e] = ds[e] + st.y * (dz * s_lng[c0 + 4 * j4 + e] - m1 - xh * m2);
-                    }
-                    if (valid) reinterpret_cast<float4*>(a.dx + grow * kH + c0)[j4] = make_float4(o[0], o[1], o[2], o[3]);
-                }
-                const float sw = warp_colsum16(dzx, lane), sb = warp_colsum16(dzv, lane);
-                if (!(lane & 1)) {
-                    atomicAdd(acc + 384 + c0 + (lane >> 1), sw);
-                    atomicAdd(acc + 480 + c0 + (lane >> 1), sb);
-                }
-            }
+            // E5b: warp per frame: LayerNorm backward + residual, coalesced
+            ln_bwd_rows(hbuf, kCS, 1, a.x + (size_t)slab * T * kH, dys, a.dx + (size_t)slab * T * kH, a.ln_stats + (size_t)slab * T * 2, T,
+                        lng4, dlng4, dlnb4, warp, lane, kFfnBwdThreads / 32);
         }
         tc_fence_before();
         __syncthreads();
     }
     // flush the affine-parameter gradients
     for (int i = tid; i < 192; i += kFfnBwdThreads) { atomicAdd(a.d_gnw + i, acc[i]); atomicAdd(a.d_gnb + i, acc[192 + i]); }
-    for (int i = tid; i < 96; i += kFfnBwdThreads) { atomicAdd(a.d_lnw + i, acc[384 + i]); atomicAdd(a.d_lnb + i, acc[480 + i]); }
+    if (lane < 24) {
+        atomicAdd(a.d_lnw + 4 * lane + 0, dlng4.x); atomicAdd(a.d_lnw + 4 * lane + 1, dlng4.y);
+        atomicAdd(a.d_lnw + 4 * lane + 2, dlng4.z); atomicAdd(a.d_lnw + 4 * lane + 3, dlng4.w);
+        atomicAdd(a.d_lnb + 4 * lane + 0, dlnb4.x); atomicAdd(a.d_lnb + 4 * lane + 1, dlnb4.y);
+        atomicAdd(a.d_lnb + 4 * lane + 2, dlnb4.z); atomicAdd(a.d_lnb + 4 * lane + 3, dlnb4.w);
+    }
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 

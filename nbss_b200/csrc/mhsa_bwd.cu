@@ -307,6 +307,8 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a
     const uint32_t id96 = make_idesc(FMT_G, 128, 96, 0, 0);
     uint32_t ph = 0, ph_ld = 0;
     bool wready = false;
+    float4 lng4 = make_float4(0, 0, 0, 0), dlng4 = lng4, dlnb4 = lng4;
+    if (lane < 24) lng4 = *reinterpret_cast<const float4*>(s_lng + 4 * lane);
     for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
         const size_t row0 = (size_t)slab * T, grow = row0 + t;
         if (tid == 0) bulk_load_chunks(at, kCS, 0, a.dqkv + tile_off(slab, 36, T, 0, 0), 36, T, bar_ld);
@@ -326,73 +328,32 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a
         mbar_wait(bar_mma, ph, a.err);
         ph ^= 1;
         tc_fence_after();
-        // LayerNorm backward (same arithmetic as ffn_bwd E5): this thread owns 48 of the 96 channels of its frame
-        const float2 st = valid ? __ldg(reinterpret_cast<const float2*>(a.ln_stats + 2 * grow)) : make_float2(0.f, 0.f);
-        const float* xr = a.x + grow * kH;
-        const int c48 = 48 * hf;
-        float m1 = 0.f, m2 = 0.f;
+        // thread = (frame, channel half): d ln (fp32) staged into the dead dQKV tile (4-float chunks), then one warp per
+        // frame does the LayerNorm backward + residual with coalesced global traffic (slab.cuh: ln_bwd_rows)
 #pragma unroll 1
-        for (int c0 = c48; c0 < c48 + 48; c0 += 16) {
+        for (int c0 = 48 * hf; c0 < 48 * hf + 48; c0 += 16) {
             uint32_t r[16];
             tmem_ld16(tacc + c0, r);
             tmem_ld_wait();
-            if (valid) {
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    const float4 xv = __ldg(reinterpret_cast<const float4*>(xr + c0) + j4);
-                    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float dzg = __uint_as_float(r[4 * j4 + e]) * s_lng[c0 + 4 * j4 + e];
-                        m1 += dzg;
-                        m2 += dzg * (xs[e] - st.x) * st.y;
-                    }
-                }
-            }
-        }
-        xch[tid] = make_float2(m1, m2);
-        __syncthreads();
-        {
-            const float2 o = xch[tid ^ 256];
-            m1 = (m1 + o.x) * (1.f / kH);
-            m2 = (m2 + o.y) * (1.f / kH);
-        }
-#pragma unroll 1
-        for (int c0 = c48; c0 < c48 + 48; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(tacc + c0, r);
-            tmem_ld_wait();
-            float dzv[16], dzx[16];
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-                float4 xv = make_float4(0, 0, 0, 0), dv = xv;
-                if (valid) {
-                    xv = __ldg(reinterpret_cast<const float4*>(xr + c0) + j4);
-                    dv = __ldg(reinterpret_cast<const float4*>(a.dy + grow * kH + c0) + j4);
-                }
-                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-                const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
-                float o[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float dz = valid ? __uint_as_float(r[4 * j4 + e]) : 0.f;
-                    const float xh = (xs[e] - st.x) * st.y;
-                    dzv[4 * j4 + e] = dz;
-                    dzx[4 * j4 + e] = dz * xh;
-                    o[e] = ds[e] + st.y * (dz * s_lng[c0 + 4 * j4 + e] - m1 - xh * m2);
-                }
-                if (valid) reinterpret_cast<float4*>(a.dx + grow * kH + c0)[j4] = make_float4(o[0], o[1], o[2], o[3]);
-            }
-            const float sw = warp_colsum16(dzx, lane), sb = warp_colsum16(dzv, lane);
-            if (!(lane & 1)) {
-                atomicAdd(acc + c0 + (lane >> 1), sw);
-                atomicAdd(acc + 96 + c0 + (lane >> 1), sb);
-            }
+            for (int j4 = 0; j4 < 4; ++j4)
+                *reinterpret_cast<float4*>(at + (size_t)(c0 / 4 + j4) * kCS + t * 16) =
+                    make_float4(__uint_as_float(r[4 * j4 + 0]), __uint_as_float(r[4 * j4 + 1]), __uint_as_float(r[4 * j4 + 2]),
+                                __uint_as_float(r[4 * j4 + 3]));
         }
         tc_fence_before();
         __syncthreads();
+        ln_bwd_rows(at, kCS, 0, a.x + row0 * kH, a.dy + row0 * kH, a.dx + row0 * kH, a.ln_stats + row0 * 2, T, lng4, dlng4, dlnb4, warp, lane,
+                    kMbThreads / 32);
+        tc_fence_before();
+        __syncthreads();
     }
-    for (int i = tid; i < 96; i += kMbThreads) { atomicAdd(a.d_lnw + i, acc[i]); atomicAdd(a.d_lnb + i, acc[96 + i]); }
+    if (lane < 24) {
+        atomicAdd(a.d_lnw + 4 * lane + 0, dlng4.x); atomicAdd(a.d_lnw + 4 * lane + 1, dlng4.y);
+        atomicAdd(a.d_lnw + 4 * lane + 2, dlng4.z); atomicAdd(a.d_lnw + 4 * lane + 3, dlng4.w);
+        atomicAdd(a.d_lnb + 4 * lane + 0, dlnb4.x); atomicAdd(a.d_lnb + 4 * lane + 1, dlnb4.y);
+        atomicAdd(a.d_lnb + 4 * lane + 2, dlnb4.z); atomicAdd(a.d_lnb + 4 * lane + 3, dlnb4.w);
+    }
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 

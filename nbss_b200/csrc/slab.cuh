@@ -154,6 +154,37 @@ __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
     return v[0];
 }
 
+// LayerNorm backward + residual, one warp per frame, fully coalesced.  `tile` holds d z (gradient wrt the LN output) as fp32
+// staged by the thread-per-frame TMEM epilogue with 4-float chunks: addr = tile + chunk*cs + (r + row_off)*16.
+// Lane l < 24 owns channels 4l..4l+3; it accumulates d gamma / d beta in registers across frames (and slabs).
+__device__ __forceinline__ void ln_bwd_rows(const unsigned char* tile, uint32_t cs, int row_off, const float* __restrict__ xs,
+                                            const float* __restrict__ dys, float* __restrict__ dxs,
+                                            const float* __restrict__ stats, int T, const float4 g4, float4& dg4, float4& db4,
+                                            int warp, int lane, int nwarps) {
+    const bool act = lane < 24;
+#pragma unroll 2
+    for (int r = warp; r < T; r += nwarps) {
+        float4 dz = make_float4(0, 0, 0, 0), xv = dz, dv = dz;
+        if (act) {
+            dz = *reinterpret_cast<const float4*>(tile + (size_t)lane * cs + (r + row_off) * 16);
+            xv = __ldg(reinterpret_cast<const float4*>(xs + (size_t)r * kH) + lane);
+            dv = __ldg(reinterpret_cast<const float4*>(dys + (size_t)r * kH) + lane);
+        }
+        const float2 st = __ldg(reinterpret_cast<const float2*>(stats + 2 * r));
+        const float4 xh = act ? make_float4((xv.x - st.x) * st.y, (xv.y - st.x) * st.y, (xv.z - st.x) * st.y, (xv.w - st.x) * st.y)
+                              : make_float4(0, 0, 0, 0);
+        const float4 dzg = make_float4(dz.x * g4.x, dz.y * g4.y, dz.z * g4.z, dz.w * g4.w);
+        const float m1 = warp_sum(dzg.x + dzg.y + dzg.z + dzg.w) * (1.f / kH);
+        const float m2 = warp_sum(dzg.x * xh.x + dzg.y * xh.y + dzg.z * xh.z + dzg.w * xh.w) * (1.f / kH);
+        dg4 = make_float4(dg4.x + dz.x * xh.x, dg4.y + dz.y * xh.y, dg4.z + dz.z * xh.z, dg4.w + dz.w * xh.w);
+        db4 = make_float4(db4.x + dz.x, db4.y + dz.y, db4.z + dz.z, db4.w + dz.w);
+        if (act)
+            reinterpret_cast<float4*>(dxs + (size_t)r * kH)[lane] =
+                make_float4(dv.x + st.y * (dzg.x - m1 - xh.x * m2), dv.y + st.y * (dzg.y - m1 - xh.y * m2),
+                            dv.z + st.y * (dzg.z - m1 - xh.z * m2), dv.w + st.y * (dzg.w - m1 - xh.w * m2));
+    }
+}
+
 // Block-wide sum of NV per-thread values (256 threads). `red` is smem scratch of 8*NV floats. Result broadcast.
 template <int NV>
 __device__ __forceinline__ void block_sum(float (&v)[NV], float* red, int warp, int lane) {

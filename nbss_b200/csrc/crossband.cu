@@ -426,14 +426,16 @@ __global__ void __launch_bounds__(256) unsqueeze_bwd_kernel(const float* __restr
             if (act) dyv = ld_f4(dy + (((size_t)b * F + f) * T + t) * kH + 4 * lane);
             const float dv[4] = {dyv.x * silu_grad(a[0]), dyv.y * silu_grad(a[1]), dyv.z * silu_grad(a[2]), dyv.w * silu_grad(a[3])};
             dbu = make_float4(dbu.x + dv[0], dbu.y + dv[1], dbu.z + dv[2], dbu.w + dv[3]);
+            float pg[kHS];
 #pragma unroll
             for (int g = 0; g < kHS; ++g) {
                 float p = 0.f;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) { p = fmaf(dv[c], wun[c][g], p); dwun[c][g] = fmaf(dv[c], uv[g], dwun[c][g]); }
-                p = warp_sum(p);
-                if (lane == g) dut[(tt * kHS + g) * F + f] = p;
+                pg[g] = p;
             }
+            const float tot = warp_reduce8(pg, lane);  // lane holds group lane >> 2
+            if ((lane & 3) == 0) dut[(tt * kHS + (lane >> 2)) * F + f] = tot;
         }
         __syncthreads();
         for (int i = tid; i < kSQT * kHS * F; i += 256) {
@@ -635,7 +637,7 @@ extern "C" int nbss_full_bwd(const float* x, const float* dy, float* dx, const f
     const int tiles = B * ((T + kSQT - 1) / kSQT), M = B * T;
     float* du = ws;
     float* ds = ws + (size_t)M * kHS * F;
-    const int pg = tiles < 6 * sms ? tiles : 6 * sms;  // persistent row kernels: 6 CTAs (48 warps) per SM hide the load latency
+    const int pg = tiles < 4 * sms ? tiles : 4 * sms;  // persistent row kernels: 4 CTAs (32 warps) per SM
     cudaFuncSetAttribute(unsqueeze_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * kSQT * kHS * F * 4));
     unsqueeze_bwd_kernel<<<pg, 256, (size_t)2 * kSQT * kHS * F * 4, st>>>(dy, u, du, B, F, T, Wun, bun, dWun, dbun);
     NBSS_LAUNCH_CHECK();

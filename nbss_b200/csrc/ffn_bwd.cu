@@ -139,33 +139,43 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         __syncthreads();
     };
     // g = D * SiLU'(c), s = SiLU(c): the three plain activation epilogues
-    auto silu_epilogue = [&](const unsigned char* csave, unsigned char* gout, unsigned char* sout, int slab) {
-#pragma unroll 1
-        for (int c0 = cb; c0 < cb + 96; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(tacc + c0, r);
-            tmem_ld_wait();
-            float c[16], g[16];
+    // one 16-column block: g = D * SiLU'(c) -> G tile + global, s = SiLU(c) -> global
+    auto silu_block = [&](const uint32_t (&r)[16], int c0, const unsigned char* csave, unsigned char* gout, unsigned char* sout, int slab) {
+        float c[16], g[16];
+        if (valid) {
+            load_h16x8(csave, slab, T, t, c0, c);
+            load_h16x8(csave, slab, T, t, c0 + 8, c + 8);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float cv = valid ? c[j] : 0.f;
+            const float sg = sigmoidf_(cv);
+            g[j] = __uint_as_float(r[j]) * sg * (1.f + cv * (1.f - sg)) * vmask;
+            c[j] = cv * sg;
+        }
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const uint4 gp = pack8<FMT>(g + 8 * cc);
             if (valid) {
-                load_h16x8(csave, slab, T, t, c0, c);
-                load_h16x8(csave, slab, T, t, c0 + 8, c + 8);
+                *reinterpret_cast<uint4*>(sout + tile_off(slab, 24, T, c0 / 8 + cc, t)) = pack8<FMT>(c + 8 * cc);
+                *reinterpret_cast<uint4*>(gout + tile_off(slab, 24, T, c0 / 8 + cc, t)) = gp;
             }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float cv = valid ? c[j] : 0.f;
-                const float sg = sigmoidf_(cv);
-                g[j] = __uint_as_float(r[j]) * sg * (1.f + cv * (1.f - sg)) * vmask;
-                c[j] = cv * sg;
-            }
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const uint4 gp = pack8<FMT>(g + 8 * cc);
-                if (valid) {
-                    *reinterpret_cast<uint4*>(sout + tile_off(slab, 24, T, c0 / 8 + cc, t)) = pack8<FMT>(c + 8 * cc);
-                    *reinterpret_cast<uint4*>(gout + tile_off(slab, 24, T, c0 / 8 + cc, t)) = gp;
-                }
-                *reinterpret_cast<uint4*>(hrow + (c0 / 8 + cc) * kCS) = gp;
-            }
+            *reinterpret_cast<uint4*>(hrow + (c0 / 8 + cc) * kCS) = gp;
+        }
+    };
+    // the three plain activation epilogues, TMEM loads software-pipelined over two register buffers
+    auto silu_epilogue = [&](const unsigned char* csave, unsigned char* gout, unsigned char* sout, int slab) {
+        uint32_t ra[16], rb[16];
+        tmem_ld16(tacc + cb, ra);
+        tmem_ld_wait();
+#pragma unroll 1
+        for (int c0 = cb; c0 < cb + 96; c0 += 32) {
+            tmem_ld16(tacc + c0 + 16, rb);
+            silu_block(ra, c0, csave, gout, sout, slab);
+            tmem_ld_wait();
+            if (c0 + 32 < cb + 96) tmem_ld16(tacc + c0 + 32, ra);
+            silu_block(rb, c0 + 16, csave, gout, sout, slab);
+            tmem_ld_wait();
         }
     };
 

@@ -120,6 +120,36 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         tc_fence_before();
         __syncthreads();
     };
+    // One 16-column block of an activation epilogue: pre = D + bias (optionally saved as fp16), H = SiLU(pre).
+    auto act_block = [&](const uint32_t (&r)[16], int c0, const float* bias, unsigned char* save, int slab) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + bias[c0 + j];
+        if (save && valid) {
+            *reinterpret_cast<uint4*>(save + tile_off(slab, 24, T, c0 / 8, t)) = pack8<FMT_F16>(v);
+            *reinterpret_cast<uint4*>(save + tile_off(slab, 24, T, c0 / 8 + 1, t)) = pack8<FMT_F16>(v + 8);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = silu(v[j]) * vmask;  // branch-free: keeps the chains interleaved
+        *reinterpret_cast<uint4*>(hrow + (c0 / 8) * kCS) = pack8<FMT>(v);
+        *reinterpret_cast<uint4*>(hrow + (c0 / 8 + 1) * kCS) = pack8<FMT>(v + 8);
+    };
+    // Activation epilogue over this thread's 96 channels with the TMEM loads software-pipelined: the tcgen05.ld of
+    // block i+1 is in flight while block i is processed (two register buffers).
+    auto act_epilogue = [&](const float* bias, unsigned char* save, int slab) {
+        uint32_t ra[16], rb[16];
+        tmem_ld16(tacc + cb, ra);
+        tmem_ld_wait();
+#pragma unroll 1
+        for (int c0 = cb; c0 < cb + 96; c0 += 32) {
+            tmem_ld16(tacc + c0 + 16, rb);
+            act_block(ra, c0, bias, save, slab);
+            tmem_ld_wait();
+            if (c0 + 32 < cb + 96) tmem_ld16(tacc + c0 + 32, ra);
+            act_block(rb, c0 + 16, bias, save, slab);
+            tmem_ld_wait();
+        }
+    };
 
     for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
         const float* xs = a.x + (size_t)slab * T * kH;
@@ -145,36 +175,12 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         tc_fence_after();
         if (tid == 0) load_image(ws0, a.img + IMG_WC2, IMG_WC_BYTES, bar_w0);
         // ---- E1: a1 = D + b1; H = SiLU(a1)
-#pragma unroll 1
-        for (int c0 = cb; c0 < cb + 96; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tacc + c0, r);
-            tmem_ld_wait();
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_b1[c0 + j];
-            if (a.save_a1 && valid) save_f16(a.save_a1, slab, T, t, c0, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = silu(v[j]) * vmask;  // branch-free: keeps the 32 chains interleaved
-            store_h<FMT>(hrow, c0, v);
-        }
+        act_epilogue(s_b1, a.save_a1, slab);
         end_epilogue();
         // ---- P2: conv1 ; E2: c1 = D + bc1; H = SiLU(c1)
         conv_phase(w1a, bar_w1, ph_w1);
         if (tid == 0) load_image(ws1, a.img + IMG_WC3, IMG_WC_BYTES, bar_w1);
-#pragma unroll 1
-        for (int c0 = cb; c0 < cb + 96; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tacc + c0, r);
-            tmem_ld_wait();
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bc[c0 + j];
-            if (a.save_c1 && valid) save_f16(a.save_c1, slab, T, t, c0, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = silu(v[j]) * vmask;  // branch-free: keeps the 32 chains interleaved
-            store_h<FMT>(hrow, c0, v);
-        }
+        act_epilogue(s_bc, a.save_c1, slab);
         end_epilogue();
         // ---- P3: conv2 ; E3: c2 = D + bc2; GroupNorm over (24 ch x T) per group; H = SiLU(GN(c2))
         conv_phase(w0a, bar_w0, ph_w0);
@@ -256,19 +262,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         end_epilogue();
         // ---- P4: conv3 ; E4: c3 = D + bc3; H = SiLU(c3)
         conv_phase(w1a, bar_w1, ph_w1);
-#pragma unroll 1
-        for (int c0 = cb; c0 < cb + 96; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tacc + c0, r);
-            tmem_ld_wait();
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bc[384 + c0 + j];
-            if (a.save_c3 && valid) save_f16(a.save_c3, slab, T, t, c0, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = silu(v[j]) * vmask;  // branch-free: keeps the 32 chains interleaved
-            store_h<FMT>(hrow, c0, v);
-        }
+        act_epilogue(s_bc + 384, a.save_c3, slab);
         end_epilogue();
         // ---- P5: pw2 ; E5: y = x + D + b2
         if (tid == 0) {

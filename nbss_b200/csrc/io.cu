@@ -245,12 +245,22 @@ __global__ void __launch_bounds__(192) encoder_wgrad_kernel(const float* __restr
             xs[i] = (t >= 0 && t < T) ? x[((size_t)slab * T + t) * CIN + i % CIN] : 0.f;
         }
         __syncthreads();
-        for (int r = half; r < TT; r += 2) {
-            if (t0 + r >= T) break;
-            const float g = dy[((size_t)slab * T + t0 + r) * kH + co];
-            db += g;
+        // four frames in flight per thread: the dy loads of a batch are issued before their FMAs
+        for (int r0 = half; r0 < TT; r0 += 8) {
+            float g[4];
 #pragma unroll
-            for (int i = 0; i < K * CIN; ++i) dw[i] = fmaf(g, xs[r * CIN + i], dw[i]);
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + 2 * u;
+                g[u] = (r < TT && t0 + r < T) ? dy[((size_t)slab * T + t0 + r) * kH + co] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + 2 * u;
+                if (r >= TT) break;
+                db += g[u];
+#pragma unroll
+                for (int i = 0; i < K * CIN; ++i) dw[i] = fmaf(g[u], xs[r * CIN + i], dw[i]);
+            }
         }
     }
 #pragma unroll

@@ -162,7 +162,7 @@ __device__ __forceinline__ void ln_bwd_rows(const unsigned char* tile, uint32_t 
                                             const float* __restrict__ stats, int T, const float4 g4, float4& dg4, float4& db4,
                                             int warp, int lane, int nwarps) {
     const bool act = lane < 24;
-#pragma unroll 2
+#pragma unroll 4
     for (int r = warp; r < T; r += nwarps) {
         float4 dz = make_float4(0, 0, 0, 0), xv = dz, dv = dz;
         if (act) {

@@ -22,6 +22,7 @@ struct WgJob {
     const float *ln_w, *ln_b;
     int g_fp32, g_cols, g_c0, g_chunks, g_alloc;  // g_fp32: fp32 [n,96]; else 16-bit [n,g_cols], features [g_c0, g_c0+8*g_chunks)
     int a_ln, a_cols, a_c0, a_chunks, a_row_off;  // a_ln: fp32 x [n,96] through LayerNorm; ones chunks at [a_chunks, a_chunks+2)
+    int dbl;                                      // both operands arrive by TMA: two tile sets, loads of slab i+1 overlap MMAs of slab i
     int nmma, nout;
     WgMma mma[6];
     WgOut out[8];
@@ -44,18 +45,24 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(WgArgs args) {
     unsigned char* at = smem + (size_t)J.g_alloc * kCS;
     const int a_alloc = J.a_chunks + 2;
     const int n_bulk = (J.g_fp32 ? 0 : 1) + (J.a_ln ? 0 : 1);  // operands arriving by TMA bulk copy (one arrive each)
+    const uint32_t set_bytes = (uint32_t)(J.g_alloc + a_alloc) * kCS;
+    const int nsets = J.dbl ? 2 : 1;
+    __shared__ uint64_t bar_ld2;  // load barrier of the second tile set
+    __shared__ int s_nslabs;
 
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
     if (tid == 0) {
         mbar_init(&bar_mma, 1);
         mbar_init(&bar_ld, n_bulk > 0 ? n_bulk : 1);
+        mbar_init(&bar_ld2, 2);
         fence_mbar_init();
     }
     if (J.a_ln) for (int i = tid; i < 96; i += 256) { s_ln[i] = J.ln_w[i]; s_ln[96 + i] = J.ln_b[i]; }
-    for (int i = tid; i < (int)((J.g_alloc + J.a_chunks) * kCS / 16); i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    {
+    for (int set = 0; set < nsets; ++set) {
+        unsigned char* base = smem + (size_t)set * set_bytes;
+        for (int i = tid; i < (int)((J.g_alloc + J.a_chunks) * kCS / 16); i += 256) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
         const uint32_t one2 = pack16<FMT_A>(1.f, 1.f);
-        uint4* ones = reinterpret_cast<uint4*>(at + (size_t)J.a_chunks * kCS);
+        uint4* ones = reinterpret_cast<uint4*>(base + (size_t)(J.g_alloc + J.a_chunks) * kCS);
         for (int i = tid; i < (int)(2 * kCS / 16); i += 256) ones[i] = make_uint4(one2, one2, one2, one2);
     }
     fence_async_smem();
@@ -68,6 +75,54 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(WgArgs args) {
     bool first = true;
     (void)a_alloc;
 
+    auto issue_mmas = [&](uint32_t ga, uint32_t aa, bool fresh) {
+        for (int i = 0; i < J.nmma; ++i) {
+            const WgMma mm = J.mma[i];
+            const uint32_t idesc = (1u << 4) | ((uint32_t)FMT_G << 7) | ((uint32_t)FMT_A << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(mm.n >> 3) << 17) | (8u << 24);
+            uint64_t da = sdesc_mnmajor(ga + mm.a_chunk * kCS, kCS), db = sdesc_mnmajor(aa + mm.b_chunk * kCS + mm.b_row * 16, kCS);
+            for (int ks = 0; ks < 16; ++ks) {
+                umma_f16(tmem + mm.col, da, db, idesc, (fresh && ks == 0) ? 0u : 1u);
+                da += 16;  // 16 rows x 16 B >> 4
+                db += 16;
+            }
+        }
+    };
+    if (J.dbl) {
+        // ---- pipelined path (both operands by TMA): one thread drives loads and MMAs, two tile sets
+        if (tid == 0) {
+            auto issue_loads = [&](int slab, int set) {
+                unsigned char* g0 = smem + (size_t)set * set_bytes;
+                uint64_t* bar = set ? &bar_ld2 : &bar_ld;
+                bulk_load_chunks(g0, kCS, 0, reinterpret_cast<const unsigned char*>(J.g) + tile_off(slab, J.g_cols / 8, T, J.g_c0 / 8, 0),
+                                 J.g_chunks, T, bar);
+                bulk_load_chunks(g0 + (size_t)J.g_alloc * kCS, kCS, J.a_row_off,
+                                 reinterpret_cast<const unsigned char*>(J.act) + tile_off(slab, J.a_cols / 8, T, J.a_c0 / 8, 0), J.a_chunks, T, bar);
+            };
+            uint32_t phl[2] = {0, 0};
+            int k = 0;
+            if ((int)blockIdx.x < args.nslab) issue_loads(blockIdx.x, 0);
+            for (int slab = blockIdx.x; slab < args.nslab; slab += gridDim.x, ++k) {
+                const int set = k & 1, nxt = slab + gridDim.x;
+                if (k >= 1) {  // MMAs of the previous slab (other tile set) are done: its tiles may be overwritten
+                    mbar_wait(&bar_mma, ph, args.err);
+                    ph ^= 1;
+                }
+                if (nxt < args.nslab) issue_loads(nxt, set ^ 1);
+                mbar_wait(set ? &bar_ld2 : &bar_ld, phl[set], args.err);
+                phl[set] ^= 1;
+                tc_fence_after();
+                const uint32_t ga = gta + set * set_bytes;
+                issue_mmas(ga, ga + J.g_alloc * kCS, k == 0);
+                umma_commit(&bar_mma);
+            }
+            if (k >= 1) mbar_wait(&bar_mma, ph, args.err);
+            s_nslabs = k;
+        }
+        __syncthreads();
+        first = s_nslabs == 0;
+        tc_fence_after();
+    } else
     for (int slab = blockIdx.x; slab < args.nslab; slab += gridDim.x) {
         const size_t row0 = (size_t)slab * T;
         // ---- stage G and ACT: 16-bit slab-tile tensors come in by TMA bulk copies (one per chunk column), fp32
@@ -88,14 +143,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(WgArgs args) {
         if (tid == 0) {
             tc_fence_after();
             if (n_bulk > 0) { mbar_wait(&bar_ld, ph_ld, args.err); ph_ld ^= 1; }
-            for (int i = 0; i < J.nmma; ++i) {
-                const WgMma mm = J.mma[i];
-                const uint32_t idesc = (1u << 4) | ((uint32_t)FMT_G << 7) | ((uint32_t)FMT_A << 10) | (1u << 15) | (1u << 16) |
-                                       ((uint32_t)(mm.n >> 3) << 17) | (8u << 24);
-                for (int ks = 0; ks < 16; ++ks)
-                    umma_f16(tmem + mm.col, sdesc_mnmajor(gta + mm.a_chunk * kCS + 16 * ks * 16, kCS),
-                             sdesc_mnmajor(ata + mm.b_chunk * kCS + (mm.b_row + 16 * ks) * 16, kCS), idesc, (first && ks == 0) ? 0u : 1u);
-            }
+            issue_mmas(gta, ata, first);
             umma_commit(&bar_mma);
         }
         first = false;
@@ -147,7 +195,7 @@ static int wg_sms() {
 static int launch_wgrad(WgArgs& a, int njobs, int fmt_g, int fmt_a, cudaStream_t st) {
     int maxch = 0;
     for (int j = 0; j < njobs; ++j) {
-        const int ch = a.job[j].g_alloc + a.job[j].a_chunks + 2;
+        const int ch = (a.job[j].g_alloc + a.job[j].a_chunks + 2) * (a.job[j].dbl ? 2 : 1);
         maxch = ch > maxch ? ch : maxch;
     }
     const size_t smem = (size_t)maxch * kCS;
@@ -225,9 +273,10 @@ extern "C" int nbss_ffn_wgrad(const float* x, const float* dy, int nslab, int T,
         a.nslab = nslab; a.T = T; a.err = err;
         for (int c = 0; c < 3; ++c) {
             WgJob& j = a.job[c];
-            j.g = gs[c]; j.g_fp32 = 0; j.g_cols = 192; j.g_c0 = half ? 64 : 0; j.g_chunks = 16; j.g_alloc = 16;
+            j.g = gs[c]; j.g_fp32 = 0; j.g_cols = 192; j.g_c0 = 96 * half; j.g_chunks = 12; j.g_alloc = 12;  // M window rows 0..95
+            j.dbl = 1;
             j.act = as[c]; j.a_cols = 192; j.a_c0 = 96 * half; j.a_chunks = 12; j.a_row_off = 1;
-            const int l0 = half ? 32 : 0;  // TMEM lane of output channel 96*half
+            const int l0 = 0;  // TMEM lane of output channel 96*half (window starts at the half's first channel)
             for (int tap = 0; tap < 3; ++tap) {
                 add_mma(j, 0, 0, 96, 96 * tap, tap);
                 add_out(j, dWs[c] + (96 * half) * 72, 96 * tap, l0, 48, 48, 1, 0, tap);

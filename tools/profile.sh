@@ -8,7 +8,8 @@ TAG=${3:-r01}
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file gpurun_out/launches_$TAG.csv python bench.py --profile --batch $BATCH > gpurun_out/prof_launch.log 2>&1
 echo "launch list rc=$?"
-timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"$PAT" -c 12 \
-    -o gpurun_out/prof_$TAG -f python bench.py --profile --batch $BATCH > gpurun_out/prof_full.log 2>&1
+# full captures on a ONE-layer network: one step then holds exactly one launch of every kernel (fwd and bwd)
+timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"$PAT" -c 24 \
+    -o gpurun_out/prof_$TAG -f python bench.py --profile --batch $BATCH --layers 1 > gpurun_out/prof_full.log 2>&1
 echo "full capture rc=$?"
 ncu -i gpurun_out/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null

@@ -57,39 +57,43 @@ __device__ __forceinline__ void fc_stage(const FcGeom& g, const float* __restric
     const bool act = lane < 24;
     float4 gw = make_float4(0, 0, 0, 0), gb = gw;
     if (act) { gw = *reinterpret_cast<const float4*>(s_lnw + 4 * lane); gb = *reinterpret_cast<const float4*>(s_lnb + 4 * lane); }
-    const int nrows = g.nfr * g.F;
+    // rows are walked per frame slot: f = warp, warp+8, ... (4 rows in flight per warp), no integer divisions
 #pragma unroll 1
-    for (int i0 = warp; i0 < nrows; i0 += 32) {
-        float4 v[4], w[4];
+    for (int tt = 0; tt < g.nfr; ++tt) {
+        const int t = t0 + tt;
+        const bool tok = t < g.T;
+#pragma unroll 1
+        for (int f0 = warp; f0 < g.F; f0 += 32) {
+            float4 v[4], w[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int i = i0 + 8 * j;
-            const int tt = i / g.F, f = i % g.F, t = t0 + tt;
-            const bool ok = act && i < nrows && t < g.T;
-            const size_t off = (((size_t)b * g.F + f) * g.T + t) * kH;
-            v[j] = ok ? __ldg(reinterpret_cast<const float4*>(x + off) + lane) : make_float4(0, 0, 0, 0);
-            w[j] = (ok && dy) ? __ldg(reinterpret_cast<const float4*>(dy + off) + lane) : make_float4(0, 0, 0, 0);
-        }
+            for (int j = 0; j < 4; ++j) {
+                const int f = f0 + 8 * j;
+                const bool ok = act && f < g.F && tok;
+                const size_t off = (((size_t)b * g.F + f) * g.T + t) * kH;
+                v[j] = ok ? __ldg(reinterpret_cast<const float4*>(x + off) + lane) : make_float4(0, 0, 0, 0);
+                w[j] = (ok && dy) ? __ldg(reinterpret_cast<const float4*>(dy + off) + lane) : make_float4(0, 0, 0, 0);
+            }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int i = i0 + 8 * j;
-            if (i >= nrows) continue;
-            const int tt = i / g.F, f = i % g.F, t = t0 + tt, p = 2 + tt * g.FP + f;
-            const float s = warp_sum(v[j].x + v[j].y + v[j].z + v[j].w);
-            const float mean = s * (1.f / kH);
-            const float4 d = act ? make_float4(v[j].x - mean, v[j].y - mean, v[j].z - mean, v[j].w - mean) : make_float4(0, 0, 0, 0);
-            const float qv = warp_sum(d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w);
-            const float rstd = rsqrtf(qv * (1.f / kH) + 1e-5f);
-            if (s_stats && lane == 0) s_stats[p] = make_float2(mean, rstd);
-            if (act) {
-                uint2 pk = make_uint2(0u, 0u);
-                if (t < g.T)
-                    pk = make_uint2(pack16<FMT>(d.x * rstd * gw.x + gb.x, d.y * rstd * gw.y + gb.y),
-                                    pack16<FMT>(d.z * rstd * gw.z + gb.z, d.w * rstd * gw.w + gb.w));
-                *reinterpret_cast<uint2*>(tile + (size_t)(lane >> 1) * g.cs + p * 16 + (lane & 1) * 8) = pk;
-                if (dytile)  // upstream gradient of the same row, 16-bit, same slot of the second tile
-                    *reinterpret_cast<uint2*>(dytile + (size_t)(lane >> 1) * g.cs + p * 16 + (lane & 1) * 8) =
-                        make_uint2(pack16<FMT>(w[j].x, w[j].y), pack16<FMT>(w[j].z, w[j].w));
+            for (int j = 0; j < 4; ++j) {
+                const int f = f0 + 8 * j;
+                if (f >= g.F) continue;
+                const int p = 2 + tt * g.FP + f;
+                const float s = warp_sum(v[j].x + v[j].y + v[j].z + v[j].w);
+                const float mean = s * (1.f / kH);
+                const float4 d = act ? make_float4(v[j].x - mean, v[j].y - mean, v[j].z - mean, v[j].w - mean) : make_float4(0, 0, 0, 0);
+                const float qv = warp_sum(d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w);
+                const float rstd = rsqrtf(qv * (1.f / kH) + 1e-5f);
+                if (s_stats && lane == 0) s_stats[p] = make_float2(mean, rstd);
+                if (act) {
+                    uint2 pk = make_uint2(0u, 0u);
+                    if (tok)
+                        pk = make_uint2(pack16<FMT>(d.x * rstd * gw.x + gb.x, d.y * rstd * gw.y + gb.y),
+                                        pack16<FMT>(d.z * rstd * gw.z + gb.z, d.w * rstd * gw.w + gb.w));
+                    *reinterpret_cast<uint2*>(tile + (size_t)(lane >> 1) * g.cs + p * 16 + (lane & 1) * 8) = pk;
+                    if (dytile)  // upstream gradient of the same row, 16-bit, same slot of the second tile
+                        *reinterpret_cast<uint2*>(dytile + (size_t)(lane >> 1) * g.cs + p * 16 + (lane & 1) * 8) =
+                            make_uint2(pack16<FMT>(w[j].x, w[j].y), pack16<FMT>(w[j].z, w[j].w));
+                }
             }
         }
     }
@@ -191,28 +195,30 @@ __global__ void __launch_bounds__(256, 2) fconv_tc_fwd_kernel(FcFwdArgs a) {
         // epilogue 2: warp per (frame, f) row, coalesced: y = x + branch
         {
             const bool act = lane < 24;
-            const int nrows = g.nfr * g.F;
 #pragma unroll 1
-            for (int i0 = warp; i0 < nrows; i0 += 32) {
-                float4 xv[4];
+            for (int tt = 0; tt < g.nfr; ++tt) {
+                const int t = t0 + tt;
+                if (t >= g.T) break;
+#pragma unroll 1
+                for (int f0 = warp; f0 < g.F; f0 += 32) {
+                    float4 xv[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = i0 + 8 * j;
-                    const int tt = i / g.F, f = i % g.F, t = t0 + tt;
-                    xv[j] = (act && i < nrows && t < g.T) ? __ldg(reinterpret_cast<const float4*>(a.x + (((size_t)b * g.F + f) * g.T + t) * kH) + lane)
-                                                          : make_float4(0, 0, 0, 0);
-                }
+                    for (int j = 0; j < 4; ++j) {
+                        const int f = f0 + 8 * j;
+                        xv[j] = (act && f < g.F) ? __ldg(reinterpret_cast<const float4*>(a.x + (((size_t)b * g.F + f) * g.T + t) * kH) + lane)
+                                                 : make_float4(0, 0, 0, 0);
+                    }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = i0 + 8 * j;
-                    const int tt = i / g.F, f = i % g.F, t = t0 + tt;
-                    if (!(act && i < nrows && t < g.T)) continue;
-                    const uint2 pk = *reinterpret_cast<const uint2*>(tile + (size_t)(lane >> 1) * g.cs + (2 + tt * g.FP + f) * 16 + (lane & 1) * 8);
-                    float b0, b1, b2, b3;
-                    unpack16<FMT>(pk.x, b0, b1);
-                    unpack16<FMT>(pk.y, b2, b3);
-                    reinterpret_cast<float4*>(a.y + (((size_t)b * g.F + f) * g.T + t) * kH)[lane] =
-                        make_float4(xv[j].x + b0, xv[j].y + b1, xv[j].z + b2, xv[j].w + b3);
+                    for (int j = 0; j < 4; ++j) {
+                        const int f = f0 + 8 * j;
+                        if (!(act && f < g.F)) continue;
+                        const uint2 pk = *reinterpret_cast<const uint2*>(tile + (size_t)(lane >> 1) * g.cs + (2 + tt * g.FP + f) * 16 + (lane & 1) * 8);
+                        float b0, b1, b2, b3;
+                        unpack16<FMT>(pk.x, b0, b1);
+                        unpack16<FMT>(pk.y, b2, b3);
+                        reinterpret_cast<float4*>(a.y + (((size_t)b * g.F + f) * g.T + t) * kH)[lane] =
+                            make_float4(xv[j].x + b0, xv[j].y + b1, xv[j].z + b2, xv[j].w + b3);
+                    }
                 }
             }
         }
@@ -408,42 +414,44 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
         __syncthreads();
         // ---- E-B2: warp per (frame, f) row, coalesced: LayerNorm backward + residual; d gamma / d beta per lane
         {
-            const int nrows = g.nfr * g.F;
 #pragma unroll 1
-            for (int i0 = warp; i0 < nrows; i0 += 32) {
-                float4 xv[4], dv[4];
+            for (int tt = 0; tt < g.nfr; ++tt) {
+                const int t = t0 + tt;
+                if (t >= g.T) break;
+#pragma unroll 1
+                for (int f0 = warp; f0 < g.F; f0 += 32) {
+                    float4 xv[4], dv[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = i0 + 8 * j;
-                    const int tt = i / g.F, f = i % g.F, t = t0 + tt;
-                    const bool ok = act24 && i < nrows && t < g.T;
-                    const size_t off = (((size_t)b * g.F + f) * g.T + t) * kH;
-                    xv[j] = ok ? __ldg(reinterpret_cast<const float4*>(a.x + off) + lane) : make_float4(0, 0, 0, 0);
-                    dv[j] = ok ? __ldg(reinterpret_cast<const float4*>(a.dy + off) + lane) : make_float4(0, 0, 0, 0);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = i0 + 8 * j;
-                    const int tt = i / g.F, f = i % g.F, t = t0 + tt;
-                    if (i >= nrows || t >= g.T) continue;  // warp-uniform
-                    const int p = 2 + tt * g.FP + f;
-                    const float2 st = stats[p];
-                    float4 dh = make_float4(0, 0, 0, 0), xh = dh;
-                    if (act24) {
-                        const uint2 pk = *reinterpret_cast<const uint2*>(htile + (size_t)(lane >> 1) * g.cs + p * 16 + (lane & 1) * 8);
-                        unpack16<FMT>(pk.x, dh.x, dh.y);
-                        unpack16<FMT>(pk.y, dh.z, dh.w);
-                        xh = make_float4((xv[j].x - st.x) * st.y, (xv[j].y - st.x) * st.y, (xv[j].z - st.x) * st.y, (xv[j].w - st.x) * st.y);
+                    for (int j = 0; j < 4; ++j) {
+                        const int f = f0 + 8 * j;
+                        const bool ok = act24 && f < g.F;
+                        const size_t off = (((size_t)b * g.F + f) * g.T + t) * kH;
+                        xv[j] = ok ? __ldg(reinterpret_cast<const float4*>(a.x + off) + lane) : make_float4(0, 0, 0, 0);
+                        dv[j] = ok ? __ldg(reinterpret_cast<const float4*>(a.dy + off) + lane) : make_float4(0, 0, 0, 0);
                     }
-                    const float4 dxh = make_float4(dh.x * gw4.x, dh.y * gw4.y, dh.z * gw4.z, dh.w * gw4.w);
-                    const float m1 = warp_sum(dxh.x + dxh.y + dxh.z + dxh.w) * (1.f / kH);
-                    const float m2 = warp_sum(dxh.x * xh.x + dxh.y * xh.y + dxh.z * xh.z + dxh.w * xh.w) * (1.f / kH);
-                    dg4 = make_float4(dg4.x + dh.x * xh.x, dg4.y + dh.y * xh.y, dg4.z + dh.z * xh.z, dg4.w + dh.w * xh.w);
-                    db4 = make_float4(db4.x + dh.x, db4.y + dh.y, db4.z + dh.z, db4.w + dh.w);
-                    if (act24)
-                        reinterpret_cast<float4*>(a.dx + (((size_t)b * g.F + f) * g.T + t) * kH)[lane] =
-                            make_float4(dv[j].x + st.y * (dxh.x - m1 - xh.x * m2), dv[j].y + st.y * (dxh.y - m1 - xh.y * m2),
-                                        dv[j].z + st.y * (dxh.z - m1 - xh.z * m2), dv[j].w + st.y * (dxh.w - m1 - xh.w * m2));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int f = f0 + 8 * j;
+                        if (f >= g.F) continue;  // warp-uniform
+                        const int p = 2 + tt * g.FP + f;
+                        const float2 st = stats[p];
+                        float4 dh = make_float4(0, 0, 0, 0), xh = dh;
+                        if (act24) {
+                            const uint2 pk = *reinterpret_cast<const uint2*>(htile + (size_t)(lane >> 1) * g.cs + p * 16 + (lane & 1) * 8);
+                            unpack16<FMT>(pk.x, dh.x, dh.y);
+                            unpack16<FMT>(pk.y, dh.z, dh.w);
+                            xh = make_float4((xv[j].x - st.x) * st.y, (xv[j].y - st.x) * st.y, (xv[j].z - st.x) * st.y, (xv[j].w - st.x) * st.y);
+                        }
+                        const float4 dxh = make_float4(dh.x * gw4.x, dh.y * gw4.y, dh.z * gw4.z, dh.w * gw4.w);
+                        const float m1 = warp_sum(dxh.x + dxh.y + dxh.z + dxh.w) * (1.f / kH);
+                        const float m2 = warp_sum(dxh.x * xh.x + dxh.y * xh.y + dxh.z * xh.z + dxh.w * xh.w) * (1.f / kH);
+                        dg4 = make_float4(dg4.x + dh.x * xh.x, dg4.y + dh.y * xh.y, dg4.z + dh.z * xh.z, dg4.w + dh.w * xh.w);
+                        db4 = make_float4(db4.x + dh.x, db4.y + dh.y, db4.z + dh.z, db4.w + dh.w);
+                        if (act24)
+                            reinterpret_cast<float4*>(a.dx + (((size_t)b * g.F + f) * g.T + t) * kH)[lane] =
+                                make_float4(dv[j].x + st.y * (dxh.x - m1 - xh.x * m2), dv[j].y + st.y * (dxh.y - m1 - xh.y * m2),
+                                            dv[j].z + st.y * (dxh.z - m1 - xh.z * m2), dv[j].w + st.y * (dxh.w - m1 - xh.w * m2));
+                    }
                 }
             }
         }

@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--batch", type=int, default=CFG["B"], help="global batch (utterances)")
     ap.add_argument("--profile", action="store_true", help="1 warm-up + 1 step only (for ncu); prints no bench line")
     ap.add_argument("--layers", type=int, default=CFG["L"], help="number of SpatialNet layers (profiling only; default 8)")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -200,7 +201,7 @@ def main():
                      dim_hidden=96, dim_ffn=192, num_heads=4).to(dev)
     pipe = SeparationPipeline(net, CFG["n_fft"], CFG["hop"], channels=None, ref_channel=0)
     params = [p for p in net.parameters()]
-    opt = torch.optim.Adam(params, lr=1e-3, fused=True)
+    opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
 
     # rank r takes utterances r::world of the global batch (data_loaders/utils/my_distributed_sampler.py:78)
     x_all, y_all = synth_batch(args.batch, seed=777)
@@ -209,18 +210,57 @@ def main():
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
     loss_host = torch.zeros(1).pin_memory()
 
-    def step(x, y):
+    def fwd_bwd(x, y):
         opt.zero_grad(set_to_none=True)
         est = pipe(x)
         loss = neg_si_sdr_pit(est, y)
         loss.backward()
+        return loss
+
+    def reduce_grads():
         if world > 1:
-            flat = net._last_flat_grad
+            flat = net._last_flat_grad  # every p.grad is a view of this buffer (checked below): ONE all-reduce
             dist.all_reduce(flat)
             flat.mul_(1.0 / world)
+
+    def opt_step():
         torch.nn.utils.clip_grad_norm_(params, 5.0, foreach=True)
         opt.step()
+
+    def step(x, y):  # eager step
+        loss = fwd_bwd(x, y)
+        reduce_grads()
+        opt_step()
         return loss
+
+    graphs = {}
+
+    def build_graphs():
+        """Capture the step as CUDA graphs: A = (H2D copies +) forward + backward (+ D2H loss), B = clip + Adam.  The
+        gradient all-reduce runs between them, outside any capture.  Replays cost microseconds of CPU time, which
+        matters at 4 utterances per GPU (8-GPU strong scaling), where eager launches would bound the step."""
+        x_st, y_st = x_dev.clone(), y_dev.clone()
+        gA = torch.cuda.CUDAGraph()
+        ops.LAUNCHES = 0
+        with torch.cuda.graph(gA):
+            lossA = fwd_bwd(x_st, y_st)
+        graphs["launches"] = ops.LAUNCHES
+        gH = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gH, pool=gA.pool()):
+            x_st.copy_(x_host, non_blocking=True)
+            y_st.copy_(y_host, non_blocking=True)
+            lossH = fwd_bwd(x_st, y_st)
+            loss_host.copy_(lossH.detach().reshape(1), non_blocking=True)
+        gB = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gB, pool=gA.pool()):
+            opt_step()
+        graphs.update(A=gA, H=gH, B=gB, lossA=lossA, lossH=lossH)
+
+    def gstep(host_io):
+        (graphs["H"] if host_io else graphs["A"]).replay()
+        reduce_grads()
+        graphs["B"].replay()
+        return graphs["lossH"] if host_io else graphs["lossA"]
 
     def timed(nsteps, host_io):
         if world > 1:
@@ -229,7 +269,9 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(nsteps):
-            if host_io:
+            if use_graphs:
+                loss = gstep(host_io)
+            elif host_io:
                 x = x_host.to(dev, non_blocking=True)
                 y = y_host.to(dev, non_blocking=True)
                 loss = step(x, y)
@@ -253,10 +295,24 @@ def main():
         torch.cuda.profiler.stop()
         return
     log("setup done; warm-up")
+    use_graphs = False
     for i in range(max(args.warmup, 3)):
         step(x_dev, y_dev)
         torch.cuda.synchronize()
         log(f"warm-up step {i} done")
+    assert net.grads_alias_flat(), "p.grad tensors are not views of the flat gradient buffer"
+    if not args.no_graphs:
+        try:
+            build_graphs()
+            use_graphs = True
+            for _ in range(2):
+                gstep(False)
+            torch.cuda.synchronize()
+            log("CUDA graphs captured (fwd+bwd, host-I/O variant, optimizer)")
+        except Exception as e:  # fall back to eager launches, say so in the JSON line
+            log(f"CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly")
+            use_graphs = False
+            torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -264,19 +320,22 @@ def main():
     ops.LAUNCHES = 0
     ms_dev, loss_v = timed(args.steps, host_io=False)
     log(f"device-resident: {ms_dev:.2f} ms/step")
-    launches = ops.LAUNCHES // args.steps
+    launches = graphs["launches"] if use_graphs else ops.LAUNCHES // args.steps
     ms_e2e, _ = timed(args.steps, host_io=True)
     log(f"e2e: {ms_e2e:.2f} ms/step")
     clocks = sampler.stop() if rank == 0 else None
 
     # per-kernel live timing (CUDA events around every C-ABI call on the launching stream) for the roofline
     ops.TIMING = {}
+    was_graphs, use_graphs = use_graphs, False  # the per-kernel event timing pass launches eagerly
     timed(max(2, min(args.steps, 5)), host_io=False)
+    use_graphs = was_graphs
     torch.cuda.synchronize()
     per_kernel = {k: (sum(a.elapsed_time(b) for a, b in v) / len(v), len(v)) for k, v in ops.TIMING.items()}
     ops.TIMING = None
     nsteps_prof = max(2, min(args.steps, 5))
 
+    net.check_device_errors()  # sticky device flag: no kernel hit an mbarrier time-out during the whole run
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -317,7 +376,7 @@ def main():
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "fp16 tensor-core operands (fwd + loss-scaled bwd), fp32 accumulate, fp32 stream", "data": "synthetic",
         "config": {"workload": "SpatialNet-small 6ch F=129 T=250 fwd+bwd, batch=32 (BASELINE configs[1])", "global_batch": args.batch,
-                   "per_gpu_batch": b_local, "frames_per_utt": CFG["T"], "parallelism": f"dp{world}",
+                   "per_gpu_batch": b_local, "frames_per_utt": CFG["T"], "parallelism": f"dp{world}", "cuda_graphs": bool(use_graphs),
                    "l2": "activations per step (>10 GB) far exceed the 126 MB L2; no explicit flush"},
         "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4) * world, "d2h_bytes_per_step": 4 * world},

@@ -23,7 +23,17 @@ TIMING = None
 _NLAUNCH = {"nbss_full_fwd": 3, "nbss_full_bwd": 4, "nbss_ffn_wgrad": 3, "nbss_mhsa_bwd": 2, "nbss_istft": 2}
 
 
+_KCACHE = {}
+
+
 def _K(name: str):
+    c = _KCACHE.get(name)
+    if c is None:
+        c = _KCACHE[name] = _make_call(name)
+    return c
+
+
+def _make_call(name: str):
     fn = getattr(_lib.lib(), name)
 
     def call(*args):
@@ -46,8 +56,16 @@ def _f32c(t: Tensor) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+_ERR_FLAGS = {}
+
+
 def device_err_flag(device) -> Tensor:
-    return torch.zeros(1, dtype=torch.int32, device=device)
+    """One persistent device int per device, shared by every tensor-core kernel launch (set to 0x7001 by a kernel whose
+    mbarrier wait timed out; it stays set, so checking it once after a step is enough)."""
+    f = _ERR_FLAGS.get(device)
+    if f is None:
+        f = _ERR_FLAGS[device] = torch.zeros(1, dtype=torch.int32, device=device)
+    return f
 
 
 def check_err_flag(flag: Tensor, what: str) -> None:

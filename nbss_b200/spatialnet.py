@@ -22,6 +22,11 @@ from torch import Tensor
 from . import ops
 
 
+import os as _os
+
+_CHECK_EVERY_STEP = _os.environ.get("NBSS_CHECK_EVERY_STEP", "0") == "1"
+
+
 class LinearGroup(nn.Module):
     """Parameter container for the full-band linear (models/arch/base/linear_group.py:7-37): weight [G,out,in]."""
 
@@ -86,7 +91,8 @@ class Engine:
             names += [pre + "tconvffn.1.weight", pre + "tconvffn.3.weight", pre + "tconvffn.5.weight", pre + "tconvffn.8.weight",
                       pre + "tconvffn.10.weight", pre + "mhsa.in_proj_weight", pre + "mhsa.out_proj.weight"]
         key = tuple((P[n].data_ptr(), P[n]._version) for n in names)
-        if self._imgs is None or key != self._img_key:
+        # under CUDA-graph capture the pack kernels must be part of the graph (weights change between replays)
+        if self._imgs is None or key != self._img_key or torch.cuda.is_current_stream_capturing():
             old = self._imgs
             self._imgs = [ops.pack_layer_weights(P, f"layers.{i}.", old[i] if old else None, self.fwd_fmt, self.grad_fmt)
                           for i in range(self.L)]
@@ -97,7 +103,7 @@ class Engine:
         """Per-layer UMMA images of the two F-conv weights (fconv_tc.cu), rebuilt when a weight changed."""
         names = [f"layers.{i}.fconv{j}.1.weight" for i in range(self.L) for j in (1, 2)]
         key = tuple((P[n].data_ptr(), P[n]._version) for n in names)
-        if self._fimgs is None or key != self._fimg_key:
+        if self._fimgs is None or key != self._fimg_key or torch.cuda.is_current_stream_capturing():
             old = self._fimgs
             self._fimgs = [[ops.fconv_pack(P[f"layers.{i}.fconv{j}.1.weight"], old[i][j - 1] if old else None, self.fwd_fmt)
                             for j in (1, 2)] for i in range(self.L)]
@@ -179,8 +185,11 @@ class _SpatialNetFn(torch.autograd.Function):
         errs = module.engine.backward(P, fctx.ctx, dy * scale, G)
         flat.mul_(1.0 / scale)
         module._last_flat_grad = flat  # one contiguous buffer: a single NCCL all-reduce covers every gradient
-        for e in fctx.errs + errs:
-            ops.check_err_flag(e, "nbss_b200 kernel")
+        # The device error flag is sticky and shared by all launches; reading it needs a host sync, so the hot path does
+        # it only on request (NBSS_CHECK_EVERY_STEP=1) — `SpatialNet.check_device_errors()` reads it at any time.
+        module._last_errs = fctx.errs + errs
+        if _CHECK_EVERY_STEP:
+            module.check_device_errors()
         fctx.ctx = None
         return (None, None) + tuple(views)
 
@@ -229,9 +238,22 @@ class SpatialNet(nn.Module):
 
     def make_flat_grads(self, device):
         """One contiguous zero fp32 buffer holding every parameter gradient; returns (flat, name->view dict covering all
-        state-dict aliases of shared tensors, list of views in parameter registration order)."""
+        state-dict aliases of shared tensors, list of views in parameter registration order).
+
+        The buffer is persistent (same storage every step, which is what CUDA-graph replays and a standing NCCL
+        registration want) unless some parameter's .grad still lives in it (gradient accumulation without zero_grad):
+        then a fresh buffer is used and autograd adds it to the existing gradients."""
         uniq = self._unique_params()
-        flat = torch.zeros(sum(p.numel() for _, p in uniq), dtype=torch.float32, device=device)
+        n = sum(p.numel() for _, p in uniq)
+        flat = getattr(self, "_flat_grad_buf", None)
+        if flat is None or flat.device != torch.device(device) or flat.numel() != n:
+            flat = self._flat_grad_buf = torch.zeros(n, dtype=torch.float32, device=device)
+        else:
+            base = flat.untyped_storage().data_ptr()
+            if any(p.grad is not None and p.grad.untyped_storage().data_ptr() == base for _, p in uniq):
+                flat = torch.zeros(n, dtype=torch.float32, device=device)
+            else:
+                flat.zero_()
         G, off, views = {}, 0, []
         for name, p in uniq:
             v = flat[off:off + p.numel()].view_as(p)
@@ -240,6 +262,15 @@ class SpatialNet(nn.Module):
             for alias in self._aliases[name]:
                 G[alias] = v
         return flat, G, views
+
+    def grads_alias_flat(self) -> bool:
+        """True when every parameter's .grad is a view of the last flat gradient buffer (autograd adopted the views
+        returned by the backward instead of cloning them), i.e. one all-reduce of that buffer reduces every gradient."""
+        flat = getattr(self, "_last_flat_grad", None)
+        if flat is None:
+            return False
+        base = flat.untyped_storage().data_ptr()
+        return all(p.grad is not None and p.grad.untyped_storage().data_ptr() == base for p in self.parameters())
 
     def _unique_params(self):
         return list(self.named_parameters())  # duplicates removed, registration order
@@ -259,5 +290,9 @@ class SpatialNet(nn.Module):
         return y
 
     def check_device_errors(self) -> None:
+        """Raises if any tensor-core kernel launched so far reported an mbarrier time-out (host sync)."""
+        seen = set()
         for e in getattr(self, "_last_errs", []):
-            ops.check_err_flag(e, "nbss_b200 kernel")
+            if id(e) not in seen:
+                seen.add(id(e))
+                ops.check_err_flag(e, "nbss_b200 kernel")

@@ -65,6 +65,8 @@ def test_forward_backward_grads():
     y = net(x.cuda())
     y.backward(dy.cuda())
     torch.cuda.synchronize()
+    net.check_device_errors()
+    assert net.grads_alias_flat(), "parameter gradients must be views of the single flat buffer (one all-reduce)"
     ref = O.spatialnet_forward(Pl, x, cfg)
     ref.backward(dy)
     assert O.rel_l2(y.detach().cpu(), ref.detach()) < 1e-3

@@ -32,12 +32,12 @@ CFG = dict(B=32, C=6, F=129, T=250, n_fft=256, hop=128, S=2, L=8)
 TS = CFG["hop"] * (CFG["T"] - 1)  # 31872 samples -> T = 250 frames
 FLOP_PER_POINT = {  # algorithmic FLOPs per T-F point
     "ffn_fwd": 156_672, "mhsa_fwd": 169_728, "ffn_bwd": 156_672, "ffn_wgrad": 156_672, "mhsa_bwd": 265_728,
-    "mhsa_wgrad": 73_728, "fconv_fwd": 11_520, "fconv_bwd": 34_560, "fconv_tc_fwd": 11_520, "fconv_tc_bwd": 34_560, "full_fwd": 5_136, "full_bwd": 10_272,
+    "mhsa_wgrad": 73_728, "fconv_fwd": 11_520, "fconv_bwd": 34_560, "fconv_tc_fwd": 11_520, "fconv_tc_bwd": 34_560, "full_fwd": 5_136, "full_bwd": 10_272, "full_fwd_tc": 5_136, "full_bwd_tc": 10_272,
 }
 # algorithmic HBM bytes per T-F point with one fused kernel per sub-block and an fp32 stream:
 # forward = x in + y out; data-gradient = x, dy in + dx out; weight-gradient = x, dy in.  (What the kernels move on top
 # of this — 16-bit saves and gradient operands — is design overhead and shows up as a lower fraction.)
-BYTES_PER_POINT = {"ffn_fwd": 768, "mhsa_fwd": 768, "fconv_tc_fwd": 768, "full_fwd": 768, "ffn_bwd": 1152, "mhsa_bwd": 1152,
+BYTES_PER_POINT = {"ffn_fwd": 768, "mhsa_fwd": 768, "fconv_tc_fwd": 768, "full_fwd": 768, "full_fwd_tc": 768, "full_bwd_tc": 1152, "ffn_bwd": 1152, "mhsa_bwd": 1152,
                    "fconv_tc_bwd": 1152, "full_bwd": 1152, "ffn_wgrad": 768, "mhsa_wgrad": 768}
 TENSOR_BOUND = ("ffn_fwd", "mhsa_fwd", "ffn_bwd", "ffn_wgrad", "mhsa_bwd", "mhsa_wgrad")  # AI >= ~200 FLOP/B: narrow-band block
 

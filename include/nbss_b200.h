@@ -86,6 +86,23 @@ int nbss_full_bwd(const float* x, const float* dy, float* dx, const float* s, co
                   const float* bun, float* dlnw, float* dlnb, float* dWsq, float* dbsq, float* dWf, float* dbf, float* dWun,
                   float* dbun, void* stream);
 
+/* The same block with the LinearGroup (models/arch/base/linear_group.py:29-34) on tensor cores (fullband_tc.cu):
+ * img = nbss_lg_pack(full.weight [8,F,F]) (nbss_lg_image_bytes(F) bytes, F <= 256; one image serves forward and data
+ * gradient).  nbss_lg_tc_apply: mode 0 out = in W^T + bias, mode 1 out = in W; in/out fp32 [M,8,F].
+ * nbss_lg_tc_wgrad: dW [8,F,F] += du^T s, db [8,F] += column sums of du. */
+unsigned int nbss_lg_image_bytes(int F);
+int nbss_lg_pack(const float* Wf, void* img, int F, int fmt, void* stream);
+int nbss_lg_tc_apply(const float* in, float* out, int M, int F, const void* img, const float* bias, int mode, int fmt,
+                     int* err, void* stream);
+int nbss_lg_tc_wgrad(const float* du, const float* s, int M, int F, float* dW, float* db, int fmt, int* err, void* stream);
+int nbss_full_fwd_tc(const float* x, float* y, float* s_out, float* u_out, int B, int F, int T, const float* lnw,
+                     const float* lnb, const float* Wsq, const float* bsq, const float* bf, const float* Wun,
+                     const float* bun, const void* img, int fmt, int* err, void* stream);
+int nbss_full_bwd_tc(const float* x, const float* dy, float* dx, const float* s, const float* u, float* ws, int B, int F,
+                     int T, const float* lnw, const float* lnb, const float* Wsq, const float* bsq, const float* Wun,
+                     const float* bun, const void* img, float* dlnw, float* dlnb, float* dWsq, float* dbsq, float* dWf,
+                     float* dbf, float* dWun, float* dbun, int fmt, int* err, void* stream);
+
 /* ---- encoder / decoder, fp32 (models/arch/SpatialNet.py:175,205 and :200,216) --------------------------------------- */
 int nbss_encoder_fwd(const float* x, float* y, int nslab, int T, int cin, const float* W, const float* bias, void* stream);
 int nbss_encoder_wgrad(const float* x, const float* dy, int nslab, int T, int cin, float* dW, float* dbias, void* stream);

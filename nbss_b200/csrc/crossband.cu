@@ -232,6 +232,29 @@ __global__ void __launch_bounds__(96 * TT) fconv_bwd_kernel(const float* __restr
 // s[b,t,g,f] = SiLU(sum_c Wsq[g,c] LN(x)[b,f,t,c] + bsq[g]).  CTA per (b, 4 frames); results transposed through smem
 // so the [B,T,8,F] tensor is written with f contiguous.
 constexpr int kSQT = 4;
+
+// Copies between the [kSQT][8][F] shared tile and a [B,T,8,F] tensor for frames t0..t0+3 and the range [f0, f0+FR):
+// one warp per (tt, g) line, lanes along f (coalesced, no integer divisions).
+__device__ __forceinline__ void sq_tile_load(float* tile, const float* __restrict__ src, int b, int t0, int T, int F, int f0,
+                                             int FR, int warp, int lane) {
+    for (int row = warp; row < kSQT * kHS; row += 8) {
+        const int tt = row >> 3;
+        const bool ok = t0 + tt < T;
+        const float* sp = src + ((size_t)b * T + t0 + tt) * kHS * F + (size_t)(row & 7) * F + f0;
+        float* tp = tile + row * F + f0;
+        for (int fo = lane; fo < FR; fo += 32) tp[fo] = ok ? sp[fo] : 0.f;
+    }
+}
+__device__ __forceinline__ void sq_tile_store(const float* tile, float* __restrict__ dst, int b, int t0, int T, int F, int f0,
+                                              int FR, int warp, int lane) {
+    for (int row = warp; row < kSQT * kHS; row += 8) {
+        const int tt = row >> 3;
+        if (t0 + tt >= T) continue;
+        float* dp = dst + ((size_t)b * T + t0 + tt) * kHS * F + (size_t)(row & 7) * F + f0;
+        const float* tp = tile + row * F + f0;
+        for (int fo = lane; fo < FR; fo += 32) dp[fo] = tp[fo];
+    }
+}
 __global__ void __launch_bounds__(256) squeeze_fwd_kernel(const float* __restrict__ x, float* __restrict__ s, int B, int F,
                                                           int T, const float* lnw, const float* lnb, const float* Wsq,
                                                           const float* bsq) {
@@ -240,13 +263,14 @@ __global__ void __launch_bounds__(256) squeeze_fwd_kernel(const float* __restric
     float* st = sm + kHS * kH;        // [4][8][F]
     const int tiles = (T + kSQT - 1) / kSQT, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.x / tiles, t0 = (blockIdx.x % tiles) * kSQT;
+    const int f0 = (int)blockIdx.y * F / (int)gridDim.y, FR = ((int)blockIdx.y + 1) * F / (int)gridDim.y - f0;
     const bool act = lane < 24;
     for (int i = tid; i < kHS * kH; i += 256) wsq[i] = Wsq[i];
     __syncthreads();
     float4 g4 = make_float4(0, 0, 0, 0), b4 = g4;
     if (act) { g4 = ld_f4(lnw + 4 * lane); b4 = ld_f4(lnb + 4 * lane); }
-    for (int i = warp; i < F * kSQT; i += 8) {
-        const int f = i / kSQT, tt = i % kSQT, t = t0 + tt;
+    for (int i = warp; i < FR * kSQT; i += 8) {
+        const int f = f0 + i / kSQT, tt = i % kSQT, t = t0 + tt;
         if (t >= T) continue;
         float4 v = make_float4(0, 0, 0, 0);
         if (act) v = ld_f4(x + (((size_t)b * F + f) * T + t) * kH + 4 * lane);
@@ -261,10 +285,7 @@ __global__ void __launch_bounds__(256) squeeze_fwd_kernel(const float* __restric
         if ((lane & 3) == 0) st[(tt * kHS + (lane >> 2)) * F + f] = silu(tot + bsq[lane >> 2]);
     }
     __syncthreads();
-    for (int i = tid; i < kSQT * kHS * F; i += 256) {
-        const int tt = i / (kHS * F), r = i % (kHS * F);
-        if (t0 + tt < T) s[((size_t)b * T + t0 + tt) * kHS * F + r] = st[i];
-    }
+    sq_tile_store(st, s, b, t0, T, F, f0, FR, warp, lane);
 }
 
 // Backward of squeeze + its LayerNorm; also adds the residual: dx = dy + dLN.  ds: [B,T,8,F] gradient wrt s.
@@ -272,7 +293,7 @@ __global__ void __launch_bounds__(256) squeeze_bwd_kernel(const float* __restric
                                                           const float* __restrict__ ds, float* __restrict__ dx, int B,
                                                           int F, int T, const float* lnw, const float* lnb,
                                                           const float* Wsq, const float* bsq, float* dWsq, float* dbsq,
-                                                          float* dlnw, float* dlnb) {
+                                                          float* dlnw, float* dlnb, int fsplit) {
     extern __shared__ __align__(16) float sm[];
     float* wsq = sm;                  // [8][96]
     float* st = sm + kHS * kH;        // [4][8][F] ds tile
@@ -285,16 +306,15 @@ __global__ void __launch_bounds__(256) squeeze_bwd_kernel(const float* __restric
 #pragma unroll
     for (int g = 0; g < kHS; ++g) dwq[g] = make_float4(0, 0, 0, 0);
     float dbq = 0.f;  // lane g accumulates dbsq[g]
-    for (int tile = blockIdx.x; tile < B * tiles; tile += gridDim.x) {
+    for (int job = blockIdx.x; job < B * tiles * fsplit; job += gridDim.x) {
+        const int fs = job % fsplit, tile = job / fsplit;
+        const int f0 = fs * F / fsplit, FR = (fs + 1) * F / fsplit - f0;
         const int b = tile / tiles, t0 = (tile % tiles) * kSQT;
         __syncthreads();
-        for (int i = tid; i < kSQT * kHS * F; i += 256) {
-            const int tt = i / (kHS * F), r = i % (kHS * F);
-            st[i] = (t0 + tt < T) ? ds[((size_t)b * T + t0 + tt) * kHS * F + r] : 0.f;
-        }
+        sq_tile_load(st, ds, b, t0, T, F, f0, FR, warp, lane);
         __syncthreads();
-        for (int i = warp; i < F * kSQT; i += 8) {
-            const int f = i / kSQT, tt = i % kSQT, t = t0 + tt;
+        for (int i = warp; i < FR * kSQT; i += 8) {
+            const int f = f0 + i / kSQT, tt = i % kSQT, t = t0 + tt;
             if (t >= T) continue;
             const size_t base = (((size_t)b * F + f) * T + t) * kH + 4 * lane;
             float4 v = make_float4(0, 0, 0, 0), dyv = v;
@@ -333,18 +353,28 @@ __global__ void __launch_bounds__(256) squeeze_bwd_kernel(const float* __restric
             }
         }
     }
+    // flush: warps -> shared accumulators -> one set of global atomics per CTA
+    float* red = st + kSQT * kHS * F;  // [768 dWsq | 96 dlnw | 96 dlnb | 8 dbsq]
+    __syncthreads();
+    for (int i = tid; i < 968; i += 256) red[i] = 0.f;
+    __syncthreads();
     if (act) {
 #pragma unroll
         for (int g = 0; g < kHS; ++g) {
-            atomicAdd(dWsq + g * kH + 4 * lane + 0, dwq[g].x); atomicAdd(dWsq + g * kH + 4 * lane + 1, dwq[g].y);
-            atomicAdd(dWsq + g * kH + 4 * lane + 2, dwq[g].z); atomicAdd(dWsq + g * kH + 4 * lane + 3, dwq[g].w);
+            atomicAdd(red + g * kH + 4 * lane + 0, dwq[g].x); atomicAdd(red + g * kH + 4 * lane + 1, dwq[g].y);
+            atomicAdd(red + g * kH + 4 * lane + 2, dwq[g].z); atomicAdd(red + g * kH + 4 * lane + 3, dwq[g].w);
         }
-        atomicAdd(dlnw + 4 * lane + 0, dg4.x); atomicAdd(dlnw + 4 * lane + 1, dg4.y);
-        atomicAdd(dlnw + 4 * lane + 2, dg4.z); atomicAdd(dlnw + 4 * lane + 3, dg4.w);
-        atomicAdd(dlnb + 4 * lane + 0, db4.x); atomicAdd(dlnb + 4 * lane + 1, db4.y);
-        atomicAdd(dlnb + 4 * lane + 2, db4.z); atomicAdd(dlnb + 4 * lane + 3, db4.w);
+        atomicAdd(red + 768 + 4 * lane + 0, dg4.x); atomicAdd(red + 768 + 4 * lane + 1, dg4.y);
+        atomicAdd(red + 768 + 4 * lane + 2, dg4.z); atomicAdd(red + 768 + 4 * lane + 3, dg4.w);
+        atomicAdd(red + 864 + 4 * lane + 0, db4.x); atomicAdd(red + 864 + 4 * lane + 1, db4.y);
+        atomicAdd(red + 864 + 4 * lane + 2, db4.z); atomicAdd(red + 864 + 4 * lane + 3, db4.w);
     }
-    if (lane < kHS) atomicAdd(dbsq + lane, dbq);
+    if (lane < kHS) atomicAdd(red + 960 + lane, dbq);
+    __syncthreads();
+    for (int i = tid; i < 968; i += 256) {
+        float* dst = i < 768 ? dWsq + i : (i < 864 ? dlnw + (i - 768) : (i < 960 ? dlnb + (i - 864) : dbsq + (i - 960)));
+        atomicAdd(dst, red[i]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ unsqueeze
@@ -356,11 +386,9 @@ __global__ void __launch_bounds__(256) unsqueeze_fwd_kernel(const float* __restr
     float* ut = sm;  // [4][8][F]
     const int tiles = (T + kSQT - 1) / kSQT, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.x / tiles, t0 = (blockIdx.x % tiles) * kSQT;
+    const int f0 = (int)blockIdx.y * F / (int)gridDim.y, FR = ((int)blockIdx.y + 1) * F / (int)gridDim.y - f0;
     const bool act = lane < 24;
-    for (int i = tid; i < kSQT * kHS * F; i += 256) {
-        const int tt = i / (kHS * F), r = i % (kHS * F);
-        ut[i] = (t0 + tt < T) ? u[((size_t)b * T + t0 + tt) * kHS * F + r] : 0.f;
-    }
+    sq_tile_load(ut, u, b, t0, T, F, f0, FR, warp, lane);
     float wun[4][kHS];
     float4 bu = make_float4(0, 0, 0, 0);
     if (act) {
@@ -372,8 +400,8 @@ __global__ void __launch_bounds__(256) unsqueeze_fwd_kernel(const float* __restr
     }
     __syncthreads();
     if (!act) return;
-    for (int i = warp; i < F * kSQT; i += 8) {
-        const int f = i / kSQT, tt = i % kSQT, t = t0 + tt;
+    for (int i = warp; i < FR * kSQT; i += 8) {
+        const int f = f0 + i / kSQT, tt = i % kSQT, t = t0 + tt;
         if (t >= T) continue;
         float a[4] = {bu.x, bu.y, bu.z, bu.w};
 #pragma unroll
@@ -391,7 +419,7 @@ __global__ void __launch_bounds__(256) unsqueeze_fwd_kernel(const float* __restr
 // Backward of the unsqueeze branch only: du[b,t,g,f] and dWun/dbun.  (The residual dy is added by squeeze_bwd.)
 __global__ void __launch_bounds__(256) unsqueeze_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ u,
                                                             float* __restrict__ du, int B, int F, int T, const float* Wun,
-                                                            const float* bun, float* dWun, float* dbun) {
+                                                            const float* bun, float* dWun, float* dbun, int fsplit) {
     extern __shared__ __align__(16) float sm[];
     float* ut = sm;                      // [4][8][F]
     float* dut = sm + kSQT * kHS * F;    // [4][8][F]
@@ -404,16 +432,15 @@ __global__ void __launch_bounds__(256) unsqueeze_bwd_kernel(const float* __restr
 #pragma unroll
         for (int g = 0; g < kHS; ++g) { wun[c][g] = act ? Wun[(4 * lane + c) * kHS + g] : 0.f; dwun[c][g] = 0.f; }
     if (act) bu = ld_f4(bun + 4 * lane);
-    for (int tile = blockIdx.x; tile < B * tiles; tile += gridDim.x) {
+    for (int job = blockIdx.x; job < B * tiles * fsplit; job += gridDim.x) {
+        const int fs = job % fsplit, tile = job / fsplit;
+        const int f0 = fs * F / fsplit, FR = (fs + 1) * F / fsplit - f0;
         const int b = tile / tiles, t0 = (tile % tiles) * kSQT;
         __syncthreads();
-        for (int i = tid; i < kSQT * kHS * F; i += 256) {
-            const int tt = i / (kHS * F), r = i % (kHS * F);
-            ut[i] = (t0 + tt < T) ? u[((size_t)b * T + t0 + tt) * kHS * F + r] : 0.f;
-        }
+        sq_tile_load(ut, u, b, t0, T, F, f0, FR, warp, lane);
         __syncthreads();
-        for (int i = warp; i < F * kSQT; i += 8) {
-            const int f = i / kSQT, tt = i % kSQT, t = t0 + tt;
+        for (int i = warp; i < FR * kSQT; i += 8) {
+            const int f = f0 + i / kSQT, tt = i % kSQT, t = t0 + tt;
             if (t >= T) continue;
             float a[4] = {bu.x, bu.y, bu.z, bu.w}, uv[kHS];
 #pragma unroll
@@ -438,19 +465,23 @@ __global__ void __launch_bounds__(256) unsqueeze_bwd_kernel(const float* __restr
             if ((lane & 3) == 0) dut[(tt * kHS + (lane >> 2)) * F + f] = tot;
         }
         __syncthreads();
-        for (int i = tid; i < kSQT * kHS * F; i += 256) {
-            const int tt = i / (kHS * F), r = i % (kHS * F);
-            if (t0 + tt < T) du[((size_t)b * T + t0 + tt) * kHS * F + r] = dut[i];
-        }
+        sq_tile_store(dut, du, b, t0, T, F, f0, FR, warp, lane);
     }
+    // flush: warps -> shared accumulators -> one set of global atomics per CTA
+    float* red = sm + 2 * kSQT * kHS * F;  // [768 dWun | 96 dbun]
+    __syncthreads();
+    for (int i = tid; i < 864; i += 256) red[i] = 0.f;
+    __syncthreads();
     if (act) {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int g = 0; g < kHS; ++g) atomicAdd(dWun + (4 * lane + c) * kHS + g, dwun[c][g]);
-        atomicAdd(dbun + 4 * lane + 0, dbu.x); atomicAdd(dbun + 4 * lane + 1, dbu.y);
-        atomicAdd(dbun + 4 * lane + 2, dbu.z); atomicAdd(dbun + 4 * lane + 3, dbu.w);
+            for (int g = 0; g < kHS; ++g) atomicAdd(red + (4 * lane + c) * kHS + g, dwun[c][g]);
+        atomicAdd(red + 768 + 4 * lane + 0, dbu.x); atomicAdd(red + 768 + 4 * lane + 1, dbu.y);
+        atomicAdd(red + 768 + 4 * lane + 2, dbu.z); atomicAdd(red + 768 + 4 * lane + 3, dbu.w);
     }
+    __syncthreads();
+    for (int i = tid; i < 864; i += 256) atomicAdd(i < 768 ? dWun + i : dbun + (i - 768), red[i]);
 }
 
 // ------------------------------------------------------------------------------------------------ LinearGroup
@@ -557,6 +588,15 @@ static int num_sms() {
     return sms;
 }
 
+// Small batches: split every (b, 4-frame) tile of the squeeze/unsqueeze row kernels into frequency ranges so that the
+// grid still fills 4 CTAs per SM.
+static int f_split(int tiles, int F) {
+    const int want = 4 * num_sms();
+    int fs = 1;
+    while (fs < 4 && tiles * fs < want && F / (2 * fs) >= 8) fs *= 2;
+    return fs;
+}
+
 }  // namespace nbss
 
 using namespace nbss;
@@ -611,7 +651,8 @@ extern "C" int nbss_full_fwd(const float* x, float* y, float* s_out, float* u_ou
     cudaStream_t st = (cudaStream_t)stream;
     const int tiles = B * ((T + kSQT - 1) / kSQT);
     const size_t sm_sq = (size_t)(kHS * kH + kSQT * kHS * F) * 4;
-    squeeze_fwd_kernel<<<tiles, 256, sm_sq, st>>>(x, s_out, B, F, T, lnw, lnb, Wsq, bsq);
+    const int fsplit = f_split(tiles, F);
+    squeeze_fwd_kernel<<<dim3(tiles, fsplit), 256, sm_sq, st>>>(x, s_out, B, F, T, lnw, lnb, Wsq, bsq);
     NBSS_LAUNCH_CHECK();
     const size_t sm_g = (size_t)(F + 64) * (F + 1) * 4;
     cudaError_t e = cudaFuncSetAttribute(fullgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_g);
@@ -619,7 +660,7 @@ extern "C" int nbss_full_fwd(const float* x, float* y, float* s_out, float* u_ou
     const int M = B * T;
     fullgemm_kernel<<<dim3((M + 63) / 64, kHS), 256, sm_g, st>>>(s_out, u_out, M, F, Wf, bf, 0);
     NBSS_LAUNCH_CHECK();
-    unsqueeze_fwd_kernel<<<tiles, 256, (size_t)kSQT * kHS * F * 4, st>>>(x, u_out, y, B, F, T, Wun, bun);
+    unsqueeze_fwd_kernel<<<dim3(tiles, fsplit), 256, (size_t)kSQT * kHS * F * 4, st>>>(x, u_out, y, B, F, T, Wun, bun);
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
 }
@@ -637,9 +678,10 @@ extern "C" int nbss_full_bwd(const float* x, const float* dy, float* dx, const f
     const int tiles = B * ((T + kSQT - 1) / kSQT), M = B * T;
     float* du = ws;
     float* ds = ws + (size_t)M * kHS * F;
-    const int pg = tiles < 4 * sms ? tiles : 4 * sms;  // persistent row kernels: 4 CTAs (32 warps) per SM
-    cudaFuncSetAttribute(unsqueeze_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * kSQT * kHS * F * 4));
-    unsqueeze_bwd_kernel<<<pg, 256, (size_t)2 * kSQT * kHS * F * 4, st>>>(dy, u, du, B, F, T, Wun, bun, dWun, dbun);
+    const int fsplit = f_split(tiles, F);
+    const int pg = tiles * fsplit < 4 * sms ? tiles * fsplit : 4 * sms;  // persistent row kernels: 4 CTAs (32 warps) per SM
+    cudaFuncSetAttribute(unsqueeze_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(2 * kSQT * kHS * F + 1024) * 4));
+    unsqueeze_bwd_kernel<<<pg, 256, (size_t)(2 * kSQT * kHS * F + 1024) * 4, st>>>(dy, u, du, B, F, T, Wun, bun, dWun, dbun, fsplit);
     NBSS_LAUNCH_CHECK();
     const size_t sm_g = (size_t)(F + 64) * (F + 1) * 4;
     cudaError_t e = cudaFuncSetAttribute(fullgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_g);
@@ -650,8 +692,61 @@ extern "C" int nbss_full_bwd(const float* x, const float* dy, float* dx, const f
     const int nkb = (F + 143) / 144, nfb = (F + 1 + 143) / 144;
     fullwgrad_kernel<<<dim3(chunks, kHS, nkb * nfb), 256, (size_t)2 * 32 * 144 * 4, st>>>(du, s, M, F, dWf, dbf);
     NBSS_LAUNCH_CHECK();
+    const size_t sm_sq = (size_t)(kHS * kH + kSQT * kHS * F + 1024) * 4;
+    squeeze_bwd_kernel<<<pg, 256, sm_sq, st>>>(x, dy, ds, dx, B, F, T, lnw, lnb, Wsq, bsq, dWsq, dbsq, dlnw, dlnb, fsplit);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+
+// ---- the same block with the LinearGroup on tensor cores (fullband_tc.cu); img from nbss_lg_pack ---------------------
+extern "C" int nbss_lg_tc_apply(const float* in, float* out, int M, int F, const void* img, const float* bias, int mode,
+                                int fmt, int* err, void* stream);
+extern "C" int nbss_lg_tc_wgrad(const float* du, const float* s, int M, int F, float* dW, float* db, int fmt, int* err,
+                                void* stream);
+
+extern "C" int nbss_full_fwd_tc(const float* x, float* y, float* s_out, float* u_out, int B, int F, int T, const float* lnw,
+                                const float* lnb, const float* Wsq, const float* bsq, const float* bf, const float* Wun,
+                                const float* bun, const void* img, int fmt, int* err, void* stream) {
+    if (!x || !y || !s_out || !u_out || !lnw || !lnb || !Wsq || !bsq || !bf || !Wun || !bun || !img) return NBSS_ERR_NULL;
+    if (B < 1 || F < 1 || T < 1) return NBSS_ERR_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tiles = B * ((T + kSQT - 1) / kSQT);
     const size_t sm_sq = (size_t)(kHS * kH + kSQT * kHS * F) * 4;
-    squeeze_bwd_kernel<<<pg, 256, sm_sq, st>>>(x, dy, ds, dx, B, F, T, lnw, lnb, Wsq, bsq, dWsq, dbsq, dlnw, dlnb);
+    if (sm_sq > 48 * 1024) return NBSS_ERR_UNSUPPORTED;
+    const int fsplit = f_split(tiles, F);
+    squeeze_fwd_kernel<<<dim3(tiles, fsplit), 256, sm_sq, st>>>(x, s_out, B, F, T, lnw, lnb, Wsq, bsq);
+    NBSS_LAUNCH_CHECK();
+    const int rc = nbss_lg_tc_apply(s_out, u_out, B * T, F, img, bf, 0, fmt, err, stream);
+    if (rc != NBSS_OK) return rc;
+    unsqueeze_fwd_kernel<<<dim3(tiles, fsplit), 256, (size_t)kSQT * kHS * F * 4, st>>>(x, u_out, y, B, F, T, Wun, bun);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+
+extern "C" int nbss_full_bwd_tc(const float* x, const float* dy, float* dx, const float* s, const float* u, float* ws, int B,
+                                int F, int T, const float* lnw, const float* lnb, const float* Wsq, const float* bsq,
+                                const float* Wun, const float* bun, const void* img, float* dlnw, float* dlnb, float* dWsq,
+                                float* dbsq, float* dWf, float* dbf, float* dWun, float* dbun, int fmt, int* err,
+                                void* stream) {
+    if (!x || !dy || !dx || !s || !u || !ws || !img) return NBSS_ERR_NULL;
+    if (B < 1 || F < 1 || T < 1) return NBSS_ERR_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sms = num_sms();
+    const int tiles = B * ((T + kSQT - 1) / kSQT), M = B * T;
+    float* du = ws;
+    float* ds = ws + (size_t)M * kHS * F;
+    const int fsplit = f_split(tiles, F);
+    const int pg = tiles * fsplit < 4 * sms ? tiles * fsplit : 4 * sms;
+    const size_t sm_un = (size_t)(2 * kSQT * kHS * F + 1024) * 4, sm_sq = (size_t)(kHS * kH + kSQT * kHS * F + 1024) * 4;
+    if (sm_un > 227 * 1024) return NBSS_ERR_UNSUPPORTED;
+    cudaFuncSetAttribute(unsqueeze_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_un);
+    unsqueeze_bwd_kernel<<<pg, 256, sm_un, st>>>(dy, u, du, B, F, T, Wun, bun, dWun, dbun, fsplit);
+    NBSS_LAUNCH_CHECK();
+    int rc = nbss_lg_tc_apply(du, ds, M, F, img, nullptr, 1, fmt, err, stream);
+    if (rc != NBSS_OK) return rc;
+    rc = nbss_lg_tc_wgrad(du, s, M, F, dWf, dbf, fmt, err, stream);
+    if (rc != NBSS_OK) return rc;
+    squeeze_bwd_kernel<<<pg, 256, sm_sq, st>>>(x, dy, ds, dx, B, F, T, lnw, lnb, Wsq, bsq, dWsq, dbsq, dlnw, dlnb, fsplit);
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
 }

@@ -48,51 +48,69 @@ struct FcGeom {
     int groups_per_b, ngroups;
 };
 
-// ------------------------------------------------------------------------------------------------ staging
-// LN(x) of the group's frames into the tile (fp16); rows of frames beyond T are zero; optional (mean, rstd) per tile row.
-template <int FMT>
+// ------------------------------------------------------------------------------------------------ row phases
+// The fp32 row phases walk the group's nfr*F (frame, f) rows with eight lanes per row (slab.cuh): a warp handles 4*U rows
+// per pass, row index i = R + U*sub + u.  nfr <= 4.
+__device__ __forceinline__ void fc_row(const FcGeom& g, int i, int& tt, int& f) {
+    tt = (i >= g.F) + (i >= 2 * g.F) + (i >= 3 * g.F);
+    f = i - tt * g.F;
+}
+
+// LN(x) of the group's frames into the tile (16-bit); rows of frames beyond T are zero; optional (mean, rstd) per tile row;
+// optionally the upstream gradient dy of the same rows into a second tile.
+template <int FMT, int U>
 __device__ __forceinline__ void fc_stage(const FcGeom& g, const float* __restrict__ x, int b, int t0, unsigned char* tile,
                                          const float* s_lnw, const float* s_lnb, float2* s_stats, int warp, int lane,
                                          const float* __restrict__ dy = nullptr, unsigned char* dytile = nullptr) {
-    const bool act = lane < 24;
-    float4 gw = make_float4(0, 0, 0, 0), gb = gw;
-    if (act) { gw = *reinterpret_cast<const float4*>(s_lnw + 4 * lane); gb = *reinterpret_cast<const float4*>(s_lnb + 4 * lane); }
-    // rows are walked per frame slot: f = warp, warp+8, ... (4 rows in flight per warp), no integer divisions
+    const int sub = lane >> 3, l8 = lane & 7, N = g.nfr * g.F;
+    Oct12 gw, gb;
+    gw.load(s_lnw, l8);
+    gb.load(s_lnb, l8);
+    const size_t loff = (size_t)(l8 >> 1) * g.cs + (l8 & 1) * 8;
 #pragma unroll 1
-    for (int tt = 0; tt < g.nfr; ++tt) {
-        const int t = t0 + tt;
-        const bool tok = t < g.T;
-#pragma unroll 1
-        for (int f0 = warp; f0 < g.F; f0 += 32) {
-            float4 v[4], w[4];
+    for (int R = 4 * U * warp; R < N; R += 32 * U) {
+        float4 v[U][3], w[U][3];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int f = f0 + 8 * j;
-                const bool ok = act && f < g.F && tok;
-                const size_t off = (((size_t)b * g.F + f) * g.T + t) * kH;
-                v[j] = ok ? __ldg(reinterpret_cast<const float4*>(x + off) + lane) : make_float4(0, 0, 0, 0);
-                w[j] = (ok && dy) ? __ldg(reinterpret_cast<const float4*>(dy + off) + lane) : make_float4(0, 0, 0, 0);
+        for (int u = 0; u < U; ++u) {
+            const int i = R + U * sub + u;
+            int tt, f;
+            fc_row(g, i, tt, f);
+            const bool ok = i < N && t0 + tt < g.T;
+            const float4* px = reinterpret_cast<const float4*>(x + (((size_t)b * g.F + f) * g.T + t0 + tt) * kH) + l8;
+            const float4* pd = reinterpret_cast<const float4*>((dy ? dy : x) + (((size_t)b * g.F + f) * g.T + t0 + tt) * kH) + l8;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                v[u][j] = ok ? __ldg(px + 8 * j) : make_float4(0, 0, 0, 0);
+                w[u][j] = (ok && dy) ? __ldg(pd + 8 * j) : make_float4(0, 0, 0, 0);
             }
+        }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int f = f0 + 8 * j;
-                if (f >= g.F) continue;
-                const int p = 2 + tt * g.FP + f;
-                const float s = warp_sum(v[j].x + v[j].y + v[j].z + v[j].w);
-                const float mean = s * (1.f / kH);
-                const float4 d = act ? make_float4(v[j].x - mean, v[j].y - mean, v[j].z - mean, v[j].w - mean) : make_float4(0, 0, 0, 0);
-                const float qv = warp_sum(d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w);
-                const float rstd = rsqrtf(qv * (1.f / kH) + 1e-5f);
-                if (s_stats && lane == 0) s_stats[p] = make_float2(mean, rstd);
-                if (act) {
+        for (int u = 0; u < U; ++u) {
+            const int i = R + U * sub + u;
+            int tt, f;
+            fc_row(g, i, tt, f);
+            const bool tok = t0 + tt < g.T;
+            const int p = 2 + tt * g.FP + f;
+            const float mean = oct_sum(f4_hsum(v[u][0]) + f4_hsum(v[u][1]) + f4_hsum(v[u][2])) * (1.f / kH);
+            float q = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                v[u][j] = make_float4(v[u][j].x - mean, v[u][j].y - mean, v[u][j].z - mean, v[u][j].w - mean);
+                q += f4_dot(v[u][j], v[u][j]);
+            }
+            const float rstd = rsqrtf(oct_sum(q) * (1.f / kH) + 1e-5f);
+            if (i < N) {
+                if (s_stats && l8 == 0) s_stats[p] = make_float2(mean, rstd);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
                     uint2 pk = make_uint2(0u, 0u);
                     if (tok)
-                        pk = make_uint2(pack16<FMT>(d.x * rstd * gw.x + gb.x, d.y * rstd * gw.y + gb.y),
-                                        pack16<FMT>(d.z * rstd * gw.z + gb.z, d.w * rstd * gw.w + gb.w));
-                    *reinterpret_cast<uint2*>(tile + (size_t)(lane >> 1) * g.cs + p * 16 + (lane & 1) * 8) = pk;
+                        pk = make_uint2(pack16<FMT>(v[u][j].x * rstd * gw.v[j].x + gb.v[j].x, v[u][j].y * rstd * gw.v[j].y + gb.v[j].y),
+                                        pack16<FMT>(v[u][j].z * rstd * gw.v[j].z + gb.v[j].z, v[u][j].w * rstd * gw.v[j].w + gb.v[j].w));
+                    *reinterpret_cast<uint2*>(tile + loff + (size_t)(4 * j) * g.cs + p * 16) = pk;
                     if (dytile)  // upstream gradient of the same row, 16-bit, same slot of the second tile
-                        *reinterpret_cast<uint2*>(dytile + (size_t)(lane >> 1) * g.cs + p * 16 + (lane & 1) * 8) =
-                            make_uint2(pack16<FMT>(w[j].x, w[j].y), pack16<FMT>(w[j].z, w[j].w));
+                        *reinterpret_cast<uint2*>(dytile + loff + (size_t)(4 * j) * g.cs + p * 16) =
+                            make_uint2(pack16<FMT>(w[u][j].x, w[u][j].y), pack16<FMT>(w[u][j].z, w[u][j].w));
                 }
             }
         }
@@ -153,7 +171,7 @@ __global__ void __launch_bounds__(256, 2) fconv_tc_fwd_kernel(FcFwdArgs a) {
     bool wready = false;
     for (int grp = blockIdx.x; grp < g.ngroups; grp += gridDim.x) {
         const int b = grp / g.groups_per_b, t0 = (grp % g.groups_per_b) * g.nfr;
-        fc_stage<FMT>(g, a.x, b, t0, tile, cst, cst + 96, nullptr, warp, lane);
+        fc_stage<FMT, 5>(g, a.x, b, t0, tile, cst, cst + 96, nullptr, warp, lane);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -192,32 +210,38 @@ __global__ void __launch_bounds__(256, 2) fconv_tc_fwd_kernel(FcFwdArgs a) {
         }
         tc_fence_before();
         __syncthreads();
-        // epilogue 2: warp per (frame, f) row, coalesced: y = x + branch
+        // epilogue 2: eight lanes per (frame, f) row, coalesced: y = x + branch
         {
-            const bool act = lane < 24;
+            constexpr int U = 5;
+            const int sub = lane >> 3, l8 = lane & 7, N = g.nfr * g.F;
+            const size_t loff = (size_t)(l8 >> 1) * g.cs + (l8 & 1) * 8;
 #pragma unroll 1
-            for (int tt = 0; tt < g.nfr; ++tt) {
-                const int t = t0 + tt;
-                if (t >= g.T) break;
-#pragma unroll 1
-                for (int f0 = warp; f0 < g.F; f0 += 32) {
-                    float4 xv[4];
+            for (int R = 4 * U * warp; R < N; R += 32 * U) {
+                float4 xv[U][3];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int f = f0 + 8 * j;
-                        xv[j] = (act && f < g.F) ? __ldg(reinterpret_cast<const float4*>(a.x + (((size_t)b * g.F + f) * g.T + t) * kH) + lane)
-                                                 : make_float4(0, 0, 0, 0);
-                    }
+                for (int u = 0; u < U; ++u) {
+                    const int i = R + U * sub + u;
+                    int tt, f;
+                    fc_row(g, i, tt, f);
+                    const bool ok = i < N && t0 + tt < g.T;
+                    const float4* px = reinterpret_cast<const float4*>(a.x + (((size_t)b * g.F + f) * g.T + t0 + tt) * kH) + l8;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int f = f0 + 8 * j;
-                        if (!(act && f < g.F)) continue;
-                        const uint2 pk = *reinterpret_cast<const uint2*>(tile + (size_t)(lane >> 1) * g.cs + (2 + tt * g.FP + f) * 16 + (lane & 1) * 8);
+                    for (int j = 0; j < 3; ++j) xv[u][j] = ok ? __ldg(px + 8 * j) : make_float4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = R + U * sub + u;
+                    int tt, f;
+                    fc_row(g, i, tt, f);
+                    if (!(i < N && t0 + tt < g.T)) continue;
+                    float4* py = reinterpret_cast<float4*>(a.y + (((size_t)b * g.F + f) * g.T + t0 + tt) * kH) + l8;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const uint2 pk = *reinterpret_cast<const uint2*>(tile + loff + (size_t)(4 * j) * g.cs + (2 + tt * g.FP + f) * 16);
                         float b0, b1, b2, b3;
                         unpack16<FMT>(pk.x, b0, b1);
                         unpack16<FMT>(pk.y, b2, b3);
-                        reinterpret_cast<float4*>(a.y + (((size_t)b * g.F + f) * g.T + t) * kH)[lane] =
-                            make_float4(xv[j].x + b0, xv[j].y + b1, xv[j].z + b2, xv[j].w + b3);
+                        py[8 * j] = make_float4(xv[u][j].x + b0, xv[u][j].y + b1, xv[u][j].z + b2, xv[u][j].w + b3);
                     }
                 }
             }
@@ -278,10 +302,10 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
     float dw[60];
 #pragma unroll
     for (int i = 0; i < 60; ++i) dw[i] = 0.f;
-    // LayerNorm affine gradients: lane l < 24 owns channels 4l..4l+3 in the warp-per-row phase
-    const bool act24 = lane < 24;
-    float4 gw4 = make_float4(0, 0, 0, 0), dg4 = gw4, db4 = gw4;
-    if (act24) gw4 = *reinterpret_cast<const float4*>(cst + 4 * lane);
+    // LayerNorm affine gradients: every lane owns 12 channels in the eight-lanes-per-row phase (slab.cuh: Oct12)
+    Oct12 dlg, dlb;
+    dlg.zero();
+    dlb.zero();
 
     auto wait_mma = [&]() {
         __syncwarp();
@@ -292,7 +316,7 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
     for (int grp = blockIdx.x; grp < g.ngroups; grp += gridDim.x) {
         const int b = grp / g.groups_per_b, t0 = (grp % g.groups_per_b) * g.nfr;
         if (tid == 0) load_image(wimg, a.img, FC_IMG_BYTES, bar_w);
-        fc_stage<FMT>(g, a.x, b, t0, htile, cst, cst + 96, stats, warp, lane, a.dy, gtile);
+        fc_stage<FMT, 3>(g, a.x, b, t0, htile, cst, cst + 96, stats, warp, lane, a.dy, gtile);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -412,45 +436,62 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
         }
         tc_fence_before();
         __syncthreads();
-        // ---- E-B2: warp per (frame, f) row, coalesced: LayerNorm backward + residual; d gamma / d beta per lane
+        // ---- E-B2: eight lanes per (frame, f) row, coalesced: LayerNorm backward + residual; d gamma / d beta per lane
         {
+            constexpr int U = 3;
+            const int sub = lane >> 3, l8 = lane & 7, N = g.nfr * g.F;
+            const size_t loff = (size_t)(l8 >> 1) * g.cs + (l8 & 1) * 8;
 #pragma unroll 1
-            for (int tt = 0; tt < g.nfr; ++tt) {
-                const int t = t0 + tt;
-                if (t >= g.T) break;
-#pragma unroll 1
-                for (int f0 = warp; f0 < g.F; f0 += 32) {
-                    float4 xv[4], dv[4];
+            for (int R = 4 * U * warp; R < N; R += 32 * U) {
+                float4 xv[U][3], dv[U][3];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int f = f0 + 8 * j;
-                        const bool ok = act24 && f < g.F;
-                        const size_t off = (((size_t)b * g.F + f) * g.T + t) * kH;
-                        xv[j] = ok ? __ldg(reinterpret_cast<const float4*>(a.x + off) + lane) : make_float4(0, 0, 0, 0);
-                        dv[j] = ok ? __ldg(reinterpret_cast<const float4*>(a.dy + off) + lane) : make_float4(0, 0, 0, 0);
+                for (int u = 0; u < U; ++u) {
+                    const int i = R + U * sub + u;
+                    int tt, f;
+                    fc_row(g, i, tt, f);
+                    const bool ok = i < N && t0 + tt < g.T;
+                    const size_t off = (((size_t)b * g.F + f) * g.T + t0 + tt) * kH;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        xv[u][j] = ok ? __ldg(reinterpret_cast<const float4*>(a.x + off) + l8 + 8 * j) : make_float4(0, 0, 0, 0);
+                        dv[u][j] = ok ? __ldg(reinterpret_cast<const float4*>(a.dy + off) + l8 + 8 * j) : make_float4(0, 0, 0, 0);
                     }
+                }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int f = f0 + 8 * j;
-                        if (f >= g.F) continue;  // warp-uniform
-                        const int p = 2 + tt * g.FP + f;
-                        const float2 st = stats[p];
-                        float4 dh = make_float4(0, 0, 0, 0), xh = dh;
-                        if (act24) {
-                            const uint2 pk = *reinterpret_cast<const uint2*>(htile + (size_t)(lane >> 1) * g.cs + p * 16 + (lane & 1) * 8);
-                            unpack16<FMT>(pk.x, dh.x, dh.y);
-                            unpack16<FMT>(pk.y, dh.z, dh.w);
-                            xh = make_float4((xv[j].x - st.x) * st.y, (xv[j].y - st.x) * st.y, (xv[j].z - st.x) * st.y, (xv[j].w - st.x) * st.y);
+                for (int u = 0; u < U; ++u) {
+                    const int i = R + U * sub + u;
+                    int tt, f;
+                    fc_row(g, i, tt, f);
+                    const bool ok = i < N && t0 + tt < g.T;
+                    const int p = 2 + tt * g.FP + f;
+                    const float2 st = ok ? stats[p] : make_float2(0.f, 0.f);
+                    float4 dh[3];
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        dh[j] = make_float4(0, 0, 0, 0);
+                        if (ok) {
+                            const uint2 pk = *reinterpret_cast<const uint2*>(htile + loff + (size_t)(4 * j) * g.cs + p * 16);
+                            unpack16<FMT>(pk.x, dh[j].x, dh[j].y);
+                            unpack16<FMT>(pk.y, dh[j].z, dh[j].w);
                         }
-                        const float4 dxh = make_float4(dh.x * gw4.x, dh.y * gw4.y, dh.z * gw4.z, dh.w * gw4.w);
-                        const float m1 = warp_sum(dxh.x + dxh.y + dxh.z + dxh.w) * (1.f / kH);
-                        const float m2 = warp_sum(dxh.x * xh.x + dxh.y * xh.y + dxh.z * xh.z + dxh.w * xh.w) * (1.f / kH);
-                        dg4 = make_float4(dg4.x + dh.x * xh.x, dg4.y + dh.y * xh.y, dg4.z + dh.z * xh.z, dg4.w + dh.w * xh.w);
-                        db4 = make_float4(db4.x + dh.x, db4.y + dh.y, db4.z + dh.z, db4.w + dh.w);
-                        if (act24)
-                            reinterpret_cast<float4*>(a.dx + (((size_t)b * g.F + f) * g.T + t) * kH)[lane] =
-                                make_float4(dv[j].x + st.y * (dxh.x - m1 - xh.x * m2), dv[j].y + st.y * (dxh.y - m1 - xh.y * m2),
-                                            dv[j].z + st.y * (dxh.z - m1 - xh.z * m2), dv[j].w + st.y * (dxh.w - m1 - xh.w * m2));
+                        xv[u][j] = make_float4((xv[u][j].x - st.x) * st.y, (xv[u][j].y - st.x) * st.y, (xv[u][j].z - st.x) * st.y,
+                                               (xv[u][j].w - st.x) * st.y);  // x hat (0 for rows that are not ok)
+                        dlg.v[j] = make_float4(dlg.v[j].x + dh[j].x * xv[u][j].x, dlg.v[j].y + dh[j].y * xv[u][j].y,
+                                               dlg.v[j].z + dh[j].z * xv[u][j].z, dlg.v[j].w + dh[j].w * xv[u][j].w);
+                        dlb.v[j] = make_float4(dlb.v[j].x + dh[j].x, dlb.v[j].y + dh[j].y, dlb.v[j].z + dh[j].z, dlb.v[j].w + dh[j].w);
+                        const float4 gj = *reinterpret_cast<const float4*>(cst + 4 * (l8 + 8 * j));
+                        dh[j] = make_float4(dh[j].x * gj.x, dh[j].y * gj.y, dh[j].z * gj.z, dh[j].w * gj.w);
+                        s1 += f4_hsum(dh[j]);
+                        s2 += f4_dot(dh[j], xv[u][j]);
+                    }
+                    const float m1 = oct_sum(s1) * (1.f / kH), m2 = oct_sum(s2) * (1.f / kH);
+                    if (ok) {
+                        float4* pdx = reinterpret_cast<float4*>(a.dx + (((size_t)b * g.F + f) * g.T + t0 + tt) * kH) + l8;
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+                            pdx[8 * j] = make_float4(dv[u][j].x + st.y * (dh[j].x - m1 - xv[u][j].x * m2), dv[u][j].y + st.y * (dh[j].y - m1 - xv[u][j].y * m2),
+                                                     dv[u][j].z + st.y * (dh[j].z - m1 - xv[u][j].z * m2), dv[u][j].w + st.y * (dh[j].w - m1 - xv[u][j].w * m2));
                     }
                 }
             }
@@ -467,12 +508,8 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
         atomicAdd(a.dbias + i, acc[i]);
         atomicAdd(a.dslope + i, acc[96 + i]);
     }
-    if (act24) {
-        atomicAdd(a.dlnw + 4 * lane + 0, dg4.x); atomicAdd(a.dlnw + 4 * lane + 1, dg4.y);
-        atomicAdd(a.dlnw + 4 * lane + 2, dg4.z); atomicAdd(a.dlnw + 4 * lane + 3, dg4.w);
-        atomicAdd(a.dlnb + 4 * lane + 0, db4.x); atomicAdd(a.dlnb + 4 * lane + 1, db4.y);
-        atomicAdd(a.dlnb + 4 * lane + 2, db4.z); atomicAdd(a.dlnb + 4 * lane + 3, db4.w);
-    }
+    dlg.flush_atomic(a.dlnw, lane);
+    dlb.flush_atomic(a.dlnb, lane);
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 

@@ -108,9 +108,6 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
                    id96 = make_idesc(FMT, 128, 96, 0, 0);
     uint32_t ph_mma = 0, ph_w0 = 0, ph_w1 = 0;
     const float inv_n = 1.f / (float)(kGC * T);
-    // LayerNorm affine gradients: lane l < 24 owns channels 4l..4l+3 in the warp-per-frame phase
-    float4 lng4 = make_float4(0, 0, 0, 0), dlng4 = lng4, dlnb4 = lng4;
-    if (lane < 24) lng4 = *reinterpret_cast<const float4*>(s_lng + 4 * lane);
 
     auto wait_mma = [&]() {
         __syncwarp();
@@ -187,7 +184,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
             load_image(ws1, a.img + IMG_WC3T, IMG_WC_BYTES, bar_w1);
         }
         // ---- B0: dy -> G (chunks 0..11)
-        stage_rows96<FMT, false>(dys, T, hbuf, 1, nullptr, nullptr, warp, lane, nullptr, kFfnBwdThreads / 32);
+        stage_rows96<FMT, false, 2>(dys, T, hbuf, 1, nullptr, nullptr, warp, lane, nullptr, kFfnBwdThreads / 32);
         end_epilogue();
         // ---- B1: d s4 = dy W2
         if (tid == 0) {
@@ -313,21 +310,21 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
             }
             tc_fence_before();
             __syncthreads();
-            // E5b: warp per frame: LayerNorm backward + residual, coalesced
+            // E5b: eight lanes per frame: LayerNorm backward + residual, coalesced; d gamma / d beta -> smem accumulators
+            Oct12 dlng, dlnb;
+            dlng.zero();
+            dlnb.zero();
             ln_bwd_rows(hbuf, kCS, 1, a.x + (size_t)slab * T * kH, dys, a.dx + (size_t)slab * T * kH, a.ln_stats + (size_t)slab * T * 2, T,
-                        lng4, dlng4, dlnb4, warp, lane, kFfnBwdThreads / 32);
+                        s_lng, dlng, dlnb, warp, lane, kFfnBwdThreads / 32);
+            dlng.flush_atomic(acc + 384, lane);
+            dlnb.flush_atomic(acc + 480, lane);
         }
         tc_fence_before();
         __syncthreads();
     }
     // flush the affine-parameter gradients
     for (int i = tid; i < 192; i += kFfnBwdThreads) { atomicAdd(a.d_gnw + i, acc[i]); atomicAdd(a.d_gnb + i, acc[192 + i]); }
-    if (lane < 24) {
-        atomicAdd(a.d_lnw + 4 * lane + 0, dlng4.x); atomicAdd(a.d_lnw + 4 * lane + 1, dlng4.y);
-        atomicAdd(a.d_lnw + 4 * lane + 2, dlng4.z); atomicAdd(a.d_lnw + 4 * lane + 3, dlng4.w);
-        atomicAdd(a.d_lnb + 4 * lane + 0, dlnb4.x); atomicAdd(a.d_lnb + 4 * lane + 1, dlnb4.y);
-        atomicAdd(a.d_lnb + 4 * lane + 2, dlnb4.z); atomicAdd(a.d_lnb + 4 * lane + 3, dlnb4.w);
-    }
+    for (int i = tid; i < 96; i += kFfnBwdThreads) { atomicAdd(a.d_lnw + i, acc[384 + i]); atomicAdd(a.d_lnb + i, acc[480 + i]); }
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 

@@ -295,15 +295,8 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         }
         tc_fence_before();
         __syncthreads();
-        // E5b: warp per frame: y = x + branch (24 lanes x float4 = one 384-byte row)
-        if (lane < 24) {
-#pragma unroll 4
-            for (int r = warp; r < T; r += kFfnThreads / 32) {
-                const float4 v = *reinterpret_cast<const float4*>(hbuf + lane * kCS + (r + 1) * 16);
-                const float4 xv = __ldg(reinterpret_cast<const float4*>(xs + (size_t)r * kH) + lane);
-                reinterpret_cast<float4*>(a.y + ((size_t)slab * T + r) * kH)[lane] = make_float4(xv.x + v.x, xv.y + v.y, xv.z + v.z, xv.w + v.w);
-            }
-        }
+        // E5b: eight lanes per frame: y = x + branch, coalesced
+        add_rows(hbuf, kCS, 1, xs, a.y + (size_t)slab * T * kH, T, warp, lane, kFfnThreads / 32);
         tc_fence_before();
         __syncthreads();  // TMEM + H are reused by the next slab
     }

@@ -307,8 +307,6 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a
     const uint32_t id96 = make_idesc(FMT_G, 128, 96, 0, 0);
     uint32_t ph = 0, ph_ld = 0;
     bool wready = false;
-    float4 lng4 = make_float4(0, 0, 0, 0), dlng4 = lng4, dlnb4 = lng4;
-    if (lane < 24) lng4 = *reinterpret_cast<const float4*>(s_lng + 4 * lane);
     for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
         const size_t row0 = (size_t)slab * T, grow = row0 + t;
         if (tid == 0) bulk_load_chunks(at, kCS, 0, a.dqkv + tile_off(slab, 36, T, 0, 0), 36, T, bar_ld);
@@ -343,17 +341,19 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a
         }
         tc_fence_before();
         __syncthreads();
-        ln_bwd_rows(at, kCS, 0, a.x + row0 * kH, a.dy + row0 * kH, a.dx + row0 * kH, a.ln_stats + row0 * 2, T, lng4, dlng4, dlnb4, warp, lane,
-                    kMbThreads / 32);
+        {
+            Oct12 dlng, dlnb;
+            dlng.zero();
+            dlnb.zero();
+            ln_bwd_rows(at, kCS, 0, a.x + row0 * kH, a.dy + row0 * kH, a.dx + row0 * kH, a.ln_stats + row0 * 2, T, s_lng, dlng, dlnb, warp, lane,
+                        kMbThreads / 32);
+            dlng.flush_atomic(acc, lane);
+            dlnb.flush_atomic(acc + 96, lane);
+        }
         tc_fence_before();
         __syncthreads();
     }
-    if (lane < 24) {
-        atomicAdd(a.d_lnw + 4 * lane + 0, dlng4.x); atomicAdd(a.d_lnw + 4 * lane + 1, dlng4.y);
-        atomicAdd(a.d_lnw + 4 * lane + 2, dlng4.z); atomicAdd(a.d_lnw + 4 * lane + 3, dlng4.w);
-        atomicAdd(a.d_lnb + 4 * lane + 0, dlnb4.x); atomicAdd(a.d_lnb + 4 * lane + 1, dlnb4.y);
-        atomicAdd(a.d_lnb + 4 * lane + 2, dlnb4.z); atomicAdd(a.d_lnb + 4 * lane + 3, dlnb4.w);
-    }
+    for (int i = tid; i < 96; i += kMbThreads) { atomicAdd(a.d_lnw + i, acc[i]); atomicAdd(a.d_lnb + i, acc[96 + i]); }
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 

@@ -278,29 +278,28 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         ph_w ^= 1;
         wait_mma();
         {
-            // NOTE: tcgen05.ld is warp-collective (.sync.aligned): issue it for every lane, predicate only the stores
-            const bool valid = t < T;
+            // thread = (frame, channel half): D + b_out -> fp32, staged into the dead K|V tiles at the frame's row slot (24
+            // four-float chunks = the 12 K data chunks + V chunks 0..11; the zero pad chunks of K stay untouched:
+            // slab.cuh skip4_chunk); then eight lanes per frame add the residual with coalesced traffic
             const uint32_t tacc = tmem + lane_off + 192 + m * 96;
-            const float4* xr = reinterpret_cast<const float4*>(xs + (size_t)(valid ? t : 0) * kH);
-            float4* yr = reinterpret_cast<float4*>(a.y + ((size_t)slab * T + (valid ? t : 0)) * kH);
 #pragma unroll 1
             for (int c0 = 48 * hf; c0 < 48 * hf + 48; c0 += 16) {
                 uint32_t r[16];
                 tmem_ld16(tacc + c0, r);
                 tmem_ld_wait();
-                if (valid) {
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        float4 xv = __ldg(xr + c0 / 4 + j4);
-                        float4 o;
-                        o.x = xv.x + __uint_as_float(r[4 * j4 + 0]) + s_bout[c0 + 4 * j4 + 0];
-                        o.y = xv.y + __uint_as_float(r[4 * j4 + 1]) + s_bout[c0 + 4 * j4 + 1];
-                        o.z = xv.z + __uint_as_float(r[4 * j4 + 2]) + s_bout[c0 + 4 * j4 + 2];
-                        o.w = xv.w + __uint_as_float(r[4 * j4 + 3]) + s_bout[c0 + 4 * j4 + 3];
-                        yr[c0 / 4 + j4] = o;
-                    }
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    float4 o;
+                    o.x = __uint_as_float(r[4 * j4 + 0]) + s_bout[c0 + 4 * j4 + 0];
+                    o.y = __uint_as_float(r[4 * j4 + 1]) + s_bout[c0 + 4 * j4 + 1];
+                    o.z = __uint_as_float(r[4 * j4 + 2]) + s_bout[c0 + 4 * j4 + 2];
+                    o.w = __uint_as_float(r[4 * j4 + 3]) + s_bout[c0 + 4 * j4 + 3];
+                    *reinterpret_cast<float4*>(kt + (size_t)skip4_chunk(c0 / 4 + j4) * kCS + t * 16) = o;
                 }
             }
+            tc_fence_before();
+            __syncthreads();
+            add_rows<true>(kt, kCS, 0, xs, a.y + (size_t)slab * T * kH, T, warp, lane, kMhThreads / 32);
         }
         tc_fence_before();
         __syncthreads();

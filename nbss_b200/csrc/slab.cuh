@@ -73,47 +73,90 @@ __device__ __forceinline__ void unpack16(uint32_t p, float& lo, float& hi) {
     else { lo = bf16lo_to_f32(p); hi = bf16hi_to_f32(p); }
 }
 
+// ---------------------------------------------------------------- 8-lanes-per-row helpers
+// The fp32 row phases give every 96-channel row to EIGHT lanes (a warp works on 4 rows at once): lane l8 = lane & 7 of
+// row-group sub = lane >> 3 owns the three float4 at channels 4*(l8 + 8j), j = 0..2.  A row's three loads are three
+// coalesced 128-byte segments, a row reduction is 3 shuffles shared by 4 rows (instead of 5 for one row), and all 32
+// lanes work (a warp-per-row walk only uses 24).
+__device__ __forceinline__ float oct_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+__device__ __forceinline__ float f4_hsum(const float4 a) { return (a.x + a.y) + (a.z + a.w); }
+__device__ __forceinline__ float f4_dot(const float4 a, const float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+
+// Per-lane channel-owned accumulators of the row phases (d gamma / d beta ...): 3 float4 at channels 4*(l8 + 8j).
+struct Oct12 {
+    float4 v[3];
+    __device__ __forceinline__ void zero() { v[0] = v[1] = v[2] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ void load(const float* p, int l8) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) v[j] = *reinterpret_cast<const float4*>(p + 4 * (l8 + 8 * j));
+    }
+    // sum over the 4 row-groups of the warp, then lanes 0..7 add their 12 channels into dst[96]
+    __device__ __forceinline__ void flush_atomic(float* dst, int lane) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float c[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                c[e] += __shfl_xor_sync(0xffffffffu, c[e], 8);
+                c[e] += __shfl_xor_sync(0xffffffffu, c[e], 16);
+                if (lane < 8) atomicAdd(dst + 4 * (lane + 8 * j) + e, c[e]);
+            }
+        }
+    }
+};
+
 // ---------------------------------------------------------------- staging: fp32 rows -> (LayerNorm) -> 16-bit tile
-// Warp-per-row, coalesced float4 loads (24 lanes x 16 B = one 96-channel row).  Writes rows [row_off, row_off+256)
-// of the tile; rows t >= T are written as zeros.  gamma/beta in shared memory.
-template <int FMT, bool LN>
+// Writes rows [row_off, row_off+256) of the tile; rows t >= T are written as zeros.  gamma/beta in shared memory.
+// Each warp takes 16-row blocks; one load/store instruction covers rows R + 4*sub + u (u = 0..3 unrolled), which spreads
+// the 8-byte tile stores of a warp over all 32 banks twice (the minimum for 256 bytes).
+template <int FMT, bool LN, int U = 4>
 __device__ __forceinline__ void stage_rows96(const float* __restrict__ xslab, int T, unsigned char* tile, int row_off,
                                              const float* s_gamma, const float* s_beta, int warp, int lane,
                                              float* stats_out = nullptr /* [T,2] (mean, rstd) of this slab */,
                                              int nwarps = 8) {
-    const bool act = lane < 24;
-    float4 g = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (LN && act) {
-        g = *reinterpret_cast<const float4*>(s_gamma + 4 * lane);
-        be = *reinterpret_cast<const float4*>(s_beta + 4 * lane);
-    }
-    const int iters = 256 / nwarps;
+    const int sub = lane >> 3, l8 = lane & 7;
+    Oct12 g, be;
+    if (LN) { g.load(s_gamma, l8); be.load(s_beta, l8); }
+    unsigned char* tl = tile + (size_t)(l8 >> 1) * kCS + (l8 & 1) * 8 + (size_t)row_off * 16;
 #pragma unroll 1
-    for (int i = 0; i < iters; i += 4) {
-        float4 v[4];
+    for (int R = 4 * U * warp; R < 256; R += 4 * U * nwarps) {
+        float4 v[U][3];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int r = warp + nwarps * (i + j);
-            v[j] = (act && r < T) ? __ldg(reinterpret_cast<const float4*>(xslab + (size_t)r * kH) + lane)
+        for (int u = 0; u < U; ++u) {
+            const int r = R + U * sub + u;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                v[u][j] = (r < T) ? __ldg(reinterpret_cast<const float4*>(xslab + (size_t)r * kH) + l8 + 8 * j)
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int r = warp + nwarps * (i + j);
-            float4 y = v[j];
+        for (int u = 0; u < U; ++u) {
+            const int r = R + U * sub + u;
+            const bool ok = r < T;
             if (LN) {
-                float s = warp_sum(y.x + y.y + y.z + y.w);
-                const float mean = s * (1.f / kH);
-                float4 d = act ? make_float4(y.x - mean, y.y - mean, y.z - mean, y.w - mean) : make_float4(0, 0, 0, 0);
-                float q = warp_sum(d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w);
-                const float rstd = rsqrtf(q * (1.f / kH) + 1e-5f);
-                y = make_float4(d.x * rstd * g.x + be.x, d.y * rstd * g.y + be.y, d.z * rstd * g.z + be.z,
-                                d.w * rstd * g.w + be.w);
-                if (stats_out && lane == 0 && r < T) *reinterpret_cast<float2*>(stats_out + 2 * r) = make_float2(mean, rstd);
+                const float mean = oct_sum(f4_hsum(v[u][0]) + f4_hsum(v[u][1]) + f4_hsum(v[u][2])) * (1.f / kH);
+                float q = 0.f;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    v[u][j] = make_float4(v[u][j].x - mean, v[u][j].y - mean, v[u][j].z - mean, v[u][j].w - mean);
+                    q += f4_dot(v[u][j], v[u][j]);
+                }
+                const float rstd = rsqrtf(oct_sum(q) * (1.f / kH) + 1e-5f);
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    v[u][j] = make_float4(v[u][j].x * rstd * g.v[j].x + be.v[j].x, v[u][j].y * rstd * g.v[j].y + be.v[j].y,
+                                          v[u][j].z * rstd * g.v[j].z + be.v[j].z, v[u][j].w * rstd * g.v[j].w + be.v[j].w);
+                if (stats_out && l8 == 0 && ok) *reinterpret_cast<float2*>(stats_out + 2 * r) = make_float2(mean, rstd);
             }
-            if (act) {
-                uint2 p = (r < T) ? make_uint2(pack16<FMT>(y.x, y.y), pack16<FMT>(y.z, y.w)) : make_uint2(0u, 0u);
-                *reinterpret_cast<uint2*>(tile + (lane >> 1) * kCS + (r + row_off) * 16 + (lane & 1) * 8) = p;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const uint2 p = ok ? make_uint2(pack16<FMT>(v[u][j].x, v[u][j].y), pack16<FMT>(v[u][j].z, v[u][j].w)) : make_uint2(0u, 0u);
+                *reinterpret_cast<uint2*>(tl + (size_t)(4 * j) * kCS + r * 16) = p;
             }
         }
     }
@@ -154,34 +197,94 @@ __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
     return v[0];
 }
 
-// LayerNorm backward + residual, one warp per frame, fully coalesced.  `tile` holds d z (gradient wrt the LN output) as fp32
-// staged by the thread-per-frame TMEM epilogue with 4-float chunks: addr = tile + chunk*cs + (r + row_off)*16.
-// Lane l < 24 owns channels 4l..4l+3; it accumulates d gamma / d beta in registers across frames (and slabs).
+// LayerNorm backward + residual, eight lanes per frame (see above), fully coalesced.  `tile` holds d z (gradient wrt the
+// LN output) as fp32 staged by the thread-per-frame TMEM epilogue with 4-float chunks: addr = tile + chunk*cs + (r + row_off)*16.
+// Every lane accumulates d gamma / d beta of its 12 channels in registers across frames (and slabs): Oct12::flush_atomic.
 __device__ __forceinline__ void ln_bwd_rows(const unsigned char* tile, uint32_t cs, int row_off, const float* __restrict__ xs,
                                             const float* __restrict__ dys, float* __restrict__ dxs,
-                                            const float* __restrict__ stats, int T, const float4 g4, float4& dg4, float4& db4,
-                                            int warp, int lane, int nwarps) {
-    const bool act = lane < 24;
-#pragma unroll 4
-    for (int r = warp; r < T; r += nwarps) {
-        float4 dz = make_float4(0, 0, 0, 0), xv = dz, dv = dz;
-        if (act) {
-            dz = *reinterpret_cast<const float4*>(tile + (size_t)lane * cs + (r + row_off) * 16);
-            xv = __ldg(reinterpret_cast<const float4*>(xs + (size_t)r * kH) + lane);
-            dv = __ldg(reinterpret_cast<const float4*>(dys + (size_t)r * kH) + lane);
+                                            const float* __restrict__ stats, int T, const float* s_gamma /* smem */, Oct12& dg,
+                                            Oct12& db, int warp, int lane, int nwarps) {
+    const int sub = lane >> 3, l8 = lane & 7;
+    const unsigned char* tl = tile + (size_t)l8 * cs + (size_t)row_off * 16;
+#pragma unroll 1
+    for (int R = 8 * warp; R < T; R += 8 * nwarps) {
+        float4 xv[2][3], dv[2][3];
+        float2 st[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int r = R + 2 * sub + u;
+            const bool ok = r < T;
+            st[u] = ok ? __ldg(reinterpret_cast<const float2*>(stats + 2 * r)) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                xv[u][j] = ok ? __ldg(reinterpret_cast<const float4*>(xs + (size_t)r * kH) + l8 + 8 * j) : make_float4(0, 0, 0, 0);
+                dv[u][j] = ok ? __ldg(reinterpret_cast<const float4*>(dys + (size_t)r * kH) + l8 + 8 * j) : make_float4(0, 0, 0, 0);
+            }
         }
-        const float2 st = __ldg(reinterpret_cast<const float2*>(stats + 2 * r));
-        const float4 xh = act ? make_float4((xv.x - st.x) * st.y, (xv.y - st.x) * st.y, (xv.z - st.x) * st.y, (xv.w - st.x) * st.y)
-                              : make_float4(0, 0, 0, 0);
-        const float4 dzg = make_float4(dz.x * g4.x, dz.y * g4.y, dz.z * g4.z, dz.w * g4.w);
-        const float m1 = warp_sum(dzg.x + dzg.y + dzg.z + dzg.w) * (1.f / kH);
-        const float m2 = warp_sum(dzg.x * xh.x + dzg.y * xh.y + dzg.z * xh.z + dzg.w * xh.w) * (1.f / kH);
-        dg4 = make_float4(dg4.x + dz.x * xh.x, dg4.y + dz.y * xh.y, dg4.z + dz.z * xh.z, dg4.w + dz.w * xh.w);
-        db4 = make_float4(db4.x + dz.x, db4.y + dz.y, db4.z + dz.z, db4.w + dz.w);
-        if (act)
-            reinterpret_cast<float4*>(dxs + (size_t)r * kH)[lane] =
-                make_float4(dv.x + st.y * (dzg.x - m1 - xh.x * m2), dv.y + st.y * (dzg.y - m1 - xh.y * m2),
-                            dv.z + st.y * (dzg.z - m1 - xh.z * m2), dv.w + st.y * (dzg.w - m1 - xh.w * m2));
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int r = R + 2 * sub + u;
+            const bool ok = r < T;
+            float4 dz[3];
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                dz[j] = ok ? *reinterpret_cast<const float4*>(tl + (size_t)(8 * j) * cs + r * 16) : make_float4(0, 0, 0, 0);
+                xv[u][j] = make_float4((xv[u][j].x - st[u].x) * st[u].y, (xv[u][j].y - st[u].x) * st[u].y,
+                                       (xv[u][j].z - st[u].x) * st[u].y, (xv[u][j].w - st[u].x) * st[u].y);  // x hat (0 if !ok)
+                dg.v[j] = make_float4(dg.v[j].x + dz[j].x * xv[u][j].x, dg.v[j].y + dz[j].y * xv[u][j].y,
+                                      dg.v[j].z + dz[j].z * xv[u][j].z, dg.v[j].w + dz[j].w * xv[u][j].w);
+                db.v[j] = make_float4(db.v[j].x + dz[j].x, db.v[j].y + dz[j].y, db.v[j].z + dz[j].z, db.v[j].w + dz[j].w);
+                const float4 gj = *reinterpret_cast<const float4*>(s_gamma + 4 * (l8 + 8 * j));
+                dz[j] = make_float4(dz[j].x * gj.x, dz[j].y * gj.y, dz[j].z * gj.z, dz[j].w * gj.w);
+                s1 += f4_hsum(dz[j]);
+                s2 += f4_dot(dz[j], xv[u][j]);
+            }
+            const float m1 = oct_sum(s1) * (1.f / kH), m2 = oct_sum(s2) * (1.f / kH);
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    reinterpret_cast<float4*>(dxs + (size_t)r * kH)[l8 + 8 * j] =
+                        make_float4(dv[u][j].x + st[u].y * (dz[j].x - m1 - xv[u][j].x * m2), dv[u][j].y + st[u].y * (dz[j].y - m1 - xv[u][j].y * m2),
+                                    dv[u][j].z + st[u].y * (dz[j].z - m1 - xv[u][j].z * m2), dv[u][j].w + st[u].y * (dz[j].w - m1 - xv[u][j].w * m2));
+            }
+        }
+    }
+}
+
+// Residual add, eight lanes per frame, coalesced: y[r] = x[r] + branch[r], the branch staged as fp32 in `tile` with 4-float
+// chunks (addr = tile + chunk*cs + (r + row_off)*16) by a thread-per-frame TMEM epilogue.
+// SKIP4: the staging area is a tile whose every 4th chunk among the first 16 must stay untouched (zero padding of the
+// per-head K tile in mhsa_fwd): four-float chunk c lives at tile chunk skip4_chunk(c).
+__device__ __forceinline__ int skip4_chunk(int c) { return c + (c < 12 ? c / 3 : 4); }
+template <bool SKIP4 = false>
+__device__ __forceinline__ void add_rows(const unsigned char* tile, uint32_t cs, int row_off, const float* __restrict__ xs,
+                                         float* __restrict__ ys, int T, int warp, int lane, int nwarps) {
+    const int sub = lane >> 3, l8 = lane & 7;
+    const unsigned char* tl = tile + (size_t)row_off * 16;
+#pragma unroll 1
+    for (int R = 16 * warp; R < T; R += 16 * nwarps) {
+        float4 xv[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = R + 4 * sub + u;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                xv[u][j] = (r < T) ? __ldg(reinterpret_cast<const float4*>(xs + (size_t)r * kH) + l8 + 8 * j) : make_float4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = R + 4 * sub + u;
+            if (r < T) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int ch = SKIP4 ? skip4_chunk(l8 + 8 * j) : l8 + 8 * j;
+                    const float4 v = *reinterpret_cast<const float4*>(tl + (size_t)ch * cs + r * 16);
+                    reinterpret_cast<float4*>(ys + (size_t)r * kH)[l8 + 8 * j] =
+                        make_float4(xv[u][j].x + v.x, xv[u][j].y + v.y, xv[u][j].z + v.z, xv[u][j].w + v.w);
+                }
+            }
+        }
     }
 }
 

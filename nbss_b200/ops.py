@@ -20,7 +20,7 @@ Tensor = torch.Tensor
 # every C-ABI call is bracketed by CUDA events on the launching (current) stream.
 LAUNCHES = 0
 TIMING = None
-_NLAUNCH = {"nbss_full_fwd": 3, "nbss_full_bwd": 4, "nbss_ffn_wgrad": 3, "nbss_mhsa_bwd": 2, "nbss_istft": 2}
+_NLAUNCH = {"nbss_full_fwd": 3, "nbss_full_bwd": 4, "nbss_full_fwd_tc": 3, "nbss_full_bwd_tc": 5, "nbss_ffn_wgrad": 3, "nbss_mhsa_bwd": 2, "nbss_istft": 2}
 
 
 _KCACHE = {}
@@ -213,6 +213,76 @@ def full_bwd(x: Tensor, dy: Tensor, s: Tensor, u: Tensor, P, pre: str, G) -> Ten
                          ptr(G[pre + "squeeze.0.bias"]), ptr(G[pre + "full.weight"]), ptr(G[pre + "full.bias"]),
                          ptr(G[pre + "unsqueeze.0.weight"]), ptr(G[pre + "unsqueeze.0.bias"]), stream_ptr())
     check(st, "nbss_full_bwd")
+    return dx
+
+
+def lg_image_bytes(F: int) -> int:
+    n = int(_lib.lib().nbss_lg_image_bytes(F))
+    if n == 0:
+        raise _lib.NbssError(f"nbss_lg_image_bytes: unsupported num_freqs {F} (tensor-core LinearGroup needs F <= 256)")
+    return n
+
+
+def lg_pack(Wf: Tensor, img: Optional[Tensor] = None, fmt: int = FMT_F16) -> Tensor:
+    """UMMA operand images of the LinearGroup weight full.weight [8,F,F] (fullband_tc.cu)."""
+    F = Wf.shape[-1]
+    if img is None:
+        img = torch.empty(lg_image_bytes(F), dtype=torch.uint8, device=Wf.device)
+    check(_K("nbss_lg_pack")(ptr(_f32c(Wf)), ptr(img), F, fmt, stream_ptr()), "nbss_lg_pack")
+    return img
+
+
+def lg_tc_apply(x: Tensor, img: Tensor, bias: Optional[Tensor], mode: int, fmt: int = FMT_F16) -> Tensor:
+    """LinearGroup on tensor cores: x [M,8,F] fp32 -> mode 0: x W^T + bias, mode 1: x W (data gradient)."""
+    x = _f32c(x)
+    M, G8, F = x.shape
+    assert G8 == 8
+    out = torch.empty_like(x)
+    err = device_err_flag(x.device)
+    check(_K("nbss_lg_tc_apply")(ptr(x), ptr(out), M, F, ptr(img), ptr(None if bias is None else _f32c(bias)), mode, fmt, ptr(err),
+                                 stream_ptr()), "nbss_lg_tc_apply")
+    return out
+
+
+def lg_tc_wgrad(du: Tensor, s: Tensor, dW: Tensor, db: Tensor, fmt: int = FMT_F16) -> None:
+    """dW [8,F,F] += du^T s, db [8,F] += sum_m du  (du, s: [M,8,F] fp32)."""
+    du, s = _f32c(du), _f32c(s)
+    M, G8, F = du.shape
+    err = device_err_flag(du.device)
+    check(_K("nbss_lg_tc_wgrad")(ptr(du), ptr(s), M, F, ptr(dW), ptr(db), fmt, ptr(err), stream_ptr()), "nbss_lg_tc_wgrad")
+
+
+def full_fwd_tc(x: Tensor, P, pre: str, img: Tensor, out: Optional[Tensor] = None, fmt: int = FMT_F16):
+    """full_fwd with the LinearGroup on tensor cores; img = lg_pack(P[pre + 'full.weight'])."""
+    x = _f32c(x)
+    B, F, T, H = x.shape
+    y = torch.empty_like(x) if out is None else out
+    s = torch.empty(B, T, 8, F, dtype=torch.float32, device=x.device)
+    u = torch.empty_like(s)
+    err = device_err_flag(x.device)
+    st = _K("nbss_full_fwd_tc")(ptr(x), ptr(y), ptr(s), ptr(u), B, F, T, ptr(_f32c(P[pre + "norm_full.weight"])),
+                                ptr(_f32c(P[pre + "norm_full.bias"])), ptr(_f32c(P[pre + "squeeze.0.weight"])),
+                                ptr(_f32c(P[pre + "squeeze.0.bias"])), ptr(_f32c(P[pre + "full.bias"])),
+                                ptr(_f32c(P[pre + "unsqueeze.0.weight"])), ptr(_f32c(P[pre + "unsqueeze.0.bias"])), ptr(img), fmt,
+                                ptr(err), stream_ptr())
+    check(st, "nbss_full_fwd_tc")
+    return y, s, u
+
+
+def full_bwd_tc(x: Tensor, dy: Tensor, s: Tensor, u: Tensor, P, pre: str, img: Tensor, G, fmt: int = FMT_F16) -> Tensor:
+    x, dy = _f32c(x), _f32c(dy)
+    B, F, T, H = x.shape
+    dx = torch.empty_like(x)
+    ws = torch.empty(2 * s.numel(), dtype=torch.float32, device=x.device)
+    err = device_err_flag(x.device)
+    st = _K("nbss_full_bwd_tc")(ptr(x), ptr(dy), ptr(dx), ptr(s), ptr(u), ptr(ws), B, F, T, ptr(_f32c(P[pre + "norm_full.weight"])),
+                                ptr(_f32c(P[pre + "norm_full.bias"])), ptr(_f32c(P[pre + "squeeze.0.weight"])),
+                                ptr(_f32c(P[pre + "squeeze.0.bias"])), ptr(_f32c(P[pre + "unsqueeze.0.weight"])),
+                                ptr(_f32c(P[pre + "unsqueeze.0.bias"])), ptr(img), ptr(G[pre + "norm_full.weight"]),
+                                ptr(G[pre + "norm_full.bias"]), ptr(G[pre + "squeeze.0.weight"]), ptr(G[pre + "squeeze.0.bias"]),
+                                ptr(G[pre + "full.weight"]), ptr(G[pre + "full.bias"]), ptr(G[pre + "unsqueeze.0.weight"]),
+                                ptr(G[pre + "unsqueeze.0.bias"]), fmt, ptr(err), stream_ptr())
+    check(st, "nbss_full_bwd_tc")
     return dx
 
 

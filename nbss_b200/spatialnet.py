@@ -82,6 +82,10 @@ class Engine:
         self._img_key = None
         self._fimgs: Optional[List[List[Tensor]]] = None
         self._fimg_key = None
+        self._limgs: Optional[List[Tensor]] = None
+        self._limg_key = None
+        # NBSS_FULL_SIMT=1 keeps the full-band LinearGroup on the fp32 CUDA-core kernels (cross-check of fullband_tc.cu)
+        self.full_tc = _os.environ.get("NBSS_FULL_SIMT", "0") != "1"
 
     def images(self, P: Dict[str, Tensor]) -> List[Tensor]:
         """Per-layer UMMA weight images; rebuilt whenever a narrow-band weight changed (tensor version counters)."""
@@ -110,11 +114,30 @@ class Engine:
             self._fimg_key = key
         return self._fimgs
 
+    def lg_images(self, P: Dict[str, Tensor]) -> List[Tensor]:
+        """Per-layer UMMA images of the full-band LinearGroup weight (fullband_tc.cu); layers that share the module
+        (full_share) share the image.  One image serves the forward and the data gradient, so it is packed in fwd_fmt
+        and the backward of this sub-block uses fwd_fmt operands too."""
+        names = [f"layers.{i}.full.weight" for i in range(self.L)]
+        key = tuple((P[n].data_ptr(), P[n]._version) for n in names)
+        if self._limgs is None or key != self._limg_key or torch.cuda.is_current_stream_capturing():
+            old = self._limgs
+            done: Dict[int, Tensor] = {}
+            imgs = []
+            for i, n in enumerate(names):
+                k = P[n].data_ptr()
+                if k not in done:
+                    done[k] = ops.lg_pack(P[n], old[i] if old else None, self.fwd_fmt)
+                imgs.append(done[k])
+            self._limgs, self._limg_key = imgs, key
+        return self._limgs
+
     def forward(self, P: Dict[str, Tensor], x: Tensor, save: bool):
         if not x.is_cuda:
             raise ops._lib.NbssError("nbss_b200.SpatialNet runs on CUDA tensors only (there is no CPU path)")
         imgs = self.images(P)
         fimgs = self.fconv_images(P)
+        limgs = self.lg_images(P) if self.full_tc else None
         ctx = {"x_in": x, "layers": []} if save else None
         errs = []
         h = ops.encoder_fwd(x, P)
@@ -123,7 +146,7 @@ class Engine:
             if save:
                 lc = {"x0": h}
                 h1, e3 = ops.fconv_tc_fwd(h, P, pre + "fconv1", fimgs[i][0], fmt=self.fwd_fmt)
-                h2, s, u = ops.full_fwd(h1, P, pre)
+                h2, s, u = (ops.full_fwd_tc(h1, P, pre, limgs[i], fmt=self.fwd_fmt) if self.full_tc else ops.full_fwd(h1, P, pre))
                 h3, e4 = ops.fconv_tc_fwd(h2, P, pre + "fconv2", fimgs[i][1], fmt=self.fwd_fmt)
                 h4, msave, e1 = ops.mhsa_fwd(h3, P, pre, imgs[i], save=True, fmt=self.fwd_fmt)
                 h5, fsave, gstats, e2 = ops.ffn_fwd(h4, P, pre, imgs[i], save=True, fmt=self.fwd_fmt)
@@ -133,7 +156,7 @@ class Engine:
             else:
                 # inference: every sub-block updates the stream in place (each kernel reads a row before writing it)
                 h, e3 = ops.fconv_tc_fwd(h, P, pre + "fconv1", fimgs[i][0], out=h, fmt=self.fwd_fmt)
-                h, _, _ = ops.full_fwd(h, P, pre, out=h)
+                h, _, _ = (ops.full_fwd_tc(h, P, pre, limgs[i], out=h, fmt=self.fwd_fmt) if self.full_tc else ops.full_fwd(h, P, pre, out=h))
                 h, e4 = ops.fconv_tc_fwd(h, P, pre + "fconv2", fimgs[i][1], out=h, fmt=self.fwd_fmt)
                 h, e1 = ops.mhsa_fwd(h, P, pre, imgs[i], fmt=self.fwd_fmt, out=h)
                 h, e2 = ops.ffn_fwd(h, P, pre, imgs[i], fmt=self.fwd_fmt, out=h)
@@ -148,6 +171,7 @@ class Engine:
         (SharedTrainer.py:113-120: X comes from the STFT of the data)."""
         imgs = self.images(P)
         fimgs = self.fconv_images(P)
+        limgs = self.lg_images(P) if self.full_tc else None
         errs = []
         d = ops.decoder_bwd(ctx["x_last"], dy, P, G)
         for i in reversed(range(self.L)):
@@ -156,7 +180,8 @@ class Engine:
             d, e1 = ops.ffn_bwd(lc["x4"], d, lc["fsave"], lc["gstats"], P, pre, imgs[i], G, fmt_g=self.grad_fmt)
             d, e2 = ops.mhsa_bwd(lc["x3"], d, lc["msave"], P, pre, imgs[i], G, fmt_g=self.grad_fmt)
             d, e3 = ops.fconv_tc_bwd(lc["x2"], d, P, pre + "fconv2", fimgs[i][1], G, fmt=self.grad_fmt)
-            d = ops.full_bwd(lc["x1"], d, lc["s"], lc["u"], P, pre, G)
+            d = (ops.full_bwd_tc(lc["x1"], d, lc["s"], lc["u"], P, pre, limgs[i], G, fmt=self.fwd_fmt) if self.full_tc
+                 else ops.full_bwd(lc["x1"], d, lc["s"], lc["u"], P, pre, G))
             d, e4 = ops.fconv_tc_bwd(lc["x0"], d, P, pre + "fconv1", fimgs[i][0], G, fmt=self.grad_fmt)
             errs += [e1, e2, e3, e4]
             ctx["layers"][i] = None  # free this layer's saved activations

@@ -125,6 +125,58 @@ def test_full_fwd_bwd(shape):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("M,F", [(300, 129), (128, 129), (77, 65), (130, 20), (40, 131), (33, 140), (1000, 129)])
+def test_lg_tc(M, F):
+    """LinearGroup (linear_group.py:29-34) on tensor cores against fp32 einsums; fp16 operands: <= 2e-3 rel-L2."""
+    g = torch.Generator().manual_seed(M + F)
+    W = torch.randn(8, F, F, generator=g) / F ** 0.5
+    b = torch.randn(8, F, generator=g)
+    s = torch.randn(M, 8, F, generator=g)
+    du = torch.randn(M, 8, F, generator=g)
+    img = ops.lg_pack(W.cuda())
+    u = ops.lg_tc_apply(s.cuda(), img, b.cuda(), mode=0)
+    assert O.rel_l2(u.cpu(), torch.einsum("mgf,gkf->mgk", s, W) + b) < 2e-3
+    ds = ops.lg_tc_apply(du.cuda(), img, None, mode=1)
+    assert O.rel_l2(ds.cpu(), torch.einsum("mgk,gkf->mgf", du, W)) < 2e-3
+    dW = torch.zeros(8, F, F, device="cuda")
+    db = torch.zeros(8, F, device="cuda")
+    ops.lg_tc_wgrad(du.cuda(), s.cuda(), dW, db)
+    ops.lg_tc_wgrad(du.cuda(), s.cuda(), dW, db)  # accumulates
+    torch.cuda.synchronize()
+    ops.check_err_flag(ops.device_err_flag(dW.device), "lg_tc")
+    assert O.rel_l2(dW.cpu(), 2 * torch.einsum("mgk,mgf->gkf", du, s)) < 2e-3
+    assert O.rel_l2(db.cpu(), 2 * du.sum(0)) < 2e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 129, 7), (1, 129, 250), (1, 65, 5), (3, 129, 40)])
+def test_full_tc_fwd_bwd(shape):
+    """The full-band sub-block with the LinearGroup on tensor cores (fp16 operands): <= 2e-3 / 3e-3 rel-L2."""
+    B, F, T = shape
+    cfg = dict(CFG, num_freqs=F)
+    P = O.synth_params(cfg, 5)
+    Pd = {k: v.cuda() for k, v in P.items()}
+    Pl = _leaf(P)
+    pre = "layers.1."
+    g = torch.Generator().manual_seed(F + T)
+    x = torch.randn(B, F, T, 96, generator=g, requires_grad=True)
+    dy = torch.randn(B, F, T, 96, generator=g)
+    y_ref = x + O.full(x, Pl, pre)
+    y_ref.backward(dy)
+    img = ops.lg_pack(Pd[pre + "full.weight"])
+    y, s, u = ops.full_fwd_tc(x.detach().cuda(), Pd, pre, img)
+    assert O.rel_l2(y.cpu() - x.detach(), (y_ref - x).detach()) < 2e-3
+    G = _grads_like(Pd)
+    dx = ops.full_bwd_tc(x.detach().cuda(), dy.cuda(), s, u, Pd, pre, img, G)
+    torch.cuda.synchronize()
+    ops.check_err_flag(ops.device_err_flag(dx.device), "full_tc")
+    assert O.rel_l2(dx.cpu() - dy, x.grad - dy) < 3e-3
+    for k in ("norm_full.weight", "norm_full.bias", "squeeze.0.weight", "squeeze.0.bias", "full.weight", "full.bias",
+              "unsqueeze.0.weight", "unsqueeze.0.bias"):
+        assert O.rel_l2(G[pre + k].cpu().reshape(-1), Pl[pre + k].grad.reshape(-1)) < 3e-3, k
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("cin,T", [(12, 250), (4, 64), (12, 37)])
 def test_encoder_decoder(cin, T):
     cfg = dict(CFG, dim_input=cin)

@@ -103,6 +103,18 @@ int nbss_full_bwd_tc(const float* x, const float* dy, float* dx, const float* s,
                      const float* bun, const void* img, float* dlnw, float* dlnb, float* dWsq, float* dbsq, float* dWf,
                      float* dbf, float* dWun, float* dbun, int fmt, int* err, void* stream);
 
+/* The per-point halves of that block on tensor cores (fullband_rows_tc.cu), used by nbss_full_{fwd,bwd}_tc
+ * (models/arch/SpatialNet.py:129-137 squeeze, :143-146 unsqueeze; modules :41-48).  s, u, ds, du: fp32 [B,T,8,F]. */
+int nbss_squeeze_fwd_tc(const float* x, float* s, int B, int F, int T, const float* lnw, const float* lnb, const float* Wsq,
+                        const float* bsq, int fmt, int* err, void* stream);
+int nbss_unsqueeze_fwd_tc(const float* x, const float* u, float* y, int B, int F, int T, const float* Wun, const float* bun,
+                          int fmt, int* err, void* stream);
+int nbss_unsqueeze_bwd_tc(const float* dy, const float* u, float* du, int B, int F, int T, const float* Wun, const float* bun,
+                          float* dWun, float* dbun, int fmt, int* err, void* stream);
+int nbss_squeeze_bwd_tc(const float* x, const float* dy, const float* ds, float* dx, int B, int F, int T, const float* lnw,
+                        const float* lnb, const float* Wsq, const float* bsq, float* dWsq, float* dbsq, float* dlnw,
+                        float* dlnb, int fmt, int* err, void* stream);
+
 /* ---- encoder / decoder, fp32 (models/arch/SpatialNet.py:175,205 and :200,216) --------------------------------------- */
 int nbss_encoder_fwd(const float* x, float* y, int nslab, int T, int cin, const float* W, const float* bias, void* stream);
 int nbss_encoder_wgrad(const float* x, const float* dy, int nslab, int T, int cin, float* dW, float* dbias, void* stream);

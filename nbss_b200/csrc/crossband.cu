@@ -5,6 +5,8 @@
 //   fullgemm           : u[b,t,g,:] = Wf[g] s[b,t,g,:] + bf  (LinearGroup, linear_group.py:29-34) + dgrad + wgrad
 //   unsqueeze_{fwd,bwd}: y = x + SiLU(Wun u + b)
 // These are 8 % of the layer FLOPs; they are HBM/L2-streaming kernels, fp32 end to end.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "layout.cuh"
 
@@ -704,6 +706,27 @@ extern "C" int nbss_lg_tc_apply(const float* in, float* out, int M, int F, const
 extern "C" int nbss_lg_tc_wgrad(const float* du, const float* s, int M, int F, float* dW, float* db, int fmt, int* err,
                                 void* stream);
 
+extern "C" int nbss_squeeze_fwd_tc(const float* x, float* s, int B, int F, int T, const float* lnw, const float* lnb,
+                                   const float* Wsq, const float* bsq, int fmt, int* err, void* stream);
+extern "C" int nbss_unsqueeze_fwd_tc(const float* x, const float* u, float* y, int B, int F, int T, const float* Wun,
+                                     const float* bun, int fmt, int* err, void* stream);
+extern "C" int nbss_unsqueeze_bwd_tc(const float* dy, const float* u, float* du, int B, int F, int T, const float* Wun,
+                                     const float* bun, float* dWun, float* dbun, int fmt, int* err, void* stream);
+extern "C" int nbss_squeeze_bwd_tc(const float* x, const float* dy, const float* ds, float* dx, int B, int F, int T,
+                                   const float* lnw, const float* lnb, const float* Wsq, const float* bsq, float* dWsq,
+                                   float* dbsq, float* dlnw, float* dlnb, int fmt, int* err, void* stream);
+
+// NBSS_ROWS_SIMT=1: keep the squeeze / unsqueeze halves on the fp32 CUDA-core kernels above (cross-check of
+// fullband_rows_tc.cu); the LinearGroup stays on tensor cores.
+static bool rows_simt() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NBSS_ROWS_SIMT");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 extern "C" int nbss_full_fwd_tc(const float* x, float* y, float* s_out, float* u_out, int B, int F, int T, const float* lnw,
                                 const float* lnb, const float* Wsq, const float* bsq, const float* bf, const float* Wun,
                                 const float* bun, const void* img, int fmt, int* err, void* stream) {
@@ -714,12 +737,17 @@ extern "C" int nbss_full_fwd_tc(const float* x, float* y, float* s_out, float* u
     const size_t sm_sq = (size_t)(kHS * kH + kSQT * kHS * F) * 4;
     if (sm_sq > 48 * 1024) return NBSS_ERR_UNSUPPORTED;
     const int fsplit = f_split(tiles, F);
-    squeeze_fwd_kernel<<<dim3(tiles, fsplit), 256, sm_sq, st>>>(x, s_out, B, F, T, lnw, lnb, Wsq, bsq);
-    NBSS_LAUNCH_CHECK();
-    const int rc = nbss_lg_tc_apply(s_out, u_out, B * T, F, img, bf, 0, fmt, err, stream);
+    int rc;
+    if (rows_simt()) {
+        squeeze_fwd_kernel<<<dim3(tiles, fsplit), 256, sm_sq, st>>>(x, s_out, B, F, T, lnw, lnb, Wsq, bsq);
+        NBSS_LAUNCH_CHECK();
+    } else if ((rc = nbss_squeeze_fwd_tc(x, s_out, B, F, T, lnw, lnb, Wsq, bsq, fmt, err, stream)) != NBSS_OK) return rc;
+    rc = nbss_lg_tc_apply(s_out, u_out, B * T, F, img, bf, 0, fmt, err, stream);
     if (rc != NBSS_OK) return rc;
-    unsqueeze_fwd_kernel<<<dim3(tiles, fsplit), 256, (size_t)kSQT * kHS * F * 4, st>>>(x, u_out, y, B, F, T, Wun, bun);
-    NBSS_LAUNCH_CHECK();
+    if (rows_simt()) {
+        unsqueeze_fwd_kernel<<<dim3(tiles, fsplit), 256, (size_t)kSQT * kHS * F * 4, st>>>(x, u_out, y, B, F, T, Wun, bun);
+        NBSS_LAUNCH_CHECK();
+    } else if ((rc = nbss_unsqueeze_fwd_tc(x, u_out, y, B, F, T, Wun, bun, fmt, err, stream)) != NBSS_OK) return rc;
     return NBSS_OK;
 }
 
@@ -739,14 +767,19 @@ extern "C" int nbss_full_bwd_tc(const float* x, const float* dy, float* dx, cons
     const int pg = tiles * fsplit < 4 * sms ? tiles * fsplit : 4 * sms;
     const size_t sm_un = (size_t)(2 * kSQT * kHS * F + 1024) * 4, sm_sq = (size_t)(kHS * kH + kSQT * kHS * F + 1024) * 4;
     if (sm_un > 227 * 1024) return NBSS_ERR_UNSUPPORTED;
-    cudaFuncSetAttribute(unsqueeze_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_un);
-    unsqueeze_bwd_kernel<<<pg, 256, sm_un, st>>>(dy, u, du, B, F, T, Wun, bun, dWun, dbun, fsplit);
-    NBSS_LAUNCH_CHECK();
-    int rc = nbss_lg_tc_apply(du, ds, M, F, img, nullptr, 1, fmt, err, stream);
+    int rc;
+    if (rows_simt()) {
+        cudaFuncSetAttribute(unsqueeze_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_un);
+        unsqueeze_bwd_kernel<<<pg, 256, sm_un, st>>>(dy, u, du, B, F, T, Wun, bun, dWun, dbun, fsplit);
+        NBSS_LAUNCH_CHECK();
+    } else if ((rc = nbss_unsqueeze_bwd_tc(dy, u, du, B, F, T, Wun, bun, dWun, dbun, fmt, err, stream)) != NBSS_OK) return rc;
+    rc = nbss_lg_tc_apply(du, ds, M, F, img, nullptr, 1, fmt, err, stream);
     if (rc != NBSS_OK) return rc;
     rc = nbss_lg_tc_wgrad(du, s, M, F, dWf, dbf, fmt, err, stream);
     if (rc != NBSS_OK) return rc;
-    squeeze_bwd_kernel<<<pg, 256, sm_sq, st>>>(x, dy, ds, dx, B, F, T, lnw, lnb, Wsq, bsq, dWsq, dbsq, dlnw, dlnb, fsplit);
-    NBSS_LAUNCH_CHECK();
+    if (rows_simt()) {
+        squeeze_bwd_kernel<<<pg, 256, sm_sq, st>>>(x, dy, ds, dx, B, F, T, lnw, lnb, Wsq, bsq, dWsq, dbsq, dlnw, dlnb, fsplit);
+        NBSS_LAUNCH_CHECK();
+    } else if ((rc = nbss_squeeze_bwd_tc(x, dy, ds, dx, B, F, T, lnw, lnb, Wsq, bsq, dWsq, dbsq, dlnw, dlnb, fmt, err, stream)) != NBSS_OK) return rc;
     return NBSS_OK;
 }

@@ -125,7 +125,7 @@ def test_full_fwd_bwd(shape):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("M,F", [(300, 129), (128, 129), (77, 65), (130, 20), (40, 131), (33, 140), (1000, 129)])
+@pytest.mark.parametrize("M,F", [(300, 129), (128, 129), (77, 65), (130, 20), (40, 131), (33, 140), (1000, 129), (6100, 129)])
 def test_lg_tc(M, F):
     """LinearGroup (linear_group.py:29-34) on tensor cores against fp32 einsums; fp16 operands: <= 2e-3 rel-L2."""
     g = torch.Generator().manual_seed(M + F)
@@ -149,7 +149,7 @@ def test_lg_tc(M, F):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(2, 129, 7), (1, 129, 250), (1, 65, 5), (3, 129, 40)])
+@pytest.mark.parametrize("shape", [(2, 129, 7), (1, 129, 250), (1, 65, 5), (3, 129, 40), (1, 200, 6), (2, 128, 5)])
 def test_full_tc_fwd_bwd(shape):
     """The full-band sub-block with the LinearGroup on tensor cores (fp16 operands): <= 2e-3 / 3e-3 rel-L2."""
     B, F, T = shape
@@ -174,6 +174,32 @@ def test_full_tc_fwd_bwd(shape):
     for k in ("norm_full.weight", "norm_full.bias", "squeeze.0.weight", "squeeze.0.bias", "full.weight", "full.bias",
               "unsqueeze.0.weight", "unsqueeze.0.bias"):
         assert O.rel_l2(G[pre + k].cpu().reshape(-1), Pl[pre + k].grad.reshape(-1)) < 3e-3, k
+
+
+@pytest.mark.gpu
+def test_full_tc_large_vs_fp32():
+    """Bench-scale shape (several row tiles per CTA in the weight-gradient kernels): the tensor-core full-band block
+    against the fp32 CUDA-core kernels (themselves checked against the oracle above)."""
+    B, F, T = 24, 129, 250
+    P = O.synth_params(CFG, 5)
+    Pd = {k: v.cuda() for k, v in P.items()}
+    pre = "layers.1."
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(B, F, T, 96, generator=g, device="cuda")
+    dy = torch.randn(B, F, T, 96, generator=g, device="cuda")
+    y0, s0, u0 = ops.full_fwd(x, Pd, pre)
+    img = ops.lg_pack(Pd[pre + "full.weight"])
+    y1, s1, u1 = ops.full_fwd_tc(x, Pd, pre, img)
+    assert O.rel_l2((y1 - x).cpu(), (y0 - x).cpu()) < 2e-3
+    G0, G1 = _grads_like(Pd), _grads_like(Pd)
+    dx0 = ops.full_bwd(x, dy, s0, u0, Pd, pre, G0)
+    dx1 = ops.full_bwd_tc(x, dy, s1, u1, Pd, pre, img, G1)
+    torch.cuda.synchronize()
+    ops.check_err_flag(ops.device_err_flag(x.device), "full_tc")
+    assert O.rel_l2((dx1 - dy).cpu(), (dx0 - dy).cpu()) < 3e-3
+    for k in ("norm_full.weight", "norm_full.bias", "squeeze.0.weight", "squeeze.0.bias", "full.weight", "full.bias",
+              "unsqueeze.0.weight", "unsqueeze.0.bias"):
+        assert O.rel_l2(G1[pre + k].cpu().reshape(-1), G0[pre + k].cpu().reshape(-1)) < 3e-3, k
 
 
 @pytest.mark.gpu

@@ -58,7 +58,7 @@ __device__ __forceinline__ void fc_row(const FcGeom& g, int i, int& tt, int& f) 
 
 // LN(x) of the group's frames into the tile (16-bit); rows of frames beyond T are zero; optional (mean, rstd) per tile row;
 // optionally the upstream gradient dy of the same rows into a second tile.
-template <int FMT, int U>
+template <int FMT, int U, int NW = 8>
 __device__ __forceinline__ void fc_stage(const FcGeom& g, const float* __restrict__ x, int b, int t0, unsigned char* tile,
                                          const float* s_lnw, const float* s_lnb, float2* s_stats, int warp, int lane,
                                          const float* __restrict__ dy = nullptr, unsigned char* dytile = nullptr) {
@@ -68,7 +68,7 @@ __device__ __forceinline__ void fc_stage(const FcGeom& g, const float* __restric
     gb.load(s_lnb, l8);
     const size_t loff = (size_t)(l8 >> 1) * g.cs + (l8 & 1) * 8;
 #pragma unroll 1
-    for (int R = 4 * U * warp; R < N; R += 32 * U) {
+    for (int R = 4 * U * warp; R < N; R += 4 * U * NW) {
         float4 v[U][3], w[U][3];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -117,15 +117,49 @@ __device__ __forceinline__ void fc_stage(const FcGeom& g, const float* __restric
     }
 }
 
+// rows of a second stream tensor (the upstream gradient) -> 16-bit tile, same row slots, no LayerNorm
+template <int FMT, int U, int NW>
+__device__ __forceinline__ void fc_stage_plain(const FcGeom& g, const float* __restrict__ dy, int b, int t0, unsigned char* tile,
+                                               int warp, int lane) {
+    const int sub = lane >> 3, l8 = lane & 7, N = g.nfr * g.F;
+    const size_t loff = (size_t)(l8 >> 1) * g.cs + (l8 & 1) * 8;
+#pragma unroll 1
+    for (int R = 4 * U * warp; R < N; R += 4 * U * NW) {
+        float4 w[U][3];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = R + U * sub + u;
+            int tt, f;
+            fc_row(g, i, tt, f);
+            const bool ok = i < N && t0 + tt < g.T;
+            const float4* pd = reinterpret_cast<const float4*>(dy + (((size_t)b * g.F + f) * g.T + t0 + tt) * kH) + l8;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) w[u][j] = ok ? __ldg(pd + 8 * j) : make_float4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = R + U * sub + u;
+            int tt, f;
+            fc_row(g, i, tt, f);
+            if (i >= N) continue;
+            const int p = 2 + tt * g.FP + f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                *reinterpret_cast<uint2*>(tile + loff + (size_t)(4 * j) * g.cs + p * 16) =
+                    make_uint2(pack16<FMT>(w[u][j].x, w[u][j].y), pack16<FMT>(w[u][j].z, w[u][j].w));
+        }
+    }
+}
+
 // conv (or transposed conv) MMAs of one group: D[tile m][half q] = sum_tap A(rows shifted) * Wimg(q, tap)
 __device__ __forceinline__ void fc_conv_mmas(const FcGeom& g, uint32_t tmem, uint32_t tile_addr, uint32_t w_addr, uint32_t idesc,
-                                             bool transposed) {
+                                             bool transposed, bool leader) {
     for (int m = 0; m < g.nt; ++m)
         for (int q = 0; q < kFQ; ++q)
             for (int tap = 0; tap < kFTaps; ++tap) {
                 const int row = 128 * m + (transposed ? 4 - tap : tap);  // tile row of output q0: 2 + q0 + (tap-2) resp. 2 + q0 - (tap-2)
                 mma_kk(tmem + m * 96 + q * 48, tile_addr + 6 * q * g.cs + row * 16, g.cs, w_addr + (q * kFTaps + tap) * FC_IMG_TILE, 768, 3,
-                       idesc, tap > 0);
+                       idesc, tap > 0, leader);
             }
 }
 
@@ -175,11 +209,12 @@ __global__ void __launch_bounds__(256, 2) fconv_tc_fwd_kernel(FcFwdArgs a) {
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             if (!wready) mbar_wait(bar_w, 0, a.err);
-            fc_conv_mmas(g, tmem, ta, wa, id48, false);
-            umma_commit(bar_mma);
+            const bool leader = elect_one();
+            fc_conv_mmas(g, tmem, ta, wa, id48, false, leader);
+            if (leader) umma_commit(bar_mma);
         }
         wready = true;
         __syncwarp();
@@ -263,9 +298,12 @@ struct FcBwdArgs {
     int* err;
 };
 
+constexpr int kFcBwdThreads = 512;  // warp w -> TMEM lane quarter w & 3, work group w >> 2 (tiles x column blocks, taps)
+
 template <int FMT>
-__global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
+__global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NT = kFcBwdThreads, NW = NT / 32;
     const FcGeom g = a.g;
     unsigned char* htile = smem;                           // LN(x)
     unsigned char* gtile = smem + (size_t)12 * g.cs;       // dc
@@ -273,20 +311,22 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
                                                            // over-read area of the 128-feature MN-major window of gtile
     float* cst = reinterpret_cast<float*>(wimg + FC_IMG_BYTES);  // lnw, lnb, bias, slope (384) + acc (384): dbias, dslope, dlnw, dlnb
     float* acc = cst + 384;
-    float2* stats = reinterpret_cast<float2*>(acc + 384);  // [rows] (mean, rstd)
+    float* accdw = acc + 384;                               // [96][60] weight-gradient accumulators (thread-owned rows)
+    float2* stats = reinterpret_cast<float2*>(accdw + 96 * 60);  // [rows] (mean, rstd)
     uint64_t* bar_mma = reinterpret_cast<uint64_t*>(stats + g.rows);
     uint64_t* bar_w = bar_mma + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q4 = warp & 3, gq = warp >> 2;
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
         mbar_init(bar_mma, 1);
         mbar_init(bar_w, 1);
         fence_mbar_init();
     }
-    for (int i = tid; i < 96; i += 256) { cst[i] = a.lnw[i]; cst[96 + i] = a.lnb[i]; cst[192 + i] = a.bias[i]; cst[288 + i] = a.slope[i]; }
-    for (int i = tid; i < 384; i += 256) acc[i] = 0.f;
-    for (int i = tid; i < (int)(24 * g.cs / 16); i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 96; i += NT) { cst[i] = a.lnw[i]; cst[96 + i] = a.lnb[i]; cst[192 + i] = a.bias[i]; cst[288 + i] = a.slope[i]; }
+    for (int i = tid; i < 384 + 96 * 60; i += NT) acc[i] = 0.f;
+    for (int i = tid; i < (int)(24 * g.cs / 16); i += NT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -295,17 +335,8 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
     const uint32_t ha = smem_u32(htile), ga = smem_u32(gtile), wa = smem_u32(wimg);
     const uint32_t id48 = make_idesc(FMT, 128, 48, 0, 0);
     const uint32_t id_wg = make_idesc(FMT, 128, 96, 1, 1);
-    const uint32_t lane_off = (uint32_t)(32 * (warp & 3)) << 16;
+    const uint32_t lane_off = (uint32_t)(32 * q4) << 16;
     uint32_t ph = 0, ph_w = 0;
-    // weight-gradient accumulators: thread = output channel co (warps 0-2), 5 taps x 12 in-channels of its group
-    const int co = 32 * warp + lane;
-    float dw[60];
-#pragma unroll
-    for (int i = 0; i < 60; ++i) dw[i] = 0.f;
-    // LayerNorm affine gradients: every lane owns 12 channels in the eight-lanes-per-row phase (slab.cuh: Oct12)
-    Oct12 dlg, dlb;
-    dlg.zero();
-    dlb.zero();
 
     auto wait_mma = [&]() {
         __syncwarp();
@@ -316,79 +347,85 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
     for (int grp = blockIdx.x; grp < g.ngroups; grp += gridDim.x) {
         const int b = grp / g.groups_per_b, t0 = (grp % g.groups_per_b) * g.nfr;
         if (tid == 0) load_image(wimg, a.img, FC_IMG_BYTES, bar_w);
-        fc_stage<FMT, 3>(g, a.x, b, t0, htile, cst, cst + 96, stats, warp, lane, a.dy, gtile);
+        fc_stage<FMT, 5, NW>(g, a.x, b, t0, htile, cst, cst + 96, stats, warp, lane);
+        fc_stage_plain<FMT, 5, NW>(g, a.dy, b, t0, gtile, warp, lane);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
         // ---- P1: recompute the conv
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_w, ph_w, a.err);
-            fc_conv_mmas(g, tmem, ha, wa, id48, false);
-            umma_commit(bar_mma);
+            const bool leader = elect_one();
+            fc_conv_mmas(g, tmem, ha, wa, id48, false, leader);
+            if (leader) umma_commit(bar_mma);
         }
         ph_w ^= 1;
         wait_mma();
         if (tid == 0) load_image(wimg, a.img + FC_IMG_BYTES, FC_IMG_BYTES, bar_w);  // transposed image for the data gradient
-        // ---- E-A: dc = dy * PReLU'(c), in place over the staged dy in gtile; column sums for dbias / dslope
-        for (int m = warp >> 2; m < g.nt + (g.nt & 1); m += 2) {  // equal trip counts: the column sums are warp-collective
-            const bool mt = m < g.nt;
-            const int q = 128 * (mt ? m : 0) + 32 * (warp & 3) + lane;
-            unsigned char* grow_ = gtile + (size_t)(2 + q) * 16;
+        // ---- E-A: dc = dy * PReLU'(c), in place over the staged dy in gtile; column sums for dbias / dslope.
+        //      work items (M-tile, 16-column block) are dealt to the four warp groups
 #pragma unroll 1
-            for (int c0 = 0; c0 < kH; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem + lane_off + (mt ? m : 0) * 96 + c0, r);
-                tmem_ld_wait();
-                float dc[32], ds[32];
+        for (int it = gq; it < g.nt * 6; it += 4) {
+            const int m = it / 6, c0 = 16 * (it - 6 * m);
+            const int q = 128 * m + 32 * q4 + lane;
+            unsigned char* grow_ = gtile + (size_t)(2 + q) * 16;
+            uint32_t r[16];
+            tmem_ld16(tmem + lane_off + m * 96 + c0, r);
+            tmem_ld_wait();
+            float dc[16], ds[16];
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const uint4 pk = *reinterpret_cast<const uint4*>(grow_ + (size_t)(c0 / 8 + cc) * g.cs);
-                    float dys[8];
-                    unpack16<FMT>(pk.x, dys[0], dys[1]);
-                    unpack16<FMT>(pk.y, dys[2], dys[3]);
-                    unpack16<FMT>(pk.z, dys[4], dys[5]);
-                    unpack16<FMT>(pk.w, dys[6], dys[7]);
+            for (int cc = 0; cc < 2; ++cc) {
+                const uint4 pk = *reinterpret_cast<const uint4*>(grow_ + (size_t)(c0 / 8 + cc) * g.cs);
+                float dys[8];
+                unpack16<FMT>(pk.x, dys[0], dys[1]);
+                unpack16<FMT>(pk.y, dys[2], dys[3]);
+                unpack16<FMT>(pk.z, dys[4], dys[5]);
+                unpack16<FMT>(pk.w, dys[6], dys[7]);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int c = c0 + 8 * cc + e;
-                        const float cv = __uint_as_float(r[8 * cc + e]) + cst[192 + c];
-                        const float dyv = mt ? dys[e] : 0.f;  // gap / invalid rows hold zeros in gtile
-                        dc[8 * cc + e] = dyv * (cv >= 0.f ? 1.f : cst[288 + c]);
-                        ds[8 * cc + e] = cv < 0.f ? dyv * cv : 0.f;
-                    }
+                for (int e = 0; e < 8; ++e) {
+                    const int c = c0 + 8 * cc + e;
+                    const float cv = __uint_as_float(r[8 * cc + e]) + cst[192 + c];
+                    dc[8 * cc + e] = dys[e] * (cv >= 0.f ? 1.f : cst[288 + c]);  // gap / missing rows hold zeros in gtile
+                    ds[8 * cc + e] = cv < 0.f ? dys[e] * cv : 0.f;
                 }
-                if (mt) {
+            }
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(grow_ + (size_t)(c0 / 8 + cc) * g.cs) = pack8<FMT>(dc + 8 * cc);
-                }
-                const float sb = warp_colsum32(dc, lane), ss = warp_colsum32(ds, lane);
-                atomicAdd(acc + c0 + lane, sb);
-                atomicAdd(acc + 96 + c0 + lane, ss);
+            for (int cc = 0; cc < 2; ++cc) *reinterpret_cast<uint4*>(grow_ + (size_t)(c0 / 8 + cc) * g.cs) = pack8<FMT>(dc + 8 * cc);
+            const float sb = warp_colsum16(dc, lane), ss = warp_colsum16(ds, lane);  // lane pair (2k, 2k+1) holds column k
+            if (!(lane & 1)) {
+                atomicAdd(acc + c0 + (lane >> 1), sb);
+                atomicAdd(acc + 96 + c0 + (lane >> 1), ss);
             }
         }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
         // ---- P2: weight gradient  dW[co, ci, tap] += sum_q dc[q, co] * h[q + tap - 2, ci]   (MN-major x MN-major)
-        if (tid == 0) {
+        if (warp == 0) {  // the whole warp runs the (uniform) descriptor arithmetic, one elected lane issues
             tc_fence_after();
+            const bool leader = elect_one();
             const int nks = 8 * g.nt;  // 16 rows per k-step
-            for (int tap = 0; tap < kFTaps; ++tap)
-                for (int ks = 0; ks < nks; ++ks)
-                    umma_f16(tmem + 96 * tap, sdesc_mnmajor(ga + (2 + 16 * ks) * 16, g.cs), sdesc_mnmajor(ha + (tap + 16 * ks) * 16, g.cs),
-                             id_wg, ks ? 1u : 0u);
-            umma_commit(bar_mma);
+            for (int tap = 0; tap < kFTaps; ++tap) {
+                uint64_t da = sdesc_mnmajor(ga + 2 * 16, g.cs), db = sdesc_mnmajor(ha + tap * 16, g.cs);
+                for (int ks = 0; ks < nks; ++ks) {
+                    if (leader) umma_f16(tmem + 96 * tap, da, db, id_wg, ks ? 1u : 0u);
+                    da += 16;  // 16 rows x 16 B >> 4 in the start-address field
+                    db += 16;
+                }
+            }
+            if (leader) umma_commit(bar_mma);
         }
         wait_mma();
-        if (warp < 3) {
-            // thread = out channel co (TMEM lane); it keeps the 12 in-channel columns [12*(co/12), +12) of each tap.
-            // tcgen05.ld takes ONE column address per warp, so every warp loads a uniform 48-column window
-            // [24*warp, 24*warp+48) that contains the groups of its 32 channels and each lane selects its slice.
-            const int ws = 24 * warp;
+        if (q4 < 3) {
+            // thread = out channel co (TMEM lane), taps dealt to the warp groups; it keeps the 12 in-channel columns
+            // [12*(co/12), +12) of each tap.  tcgen05.ld takes ONE column address per warp, so every warp loads a uniform
+            // 48-column window [24*q4, 24*q4+48) that contains the groups of its 32 channels and each lane selects its slice.
+            const int co = 32 * q4 + lane;
+            const int ws = 24 * q4;
             const int off = 12 * (co / 12) - ws;  // 0, 12, 24 or 36
-#pragma unroll
-            for (int tap = 0; tap < kFTaps; ++tap) {
+#pragma unroll 1
+            for (int tap = gq; tap < kFTaps; tap += 4) {
                 uint32_t r[48];
 #pragma unroll
                 for (int k = 0; k < 6; ++k) {
@@ -401,38 +438,38 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
 #pragma unroll
                 for (int ci = 0; ci < 12; ++ci) {
                     const uint32_t v = off == 0 ? r[ci] : (off == 12 ? r[12 + ci] : (off == 24 ? r[24 + ci] : r[36 + ci]));
-                    dw[ci * 5 + tap] += __uint_as_float(v);
+                    accdw[co * 60 + ci * 5 + tap] += __uint_as_float(v);  // (co, tap) is owned by exactly one thread
                 }
             }
         }
         tc_fence_before();
         __syncthreads();
         // ---- P3: data gradient of the conv
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_w, ph_w, a.err);
-            fc_conv_mmas(g, tmem, ga, wa, id48, true);
-            umma_commit(bar_mma);
+            const bool leader = elect_one();
+            fc_conv_mmas(g, tmem, ga, wa, id48, true, leader);
+            if (leader) umma_commit(bar_mma);
         }
         ph_w ^= 1;
         wait_mma();
         // ---- E-B1: thread = tile row: d h (data gradient of the conv) -> 16-bit, over htile (dead after the weight
         //      gradient MMAs); gap rows are written as zeros so they keep acting as the next group's zero padding
-        for (int m = warp >> 2; m < g.nt; m += 2) {
-            const int q = 128 * m + 32 * (warp & 3) + lane;
-            const float rmask = ((q % g.FP) < g.F && (q / g.FP) < g.nfr) ? 1.f : 0.f;
 #pragma unroll 1
-            for (int c0 = 0; c0 < kH; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem + lane_off + m * 96 + c0, r);
-                tmem_ld_wait();
-                float v[32];
+        for (int it = gq; it < g.nt * 6; it += 4) {
+            const int m = it / 6, c0 = 16 * (it - 6 * m);
+            const int q = 128 * m + 32 * q4 + lane;
+            const float rmask = ((q % g.FP) < g.F && (q / g.FP) < g.nfr) ? 1.f : 0.f;
+            uint32_t r[16];
+            tmem_ld16(tmem + lane_off + m * 96 + c0, r);
+            tmem_ld_wait();
+            float v[16];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * rmask;
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * rmask;
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc)
-                    *reinterpret_cast<uint4*>(htile + (size_t)(c0 / 8 + cc) * g.cs + (2 + q) * 16) = pack8<FMT>(v + 8 * cc);
-            }
+            for (int cc = 0; cc < 2; ++cc)
+                *reinterpret_cast<uint4*>(htile + (size_t)(c0 / 8 + cc) * g.cs + (2 + q) * 16) = pack8<FMT>(v + 8 * cc);
         }
         tc_fence_before();
         __syncthreads();
@@ -441,9 +478,12 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
             constexpr int U = 3;
             const int sub = lane >> 3, l8 = lane & 7, N = g.nfr * g.F;
             const size_t loff = (size_t)(l8 >> 1) * g.cs + (l8 & 1) * 8;
+            Oct12 dlg, dlb;  // this group's d gamma / d beta of the lane's 12 channels -> shared accumulators
+            dlg.zero();
+            dlb.zero();
 #pragma unroll 1
-            for (int R = 4 * U * warp; R < N; R += 32 * U) {
-                float4 xv[U][3], dv[U][3];
+            for (int R = 4 * U * warp; R < N; R += 4 * U * NW) {
+                float4 xv[U][3];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int i = R + U * sub + u;
@@ -452,10 +492,8 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
                     const bool ok = i < N && t0 + tt < g.T;
                     const size_t off = (((size_t)b * g.F + f) * g.T + t0 + tt) * kH;
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
+                    for (int j = 0; j < 3; ++j)
                         xv[u][j] = ok ? __ldg(reinterpret_cast<const float4*>(a.x + off) + l8 + 8 * j) : make_float4(0, 0, 0, 0);
-                        dv[u][j] = ok ? __ldg(reinterpret_cast<const float4*>(a.dy + off) + l8 + 8 * j) : make_float4(0, 0, 0, 0);
-                    }
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -465,7 +503,10 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
                     const bool ok = i < N && t0 + tt < g.T;
                     const int p = 2 + tt * g.FP + f;
                     const float2 st = ok ? stats[p] : make_float2(0.f, 0.f);
-                    float4 dh[3];
+                    const size_t off = (((size_t)b * g.F + f) * g.T + t0 + tt) * kH;
+                    float4 dh[3], dv[3];  // dy of this row was staged (and L2-prefetched) by this CTA: an L2 hit
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) dv[j] = ok ? __ldg(reinterpret_cast<const float4*>(a.dy + off) + l8 + 8 * j) : make_float4(0, 0, 0, 0);
                     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
@@ -487,29 +528,28 @@ __global__ void __launch_bounds__(256, 1) fconv_tc_bwd_kernel(FcBwdArgs a) {
                     }
                     const float m1 = oct_sum(s1) * (1.f / kH), m2 = oct_sum(s2) * (1.f / kH);
                     if (ok) {
-                        float4* pdx = reinterpret_cast<float4*>(a.dx + (((size_t)b * g.F + f) * g.T + t0 + tt) * kH) + l8;
+                        float4* pdx = reinterpret_cast<float4*>(a.dx + off) + l8;
 #pragma unroll
                         for (int j = 0; j < 3; ++j)
-                            pdx[8 * j] = make_float4(dv[u][j].x + st.y * (dh[j].x - m1 - xv[u][j].x * m2), dv[u][j].y + st.y * (dh[j].y - m1 - xv[u][j].y * m2),
-                                                     dv[u][j].z + st.y * (dh[j].z - m1 - xv[u][j].z * m2), dv[u][j].w + st.y * (dh[j].w - m1 - xv[u][j].w * m2));
+                            pdx[8 * j] = make_float4(dv[j].x + st.y * (dh[j].x - m1 - xv[u][j].x * m2), dv[j].y + st.y * (dh[j].y - m1 - xv[u][j].y * m2),
+                                                     dv[j].z + st.y * (dh[j].z - m1 - xv[u][j].z * m2), dv[j].w + st.y * (dh[j].w - m1 - xv[u][j].w * m2));
                     }
                 }
             }
+            dlg.flush_atomic(acc + 192, lane);
+            dlb.flush_atomic(acc + 288, lane);
         }
         tc_fence_before();
         __syncthreads();
     }
-    // ---- flush parameter gradients
-    if (warp < 3) {
-#pragma unroll
-        for (int i = 0; i < 60; ++i) atomicAdd(a.dW + co * 60 + i, dw[i]);
-    }
-    for (int i = tid; i < 96; i += 256) {
+    // ---- flush parameter gradients: one set of global atomics per CTA
+    for (int i = tid; i < 96 * 60; i += NT) atomicAdd(a.dW + i, accdw[i]);
+    for (int i = tid; i < 96; i += NT) {
         atomicAdd(a.dbias + i, acc[i]);
         atomicAdd(a.dslope + i, acc[96 + i]);
+        atomicAdd(a.dlnw + i, acc[192 + i]);
+        atomicAdd(a.dlnb + i, acc[288 + i]);
     }
-    dlg.flush_atomic(a.dlnw, lane);
-    dlb.flush_atomic(a.dlnb, lane);
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -581,13 +621,13 @@ extern "C" int nbss_fconv_tc_bwd(const float* x, const float* dy, float* dx, int
     if (fmt != FMT_F16 && fmt != FMT_BF16) return NBSS_ERR_UNSUPPORTED;
     FcBwdArgs a{x, dy, dx, {}, lnw, lnb, bias, slope, (const unsigned char*)img, dW, dbias, dslope, dlnw, dlnb, err};
     if (!fc_geom(a.g, B, F, T, 3, 2)) return NBSS_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)24 * a.g.cs + FC_IMG_BYTES + 768 * 4 + (size_t)a.g.rows * 8 + 64;
+    const size_t smem = (size_t)24 * a.g.cs + FC_IMG_BYTES + (768 + 96 * 60) * 4 + (size_t)a.g.rows * 8 + 64;
     if (smem > 227 * 1024) return NBSS_ERR_UNSUPPORTED;
     auto kern = (fmt == FMT_F16) ? fconv_tc_bwd_kernel<FMT_F16> : fconv_tc_bwd_kernel<FMT_BF16>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int grid = a.g.ngroups < fc_sms() ? a.g.ngroups : fc_sms();
-    kern<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+    kern<<<grid, kFcBwdThreads, smem, (cudaStream_t)stream>>>(a);
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
 }

@@ -117,15 +117,16 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
     };
     // transposed conv: d_in[t] = sum_tap g[t - (tap-1)] Wt_tap  ->  A rows start at 128*mm + 2 - tap (frame t = row t+1)
     auto convT_phase = [&](uint32_t wsa, uint64_t* bar_w, uint32_t& ph_w) {
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_w, ph_w, a.err);
+            const bool leader = elect_one();
             for (int mm = 0; mm < 2; ++mm)
                 for (int p = 0; p < kPairs; ++p)
                     for (int tap = 0; tap < 3; ++tap)
                         mma_kk(tmem + mm * 192 + p * 48, hb + 6 * p * kCS + (128 * mm + 2 - tap) * 16, kCS,
-                               wsa + (p * 3 + tap) * 6 * 768, 768, 3, id48, tap > 0);
-            umma_commit(bar_mma);
+                               wsa + (p * 3 + tap) * 6 * 768, 768, 3, id48, tap > 0, leader);
+            if (leader) umma_commit(bar_mma);
         }
         ph_w ^= 1;
         wait_mma();
@@ -137,15 +138,18 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
     };
     // g = D * SiLU'(c), s = SiLU(c): the three plain activation epilogues
     // one 16-column block: g = D * SiLU'(c) -> G tile + global, s = SiLU(c) -> global
-    auto silu_block = [&](const uint32_t (&r)[16], int c0, const unsigned char* csave, unsigned char* gout, unsigned char* sout, int slab) {
+    auto silu_block = [&](const uint32_t (&r)[16], const uint4 (&cq)[2], int c0, unsigned char* gout, unsigned char* sout, int slab) {
         float c[16], g[16];
-        if (valid) {
-            load_h16x8(csave, slab, T, t, c0, c);
-            load_h16x8(csave, slab, T, t, c0 + 8, c + 8);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            unpack_f16x2(cq[cc].x, c[8 * cc + 0], c[8 * cc + 1]);
+            unpack_f16x2(cq[cc].y, c[8 * cc + 2], c[8 * cc + 3]);
+            unpack_f16x2(cq[cc].z, c[8 * cc + 4], c[8 * cc + 5]);
+            unpack_f16x2(cq[cc].w, c[8 * cc + 6], c[8 * cc + 7]);
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const float cv = valid ? c[j] : 0.f;
+            const float cv = c[j];
             const float sg = sigmoidf_(cv);
             g[j] = __uint_as_float(r[j]) * sg * (1.f + cv * (1.f - sg)) * vmask;
             c[j] = cv * sg;
@@ -160,18 +164,31 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
             *reinterpret_cast<uint4*>(hrow + (c0 / 8 + cc) * kCS) = gp;
         }
     };
-    // the three plain activation epilogues, TMEM loads software-pipelined over two register buffers
+    // saved pre-activation chunks c0/8, c0/8+1 of this thread's frame (zeros for frames >= T)
+    auto load_c = [&](const unsigned char* csave, int slab, int c0, uint4 (&cq)[2]) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc)
+            cq[cc] = valid ? __ldg(reinterpret_cast<const uint4*>(csave + tile_off(slab, 24, T, c0 / 8 + cc, t))) : make_uint4(0, 0, 0, 0);
+    };
+    // the three plain activation epilogues: TMEM loads and the global loads of the saved pre-activations are both
+    // software-pipelined over two register buffers (the global loads are issued one 16-column block ahead)
     auto silu_epilogue = [&](const unsigned char* csave, unsigned char* gout, unsigned char* sout, int slab) {
         uint32_t ra[16], rb[16];
+        uint4 ca[2], cb2[2];
+        load_c(csave, slab, cb, ca);
         tmem_ld16(tacc + cb, ra);
         tmem_ld_wait();
 #pragma unroll 1
         for (int c0 = cb; c0 < cb + 96; c0 += 32) {
             tmem_ld16(tacc + c0 + 16, rb);
-            silu_block(ra, c0, csave, gout, sout, slab);
+            load_c(csave, slab, c0 + 16, cb2);
+            silu_block(ra, ca, c0, gout, sout, slab);
             tmem_ld_wait();
-            if (c0 + 32 < cb + 96) tmem_ld16(tacc + c0 + 32, ra);
-            silu_block(rb, c0 + 16, csave, gout, sout, slab);
+            if (c0 + 32 < cb + 96) {
+                tmem_ld16(tacc + c0 + 32, ra);
+                load_c(csave, slab, c0 + 32, ca);
+            }
+            silu_block(rb, cb2, c0 + 16, gout, sout, slab);
             tmem_ld_wait();
         }
     };
@@ -183,15 +200,23 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
             load_image(ws0, a.img + IMG_W2T, IMG_W1_BYTES, bar_w0);
             load_image(ws1, a.img + IMG_WC3T, IMG_WC_BYTES, bar_w1);
         }
+        // L2 prefetch (after the weight copies: the bulk-copy engine works in order) of this slab's saved pre-activations
+        // c2, c1, a1, which the later thread-per-frame epilogues read with exposed latency
+        if (tid >= 32 && tid < 104) {
+            const int i = tid - 32, which = i / 24, ch = i % 24;
+            const unsigned char* base = which == 0 ? a.c2 : (which == 1 ? a.c1 : a.a1);
+            l2_prefetch(base + tile_off(slab, 24, T, ch, 0), (uint32_t)(T * 16));
+        }
         // ---- B0: dy -> G (chunks 0..11)
         stage_rows96<FMT, false, 2>(dys, T, hbuf, 1, nullptr, nullptr, warp, lane, nullptr, kFfnBwdThreads / 32);
         end_epilogue();
         // ---- B1: d s4 = dy W2
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_w0, ph_w0, a.err);
-            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 192 * 16, 6, id192, 0);
-            umma_commit(bar_mma);
+            const bool leader = elect_one();
+            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 192 * 16, 6, id192, 0, leader);
+            if (leader) umma_commit(bar_mma);
         }
         ph_w0 ^= 1;
         wait_mma();
@@ -287,11 +312,12 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         silu_epilogue(a.a1, a.g_a1, a.s1, slab);
         end_epilogue();
         // ---- B5: d ln = g(a1) W1 ; E5: LayerNorm backward + residual
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_w0, ph_w0, a.err);
-            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 96 * 16, 12, id96, 0);
-            umma_commit(bar_mma);
+            const bool leader = elect_one();
+            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 96 * 16, 12, id96, 0, leader);
+            if (leader) umma_commit(bar_mma);
         }
         ph_w0 ^= 1;
         wait_mma();

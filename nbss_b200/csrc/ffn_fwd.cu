@@ -99,15 +99,16 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
     const float inv_n = 1.f / (float)(kGC * T);
 
     auto conv_phase = [&](uint32_t wsa, uint64_t* bar_w, uint32_t& ph_w) {
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_w, ph_w, a.err);
+            const bool leader = elect_one();
             for (int mm = 0; mm < 2; ++mm)
                 for (int p = 0; p < kPairs; ++p)
                     for (int tap = 0; tap < 3; ++tap)
                         mma_kk(tmem + mm * 192 + p * 48, hb + 6 * p * kCS + (128 * mm + tap) * 16, kCS,
-                               wsa + (p * 3 + tap) * 6 * 768, 768, 3, id48, tap > 0);
-            umma_commit(bar_mma);
+                               wsa + (p * 3 + tap) * 6 * 768, 768, 3, id48, tap > 0, leader);
+            if (leader) umma_commit(bar_mma);
         }
         __syncwarp();
         ph_w ^= 1;
@@ -162,11 +163,12 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         stage_rows96<FMT, true>(xs, T, hbuf, 1, s_lng, s_lnb, warp, lane, a.ln_stats ? a.ln_stats + (size_t)slab * T * 2 : nullptr, kFfnThreads / 32);
         end_epilogue();
         // ---- P1: pw1
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_w0, ph_w0, a.err);
-            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 192 * 16, 6, id192, 0);
-            umma_commit(bar_mma);
+            const bool leader = elect_one();
+            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 192 * 16, 6, id192, 0, leader);
+            if (leader) umma_commit(bar_mma);
         }
         __syncwarp();
         ph_w0 ^= 1;
@@ -265,11 +267,12 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         act_epilogue(s_bc + 384, a.save_c3, slab);
         end_epilogue();
         // ---- P5: pw2 ; E5: y = x + D + b2
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_w0, ph_w0, a.err);
-            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 96 * 16, 12, id96, 0);
-            umma_commit(bar_mma);
+            const bool leader = elect_one();
+            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 96 * 16, 12, id96, 0, leader);
+            if (leader) umma_commit(bar_mma);
         }
         __syncwarp();
         ph_w0 ^= 1;

@@ -269,10 +269,11 @@ __global__ void __launch_bounds__(256, 3) squeeze_fwd_tc_kernel(RtArgs a) {
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
-            mma_kk(tmem, xa, kRtCs, ia, 256, 6, id16, 0);
-            umma_commit(bar);
+            const bool leader = elect_one();
+            mma_kk(tmem, xa, kRtCs, ia, 256, 6, id16, 0, leader);
+            if (leader) umma_commit(bar);
         }
         __syncwarp();
         mbar_wait(bar, ph, a.err);
@@ -350,10 +351,11 @@ __global__ void __launch_bounds__(256, 3) unsqueeze_fwd_tc_kernel(RtArgs a) {
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
-            mma_kk(tmem, ua, kRtCs, ia, 96 * 16, 1, id96, 0);
-            umma_commit(bar);
+            const bool leader = elect_one();
+            mma_kk(tmem, ua, kRtCs, ia, 96 * 16, 1, id96, 0, leader);
+            if (leader) umma_commit(bar);
         }
         __syncwarp();
         mbar_wait(bar, ph, a.err);
@@ -419,10 +421,11 @@ __global__ void __launch_bounds__(256, 4) unsqueeze_bwd_tc_kernel(RtArgs a) {
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
-            mma_kk(tmem, ua, kRtCs, i1, 96 * 16, 1, id96, 0);
-            umma_commit(bar);
+            const bool leader = elect_one();
+            mma_kk(tmem, ua, kRtCs, i1, 96 * 16, 1, id96, 0, leader);
+            if (leader) umma_commit(bar);
         }
         __syncwarp();
         mbar_wait(bar, ph, a.err);
@@ -455,12 +458,13 @@ __global__ void __launch_bounds__(256, 4) unsqueeze_bwd_tc_kernel(RtArgs a) {
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
-            mma_kk(tmem + 96, da, kRtCs, i2, 256, 6, id16, 0);
+            const bool leader = elect_one();
+            mma_kk(tmem + 96, da, kRtCs, i2, 256, 6, id16, 0, leader);
             for (int ks = 0; ks < kRtRows / 16; ++ks)
-                umma_f16(tmem + 112, sdesc_mnmajor(da + ks * 256, kRtCs), sdesc_mnmajor(ua + ks * 256, kRtCs), idw, (any || ks) ? 1u : 0u);
-            umma_commit(bar);
+                if (leader) umma_f16(tmem + 112, sdesc_mnmajor(da + ks * 256, kRtCs), sdesc_mnmajor(ua + ks * 256, kRtCs), idw, (any || ks) ? 1u : 0u);
+            if (leader) umma_commit(bar);
         }
         any = true;
         __syncwarp();
@@ -566,10 +570,11 @@ __global__ void __launch_bounds__(256, 2) squeeze_bwd_tc_kernel(RtArgs a) {
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
-            mma_kk(tmem, xa, kRtCs, i1, 256, 6, id16, 0);
-            umma_commit(bar);
+            const bool leader = elect_one();
+            mma_kk(tmem, xa, kRtCs, i1, 256, 6, id16, 0, leader);
+            if (leader) umma_commit(bar);
         }
         __syncwarp();
         mbar_wait(bar, ph, a.err);
@@ -591,12 +596,13 @@ __global__ void __launch_bounds__(256, 2) squeeze_bwd_tc_kernel(RtArgs a) {
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
-            mma_kk(tmem + 16, za, kRtCs, i2, 96 * 16, 1, id96, 0);
+            const bool leader = elect_one();
+            mma_kk(tmem + 16, za, kRtCs, i2, 96 * 16, 1, id96, 0, leader);
             for (int ks = 0; ks < kRtRows / 16; ++ks)
-                umma_f16(tmem + 112, sdesc_mnmajor(xa + ks * 256, kRtCs), sdesc_mnmajor(za + ks * 256, kRtCs), idw, (any || ks) ? 1u : 0u);
-            umma_commit(bar);
+                if (leader) umma_f16(tmem + 112, sdesc_mnmajor(xa + ks * 256, kRtCs), sdesc_mnmajor(za + ks * 256, kRtCs), idw, (any || ks) ? 1u : 0u);
+            if (leader) umma_commit(bar);
         }
         any = true;
         __syncwarp();

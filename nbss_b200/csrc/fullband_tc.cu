@@ -105,17 +105,18 @@ __global__ void __launch_bounds__(256, 2) lg_tc_kernel(LgArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    if (tid == 0) {
+    if (warp == 0) {
         mbar_wait(bar_w, 0, a.err);
+        const bool leader = elect_one();
         const uint32_t ta = smem_u32(tile), wa = smem_u32(wimg);
         if (MODE == 0) {
-            mma_kk(tmem, ta, kLgCsA, wa, g.csb, g.Fp / 16, make_idesc(FMT, 128, g.Fp, 0, 0), 0);
+            mma_kk(tmem, ta, kLgCsA, wa, g.csb, g.Fp / 16, make_idesc(FMT, 128, g.Fp, 0, 0), 0, leader);
         } else {
             const uint32_t id = make_idesc(FMT, 128, g.Fp, 0, 1);
             for (int ks = 0; ks < g.Fp / 16; ++ks)
-                umma_f16(tmem, sdesc_kmajor(ta + (uint32_t)(2 * ks) * kLgCsA, kLgCsA), sdesc_mnmajor(wa + ks * 256, g.csb), id, ks ? 1u : 0u);
+                if (leader) umma_f16(tmem, sdesc_kmajor(ta + (uint32_t)(2 * ks) * kLgCsA, kLgCsA), sdesc_mnmajor(wa + ks * 256, g.csb), id, ks ? 1u : 0u);
         }
-        umma_commit(bar_mma);
+        if (leader) umma_commit(bar_mma);
     }
     __syncwarp();
     mbar_wait(bar_mma, 0, a.err);
@@ -202,11 +203,12 @@ __global__ void __launch_bounds__(256, 2) lg_wgrad_kernel(LgWgArgs a) {
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
+            const bool leader = elect_one();
             for (int ks = 0; ks < kLgRows / 16; ++ks)
-                umma_f16(tmem, sdesc_mnmajor(da + ks * 256, kLgCsA), sdesc_mnmajor(sa + ks * 256, kLgCsA), id, (any || ks) ? 1u : 0u);
-            umma_commit(bar_mma);
+                if (leader) umma_f16(tmem, sdesc_mnmajor(da + ks * 256, kLgCsA), sdesc_mnmajor(sa + ks * 256, kLgCsA), id, (any || ks) ? 1u : 0u);
+            if (leader) umma_commit(bar_mma);
         }
         any = true;
         // while the tensor core works: column sums of du (bias gradient) and the k >= 128 rows of dW

@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
     for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
         const size_t row0 = (size_t)slab * T;
         if (tid == 0) load_image(pt, a.img + IMG_WOT, IMG_WQ_BYTES, bar_w);
+        if (tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab)  // next slab's upstream gradient -> L2 (after the weight copy)
+            l2_prefetch_slab(a.dy + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
         for (int i = tid; i < kNH * 256; i += kMbThreads) {
             const int h = i >> 8, tt = i & 255;
             s_lse[i] = tt < T ? a.lse[((size_t)slab * kNH + h) * T + tt] : 0.f;
@@ -115,11 +117,12 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
         stage_rows96<FMT_G, false>(a.dy + row0 * kH, T, dot, 0, nullptr, nullptr, warp, lane, nullptr, kMbThreads / 32);
         end_epilogue();
         // ---- M0: dO = dy Wo
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_w, ph_w, a.err);
-            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 96, doa + 128 * mm * 16, kCS, pa, 96 * 16, 6, id_do, 0);
-            umma_commit(bar_mma);
+            const bool leader = elect_one();
+            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 96, doa + 128 * mm * 16, kCS, pa, 96 * 16, 6, id_do, 0, leader);
+            if (leader) umma_commit(bar_mma);
         }
         ph_w ^= 1;
         wait_mma();
@@ -174,11 +177,12 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
 #pragma unroll 1
             for (int blk = 0; blk < 4; ++blk) {
                 const int qb = blk >> 1, kb = blk & 1;
-                if (tid == 0) {
+                if (warp == 0) {
                     tc_fence_after();
-                    mma_kk(tmem + C_S, qa + 128 * qb * 16, kCS, ka + 128 * kb * 16, kCS, 2, id_s, 0);
-                    mma_kk(tmem + C_DP, doa + 3 * h * kCS + 128 * qb * 16, kCS, va + 128 * kb * 16, kCS, 2, id_dp, 0);
-                    umma_commit(bar_mma);
+                    const bool leader = elect_one();
+                    mma_kk(tmem + C_S, qa + 128 * qb * 16, kCS, ka + 128 * kb * 16, kCS, 2, id_s, 0, leader);
+                    mma_kk(tmem + C_DP, doa + 3 * h * kCS + 128 * qb * 16, kCS, va + 128 * kb * 16, kCS, 2, id_dp, 0, leader);
+                    if (leader) umma_commit(bar_mma);
                 }
                 wait_mma();
                 // P and dS for this block: thread = (query row rt, key quarter kq: 32 of the 128 keys)
@@ -206,20 +210,21 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
                     }
                 }
                 end_epilogue();
-                if (tid == 0) {
+                if (warp == 0) {
                     tc_fence_after();
+                    const bool leader = elect_one();
                     for (int ks = 0; ks < 8; ++ks) {
                         // dQ[qb] += dS K[kb]: A = dS (K-major, K = keys), B = K tile MN-major (K = key rows)
-                        umma_f16(tmem + C_DQ + 32 * qb, sdesc_kmajor(dsa + 2 * ks * kCSQ, kCSQ),
+                        if (leader) umma_f16(tmem + C_DQ + 32 * qb, sdesc_kmajor(dsa + 2 * ks * kCSQ, kCSQ),
                                  sdesc_mnmajor(ka + (128 * kb + 16 * ks) * 16, kCS), id_dq, (kb | ks) ? 1u : 0u);
                         // dK[kb] += dS^T Qs[qb]: A = dS MN-major (M = keys, K = query rows), B = Qs MN-major
-                        umma_f16(tmem + C_DK + 32 * kb, sdesc_mnmajor(dsa + 16 * ks * 16, kCSQ),
+                        if (leader) umma_f16(tmem + C_DK + 32 * kb, sdesc_mnmajor(dsa + 16 * ks * 16, kCSQ),
                                  sdesc_mnmajor(qa + (128 * qb + 16 * ks) * 16, kCS), id_dk, (qb | ks) ? 1u : 0u);
                         // dV[kb] += P^T dO[qb]
-                        umma_f16(tmem + C_DV + 32 * kb, sdesc_mnmajor(pa + 16 * ks * 16, kCSQ),
+                        if (leader) umma_f16(tmem + C_DV + 32 * kb, sdesc_mnmajor(pa + 16 * ks * 16, kCSQ),
                                  sdesc_mnmajor(doa + 3 * h * kCS + (128 * qb + 16 * ks) * 16, kCS), id_dv, (qb | ks) ? 1u : 0u);
                     }
-                    umma_commit(bar_mma);
+                    if (leader) umma_commit(bar_mma);
                 }
                 wait_mma();
             }
@@ -310,15 +315,20 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a
     for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
         const size_t row0 = (size_t)slab * T, grow = row0 + t;
         if (tid == 0) bulk_load_chunks(at, kCS, 0, a.dqkv + tile_off(slab, 36, T, 0, 0), 36, T, bar_ld);
+        if (tid >= 32 && tid < 44) {  // this slab's x and dy rows (LayerNorm backward at the end of the iteration) -> L2
+            const int i = tid - 32;
+            l2_prefetch_slab((i < 6 ? a.x : a.dy) + row0 * kH, T, i % 6);
+        }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             if (!wready) mbar_wait(bar_w, 0, a.err);
             mbar_wait(bar_ld, ph_ld, a.err);
-            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 96, ata + 128 * mm * 16, kCS, wta, 96 * 16, 18, id96, 0);
-            umma_commit(bar_mma);
+            const bool leader = elect_one();
+            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 96, ata + 128 * mm * 16, kCS, wta, 96 * 16, 18, id96, 0, leader);
+            if (leader) umma_commit(bar_mma);
         }
         wready = true;
         ph_ld ^= 1;

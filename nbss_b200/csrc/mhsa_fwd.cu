@@ -108,14 +108,17 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
     for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
         const float* xs = a.x + (size_t)slab * T * kH;
         if (tid == 0) load_image(wr, a.img + IMG_WKV, IMG_W1_BYTES, bar_w);
+        if (tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab)  // next slab's input rows -> L2 (after the weight copy)
+            l2_prefetch_slab(a.x + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
         stage_rows96<FMT, true>(xs, T, ao, 0, s_lng, s_lnb, warp, lane, a.ln_stats ? a.ln_stats + (size_t)slab * T * 2 : nullptr, kMhThreads / 32);
         end_epilogue();
         // ---- P1: K|V
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_w, ph_w, a.err);
-            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 192, aoa + 128 * mm * 16, kCS, wra, 192 * 16, 6, id192, 0);
-            umma_commit(bar_mma);
+            const bool leader = elect_one();
+            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 192, aoa + 128 * mm * 16, kCS, wra, 192 * 16, 6, id192, 0, leader);
+            if (leader) umma_commit(bar_mma);
         }
         ph_w ^= 1;
         wait_mma();
@@ -154,11 +157,12 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         }
         end_epilogue();
         // ---- P2: Q (stays in TMEM cols 0..191)
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_w, ph_w, a.err);
-            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 96, aoa + 128 * mm * 16, kCS, wra, 96 * 16, 6, id96, 0);
-            umma_commit(bar_mma);
+            const bool leader = elect_one();
+            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 96, aoa + 128 * mm * 16, kCS, wra, 96 * 16, 6, id96, 0, leader);
+            if (leader) umma_commit(bar_mma);
         }
         ph_w ^= 1;
         wait_mma();
@@ -187,23 +191,29 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
             }
             end_epilogue();
             // S = Qs K_h^T
-            if (tid == 0) {
+            if (warp == 0) {
                 tc_fence_after();
-                mma_kk(tmem + 192, qsa, kCSP, kta + 4 * h * kCS, kCS, 2, id256, 0);
-                umma_commit(bar_mma);
+                const bool leader = elect_one();
+                mma_kk(tmem + 192, qsa, kCSP, kta + 4 * h * kCS, kCS, 2, id256, 0, leader);
+                if (leader) umma_commit(bar_mma);
             }
             wait_mma();
             // softmax: thread = (query row rt, key quarter kq): 64 of the 256 score columns
             const uint32_t ts = tmem + lane_off + 192 + 64 * kq;
             float mx = -INFINITY;
-#pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(ts + c0, r);
+            {
+                // both 32-column loads in flight before the single wait; four independent max chains
+                uint32_t r0[32], r1[32];
+                tmem_ld32(ts, r0);
+                tmem_ld32(ts + 32, r1);
                 tmem_ld_wait();
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    mx = fmaxf(mx, (64 * kq + c0 + j < T) ? __uint_as_float(r[j]) : -INFINITY);
+                for (int j = 0; j < 32; ++j) {
+                    m4[j & 1] = fmaxf(m4[j & 1], (64 * kq + j < T) ? __uint_as_float(r0[j]) : -INFINITY);
+                    m4[2 + (j & 1)] = fmaxf(m4[2 + (j & 1)], (64 * kq + 32 + j < T) ? __uint_as_float(r1[j]) : -INFINITY);
+                }
+                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
             }
             xmax[kq * 128 + rt] = mx;
             __syncthreads();
@@ -235,12 +245,13 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
                         *reinterpret_cast<uint4*>(pt + (8 * (kq & 1) + c) * kCSP + rt * 16) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
                 }
                 end_epilogue();
-                if (tid == 0) {
+                if (warp == 0) {
                     tc_fence_after();
+                    const bool leader = elect_one();
                     for (int ks = 0; ks < 8; ++ks)
-                        umma_f16(tmem + 448, sdesc_kmajor(pta + 2 * ks * kCSP, kCSP),
+                        if (leader) umma_f16(tmem + 448, sdesc_kmajor(pta + 2 * ks * kCSP, kCSP),
                                  sdesc_mnmajor(vta + 3 * h * kCS + (128 * half + 16 * ks) * 16, kCS), idpv, (half | ks) ? 1u : 0u);
-                    umma_commit(bar_mma);
+                    if (leader) umma_commit(bar_mma);
                 }
                 wait_mma();
             }
@@ -269,11 +280,12 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         // ---- P3: out-proj + residual
         if (tid == 0) load_image(wr, a.img + IMG_WO, IMG_WQ_BYTES, bar_w);
         end_epilogue();
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_w, ph_w, a.err);
-            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + 192 + mm * 96, aoa + 128 * mm * 16, kCS, wra, 96 * 16, 6, id96, 0);
-            umma_commit(bar_mma);
+            const bool leader = elect_one();
+            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + 192 + mm * 96, aoa + 128 * mm * 16, kCS, wra, 96 * 16, 6, id96, 0, leader);
+            if (leader) umma_commit(bar_mma);
         }
         ph_w ^= 1;
         wait_mma();

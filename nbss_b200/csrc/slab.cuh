@@ -28,6 +28,18 @@ __device__ __forceinline__ void load_image(void* dst_smem, const void* src, uint
     bulk_g2s(dst_smem, src, bytes, bar);
 }
 
+// ---------------------------------------------------------------- L2 prefetch of the next work item's inputs
+// cp.async.bulk.prefetch.L2 (SASS UBLKPF.L2): one thread asks the memory system to pull `bytes` (multiple of 16) into L2.
+// The persistent kernels issue it for the data their NEXT slab / row group will stage, so those latency-exposed loads
+// hit L2 instead of HBM.  No architectural side effects: a wrong address range would only waste bandwidth.
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// fp32 slab [T,96] (T*384 bytes) in 6 pieces; call with i = 0..5 from six different threads
+__device__ __forceinline__ void l2_prefetch_slab(const float* slab, int T, int i) {
+    l2_prefetch(reinterpret_cast<const unsigned char*>(slab) + (size_t)i * T * 64, (uint32_t)(T * 64));
+}
+
 // ---------------------------------------------------------------- 16-bit intermediates in HBM: "slab tile" layout
 // Every 16-bit tensor that only travels between these kernels (saved pre-activations, q|k|v, O, gradient operands) is
 // stored as [slab][C/8 chunks][T rows][8 elements]: the byte image of the smem operand tile.  A thread-per-frame
@@ -45,14 +57,16 @@ __device__ __forceinline__ void bulk_load_chunks(unsigned char* tile, uint32_t c
 
 // ---------------------------------------------------------------- MMA issue helpers (call from ONE thread)
 // D[128 x N] (+)= A[128 x 16*ksteps] * B[N x 16*ksteps]^T, both K-major chunk-column tiles.
+// Call it from every lane of ONE warp with `leader` = elect_one(): the descriptor arithmetic is warp-uniform (uniform
+// registers), only the tcgen05.mma itself is predicated.  (A lone `if (tid == 0)` caller may leave leader = true.)
 __device__ __forceinline__ void mma_kk(uint32_t tmem_d, uint32_t a_addr, uint32_t a_cs, uint32_t b_addr, uint32_t b_cs,
-                                       int ksteps, uint32_t idesc, uint32_t acc) {
+                                       int ksteps, uint32_t idesc, uint32_t acc, bool leader = true) {
     // the start-address field is the low 14 bits of the descriptor: advancing K is a plain add of (bytes >> 4)
     uint64_t da = sdesc_kmajor(a_addr, a_cs), db = sdesc_kmajor(b_addr, b_cs);
     const uint64_t sa = (uint64_t)((2 * a_cs) >> 4), sb = (uint64_t)((2 * b_cs) >> 4);
 #pragma unroll 1
     for (int ks = 0; ks < ksteps; ++ks) {
-        umma_f16(tmem_d, da, db, idesc, acc);
+        if (leader) umma_f16(tmem_d, da, db, idesc, acc);
         da += sa;
         db += sb;
         acc = 1;

@@ -151,6 +151,21 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One lane of a fully converged warp (elect.sync).  The MMA-issuing code is written so that the WHOLE warp runs the
+// descriptor arithmetic (warp-uniform values -> uniform registers) and only the tcgen05.mma / commit instructions
+// themselves are predicated on the elected lane: a single-thread `if (tid == 0)` block makes the compiler stage every
+// operand through R2UR.BROADCAST loops (about 20-30 instructions per MMA, more than a small MMA takes to execute).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 // Arrive on an mbarrier when all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

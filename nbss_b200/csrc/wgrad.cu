@@ -33,8 +33,10 @@ struct WgArgs {
     int* err;
 };
 
+constexpr int kWgThreads = 512;  // 16 warps: the fp32 operands of the pointwise jobs are staged by all of them
+
 template <int FMT_G, int FMT_A>
-__global__ void __launch_bounds__(256, 1) wgrad_kernel(WgArgs args) {
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(WgArgs args) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar_mma, bar_ld;
     __shared__ uint32_t tmem_slot;
@@ -57,13 +59,13 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(WgArgs args) {
         mbar_init(&bar_ld2, 2);
         fence_mbar_init();
     }
-    if (J.a_ln) for (int i = tid; i < 96; i += 256) { s_ln[i] = J.ln_w[i]; s_ln[96 + i] = J.ln_b[i]; }
+    if (J.a_ln) for (int i = tid; i < 96; i += kWgThreads) { s_ln[i] = J.ln_w[i]; s_ln[96 + i] = J.ln_b[i]; }
     for (int set = 0; set < nsets; ++set) {
         unsigned char* base = smem + (size_t)set * set_bytes;
-        for (int i = tid; i < (int)((J.g_alloc + J.a_chunks) * kCS / 16); i += 256) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < (int)((J.g_alloc + J.a_chunks) * kCS / 16); i += kWgThreads) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
         const uint32_t one2 = pack16<FMT_A>(1.f, 1.f);
         uint4* ones = reinterpret_cast<uint4*>(base + (size_t)(J.g_alloc + J.a_chunks) * kCS);
-        for (int i = tid; i < (int)(2 * kCS / 16); i += 256) ones[i] = make_uint4(one2, one2, one2, one2);
+        for (int i = tid; i < (int)(2 * kCS / 16); i += kWgThreads) ones[i] = make_uint4(one2, one2, one2, one2);
     }
     fence_async_smem();
     tc_fence_before();
@@ -75,22 +77,24 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(WgArgs args) {
     bool first = true;
     (void)a_alloc;
 
-    auto issue_mmas = [&](uint32_t ga, uint32_t aa, bool fresh) {
+    // called by every lane of warp 0 (uniform descriptor arithmetic); `leader` = the elected lane issues
+    auto issue_mmas = [&](uint32_t ga, uint32_t aa, bool fresh, bool leader) {
         for (int i = 0; i < J.nmma; ++i) {
             const WgMma mm = J.mma[i];
             const uint32_t idesc = (1u << 4) | ((uint32_t)FMT_G << 7) | ((uint32_t)FMT_A << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(mm.n >> 3) << 17) | (8u << 24);
             uint64_t da = sdesc_mnmajor(ga + mm.a_chunk * kCS, kCS), db = sdesc_mnmajor(aa + mm.b_chunk * kCS + mm.b_row * 16, kCS);
             for (int ks = 0; ks < 16; ++ks) {
-                umma_f16(tmem + mm.col, da, db, idesc, (fresh && ks == 0) ? 0u : 1u);
+                if (leader) umma_f16(tmem + mm.col, da, db, idesc, (fresh && ks == 0) ? 0u : 1u);
                 da += 16;  // 16 rows x 16 B >> 4
                 db += 16;
             }
         }
     };
     if (J.dbl) {
-        // ---- pipelined path (both operands by TMA): one thread drives loads and MMAs, two tile sets
-        if (tid == 0) {
+        // ---- pipelined path (both operands by TMA): warp 0 drives loads and MMAs (one elected lane issues), two tile sets
+        if (warp == 0) {
+            const bool leader = elect_one();
             auto issue_loads = [&](int slab, int set) {
                 unsigned char* g0 = smem + (size_t)set * set_bytes;
                 uint64_t* bar = set ? &bar_ld2 : &bar_ld;
@@ -101,23 +105,24 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(WgArgs args) {
             };
             uint32_t phl[2] = {0, 0};
             int k = 0;
-            if ((int)blockIdx.x < args.nslab) issue_loads(blockIdx.x, 0);
+            if (leader && (int)blockIdx.x < args.nslab) issue_loads(blockIdx.x, 0);
             for (int slab = blockIdx.x; slab < args.nslab; slab += gridDim.x, ++k) {
                 const int set = k & 1, nxt = slab + gridDim.x;
                 if (k >= 1) {  // MMAs of the previous slab (other tile set) are done: its tiles may be overwritten
                     mbar_wait(&bar_mma, ph, args.err);
                     ph ^= 1;
                 }
-                if (nxt < args.nslab) issue_loads(nxt, set ^ 1);
+                if (leader && nxt < args.nslab) issue_loads(nxt, set ^ 1);
                 mbar_wait(set ? &bar_ld2 : &bar_ld, phl[set], args.err);
                 phl[set] ^= 1;
                 tc_fence_after();
                 const uint32_t ga = gta + set * set_bytes;
-                issue_mmas(ga, ga + J.g_alloc * kCS, k == 0);
-                umma_commit(&bar_mma);
+                issue_mmas(ga, ga + J.g_alloc * kCS, k == 0, leader);
+                if (leader) umma_commit(&bar_mma);
+                __syncwarp();
             }
             if (k >= 1) mbar_wait(&bar_mma, ph, args.err);
-            s_nslabs = k;
+            if (leader) s_nslabs = k;
         }
         __syncthreads();
         first = s_nslabs == 0;
@@ -135,16 +140,17 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(WgArgs args) {
                 bulk_load_chunks(at, kCS, J.a_row_off, reinterpret_cast<const unsigned char*>(J.act) + tile_off(slab, J.a_cols / 8, T, J.a_c0 / 8, 0),
                                  J.a_chunks, T, &bar_ld);
         }
-        if (J.g_fp32) stage_rows96<FMT_G, false>(reinterpret_cast<const float*>(J.g) + row0 * kH, T, gt, 0, nullptr, nullptr, warp, lane);
-        if (J.a_ln) stage_rows96<FMT_A, true>(reinterpret_cast<const float*>(J.act) + row0 * kH, T, at, J.a_row_off, s_ln, s_ln + 96, warp, lane);
+        if (J.g_fp32) stage_rows96<FMT_G, false>(reinterpret_cast<const float*>(J.g) + row0 * kH, T, gt, 0, nullptr, nullptr, warp, lane, nullptr, kWgThreads / 32);
+        if (J.a_ln) stage_rows96<FMT_A, true>(reinterpret_cast<const float*>(J.act) + row0 * kH, T, at, J.a_row_off, s_ln, s_ln + 96, warp, lane, nullptr, kWgThreads / 32);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
             if (n_bulk > 0) { mbar_wait(&bar_ld, ph_ld, args.err); ph_ld ^= 1; }
-            issue_mmas(gta, ata, first);
-            umma_commit(&bar_mma);
+            const bool leader = elect_one();
+            issue_mmas(gta, ata, first, leader);
+            if (leader) umma_commit(&bar_mma);
         }
         first = false;
         __syncwarp();
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(WgArgs args) {
             const WgOut op = J.out[o];
             const int rl = L - op.lane0;
             const bool rowok = rl >= 0 && rl < op.nl;
-            for (int cb = (warp >> 2); cb * 8 < op.nc; cb += 2) {
+            for (int cb = (warp >> 2); cb * 8 < op.nc; cb += kWgThreads / 128) {
                 uint32_t r[8];
                 tmem_ld8(tl + op.col + 8 * cb, r);
                 tmem_ld_wait();
@@ -210,7 +216,7 @@ static int launch_wgrad(WgArgs& a, int njobs, int fmt_g, int fmt_a, cudaStream_t
     int per = wg_sms() / njobs;
     if (per < 1) per = 1;
     if (per > a.nslab) per = a.nslab;
-    kern<<<dim3(per, njobs), 256, smem, st>>>(a);
+    kern<<<dim3(per, njobs), kWgThreads, smem, st>>>(a);
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
 }

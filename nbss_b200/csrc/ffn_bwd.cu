@@ -200,13 +200,6 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
             load_image(ws0, a.img + IMG_W2T, IMG_W1_BYTES, bar_w0);
             load_image(ws1, a.img + IMG_WC3T, IMG_WC_BYTES, bar_w1);
         }
-        // L2 prefetch (after the weight copies: the bulk-copy engine works in order) of this slab's saved pre-activations
-        // c2, c1, a1, which the later thread-per-frame epilogues read with exposed latency
-        if (tid >= 32 && tid < 104) {
-            const int i = tid - 32, which = i / 24, ch = i % 24;
-            const unsigned char* base = which == 0 ? a.c2 : (which == 1 ? a.c1 : a.a1);
-            l2_prefetch(base + tile_off(slab, 24, T, ch, 0), (uint32_t)(T * 16));
-        }
         // ---- B0: dy -> G (chunks 0..11)
         stage_rows96<FMT, false, 2>(dys, T, hbuf, 1, nullptr, nullptr, warp, lane, nullptr, kFfnBwdThreads / 32);
         end_epilogue();

@@ -195,6 +195,191 @@ __global__ void __launch_bounds__(256) istft_bwd_kernel(IstftBwdArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ FFT framing
+// n_fft = 4^k (64, 256, 1024): radix-4 Stockham FFT in shared memory instead of the direct DFT above.  Two real frames ride
+// in one complex transform (z = a + i b; A[f] = (Z[f] + conj Z[N-f]) / 2, B[f] = (Z[f] - conj Z[N-f]) / (2i)).
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// `nb` transforms of length N in `a` ([nb][N]); `b` is scratch of the same size.  tw[k] = (cos, sin)(2 pi k / N).
+// Forward: X[k] = sum x[n] e^{-2 pi i k n / N}; INV: the conjugate kernel, not normalised.  Returns the result buffer.
+template <bool INV>
+__device__ float2* fft_r4_batch(float2* a, float2* b, int nb, int N, const float2* tw, int tid, int nthreads) {
+    const int Q = N >> 2;
+    for (int Ns = 1; Ns < N; Ns <<= 2) {
+        const int tstep = N / (4 * Ns);
+        for (int task = tid; task < nb * Q; task += nthreads) {
+            const int fi = task / Q, j = task - fi * Q;
+            const float2* src = a + (size_t)fi * N;
+            float2* dst = b + (size_t)fi * N;
+            const int k = j & (Ns - 1), m = k * tstep;
+            float2 w1 = tw[m], w2 = tw[2 * m], w3 = tw[3 * m];
+            if (!INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+            const float2 v0 = src[j], v1 = cmul(src[j + Q], w1), v2 = cmul(src[j + 2 * Q], w2), v3 = cmul(src[j + 3 * Q], w3);
+            const float2 A = make_float2(v0.x + v2.x, v0.y + v2.y), B = make_float2(v0.x - v2.x, v0.y - v2.y);
+            const float2 C = make_float2(v1.x + v3.x, v1.y + v3.y), D = make_float2(v1.x - v3.x, v1.y - v3.y);
+            const int j0 = ((j - k) << 2) + k;  // (j / Ns) * Ns * 4 + k
+            dst[j0] = make_float2(A.x + C.x, A.y + C.y);
+            dst[j0 + 2 * Ns] = make_float2(A.x - C.x, A.y - C.y);
+            // forward: y1 = B - i D, y3 = B + i D; inverse: the other way round
+            const float2 m1 = make_float2(B.x + D.y, B.y - D.x), p1 = make_float2(B.x - D.y, B.y + D.x);
+            dst[j0 + Ns] = INV ? p1 : m1;
+            dst[j0 + 3 * Ns] = INV ? m1 : p1;
+        }
+        __syncthreads();
+        float2* t = a; a = b; b = t;
+    }
+    return a;
+}
+
+constexpr int kFTF = 4;  // frames per CTA of the FFT STFT kernel
+
+__global__ void __launch_bounds__(256) stft_fft_kernel(StftArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int N = a.N, F = a.F, C = a.C, NF = kFTF * C, NB = (NF + 1) / 2;
+    float2* tw = reinterpret_cast<float2*>(sm);   // [N]
+    float2* za = tw + N;                           // [NB][N]
+    float2* zb = za + (size_t)NB * N;              // [NB][N]
+    float2* X = zb + (size_t)NB * N;               // [kFTF][C][F]
+    const int tiles = (a.T + kFTF - 1) / kFTF, tid = threadIdx.x;
+    const int b = blockIdx.x / tiles, t0 = (blockIdx.x % tiles) * kFTF;
+    for (int k = tid; k < N; k += 256) tw[k] = make_float2(cospif(2.f * k / N), sinpif(2.f * k / N));
+    for (int i = tid; i < NB * N; i += 256) {
+        const int p = i / N, n = i - p * N;
+        float v[2] = {0.f, 0.f};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int q = 2 * p + h, tt = q / C, c = q - tt * C, t = t0 + tt;
+            if (q < NF && t < a.T) {
+                int j = t * a.hop + n - N / 2;  // center=True, reflect padding
+                if (j < 0) j = -j;
+                if (j >= a.Ts) j = 2 * (a.Ts - 1) - j;
+                v[h] = a.x[((size_t)b * C + c) * a.Ts + j];
+            }
+        }
+        const float w = hann(n, N);
+        za[i] = make_float2(v[0] * w, v[1] * w);
+    }
+    __syncthreads();
+    const float2* Z = fft_r4_batch<false>(za, zb, NB, N, tw, tid, 256);
+    for (int i = tid; i < NF * F; i += 256) {
+        const int q = i / F, f = i - q * F;
+        const float2 z1 = Z[(size_t)(q >> 1) * N + f], z2 = Z[(size_t)(q >> 1) * N + ((N - f) & (N - 1))];
+        X[i] = (q & 1) ? make_float2(0.5f * (z1.y + z2.y), -0.5f * (z1.x - z2.x)) : make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
+    }
+    __syncthreads();
+    for (int i = tid; i < kFTF * C * F; i += 256) {
+        // order (f, tt, c): consecutive threads write consecutive channels / frames of one frequency
+        const int c = i % C, tt = (i / C) % kFTF, f = i / (C * kFTF), t = t0 + tt;
+        if (t >= a.T) continue;
+        float2 v = X[((size_t)tt * C + c) * F + f];
+        if (a.normalize) {
+            const float2 r = X[((size_t)tt * C + a.ref) * F + f];
+            const float mm = sqrtf(r.x * r.x + r.y * r.y) + a.eps;
+            v.x /= mm;
+            v.y /= mm;
+            if (c == a.ref) {
+                const size_t o = ((size_t)b * F + f) * a.T + t;
+                if (a.xrmm) a.xrmm[o] = mm;
+                if (a.xr) { a.xr[2 * o] = r.x; a.xr[2 * o + 1] = r.y; }
+            }
+        }
+        float* o = a.out + b * a.ob + c * a.oc + f * a.of + t * a.ot;
+        o[0] = v.x;
+        o[1] = v.y;
+    }
+}
+
+__global__ void __launch_bounds__(256) istft_fft_kernel(IstftArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int N = a.N, F = a.F, R = N / a.hop, NFR = kFT + R - 1, NB = (NFR + 1) / 2;
+    float2* tw = reinterpret_cast<float2*>(sm);                 // [N]
+    float2* X = tw + N;                                         // [NFR][F]
+    float2* za = X + (size_t)NFR * F;                           // [NB][N]
+    float2* zb = za + (size_t)NB * N;                           // [NB][N]
+    float* fr = reinterpret_cast<float*>(zb + (size_t)NB * N);  // [NFR][N] windowed inverse DFT of each frame
+    const int nseg = a.T + R - 1, tiles = (nseg + kFT - 1) / kFT, tid = threadIdx.x;
+    const int bs = blockIdx.x / tiles, k0 = (blockIdx.x % tiles) * kFT;
+    const int b = bs / a.S, s = bs % a.S;
+    const int tfirst = k0 - (R - 1);
+    for (int k = tid; k < N; k += 256) tw[k] = make_float2(cospif(2.f * k / N), sinpif(2.f * k / N));
+    for (int i = tid; i < NFR * F; i += 256) {
+        const int f = i % F, t = tfirst + i / F;
+        float2 v = make_float2(0.f, 0.f);
+        if (t >= 0 && t < a.T) {
+            const float* p = a.in + b * a.ib + s * a.is + f * a.if_ + t * a.it;
+            const float sc = a.scale ? a.scale[((size_t)b * F + f) * a.T + t] : 1.f;
+            v = make_float2(p[0] * sc, (f == 0 || f == F - 1) ? 0.f : p[1] * sc);  // DC / Nyquist: imaginary parts ignored
+        }
+        X[i] = v;
+    }
+    __syncthreads();
+    // Hermitian extension of two frames packed as Ya + i Yb
+    for (int i = tid; i < NB * N; i += 256) {
+        const int p = i / N, k = i - p * N, kk = k <= N / 2 ? k : N - k;
+        const float sg = k <= N / 2 ? 1.f : -1.f;
+        const float2 ya = X[(size_t)(2 * p) * F + kk];
+        const float2 yb = (2 * p + 1 < NFR) ? X[(size_t)(2 * p + 1) * F + kk] : make_float2(0.f, 0.f);
+        za[i] = make_float2(ya.x - sg * yb.y, sg * ya.y + yb.x);
+    }
+    __syncthreads();
+    const float2* Z = fft_r4_batch<true>(za, zb, NB, N, tw, tid, 256);
+    const float invN = 1.f / N;
+    for (int i = tid; i < NFR * N; i += 256) {
+        const int n = i % N, fi = i / N;
+        const float2 z = Z[(size_t)(fi >> 1) * N + n];
+        fr[i] = ((fi & 1) ? z.y : z.x) * invN * hann(n, N);
+    }
+    __syncthreads();
+    for (int i = tid; i < kFT * a.hop; i += 256) {
+        const int k = k0 + i / a.hop, p = k * a.hop + i % a.hop, j = p - N / 2;
+        if (k >= nseg || j < 0 || j >= a.Ts) continue;
+        float v = 0.f;
+        for (int t = max(0, k - R + 1); t <= min(k, a.T - 1); ++t) v += fr[(size_t)(t - tfirst) * N + p - t * a.hop];
+        const float e = ola_env(p, N, a.hop, a.T);
+        a.y[((size_t)b * a.S + s) * a.Ts + j] = e > 1e-11f ? v / e : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) istft_bwd_fft_kernel(IstftBwdArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int N = a.N, F = a.F, NB = kFT / 2;
+    float2* tw = reinterpret_cast<float2*>(sm);  // [N]
+    float2* za = tw + N;                          // [NB][N]: frames 2p (re) and 2p+1 (im): dy * w / env
+    float2* zb = za + (size_t)NB * N;
+    const int tiles = (a.T + kFT - 1) / kFT, tid = threadIdx.x;
+    const int bs = blockIdx.x / tiles, t0 = (blockIdx.x % tiles) * kFT;
+    const int b = bs / a.S, s = bs % a.S;
+    for (int k = tid; k < N; k += 256) tw[k] = make_float2(cospif(2.f * k / N), sinpif(2.f * k / N));
+    for (int i = tid; i < NB * N; i += 256) {
+        const int p = i / N, n = i - p * N;
+        float v[2] = {0.f, 0.f};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int t = t0 + 2 * p + h, pp = t * a.hop + n, j = pp - N / 2;
+            if (t < a.T && j >= 0 && j < a.Ts) {
+                const float e = ola_env(pp, N, a.hop, a.T);
+                if (e > 1e-11f) v[h] = a.dy[((size_t)b * a.S + s) * a.Ts + j] * hann(n, N) / e;
+            }
+        }
+        za[i] = make_float2(v[0], v[1]);
+    }
+    __syncthreads();
+    const float2* Z = fft_r4_batch<false>(za, zb, NB, N, tw, tid, 256);
+    const float invN = 1.f / N;
+    for (int i = tid; i < kFT * F; i += 256) {
+        const int tt = i % kFT, f = i / kFT, t = t0 + tt;
+        if (t >= a.T) continue;
+        const float2 z1 = Z[(size_t)(tt >> 1) * N + f], z2 = Z[(size_t)(tt >> 1) * N + ((N - f) & (N - 1))];
+        const float re = (tt & 1) ? 0.5f * (z1.y + z2.y) : 0.5f * (z1.x + z2.x);
+        const float im = (tt & 1) ? -0.5f * (z1.x - z2.x) : 0.5f * (z1.y - z2.y);
+        const bool edge = (f == 0 || f == F - 1);
+        const float c = (edge ? 1.f : 2.f) * invN * (a.scale ? a.scale[((size_t)b * F + f) * a.T + t] : 1.f);
+        float* o = a.din + b * a.ib + s * a.is + f * a.if_ + t * a.it;
+        o[0] = re * c;
+        o[1] = edge ? 0.f : im * c;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ encoder
 // y[b,f,t,co] = bias[co] + sum_k sum_ci W[co,ci,k] * x[b,f,t+k-K/2,ci]     (K = 5, zero padding)
 template <int CIN>
@@ -373,6 +558,7 @@ static int io_num_sms() {
 using namespace nbss;
 
 static bool pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+static bool pow4(int n) { return pow2(n) && (n & 0x55555555); }  // 4^k: the radix-4 FFT kernels
 
 extern "C" int nbss_stft(const float* x, int B, int C, int Ts, int n_fft, int hop, int normalize, int ref_channel,
                          float eps, float* out, long long ob, long long oc, long long of, long long ot, float* xrmm,
@@ -384,6 +570,17 @@ extern "C" int nbss_stft(const float* x, int B, int C, int Ts, int n_fft, int ho
     const size_t smem = (size_t)(2 * n_fft + kFT * C * n_fft + 2 * kFT * C * F) * 4;
     if (smem > 227 * 1024) return NBSS_ERR_UNSUPPORTED;
     StftArgs a{x, B, C, Ts, T, F, n_fft, hop, normalize, ref_channel, eps, out, ob, oc, of, ot, xrmm, xr};
+    if (pow4(n_fft)) {
+        const int NB = (kFTF * C + 1) / 2;
+        const size_t sm_f = (size_t)(n_fft + 2 * NB * n_fft + kFTF * C * F) * 8;
+        if (sm_f <= 227 * 1024) {
+            cudaError_t ef = cudaFuncSetAttribute(stft_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
+            if (ef != cudaSuccess) return (int)ef;
+            stft_fft_kernel<<<B * ((T + kFTF - 1) / kFTF), 256, sm_f, (cudaStream_t)stream>>>(a);
+            NBSS_LAUNCH_CHECK();
+            return NBSS_OK;
+        }
+    }
     cudaError_t e = cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     stft_kernel<<<B * ((T + kFT - 1) / kFT), 256, smem, (cudaStream_t)stream>>>(a);
@@ -404,6 +601,17 @@ extern "C" int nbss_istft(const float* in, long long ib, long long is, long long
     e = cudaMemsetAsync(y, 0, (size_t)B * S * Ts * 4, (cudaStream_t)stream);  // samples no frame covers stay 0
     if (e != cudaSuccess) return (int)e;
     const int nseg = T + R - 1;
+    if (pow4(n_fft)) {
+        const int NB = (NFR + 1) / 2;
+        const size_t sm_f = (size_t)(n_fft + NFR * F + 2 * NB * n_fft) * 8 + (size_t)NFR * n_fft * 4;
+        if (sm_f <= 227 * 1024) {
+            cudaError_t ef = cudaFuncSetAttribute(istft_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
+            if (ef != cudaSuccess) return (int)ef;
+            istft_fft_kernel<<<B * S * ((nseg + kFT - 1) / kFT), 256, sm_f, (cudaStream_t)stream>>>(a);
+            NBSS_LAUNCH_CHECK();
+            return NBSS_OK;
+        }
+    }
     istft_kernel<<<B * S * ((nseg + kFT - 1) / kFT), 256, smem, (cudaStream_t)stream>>>(a);
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
@@ -416,6 +624,14 @@ extern "C" int nbss_istft_bwd(const float* dy, const float* scale, float* din, l
     const int F = n_fft / 2 + 1;
     const size_t smem = (size_t)(2 * n_fft + kFT * n_fft) * 4;
     IstftBwdArgs a{dy, scale, din, ib, is, if_, it, B, S, Ts, T, F, n_fft, hop};
+    if (pow4(n_fft)) {
+        const size_t sm_f = (size_t)(n_fft + kFT * n_fft) * 8;
+        cudaError_t ef = cudaFuncSetAttribute(istft_bwd_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
+        if (ef != cudaSuccess) return (int)ef;
+        istft_bwd_fft_kernel<<<B * S * ((T + kFT - 1) / kFT), 256, sm_f, (cudaStream_t)stream>>>(a);
+        NBSS_LAUNCH_CHECK();
+        return NBSS_OK;
+    }
     cudaError_t e = cudaFuncSetAttribute(istft_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     istft_bwd_kernel<<<B * S * ((T + kFT - 1) / kFT), 256, smem, (cudaStream_t)stream>>>(a);

@@ -25,6 +25,34 @@ _NLAUNCH = {"nbss_full_fwd": 3, "nbss_full_bwd": 4, "nbss_full_fwd_tc": 3, "nbss
 
 _KCACHE = {}
 
+# Weight-gradient kernels may run on a side stream (set by spatialnet.Engine.backward): they depend only on the data
+# gradient kernel that precedes them, so they fill the SMs that the persistent slab kernels leave idle in their last
+# partial wave (at 4 utterances per GPU: 516 slabs on 148 SMs = 3.5 waves).  SIDE_KEEP holds the tensors the side stream
+# still reads until the engine joins the streams.
+WGRAD_STREAM: Optional["torch.cuda.Stream"] = None
+SIDE_KEEP: list = []
+
+
+class _side_stream:
+    """Context: run the enclosed launches on WGRAD_STREAM (after everything queued on the current stream so far)."""
+
+    def __init__(self, keep):
+        self.keep = keep
+        self.ctx = None
+
+    def __enter__(self):
+        if WGRAD_STREAM is not None:
+            WGRAD_STREAM.wait_stream(torch.cuda.current_stream())
+            SIDE_KEEP.append(self.keep)
+            self.ctx = torch.cuda.stream(WGRAD_STREAM)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
 
 def _K(name: str):
     c = _KCACHE.get(name)
@@ -405,12 +433,13 @@ def ffn_bwd(x: Tensor, dy: Tensor, saves, gn_stats: Tensor, P, pre: str, img: Te
         ptr(gbuf[3]), ptr(sbuf[0]), ptr(sbuf[1]), ptr(sbuf[2]), ptr(sbuf[3]), ptr(G[t + "0.weight"]), ptr(G[t + "0.bias"]),
         ptr(G[t + "6.weight"]), ptr(G[t + "6.bias"]), fmt_g, ptr(err), stream_ptr())
     check(st, "nbss_ffn_bwd")
-    st = _K("nbss_ffn_wgrad")(
-        ptr(x), ptr(dy), B * F, T, ptr(_f32c(P[t + "0.weight"])), ptr(_f32c(P[t + "0.bias"])), ptr(gbuf[0]), ptr(gbuf[1]),
-        ptr(gbuf[2]), ptr(gbuf[3]), ptr(sbuf[0]), ptr(sbuf[1]), ptr(sbuf[2]), ptr(sbuf[3]), ptr(G[t + "1.weight"]),
-        ptr(G[t + "1.bias"]), ptr(G[t + "3.weight"]), ptr(G[t + "3.bias"]), ptr(G[t + "5.weight"]), ptr(G[t + "5.bias"]),
-        ptr(G[t + "8.weight"]), ptr(G[t + "8.bias"]), ptr(G[t + "10.weight"]), ptr(G[t + "10.bias"]), fmt_g, fmt_g, ptr(err),
-        stream_ptr())
+    with _side_stream((x, dy, gbuf, sbuf)):
+        st = _K("nbss_ffn_wgrad")(
+            ptr(x), ptr(dy), B * F, T, ptr(_f32c(P[t + "0.weight"])), ptr(_f32c(P[t + "0.bias"])), ptr(gbuf[0]), ptr(gbuf[1]),
+            ptr(gbuf[2]), ptr(gbuf[3]), ptr(sbuf[0]), ptr(sbuf[1]), ptr(sbuf[2]), ptr(sbuf[3]), ptr(G[t + "1.weight"]),
+            ptr(G[t + "1.bias"]), ptr(G[t + "3.weight"]), ptr(G[t + "3.bias"]), ptr(G[t + "5.weight"]), ptr(G[t + "5.bias"]),
+            ptr(G[t + "8.weight"]), ptr(G[t + "8.bias"]), ptr(G[t + "10.weight"]), ptr(G[t + "10.bias"]), fmt_g, fmt_g, ptr(err),
+            stream_ptr())
     check(st, "nbss_ffn_wgrad")
     return dx, err
 
@@ -430,10 +459,11 @@ def mhsa_bwd(x: Tensor, dy: Tensor, msave, P, pre: str, img: Tensor, G, fmt_g: i
                          ptr(qkv), ptr(o), ptr(lse), ptr(dqkv), ptr(G[pre + "norm_mhsa.weight"]), ptr(G[pre + "norm_mhsa.bias"]),
                          fmt_g, ptr(err), stream_ptr())
     check(st, "nbss_mhsa_bwd")
-    st = _K("nbss_mhsa_wgrad")(ptr(x), ptr(dy), B * F, T, ptr(_f32c(P[pre + "norm_mhsa.weight"])), ptr(_f32c(P[pre + "norm_mhsa.bias"])),
-                           ptr(dqkv), ptr(o), ptr(G[pre + "mhsa.in_proj_weight"]), ptr(G[pre + "mhsa.in_proj_bias"]),
-                           ptr(G[pre + "mhsa.out_proj.weight"]), ptr(G[pre + "mhsa.out_proj.bias"]), fmt_g, FMT_F16, ptr(err),
-                           stream_ptr())
+    with _side_stream((x, dy, dqkv, o)):
+        st = _K("nbss_mhsa_wgrad")(ptr(x), ptr(dy), B * F, T, ptr(_f32c(P[pre + "norm_mhsa.weight"])),
+                                   ptr(_f32c(P[pre + "norm_mhsa.bias"])), ptr(dqkv), ptr(o), ptr(G[pre + "mhsa.in_proj_weight"]),
+                                   ptr(G[pre + "mhsa.in_proj_bias"]), ptr(G[pre + "mhsa.out_proj.weight"]),
+                                   ptr(G[pre + "mhsa.out_proj.bias"]), fmt_g, FMT_F16, ptr(err), stream_ptr())
     check(st, "nbss_mhsa_wgrad")
     return dx, err
 

@@ -86,6 +86,9 @@ class Engine:
         self._limg_key = None
         # NBSS_FULL_SIMT=1 keeps the full-band LinearGroup on the fp32 CUDA-core kernels (cross-check of fullband_tc.cu)
         self.full_tc = _os.environ.get("NBSS_FULL_SIMT", "0") != "1"
+        # NBSS_WGRAD_STREAM=0 keeps the weight-gradient kernels on the main stream (ops.WGRAD_STREAM)
+        self.use_side = _os.environ.get("NBSS_WGRAD_STREAM", "1") != "0"
+        self._side: Optional[torch.cuda.Stream] = None
 
     def images(self, P: Dict[str, Tensor]) -> List[Tensor]:
         """Per-layer UMMA weight images; rebuilt whenever a narrow-band weight changed (tensor version counters)."""
@@ -173,6 +176,20 @@ class Engine:
         fimgs = self.fconv_images(P)
         limgs = self.lg_images(P) if self.full_tc else None
         errs = []
+        if self.use_side and self._side is None:
+            self._side = torch.cuda.Stream(device=dy.device)
+        ops.WGRAD_STREAM = self._side if self.use_side else None
+        try:
+            d = self._backward_layers(P, ctx, dy, G, imgs, fimgs, limgs, errs)
+        finally:
+            if ops.WGRAD_STREAM is not None:
+                torch.cuda.current_stream().wait_stream(ops.WGRAD_STREAM)
+            ops.SIDE_KEEP.clear()
+            ops.WGRAD_STREAM = None
+        ops.encoder_wgrad(ctx["x_in"], d, G)
+        return errs
+
+    def _backward_layers(self, P, ctx, dy, G, imgs, fimgs, limgs, errs):
         d = ops.decoder_bwd(ctx["x_last"], dy, P, G)
         for i in reversed(range(self.L)):
             pre = f"layers.{i}."
@@ -184,9 +201,11 @@ class Engine:
                  else ops.full_bwd(lc["x1"], d, lc["s"], lc["u"], P, pre, G))
             d, e4 = ops.fconv_tc_bwd(lc["x0"], d, P, pre + "fconv1", fimgs[i][0], G, fmt=self.grad_fmt)
             errs += [e1, e2, e3, e4]
+            if ops.WGRAD_STREAM is not None:  # join before this layer's activations and gradient operands are freed
+                torch.cuda.current_stream().wait_stream(ops.WGRAD_STREAM)
+                ops.SIDE_KEEP.clear()
             ctx["layers"][i] = None  # free this layer's saved activations
-        ops.encoder_wgrad(ctx["x_in"], d, G)
-        return errs
+        return d
 
 
 class _SpatialNetFn(torch.autograd.Function):

@@ -234,7 +234,7 @@ def test_encoder_decoder(cin, T):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n_fft,hop,Ts", [(256, 128, 128 * 249), (256, 128, 32000), (32, 16, 16 * 19), (512, 256, 256 * 20)])
+@pytest.mark.parametrize("n_fft,hop,Ts", [(256, 128, 128 * 249), (256, 128, 32000), (32, 16, 16 * 19), (512, 256, 256 * 20), (64, 32, 32 * 21)])
 def test_stft_istft(n_fft, hop, Ts):
     g = torch.Generator().manual_seed(Ts)
     wave = 0.1 * torch.randn(2, 3, Ts, generator=g)

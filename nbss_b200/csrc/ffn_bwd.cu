@@ -73,15 +73,17 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
     float* gtot = red + 256;  // [8][2] group totals S1, S2
     float2* xch = reinterpret_cast<float2*>(smem + FB_XCH);
     uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + FB_BAR);
-    uint64_t* bar_w0 = bar_mma + 1;
-    uint64_t* bar_w1 = bar_mma + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 3);
+    uint64_t* bar_mma1 = bar_mma + 1;  // one commit barrier per M-tile: tile 0's epilogue warps start while tile 1's MMAs run
+    uint64_t* bar_w0 = bar_mma + 2;
+    uint64_t* bar_w1 = bar_mma + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = a.T;
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
         mbar_init(bar_mma, 1);
+        mbar_init(bar_mma1, 1);
         mbar_init(bar_w0, 1);
         mbar_init(bar_w1, 1);
         fence_mbar_init();
@@ -111,7 +113,10 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
 
     auto wait_mma = [&]() {
         __syncwarp();
-        mbar_wait(bar_mma, ph_mma, a.err);
+        mbar_wait(m ? bar_mma1 : bar_mma, ph_mma, a.err);
+        // tile 1's conv MMAs read G row 128 (frame 127, the halo): the tile-0 warps that own frames 96..127 must not
+        // overwrite it before tile 1 has finished too
+        if (m == 0 && q == 3) mbar_wait(bar_mma1, ph_mma, a.err);
         ph_mma ^= 1;
         tc_fence_after();
     };
@@ -121,12 +126,13 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
             tc_fence_after();
             mbar_wait(bar_w, ph_w, a.err);
             const bool leader = elect_one();
-            for (int mm = 0; mm < 2; ++mm)
+            for (int mm = 0; mm < 2; ++mm) {
                 for (int p = 0; p < kPairs; ++p)
                     for (int tap = 0; tap < 3; ++tap)
                         mma_kk(tmem + mm * 192 + p * 48, hb + 6 * p * kCS + (128 * mm + 2 - tap) * 16, kCS,
                                wsa + (p * 3 + tap) * 6 * 768, 768, 3, id48, tap > 0, leader);
-            if (leader) umma_commit(bar_mma);
+                if (leader) umma_commit(mm ? bar_mma1 : bar_mma);
+            }
         }
         ph_w ^= 1;
         wait_mma();
@@ -208,8 +214,10 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
             tc_fence_after();
             mbar_wait(bar_w0, ph_w0, a.err);
             const bool leader = elect_one();
-            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 192 * 16, 6, id192, 0, leader);
-            if (leader) umma_commit(bar_mma);
+            for (int mm = 0; mm < 2; ++mm) {
+                mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 192 * 16, 6, id192, 0, leader);
+                if (leader) umma_commit(mm ? bar_mma1 : bar_mma);
+            }
         }
         ph_w0 ^= 1;
         wait_mma();
@@ -309,8 +317,10 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
             tc_fence_after();
             mbar_wait(bar_w0, ph_w0, a.err);
             const bool leader = elect_one();
-            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 96 * 16, 12, id96, 0, leader);
-            if (leader) umma_commit(bar_mma);
+            for (int mm = 0; mm < 2; ++mm) {
+                mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 96 * 16, 12, id96, 0, leader);
+                if (leader) umma_commit(mm ? bar_mma1 : bar_mma);
+            }
         }
         ph_w0 ^= 1;
         wait_mma();

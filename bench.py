@@ -327,9 +327,10 @@ def main():
 
     # per-kernel live timing (CUDA events around every C-ABI call on the launching stream) for the roofline
     ops.TIMING = {}
-    was_graphs, use_graphs = use_graphs, False  # the per-kernel event timing pass launches eagerly
+    was_graphs, use_graphs = use_graphs, False  # the per-kernel event timing pass launches eagerly ...
+    was_side, net.engine.use_side = net.engine.use_side, False  # ... and on one stream, so that every kernel is timed alone
     timed(max(2, min(args.steps, 5)), host_io=False)
-    use_graphs = was_graphs
+    use_graphs, net.engine.use_side = was_graphs, was_side
     torch.cuda.synchronize()
     per_kernel = {k: (sum(a.elapsed_time(b) for a, b in v) / len(v), len(v)) for k, v in ops.TIMING.items()}
     ops.TIMING = None
@@ -357,15 +358,23 @@ def main():
         if k in FLOP_PER_POINT:
             ent["tflops"] = round(FLOP_PER_POINT[k] * npts / (ms * 1e-3) / 1e12, 2)
         kernels[k] = ent
+    # DRAM bytes per call from the committed ncu capture (tools/traffic_from_ncu.py), scaled linearly to this batch
+    traffic = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic = {k: v * b_local / tj["batch_per_gpu"] for k, v in tj["dram_bytes_per_call"].items()}
+    except Exception:
+        pass
+
     def roof(k):
         sec = kernels[k]["ms_per_launch"] * 1e-3
         tf = FLOP_PER_POINT[k] * npts / sec / 1e12
         gb = BYTES_PER_POINT[k] * npts / sec / 1e9
         if k in TENSOR_BOUND:
             return {"kernel": k, "bound": "tensor", "achieved": round(tf, 2), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(tf / peak_tf, 4),
-                    "traffic": None, "also_hbm_gbs": round(gb, 1), "peak_source": peak_src}
+                    "traffic": traffic.get(k), "also_hbm_gbs": round(gb, 1), "peak_source": peak_src}
         return {"kernel": k, "bound": "hbm", "achieved": round(gb, 1), "peak": peak_bw, "unit": "GB/s", "frac": round(gb / peak_bw, 4),
-                "traffic": None, "also_tflops": round(tf, 2), "peak_source": peak_src}
+                "traffic": traffic.get(k), "also_tflops": round(tf, 2), "peak_source": peak_src}
     cands = [k for k in kernels if k in FLOP_PER_POINT and k in BYTES_PER_POINT]
     top = max(cands, key=lambda k: kernels[k]["ms_per_step"])
     rooflines = sorted((dict(roof(k), ms_per_step=kernels[k]["ms_per_step"]) for k in cands), key=lambda r: -r["ms_per_step"])

@@ -174,17 +174,24 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
             }
             ph_w ^= 1;
             end_epilogue();
+            // Software pipeline over the four 128x128 (query, key) blocks of the head: the S / dP MMAs of block b+1 are
+            // issued together with the gradient MMAs of block b (different TMEM columns), so a block costs one
+            // commit / wait round trip instead of two.
+            auto issue_s_dp = [&](int blk, bool leader) {
+                const int qb = blk >> 1, kb = blk & 1;
+                mma_kk(tmem + C_S, qa + 128 * qb * 16, kCS, ka + 128 * kb * 16, kCS, 2, id_s, 0, leader);
+                mma_kk(tmem + C_DP, doa + 3 * h * kCS + 128 * qb * 16, kCS, va + 128 * kb * 16, kCS, 2, id_dp, 0, leader);
+            };
+            if (warp == 0) {
+                tc_fence_after();
+                const bool leader = elect_one();
+                issue_s_dp(0, leader);
+                if (leader) umma_commit(bar_mma);
+            }
 #pragma unroll 1
             for (int blk = 0; blk < 4; ++blk) {
                 const int qb = blk >> 1, kb = blk & 1;
-                if (warp == 0) {
-                    tc_fence_after();
-                    const bool leader = elect_one();
-                    mma_kk(tmem + C_S, qa + 128 * qb * 16, kCS, ka + 128 * kb * 16, kCS, 2, id_s, 0, leader);
-                    mma_kk(tmem + C_DP, doa + 3 * h * kCS + 128 * qb * 16, kCS, va + 128 * kb * 16, kCS, 2, id_dp, 0, leader);
-                    if (leader) umma_commit(bar_mma);
-                }
-                wait_mma();
+                wait_mma();  // S, dP of this block (and the gradient MMAs of the previous one, which read the P / dS tiles)
                 // P and dS for this block: thread = (query row rt, key quarter kq: 32 of the 128 keys)
                 {
                     const int tq = 128 * qb + rt;
@@ -224,10 +231,11 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
                         if (leader) umma_f16(tmem + C_DV + 32 * kb, sdesc_mnmajor(pa + 16 * ks * 16, kCSQ),
                                  sdesc_mnmajor(doa + 3 * h * kCS + (128 * qb + 16 * ks) * 16, kCS), id_dv, (qb | ks) ? 1u : 0u);
                     }
+                    if (blk < 3) issue_s_dp(blk + 1, leader);
                     if (leader) umma_commit(bar_mma);
                 }
-                wait_mma();
             }
+            wait_mma();  // the gradient MMAs of the last block
             // read out dQ_h, dK_h, dV_h (thread = frame t of tile m) -> dQKV
             {
                 // tcgen05.ld is warp-collective: every lane issues it, only valid frames store

@@ -39,7 +39,7 @@ for r in rows[2:]:
     elif name.startswith("fconv_tc_bwd"):
         key, tot = "fconv_tc_bwd", tot / 2
     else:
-        key = name.replace("_kernel", "")
+        key = name.replace("_kernel", "").replace("_fft", "")  # stft_fft_kernel -> stft (the C-ABI call name)
     calls[key] = calls.get(key, 0.0) + tot
 json.dump({"batch_per_gpu": batch, "source": sys.argv[1], "dram_bytes_per_call": {k: round(v) for k, v in calls.items()}}, sys.stdout, indent=1)
 print()

@@ -39,7 +39,6 @@ FLOP_PER_POINT = {  # algorithmic FLOPs per T-F point
 # of this — 16-bit saves and gradient operands — is design overhead and shows up as a lower fraction.)
 BYTES_PER_POINT = {"ffn_fwd": 768, "mhsa_fwd": 768, "fconv_tc_fwd": 768, "full_fwd": 768, "full_fwd_tc": 768, "full_bwd_tc": 1152, "ffn_bwd": 1152, "mhsa_bwd": 1152,
                    "fconv_tc_bwd": 1152, "full_bwd": 1152, "ffn_wgrad": 768, "mhsa_wgrad": 768}
-TENSOR_BOUND = ("ffn_fwd", "mhsa_fwd", "ffn_bwd", "ffn_wgrad", "mhsa_bwd", "mhsa_wgrad")  # AI >= ~200 FLOP/B: narrow-band block
 
 
 def neg_si_sdr_pit(est, ref):
@@ -372,7 +371,8 @@ def main():
         sec = kernels[k]["ms_per_launch"] * 1e-3
         tf = FLOP_PER_POINT[k] * npts / sec / 1e12
         gb = BYTES_PER_POINT[k] * npts / sec / 1e9
-        if k in TENSOR_BOUND:
+        # roofline side: arithmetic intensity of the ALGORITHMIC work against the machine balance of the measured peaks
+        if FLOP_PER_POINT[k] / BYTES_PER_POINT[k] >= peak_tf * 1e12 / (peak_bw * 1e9):
             return {"kernel": k, "bound": "tensor", "achieved": round(tf, 2), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(tf / peak_tf, 4),
                     "traffic": traffic.get(k), "also_hbm_gbs": round(gb, 1), "peak_source": peak_src}
         return {"kernel": k, "bound": "hbm", "achieved": round(gb, 1), "peak": peak_bw, "unit": "GB/s", "frac": round(gb / peak_bw, 4),

@@ -41,23 +41,6 @@ BYTES_PER_POINT = {"ffn_fwd": 768, "mhsa_fwd": 768, "fconv_tc_fwd": 768, "full_f
                    "fconv_tc_bwd": 1152, "full_bwd": 1152, "ffn_wgrad": 768, "mhsa_wgrad": 768}
 
 
-def neg_si_sdr_pit(est, ref):
-    """Loss of configs/SpatialNet.yaml:33-37 (models/io/loss.py:21-29,95-118: torchmetrics SI-SDR, zero-mean, PIT over
-    speaker permutations), restated with torch ops on the small [B,S,Ts] tensors."""
-    def si_sdr(p, t):
-        p = p - p.mean(-1, keepdim=True)
-        t = t - t.mean(-1, keepdim=True)
-        eps = torch.finfo(p.dtype).eps
-        alpha = ((p * t).sum(-1, keepdim=True) + eps) / ((t * t).sum(-1, keepdim=True) + eps)
-        ts = alpha * t
-        return 10 * torch.log10(((ts * ts).sum(-1) + eps) / (((ts - p) ** 2).sum(-1) + eps))
-    S = est.shape[1]
-    assert S == 2
-    l0 = -(si_sdr(est[:, 0], ref[:, 0]) + si_sdr(est[:, 1], ref[:, 1])) / 2
-    l1 = -(si_sdr(est[:, 0], ref[:, 1]) + si_sdr(est[:, 1], ref[:, 0])) / 2
-    return torch.minimum(l0, l1).mean()
-
-
 def synth_batch(b, seed, device="cpu"):
     """Synthetic 6-ch mixtures: 2 'speakers' = white noise through random 64-tap 6-ch FIRs + white noise at 10 dB."""
     g = torch.Generator().manual_seed(seed)
@@ -134,7 +117,7 @@ def cpu_oracle_step(threads, b=1, reps=2):
     for i in range(reps + 1):
         t0 = time.perf_counter()
         est = O.io_forward(Pl, x, O.SMALL_CFG, CFG["n_fft"], CFG["hop"], 0)
-        loss = neg_si_sdr_pit(est, tgt)
+        loss = O.neg_si_sdr_pit(est, tgt)[0]
         loss.backward()
         ts.append(time.perf_counter() - t0)
         if sum(ts) > 120:  # bounded sample: stop once ~2 minutes of CPU work have been spent
@@ -211,10 +194,12 @@ def main():
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
     loss_host = torch.zeros(1).pin_memory()
 
+    from nbss_b200.loss import neg_si_sdr_pit  # CUDA SI-SDR + PIT (csrc/loss.cu; models/io/loss.py:21-29,95-118)
+
     def fwd_bwd(x, y):
         opt.zero_grad(set_to_none=True)
         est = pipe(x)
-        loss = neg_si_sdr_pit(est, y)
+        loss = neg_si_sdr_pit(est, y)[0]
         loss.backward()
         return loss
 

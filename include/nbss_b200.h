@@ -138,6 +138,17 @@ int nbss_norm_freq_online(float* X, int B, int C, long long FT, int ref_channel,
                           void* stream);
 int nbss_inorm(const float* X, float* Y, int B, int S, long long FT, const float* xrmm, void* stream);
 
+/* ---- loss next to the path: negative SI-SDR with 2-speaker PIT ------------------------------------
+ * Loss.forward for loss_func = neg_si_sdr, pit = True (models/io/loss.py:21-29,95-118; configs/SpatialNet.yaml:33-37):
+ * torchmetrics scale_invariant_signal_distortion_ratio (zero_mean as given; the reference uses the default, 0) and
+ * permutation_invariant_training(mode="permutation-wise", eval_func="min").  est, ref: fp32 [B,2,Ts].
+ * sums: workspace of B*12 doubles; loss[1] = batch mean; loss_b[B], perm[B,2] (int), coef[B,2,5] nullable; coef feeds the
+ * backward, which writes dest = gout[0] * d loss / d est (gout: device scalar, NULL = 1). */
+int nbss_sisdr_pit_fwd(const float* est, const float* ref, int B, int S, long long Ts, int zero_mean, double* sums,
+                       float* loss, float* loss_b, int* perm, float* coef, void* stream);
+int nbss_sisdr_pit_bwd(const float* est, const float* ref, const float* coef, const float* gout, float* dest, int B, int S,
+                       long long Ts, void* stream);
+
 /* ---- test hook: one-CTA tcgen05 GEMM that pins the descriptor conventions (tests/test_umma_selftest.py) ------------- */
 int nbss_umma_selftest(const float* A, int a_rows, int a_feats, const float* B, int b_rows, int b_feats, float* D, int N,
                        int Kdim, int a_mn, int b_mn, int fmt, int a_shift, int b_shift, int a_off, int b_off, int passes,

@@ -404,8 +404,20 @@ __global__ void __launch_bounds__(192) encoder_fwd_kernel(const float* __restric
     for (int r = half; r < TT; r += 2) {
         if (t0 + r >= T) break;
         float acc = bi;
+        if constexpr (CIN % 4 == 0) {  // the K*CIN window of frame r is 16-byte aligned: one LDS.128 per four taps
+            const float4* xr = reinterpret_cast<const float4*>(xs + r * CIN);
 #pragma unroll
-        for (int i = 0; i < K * CIN; ++i) acc = fmaf(w[i], xs[r * CIN + i], acc);
+            for (int i = 0; i < K * CIN / 4; ++i) {
+                const float4 v = xr[i];
+                acc = fmaf(w[4 * i + 0], v.x, acc);
+                acc = fmaf(w[4 * i + 1], v.y, acc);
+                acc = fmaf(w[4 * i + 2], v.z, acc);
+                acc = fmaf(w[4 * i + 3], v.w, acc);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < K * CIN; ++i) acc = fmaf(w[i], xs[r * CIN + i], acc);
+        }
         y[((size_t)slab * T + t0 + r) * kH + co] = acc;
     }
 }
@@ -443,8 +455,20 @@ __global__ void __launch_bounds__(192) encoder_wgrad_kernel(const float* __restr
                 const int r = r0 + 2 * u;
                 if (r >= TT) break;
                 db += g[u];
+                if constexpr (CIN % 4 == 0) {
+                    const float4* xr = reinterpret_cast<const float4*>(xs + r * CIN);
 #pragma unroll
-                for (int i = 0; i < K * CIN; ++i) dw[i] = fmaf(g[u], xs[r * CIN + i], dw[i]);
+                    for (int i = 0; i < K * CIN / 4; ++i) {
+                        const float4 v = xr[i];
+                        dw[4 * i + 0] = fmaf(g[u], v.x, dw[4 * i + 0]);
+                        dw[4 * i + 1] = fmaf(g[u], v.y, dw[4 * i + 1]);
+                        dw[4 * i + 2] = fmaf(g[u], v.z, dw[4 * i + 2]);
+                        dw[4 * i + 3] = fmaf(g[u], v.w, dw[4 * i + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < K * CIN; ++i) dw[i] = fmaf(g[u], xs[r * CIN + i], dw[i]);
+                }
             }
         }
     }
@@ -492,18 +516,28 @@ __global__ void __launch_bounds__(256) decoder_bwd_kernel(const float* __restric
         w[o] = act ? ld_f4(W + o * kH + 4 * lane) : make_float4(0, 0, 0, 0);
         dw[o] = make_float4(0, 0, 0, 0);
     }
-    for (size_t r = warp; r < n; r += nw) {
-        const float4 v = act ? ld_f4(x + r * kH + 4 * lane) : make_float4(0, 0, 0, 0);
-        const float gl = lane < COUT ? dy[r * COUT + lane] : 0.f;
-        db += gl;
-        float4 d = make_float4(0, 0, 0, 0);
+    for (size_t r0 = warp; r0 < n; r0 += 4 * nw) {  // four rows in flight per warp
+        float4 v[4];
+        float gl[4];
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) {
-            const float g = __shfl_sync(0xffffffffu, gl, o);
-            d = make_float4(fmaf(g, w[o].x, d.x), fmaf(g, w[o].y, d.y), fmaf(g, w[o].z, d.z), fmaf(g, w[o].w, d.w));
-            dw[o] = make_float4(fmaf(g, v.x, dw[o].x), fmaf(g, v.y, dw[o].y), fmaf(g, v.z, dw[o].z), fmaf(g, v.w, dw[o].w));
+        for (int u = 0; u < 4; ++u) {
+            const size_t r = r0 + u * nw;
+            v[u] = (act && r < n) ? ld_f4(x + r * kH + 4 * lane) : make_float4(0, 0, 0, 0);
+            gl[u] = (lane < COUT && r < n) ? dy[r * COUT + lane] : 0.f;
         }
-        if (act) st_f4(dx + r * kH + 4 * lane, d);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const size_t r = r0 + u * nw;
+            db += gl[u];
+            float4 d = make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int o = 0; o < COUT; ++o) {
+                const float g = __shfl_sync(0xffffffffu, gl[u], o);
+                d = make_float4(fmaf(g, w[o].x, d.x), fmaf(g, w[o].y, d.y), fmaf(g, w[o].z, d.z), fmaf(g, w[o].w, d.w));
+                dw[o] = make_float4(fmaf(g, v[u].x, dw[o].x), fmaf(g, v[u].y, dw[o].y), fmaf(g, v[u].z, dw[o].z), fmaf(g, v[u].w, dw[o].w));
+            }
+            if (act && r < n) st_f4(dx + r * kH + 4 * lane, d);
+        }
     }
     if (act) {
 #pragma unroll

@@ -3,8 +3,9 @@
 // A slab [T<=256, C] lives in shared memory as a 16-bit UMMA operand tile in the chunk-column layout (umma.cuh):
 // 8 channels per 16-byte chunk, rows linear at 16 B, chunk stride kCS.  The T axis is split in two M-tiles of 128
 // rows; rows >= T are zero.  Accumulators: TMEM lane = row within the M-tile, column = output channel.
-// Thread mapping of every epilogue: 256 threads, warp w -> M-tile (w>>2), TMEM lane quarter (w&3), thread = one
-// frame: t = 128*(w>>2) + 32*(w&3) + lane.  Row reductions (LayerNorm, softmax) are therefore thread-local.
+// Thread mapping of every TMEM epilogue: 512 threads, warp w -> TMEM lane quarter (w&3), M-tile ((w>>2)&1), channel / key
+// half (w>>3); thread = one frame: t = 128*m + 32*(w&3) + lane, so row reductions need at most a 2- or 4-thread exchange.
+// The fp32 row phases around them (staging, LayerNorm backward, residual adds) use eight lanes per frame instead.
 #pragma once
 #include "common.cuh"
 #include "layout.cuh"

@@ -16,8 +16,8 @@
 //    descriptor with start address + 16*shift.
 //  * Accumulators: TMEM lane = tile row (M = 128), column = N index, fp32.
 //
-// Waits on mbarriers are bounded (NBSS_SPIN_LIMIT polls) and raise a device-side error flag instead of
-// hanging the GPU.
+// Waits on mbarriers are time-bounded (NBSS_WAIT_TIMEOUT_NS of %globaltimer) and raise a sticky device-side error flag
+// instead of hanging the GPU.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>

@@ -350,3 +350,32 @@ def round_tf32(t: Tensor) -> Tensor:
 def rel_l2(a: Tensor, b: Tensor) -> float:
     a, b = a.double(), b.double()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# loss next to the path.  models/io/loss.py:21-29 (neg_si_sdr) and :95-118 (Loss.forward with pit)
+# call torchmetrics.functional.audio (scale_invariant_signal_distortion_ratio, permutation_invariant_training), a
+# third-party dependency that is absent from /root/reference and unpinned (requirements.txt:2).  Restated from the
+# published torchmetrics algorithm; PARITY UNPINNED (no golden vector of the reference exists for it).
+# ----------------------------------------------------------------------------------------------------------------------
+def si_sdr(preds: Tensor, target: Tensor, zero_mean: bool = False) -> Tensor:
+    eps = torch.finfo(preds.dtype).eps
+    if zero_mean:
+        preds = preds - preds.mean(-1, keepdim=True)
+        target = target - target.mean(-1, keepdim=True)
+    alpha = ((preds * target).sum(-1, keepdim=True) + eps) / ((target * target).sum(-1, keepdim=True) + eps)
+    ts = alpha * target
+    noise = ts - preds
+    return 10 * torch.log10(((ts * ts).sum(-1) + eps) / ((noise * noise).sum(-1) + eps))
+
+
+def neg_si_sdr_pit(est: Tensor, ref: Tensor, zero_mean: bool = False):
+    """est, ref [B,S,Ts] -> (mean loss, per-utterance loss [B], perms [B,S]); permutation-wise PIT, eval_func='min':
+    loss[b] = min over permutations p of -mean_s si_sdr(est[b, p(s)], ref[b, s]) (models/io/loss.py:24-29,109-116)."""
+    import itertools
+
+    B, S, _ = est.shape
+    perms = list(itertools.permutations(range(S)))
+    per = torch.stack([-si_sdr(est[:, list(p)], ref, zero_mean).mean(-1) for p in perms], -1)  # [B, n_perm]
+    best, idx = per.min(-1)
+    return best.mean(), best, torch.tensor(perms)[idx]

@@ -108,3 +108,32 @@ def test_wave_to_wave_pipeline_and_module_api():
         Yr = norm.inorm(out, (Xr, XrMM))
         y2 = stft.istft(Yr, stft_paras)
     assert O.rel_l2(y2.cpu(), ref) < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,Ts,zero_mean", [(3, 32000, False), (1, 1000, False), (5, 31872, True)])
+def test_si_sdr_pit_loss(B, Ts, zero_mean):
+    """csrc/loss.cu against the oracle restatement of torchmetrics SI-SDR + permutation-wise PIT (models/io/loss.py:21-29,
+    95-118): loss 1e-5, permutations equal, gradient wrt the estimate 1e-4 rel-L2."""
+    from nbss_b200.loss import NegSiSdrPitLoss, neg_si_sdr_pit
+
+    g = torch.Generator().manual_seed(B + Ts)
+    ref = 0.1 * torch.randn(B, 2, Ts, generator=g) + (0.02 if zero_mean else 0.0)
+    mix = torch.rand(B, 1, 1, generator=g)
+    est = ref[:, [1, 0]] * (0.5 + mix) + 0.05 * torch.randn(B, 2, Ts, generator=g)  # mostly the swapped permutation
+    est[0] = ref[0] * 0.8 + 0.03 * torch.randn(2, Ts, generator=g)                  # ... and one identity case
+    est = est.requires_grad_(True)
+    l_ref, lb_ref, p_ref = O.neg_si_sdr_pit(est.double(), ref.double(), zero_mean)
+    l_ref.backward()
+    est_d = est.detach().cuda().requires_grad_(True)
+    loss, loss_b, perms = neg_si_sdr_pit(est_d, ref.cuda(), zero_mean)
+    (2.0 * loss).backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - l_ref.item()) < 1e-5 * max(1.0, abs(l_ref.item()))
+    assert torch.allclose(loss_b.cpu().double(), lb_ref, rtol=1e-5, atol=1e-5)
+    assert torch.equal(perms.cpu().long(), p_ref)
+    assert O.rel_l2(est_d.grad.cpu().double(), 2.0 * est.grad.double()) < 1e-4
+    # module form mirrors Loss.forward (loss, perms, reordered estimate)
+    l2, p2, yh = NegSiSdrPitLoss()(est_d.detach(), ref.cuda(), reorder=True)
+    assert abs(l2.item() - l_ref.item()) < 1e-5 * max(1.0, abs(l_ref.item()))
+    assert torch.equal(yh.cpu(), torch.gather(est.detach(), 1, p_ref[:, :, None].expand(-1, -1, Ts)))

@@ -111,3 +111,21 @@ def test_live_reference_layer_taps():
         ref_layer = m.layers[1]
         setattr(ref_layer, "need_weights", False)
         assert O.rel_l2(O.layer_forward(h, P, 1, TINY), ref_layer(h)[0]) < 2e-6
+
+
+def test_oracle_si_sdr_pit_properties():
+    """The loss restatement has no golden vector (torchmetrics is absent): pin its defining properties instead —
+    scale invariance, the right permutation, and the closed form for a known SNR."""
+    g = torch.Generator().manual_seed(0)
+    ref = torch.randn(4, 2, 4000, generator=g, dtype=torch.float64)
+    noise = torch.randn(4, 2, 4000, generator=g, dtype=torch.float64)
+    noise = noise - (noise * ref).sum(-1, keepdim=True) / (ref * ref).sum(-1, keepdim=True) * ref  # orthogonal to ref
+    noise = noise * (ref.norm(dim=-1, keepdim=True) / noise.norm(dim=-1, keepdim=True)) * 10 ** (-20 / 20)  # 20 dB
+    est = (3.7 * (ref + noise))[:, [1, 0]]  # scaled and speaker-swapped
+    loss, loss_b, perms = O.neg_si_sdr_pit(est, ref)
+    assert torch.allclose(loss_b, torch.full((4,), -20.0, dtype=torch.float64), atol=1e-6)
+    assert abs(loss.item() + 20.0) < 1e-6
+    assert torch.equal(perms, torch.tensor([[1, 0]] * 4))
+    # zero_mean=True is the plain formula on the centred signals, whatever DC offset they carry
+    centred = O.si_sdr(est - est.mean(-1, keepdim=True), ref - ref.mean(-1, keepdim=True))
+    assert torch.allclose(O.si_sdr(est + 0.3, ref - 0.1, zero_mean=True), centred, atol=1e-9)

@@ -185,7 +185,9 @@ def main():
                      dim_hidden=96, dim_ffn=192, num_heads=4).to(dev)
     pipe = SeparationPipeline(net, CFG["n_fft"], CFG["hop"], channels=None, ref_channel=0)
     params = [p for p in net.parameters()]
-    opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
+    from nbss_b200.optim import FlatClipAdam  # clip_grad_norm_(5) + Adam(1e-3) over the flat gradient buffer, two launches
+
+    opt = FlatClipAdam(net, lr=1e-3, max_norm=5.0)
 
     # rank r takes utterances r::world of the global batch (data_loaders/utils/my_distributed_sampler.py:78)
     x_all, y_all = synth_batch(args.batch, seed=777)
@@ -210,7 +212,6 @@ def main():
             flat.mul_(1.0 / world)
 
     def opt_step():
-        torch.nn.utils.clip_grad_norm_(params, 5.0, foreach=True)
         opt.step()
 
     def step(x, y):  # eager step

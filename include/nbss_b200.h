@@ -149,6 +149,15 @@ int nbss_sisdr_pit_fwd(const float* est, const float* ref, int B, int S, long lo
 int nbss_sisdr_pit_bwd(const float* est, const float* ref, const float* coef, const float* gout, float* dest, int B, int S,
                        long long Ts, void* stream);
 
+/* Optimiser tail: torch.nn.utils.clip_grad_norm_(max_norm) + torch.optim.Adam (configs/SpatialNet.yaml:
+ * 3-4,44: Adam lr 1e-3, gradient_clip_val 5) over the network's single flat gradient buffer, two launches.
+ * params: device array of ntensors parameter pointers; offsets: device array of ntensors+1 cumulative element offsets;
+ * flat_grad / exp_avg / exp_avg_sq: fp32 [n]; gnorm_sq: device double (out: squared gradient norm before clipping);
+ * step: device float step counter, incremented by the call (bias correction uses the incremented value, as torch does). */
+int nbss_clip_adam(float* const* params, const long long* offsets, int ntensors, long long n, const float* flat_grad,
+                   float* exp_avg, float* exp_avg_sq, double* gnorm_sq, float* step, float max_norm, float lr, float beta1,
+                   float beta2, float eps, void* stream);
+
 /* ---- test hook: one-CTA tcgen05 GEMM that pins the descriptor conventions (tests/test_umma_selftest.py) ------------- */
 int nbss_umma_selftest(const float* A, int a_rows, int a_feats, const float* B, int b_rows, int b_feats, float* D, int N,
                        int Kdim, int a_mn, int b_mn, int fmt, int a_shift, int b_shift, int a_off, int b_off, int passes,

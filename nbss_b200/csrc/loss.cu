@@ -7,6 +7,8 @@
 //     loss[b] = min over speaker permutations of  -mean_s val(est[b, perm(s)], ref[b, s]);   loss = mean_b loss[b]
 // Everything follows from 12 inner products per utterance, so the forward is one streaming reduction + a tiny finalize
 // kernel; the gradient wrt est is a per-utterance linear combination  c1 * ref[j] + c2 * est[i]  (one streaming kernel).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace nbss {
@@ -154,6 +156,78 @@ extern "C" int nbss_sisdr_pit_bwd(const float* est, const float* ref, const floa
     if (S != kLossS) return NBSS_ERR_UNSUPPORTED;
     const unsigned gx = (unsigned)min((long long)64, (Ts + 255) / 256);
     sisdr_bwd_kernel<<<dim3(gx, B * kLossS), 256, 0, (cudaStream_t)stream>>>(est, ref, coef, gout, dest, Ts);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ clip + Adam
+// The optimiser tail of the step: torch.nn.utils.clip_grad_norm_(max_norm) followed by
+// torch.optim.Adam (configs/SpatialNet.yaml:3-4,44; general_steps.py:243-271: Adam, lr 1e-3, gradient_clip_val 5) over the ONE
+// flat fp32 gradient buffer of the network (spatialnet.py: make_flat_grads) in two launches instead of ~40.
+namespace nbss {
+
+__global__ void __launch_bounds__(256) gradnorm_kernel(const float* __restrict__ g, long long n, double* out, float* step) {
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) s = fmaf(g[i], g[i], s);
+    s = warp_sum(s);
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += (double)red[w];
+        atomicAdd(out, t);
+        if (blockIdx.x == 0) step[0] += 1.f;  // the update kernel (next in the stream) reads the incremented step count
+    }
+}
+
+struct AdamHyper { float max_norm, lr, beta1, beta2, eps; };
+
+// element i of the flat buffer belongs to tensor t with off[t] <= i < off[t+1]; its parameter is ptrs[t][i - off[t]]
+__global__ void __launch_bounds__(256) clip_adam_kernel(float* const* __restrict__ ptrs, const long long* __restrict__ off,
+                                                        int ntensors, long long n, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v,
+                                                        const double* __restrict__ gnorm_sq, const float* __restrict__ step,
+                                                        AdamHyper h) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    int lo = 0, hi = ntensors;  // invariant: off[lo] <= i < off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= i) lo = mid; else hi = mid;
+    }
+    const float total = (float)sqrt(gnorm_sq[0]);
+    const float clip = fminf(1.f, h.max_norm / (total + 1e-6f));  // torch.nn.utils.clip_grad_norm_
+    const float t = step[0];
+    const float bc1 = 1.f - powf(h.beta1, t), bc2 = 1.f - powf(h.beta2, t);
+    const float gi = g[i] * clip;
+    const float mi = h.beta1 * m[i] + (1.f - h.beta1) * gi;
+    const float vi = h.beta2 * v[i] + (1.f - h.beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + h.eps;
+    float* p = ptrs[lo] + (i - off[lo]);
+    *p -= (h.lr / bc1) * (mi / denom);
+}
+
+}  // namespace nbss
+
+// params: device array of `ntensors` parameter pointers; offsets: device array of ntensors+1 cumulative element offsets into
+// the flat buffers (offsets[ntensors] = n); flat_grad, exp_avg, exp_avg_sq: fp32 [n]; gnorm_sq: device double (workspace /
+// output: squared total gradient norm BEFORE clipping); step: device float step counter (incremented by this call).
+extern "C" int nbss_clip_adam(float* const* params, const long long* offsets, int ntensors, long long n, const float* flat_grad,
+                              float* exp_avg, float* exp_avg_sq, double* gnorm_sq, float* step, float max_norm, float lr,
+                              float beta1, float beta2, float eps, void* stream) {
+    if (!params || !offsets || !flat_grad || !exp_avg || !exp_avg_sq || !gnorm_sq || !step) return NBSS_ERR_NULL;
+    if (ntensors < 1 || n < 1) return NBSS_ERR_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(gnorm_sq, 0, sizeof(double), st);
+    if (e != cudaSuccess) return (int)e;
+    const unsigned gb = (unsigned)std::min<long long>(1184, (n + 255) / 256);
+    nbss::gradnorm_kernel<<<gb, 256, 0, st>>>(flat_grad, n, gnorm_sq, step);
+    NBSS_LAUNCH_CHECK();
+    nbss::clip_adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, offsets, ntensors, n, flat_grad, exp_avg, exp_avg_sq,
+                                                                         gnorm_sq, step, nbss::AdamHyper{max_norm, lr, beta1, beta2, eps});
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
 }

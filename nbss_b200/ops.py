@@ -20,7 +20,7 @@ Tensor = torch.Tensor
 # every C-ABI call is bracketed by CUDA events on the launching (current) stream.
 LAUNCHES = 0
 TIMING = None
-_NLAUNCH = {"nbss_full_fwd": 3, "nbss_full_bwd": 4, "nbss_full_fwd_tc": 3, "nbss_full_bwd_tc": 4, "nbss_ffn_wgrad": 3, "nbss_mhsa_bwd": 2, "nbss_istft": 2}
+_NLAUNCH = {"nbss_full_fwd": 3, "nbss_full_bwd": 4, "nbss_full_fwd_tc": 3, "nbss_full_bwd_tc": 4, "nbss_ffn_wgrad": 3, "nbss_mhsa_bwd": 2, "nbss_istft": 2, "nbss_sisdr_pit_fwd": 2, "nbss_clip_adam": 2}
 
 
 _KCACHE = {}

@@ -90,6 +90,11 @@ class Engine:
         self.use_side = _os.environ.get("NBSS_WGRAD_STREAM", "1") != "0"
         self._side: Optional[torch.cuda.Stream] = None
 
+    def invalidate_images(self) -> None:
+        """Force a rebuild of every cached weight image at the next forward / backward (for code that updates parameters
+        without bumping their version counters, e.g. nbss_b200.optim.FlatClipAdam)."""
+        self._img_key = self._fimg_key = self._limg_key = None
+
     def images(self, P: Dict[str, Tensor]) -> List[Tensor]:
         """Per-layer UMMA weight images; rebuilt whenever a narrow-band weight changed (tensor version counters)."""
         names = []

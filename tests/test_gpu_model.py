@@ -134,6 +134,46 @@ def test_si_sdr_pit_loss(B, Ts, zero_mean):
     assert torch.equal(perms.cpu().long(), p_ref)
     assert O.rel_l2(est_d.grad.cpu().double(), 2.0 * est.grad.double()) < 1e-4
     # module form mirrors Loss.forward (loss, perms, reordered estimate)
+    with torch.no_grad():
+        lm_ref, _, pm_ref = O.neg_si_sdr_pit(est.double(), ref.double(), False)  # the module uses the reference's zero_mean=False
     l2, p2, yh = NegSiSdrPitLoss()(est_d.detach(), ref.cuda(), reorder=True)
-    assert abs(l2.item() - l_ref.item()) < 1e-5 * max(1.0, abs(l_ref.item()))
-    assert torch.equal(yh.cpu(), torch.gather(est.detach(), 1, p_ref[:, :, None].expand(-1, -1, Ts)))
+    assert abs(l2.item() - lm_ref.item()) < 1e-5 * max(1.0, abs(lm_ref.item()))
+    assert torch.equal(p2.cpu(), pm_ref)
+    assert torch.equal(yh.cpu(), torch.gather(est.detach(), 1, pm_ref[:, :, None].expand(-1, -1, Ts)))
+
+
+@pytest.mark.gpu
+def test_flat_clip_adam_matches_torch():
+    """nbss_clip_adam (two launches over the flat gradient buffer) against clip_grad_norm_(5) + torch.optim.Adam(1e-3) fed
+    with the SAME gradients (Adam's first steps are sign-like, so independently computed gradients would not do)."""
+    import copy
+
+    from nbss_b200.optim import FlatClipAdam
+
+    cfg = dict(O.SMALL_CFG, num_layers=2)
+    P = O.synth_params(cfg, 12)
+    net = _net(cfg, P)
+    ref = copy.deepcopy(net)
+    ref_params = [p for _, p in ref.named_parameters()]
+    opt_ref = torch.optim.Adam(ref_params, lr=1e-3)
+    opt = FlatClipAdam(net, lr=1e-3, max_norm=5.0)
+    g = torch.Generator().manual_seed(3)
+    for it in range(3):
+        x = torch.randn(1, 129, 40, 12, generator=g).cuda()
+        dy = (30.0 if it == 0 else 0.01) * torch.randn(1, 129, 40, 4, generator=g).cuda()  # step 0 is clipped, the others not
+        opt.zero_grad(set_to_none=True)
+        net(x).backward(dy)
+        for (_, p1), p2 in zip(net.named_parameters(), ref_params):
+            p2.grad = p1.grad.detach().clone()
+        total = torch.nn.utils.clip_grad_norm_(ref_params, 5.0)
+        opt_ref.step()
+        opt.step()
+        torch.cuda.synchronize()
+        assert (it == 0) == (total.item() > 5.0), total.item()
+        assert abs(opt.grad_norm().item() - total.item()) < 1e-5 * total.item()
+        for (n1, p1), p2 in zip(net.named_parameters(), ref_params):
+            assert torch.allclose(p1, p2, rtol=0, atol=2e-6), (it, n1, (p1 - p2).abs().max().item())
+    # the optimiser invalidated the cached weight images: the next forward uses the updated weights
+    y1 = net(x)
+    net.engine.invalidate_images()
+    assert torch.equal(y1, net(x))

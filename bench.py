@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="nbss_b200")
+    ap.add_argument("--torch-adam", action="store_true", help="clip_grad_norm_ + torch.optim.Adam(fused, capturable) instead of FlatClipAdam")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=CFG["B"], help="global batch (utterances)")
     ap.add_argument("--profile", action="store_true", help="1 warm-up + 1 step only (for ncu); prints no bench line")
@@ -187,7 +188,7 @@ def main():
     params = [p for p in net.parameters()]
     from nbss_b200.optim import FlatClipAdam  # clip_grad_norm_(5) + Adam(1e-3) over the flat gradient buffer, two launches
 
-    opt = FlatClipAdam(net, lr=1e-3, max_norm=5.0)
+    opt = FlatClipAdam(net, lr=1e-3, max_norm=5.0) if not args.torch_adam else torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
 
     # rank r takes utterances r::world of the global batch (data_loaders/utils/my_distributed_sampler.py:78)
     x_all, y_all = synth_batch(args.batch, seed=777)
@@ -212,6 +213,8 @@ def main():
             flat.mul_(1.0 / world)
 
     def opt_step():
+        if args.torch_adam:
+            torch.nn.utils.clip_grad_norm_(params, 5.0, foreach=True)
         opt.step()
 
     def step(x, y):  # eager step

@@ -158,9 +158,9 @@ def test_flat_clip_adam_matches_torch():
     opt_ref = torch.optim.Adam(ref_params, lr=1e-3)
     opt = FlatClipAdam(net, lr=1e-3, max_norm=5.0)
     g = torch.Generator().manual_seed(3)
-    for it in range(3):
+    for it in range(4):
         x = torch.randn(1, 129, 40, 12, generator=g).cuda()
-        dy = (30.0 if it == 0 else 0.01) * torch.randn(1, 129, 40, 4, generator=g).cuda()  # step 0 is clipped, the others not
+        dy = (30.0 if it == 0 else 2e-4) * torch.randn(1, 129, 40, 4, generator=g).cuda()  # step 0 is clipped, the others not
         opt.zero_grad(set_to_none=True)
         net(x).backward(dy)
         for (_, p1), p2 in zip(net.named_parameters(), ref_params):

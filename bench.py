@@ -135,7 +135,7 @@ def run_reference(args):
     cores = min(os.cpu_count() or 1, 32)
     steps = max(1, min(args.steps, 3))
     fps, t, sample = cpu_oracle_step(cores, b=1, reps=steps)
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": "T-F frames/sec (SpatialNet-small 6ch F=129, training step fwd+bwd incl. STFT/iSTFT)",
         "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -145,6 +145,15 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "rtf": t / (1 * TS / 8000.0),
     }))
+
+
+_JSON_OUT = None
+
+
+def _emit(line: str) -> None:
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(line + "\n")
+    out.flush()
 
 
 def main():
@@ -160,6 +169,12 @@ def main():
     ap.add_argument("--layers", type=int, default=CFG["L"], help="number of SpatialNet layers (profiling only; default 8)")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: everything else that a library writes to file descriptor 1 (NCCL's
+    # version banner, for one) is routed to stderr, and the JSON line goes to the saved original stdout
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -388,7 +403,7 @@ def main():
         log(f"cpu baseline on {cores} threads")
         fps, t, sample = cpu_oracle_subprocess(cores, reps=2)
         out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(out))
+    _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 

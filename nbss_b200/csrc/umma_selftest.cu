@@ -12,7 +12,7 @@ struct SelfTestArgs {
     float* D;
     int a_rows, a_feats, b_rows, b_feats;
     int N, Kdim;
-    int a_mn, b_mn;      // 1 = MN-major view
+    int a_mn, b_mn;      // 1 = MN-major view; a_mn = 2: the A operand is written to TENSOR MEMORY (columns 256..) by the threads
     int fmt;             // FMT_F16 / FMT_BF16 / FMT_TF32 (A operand)
     int fmt_b;           // B operand format (may differ from A for the 16-bit kinds)
     int a_shift, b_shift;  // row shift of the view (rows)
@@ -75,16 +75,35 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(SelfTestArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = tmem_base_s + a.tmem_col;
+    const uint32_t ta_base = tmem_base_s + 256;  // A operand in tensor memory (a_mn == 2)
+    if (a.a_mn == 2) {
+        // thread = row: two 16-bit K elements per 32-bit column
+        for (int c0 = 0; c0 < a.Kdim / 2; c0 += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = 2 * (c0 + j);
+                const float lo = (tid < a.a_rows && k < a.a_feats) ? a.A[(size_t)tid * a.a_feats + k] : 0.f;
+                const float hi = (tid < a.a_rows && k + 1 < a.a_feats) ? a.A[(size_t)tid * a.a_feats + k + 1] : 0.f;
+                v[j] = a.fmt == FMT_F16 ? pack_f16(lo, hi) : pack_bf16(lo, hi);
+            }
+            tmem_st8(tmem_addr(ta_base, (warp & 3) * 32, c0), v);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
 
     if (tid == 0) {
-        const uint32_t idesc = (make_idesc(a.fmt, 128, a.N, a.a_mn, a.b_mn) & ~(7u << 10)) | ((uint32_t)a.fmt_b << 10);
+        const uint32_t idesc = (make_idesc(a.fmt, 128, a.N, a.a_mn == 1, a.b_mn) & ~(7u << 10)) | ((uint32_t)a.fmt_b << 10);
         const int kstep = (a.fmt == FMT_TF32) ? 8 : 16;
         const int nk = a.Kdim / kstep;
         uint32_t acc = 0;
         for (int pass = 0; pass < a.passes; ++pass) {
             for (int k = 0; k < nk; ++k) {
                 uint64_t da, db;
-                if (!a.a_mn) {
+                if (a.a_mn != 1) {
                     uint32_t s = smem_u32(sA) + a.a_shift * 16 + (a.a_off / ce + 2 * k) * a_cs;
                     da = sdesc_kmajor(s, a_cs);
                 } else {
@@ -98,7 +117,8 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(SelfTestArgs a) {
                     uint32_t s = smem_u32(sB) + (a.b_off / ce) * b_cs + (a.b_shift + k * kstep) * 16;
                     db = sdesc_mnmajor(s, b_cs);
                 }
-                if (a.fmt == FMT_TF32) umma_tf32(tbase, da, db, idesc, acc);
+                if (a.a_mn == 2) umma_f16_ts(tbase, ta_base + 8 * k, db, idesc, acc);
+                else if (a.fmt == FMT_TF32) umma_tf32(tbase, da, db, idesc, acc);
                 else umma_f16(tbase, da, db, idesc, acc);
                 acc = 1;
             }
@@ -131,6 +151,7 @@ extern "C" int nbss_umma_selftest(const float* A, int a_rows, int a_feats, const
     using namespace nbss;
     if (N % 16 || N < 16 || N > 256) return NBSS_ERR_SHAPE;
     if (tmem_col + N > 512) return NBSS_ERR_SHAPE;
+    if (a_mn == 2 && (tmem_col + N > 256 || Kdim / 2 > 256 || Kdim % 16 || fmt == FMT_TF32)) return NBSS_ERR_SHAPE;
     const int es = (fmt == FMT_TF32) ? 4 : 2, ce = 16 / es;
     size_t bytes = (size_t)((a_feats + ce - 1) / ce) * (a_rows + 8) * 16 + (size_t)((b_feats + ce - 1) / ce) * (b_rows + 8) * 16;
     if (bytes > 200 * 1024) return NBSS_ERR_SHAPE;

@@ -53,6 +53,10 @@ CASES = [
     ("mk_bf16", "bf16", (64, 128), (96, 64), 96, 64, 1, 0, 0, 0, 0, 0, 1, 0),
     ("mm_f16_wgrad_bshift1", "f16", (248, 128), (250, 96), 96, 240, 1, 1, 0, 1, 0, 0, 1, 0),
     # NOTE: mixing fp16 and bf16 operands in one kind::f16 MMA raises cudaErrorIllegalInstruction on sm_100a (measured)
+    # a_mn = 2: the A operand lives in tensor memory (tcgen05.st by the row threads), B K-major / MN-major in smem
+    ("ts_f16_kmajor_b", "f16", (128, 64), (96, 64), 96, 64, 2, 0, 0, 0, 0, 0, 1, 0),
+    ("ts_f16_pv", "f16", (128, 256), (256, 104), 32, 256, 2, 1, 0, 0, 0, 24, 1, 0),
+    ("ts_bf16_passes2", "bf16", (128, 32), (16, 32), 16, 32, 2, 0, 0, 0, 0, 0, 2, 64),
 ]
 
 
@@ -68,7 +72,7 @@ def test_umma_selftest(case):
     if ":" in fmt:
         fmt, fmt_b = fmt.split(":")
     Ar, Br = _round(A, fmt), _round(B, fmt_b)
-    Av = _view(Ar, a_mn, a_shift, a_off, 128, K).double()
+    Av = _view(Ar, a_mn == 1, a_shift, a_off, 128, K).double()
     Bv = _view(Br, b_mn, b_shift, b_off, N, K).double()
     # zero-pad views that run off the end of the array (the kernel reads zero rows / features there)
     Avp = torch.zeros(128, K, dtype=torch.float64)

@@ -10,6 +10,8 @@
 //        O_h = P V_h (P fp16 [128 x 128 keys] staged twice, V read MN-major)  -> O tile (normalised by the row sum)
 //   P3 y = x + O Wo^T + bo
 // HBM traffic: x in, y out (+ fp16 q|k|v, O and the log2-sum-exp when save != 0, for the backward kernels).
+#include <cstdlib>
+
 #include "slab.cuh"
 
 namespace nbss {
@@ -46,7 +48,9 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-template <int FMT>
+// PTMEM: the softmax probabilities go back into tensor memory (over the score columns they came from) and feed the PV MMA
+// as its A operand from TMEM (umma.cuh: umma_f16_ts): one MMA round per (head, query tile) instead of two, no P tile.
+template <int FMT, bool PTMEM>
 __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* ao = smem + MH_AO;
@@ -236,6 +240,26 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
                 }
             }
             xsum[kq * 128 + rt] = sum;
+            if constexpr (PTMEM) {
+                // O_h = P V_h with P in tensor memory: key k of row rt -> column 192 + k/2 (two 16-bit values per column)
+                __syncthreads();  // every thread has read its score columns: the P columns alias them
+                const uint32_t tp = tmem + lane_off + 192 + 32 * kq;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t v8[8] = {pk[8 * c], pk[8 * c + 1], pk[8 * c + 2], pk[8 * c + 3], pk[8 * c + 4], pk[8 * c + 5], pk[8 * c + 6], pk[8 * c + 7]};
+                    tmem_st8(tp + 8 * c, v8);
+                }
+                tmem_st_wait();
+                end_epilogue();
+                if (warp == 0) {
+                    tc_fence_after();
+                    const bool leader = elect_one();
+                    for (int ks = 0; ks < 16; ++ks)
+                        if (leader) umma_f16_ts(tmem + 448, tmem + 192 + 8 * ks, sdesc_mnmajor(vta + 3 * h * kCS + 16 * ks * 16, kCS), idpv, ks ? 1u : 0u);
+                    if (leader) umma_commit(bar_mma);
+                }
+                wait_mma();
+            } else {
             // O_h = P V_h, one key half at a time (the P tile holds 128 keys = two key quarters)
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -254,6 +278,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
                     if (leader) umma_commit(bar_mma);
                 }
                 wait_mma();
+            }
             }
             // EO: normalise and place O_h into the O tile (aliases A0, dead after P2)
             if (warp < 4) {
@@ -334,7 +359,13 @@ extern "C" int nbss_mhsa_fwd(const float* x, float* y, int nslab, int T, const f
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = nslab < sms ? nslab : sms;
-    auto kern = (fmt == FMT_F16) ? mhsa_fwd_kernel<FMT_F16> : mhsa_fwd_kernel<FMT_BF16>;
+    static int ptmem = -1;  // NBSS_MHSA_PTMEM=0 keeps the softmax probabilities in a shared-memory tile (the older path)
+    if (ptmem < 0) {
+        const char* e = getenv("NBSS_MHSA_PTMEM");
+        ptmem = (e && e[0] == '0') ? 0 : 1;
+    }
+    void (*kern)(MhsaFwdArgs) = ptmem ? ((fmt == FMT_F16) ? mhsa_fwd_kernel<FMT_F16, true> : mhsa_fwd_kernel<FMT_BF16, true>)
+                                      : ((fmt == FMT_F16) ? mhsa_fwd_kernel<FMT_F16, false> : mhsa_fwd_kernel<FMT_BF16, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MH_SMEM);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, kMhThreads, MH_SMEM, (cudaStream_t)stream>>>(a);

@@ -29,6 +29,10 @@ CFG1 = dict(dim_input=4, dim_output=4, dim_squeeze=8, num_layers=8, num_freqs=65
             dim_hidden=96, dim_ffn=192, num_heads=4, kernel_size=(5, 3), conv_groups=(8, 8))  # BASELINE configs[0]
 
 
+LARGE = dict(dim_input=12, dim_output=4, dim_squeeze=16, num_layers=2, num_freqs=129, encoder_kernel_size=5,
+             dim_hidden=192, dim_ffn=384, num_heads=4, kernel_size=(5, 3), conv_groups=(8, 8))  # the YAML's "large" widths, 2 layers
+
+
 def build_ref(cfg, P):
     m = SpatialNet(**cfg)
     sd = {k: v.clone() for k, v in P.items()}
@@ -87,6 +91,20 @@ def main():
     with torch.no_grad():
         y = m(x)
     np.savez_compressed(os.path.join(HERE, "small_6ch_f129_t12.npz"), x=x.numpy(), y=y.numpy())
+
+    # 5) the large configuration's layer widths (configs/SpatialNet.yaml:16-25 comments), 2 layers, short T:
+    #    forward + gradient norms, pins the oracle for the next tile shapes (H=192, Hf=384, dim_squeeze=16, head dim 48)
+    g = torch.Generator().manual_seed(15)
+    P = O.synth_params(LARGE, seed=105)
+    m = build_ref(LARGE, P)
+    x = torch.randn(1, 129, 10, 12, generator=g)
+    dy = torch.randn(1, 129, 10, 4, generator=g)
+    y = m(x)
+    y.backward(dy)
+    lg = {"x": x.numpy(), "dy": dy.numpy(), "y": y.detach().numpy()}
+    for k, p in m.named_parameters():
+        lg["gnorm." + k] = np.float64(p.grad.double().norm().item())
+    np.savez_compressed(os.path.join(HERE, "large_widths_f129_t10.npz"), **lg)
 
     # 4) framing: STFT / Norm / iSTFT and the whole wave->wave path with the tiny-ish net (n_fft 32 -> F=17)
     g = torch.Generator().manual_seed(14)

@@ -16,6 +16,10 @@ CFG1 = dict(dim_input=4, dim_output=4, dim_squeeze=8, num_layers=8, num_freqs=65
             dim_hidden=96, dim_ffn=192, num_heads=4, kernel_size=(5, 3), conv_groups=(8, 8))
 
 
+LARGE = dict(dim_input=12, dim_output=4, dim_squeeze=16, num_layers=2, num_freqs=129, encoder_kernel_size=5,
+             dim_hidden=192, dim_ffn=384, num_heads=4, kernel_size=(5, 3), conv_groups=(8, 8))
+
+
 def _leaf_params(P):
     """requires_grad leaves; the shared full.* tensor stays ONE leaf under all its keys."""
     seen, out = {}, {}
@@ -42,6 +46,23 @@ def test_tiny_forward_backward_matches_reference():
         assert O.rel_l2(P[name].grad, torch.from_numpy(z[k])) < 2e-5, name
         checked += 1
     assert checked >= 60
+
+
+def test_large_widths_forward_and_grad_norms():
+    """The 'large' layer widths of configs/SpatialNet.yaml (H=192, Hf=384, dim_squeeze=16): the oracle is
+    already pinned for the next tile shapes."""
+    z = np.load(os.path.join(G, "large_widths_f129_t10.npz"))
+    P = _leaf_params(O.synth_params(LARGE, seed=105))
+    y = O.spatialnet_forward(P, torch.from_numpy(z["x"]), LARGE)
+    assert O.rel_l2(y.detach(), torch.from_numpy(z["y"])) < 5e-6
+    y.backward(torch.from_numpy(z["dy"]))
+    n = 0
+    for k in z.files:
+        if k.startswith("gnorm."):
+            got = float(P[k[6:]].grad.double().norm())
+            assert abs(got - float(z[k])) <= 1e-4 * float(z[k]) + 1e-12, k
+            n += 1
+    assert n >= 60
 
 
 def test_cfg1_small_2ch_forward_and_grad_norms():

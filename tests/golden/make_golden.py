@@ -106,6 +106,27 @@ def main():
         lg["gnorm." + k] = np.float64(p.grad.double().norm().item())
     np.savez_compressed(os.path.join(HERE, "large_widths_f129_t10.npz"), **lg)
 
+    # 6) NBC2 (BASELINE configs[3]): small widths, 2 layers, F=17: forward + gradient norms
+    from models.arch.NBC2 import NBC2  # noqa: E402  (reference)
+    from oracle import nbc2_oracle as N2  # noqa: E402
+
+    ncfg = dict(N2.NBC2_SMALL, n_layers=2, num_freqs=17)
+    g = torch.Generator().manual_seed(16)
+    Pn = N2.synth_params(ncfg, seed=106)
+    mn = NBC2(dim_input=16, dim_output=4, n_layers=2, dim_hidden=96, dim_ffn=192, num_freqs=17,
+              block_kwargs={'n_heads': 2, 'dropout': 0, 'conv_kernel_size': 3, 'n_conv_groups': 8, 'norms': ("LN", "GBN", "GBN"),
+                            'group_batch_norm_kwargs': {'share_along_sequence_dim': False}})
+    missing, unexpected = mn.load_state_dict({k: v.clone() for k, v in Pn.items()}, strict=True)
+    assert not missing and not unexpected
+    x = torch.randn(2, 17, 12, 16, generator=g)
+    dy = torch.randn(2, 17, 12, 4, generator=g)
+    y = mn(x)
+    y.backward(dy)
+    nb = {"x": x.numpy(), "dy": dy.numpy(), "y": y.detach().numpy()}
+    for k, p in mn.named_parameters():
+        nb["gnorm." + k] = np.float64(p.grad.double().norm().item())
+    np.savez_compressed(os.path.join(HERE, "nbc2_small_f17_t12.npz"), **nb)
+
     # 4) framing: STFT / Norm / iSTFT and the whole wave->wave path with the tiny-ish net (n_fft 32 -> F=17)
     g = torch.Generator().manual_seed(14)
     stft, norm = STFT(n_fft=32, n_hop=16), Norm(mode="frequency")

@@ -65,6 +65,25 @@ def test_large_widths_forward_and_grad_norms():
     assert n >= 60
 
 
+def test_nbc2_oracle_matches_reference():
+    """oracle/nbc2_oracle.py (BASELINE configs[3]) against the unmodified reference NBC2."""
+    from oracle import nbc2_oracle as N2
+
+    z = np.load(os.path.join(G, "nbc2_small_f17_t12.npz"))
+    cfg = dict(N2.NBC2_SMALL, n_layers=2, num_freqs=17)
+    P = {k: v.clone().requires_grad_(True) for k, v in N2.synth_params(cfg, seed=106).items()}
+    y = N2.nbc2_forward(P, torch.from_numpy(z["x"]), cfg)
+    assert O.rel_l2(y.detach(), torch.from_numpy(z["y"])) < 5e-6
+    y.backward(torch.from_numpy(z["dy"]))
+    n = 0
+    for k in z.files:
+        if k.startswith("gnorm."):
+            got = float(P[k[6:]].grad.double().norm())
+            assert abs(got - float(z[k])) <= 1e-4 * float(z[k]) + 1e-12, k
+            n += 1
+    assert n == len(P)
+
+
 def test_cfg1_small_2ch_forward_and_grad_norms():
     """BASELINE.json configs[0]: SpatialNet-small 2ch F=65 T=64 forward on CPU, batch=1."""
     z = np.load(os.path.join(G, "cfg1_small_2ch_f65_t64.npz"))

@@ -117,7 +117,6 @@ def layer_image_bytes() -> int:
 def pack_layer_weights(P: Dict[str, Tensor], pre: str, img: Optional[Tensor] = None, fwd_fmt: int = FMT_F16,
                        bwd_fmt: int = FMT_F16) -> Tensor:
     """Builds the UMMA weight images of one SpatialNet layer (pack.cu) from its fp32 parameters."""
-    L = _lib.lib()
     dev = P[pre + "tconvffn.1.weight"].device
     if img is None:
         img = torch.empty(layer_image_bytes(), dtype=torch.uint8, device=dev)
@@ -134,7 +133,6 @@ def ffn_fwd(x: Tensor, P: Dict[str, Tensor], pre: str, img: Tensor, save: bool =
             out: Optional[Tensor] = None):
     """x: [B,F,T,96] fp32 -> y = x + tconvffn(x).  With save=True also returns the fp16 pre-activations
     (a1, c1, c2, c3) [B*F*T,192] and GroupNorm stats [B*F,8,2] needed by the backward kernels."""
-    L = _lib.lib()
     x = _f32c(x)
     B, F, T, H = x.shape
     assert H == 96
@@ -160,7 +158,6 @@ def mhsa_fwd(x: Tensor, P: Dict[str, Tensor], pre: str, img: Tensor, save: bool 
              out: Optional[Tensor] = None):
     """x: [B,F,T,96] fp32 -> y = x + MHSA(LN(x)) over T per (b,f).  With save=True also returns fp16 (scaled q|k|v)
     [n,288], O [n,96] and the log2-domain logsumexp [B*F,4,T]."""
-    L = _lib.lib()
     x = _f32c(x)
     B, F, T, H = x.shape
     assert H == 96
@@ -184,7 +181,6 @@ def mhsa_fwd(x: Tensor, P: Dict[str, Tensor], pre: str, img: Tensor, save: bool 
 # ------------------------------------------------------------------------------------------------ cross-band (fp32)
 def fconv_fwd(x: Tensor, P, pre: str, out: Optional[Tensor] = None) -> Tensor:
     """y = x + PReLU(gconv_F(LN(x))); pre = 'layers.i.fconv1' / '...fconv2'."""
-    L = _lib.lib()
     x = _f32c(x)
     B, F, T, H = x.shape
     assert H == 96
@@ -198,7 +194,6 @@ def fconv_fwd(x: Tensor, P, pre: str, out: Optional[Tensor] = None) -> Tensor:
 
 def fconv_bwd(x: Tensor, dy: Tensor, P, pre: str, G) -> Tensor:
     """Returns dx; accumulates parameter gradients into the fp32 tensors G[name] (same keys as P)."""
-    L = _lib.lib()
     x, dy = _f32c(x), _f32c(dy)
     B, F, T, H = x.shape
     dx = torch.empty_like(x)
@@ -212,7 +207,6 @@ def fconv_bwd(x: Tensor, dy: Tensor, P, pre: str, G) -> Tensor:
 
 def full_fwd(x: Tensor, P, pre: str, out: Optional[Tensor] = None):
     """y = x + full-band branch; returns (y, s, u) with s,u [B,T,8,F] kept for backward."""
-    L = _lib.lib()
     x = _f32c(x)
     B, F, T, H = x.shape
     y = torch.empty_like(x) if out is None else out
@@ -228,7 +222,6 @@ def full_fwd(x: Tensor, P, pre: str, out: Optional[Tensor] = None):
 
 
 def full_bwd(x: Tensor, dy: Tensor, s: Tensor, u: Tensor, P, pre: str, G) -> Tensor:
-    L = _lib.lib()
     x, dy = _f32c(x), _f32c(dy)
     B, F, T, H = x.shape
     dx = torch.empty_like(x)
@@ -316,7 +309,6 @@ def full_bwd_tc(x: Tensor, dy: Tensor, s: Tensor, u: Tensor, P, pre: str, img: T
 
 # ------------------------------------------------------------------------------------------------ encoder / decoder
 def encoder_fwd(x: Tensor, P) -> Tensor:
-    L = _lib.lib()
     x = _f32c(x)
     B, F, T, Cin = x.shape
     y = torch.empty(B, F, T, 96, dtype=torch.float32, device=x.device)
@@ -326,7 +318,6 @@ def encoder_fwd(x: Tensor, P) -> Tensor:
 
 
 def encoder_wgrad(x: Tensor, dy: Tensor, G) -> None:
-    L = _lib.lib()
     x, dy = _f32c(x), _f32c(dy)
     B, F, T, Cin = x.shape
     st = _K("nbss_encoder_wgrad")(ptr(x), ptr(dy), B * F, T, Cin, ptr(G["encoder.weight"]), ptr(G["encoder.bias"]), stream_ptr())
@@ -334,7 +325,6 @@ def encoder_wgrad(x: Tensor, dy: Tensor, G) -> None:
 
 
 def decoder_fwd(x: Tensor, P) -> Tensor:
-    L = _lib.lib()
     x = _f32c(x)
     B, F, T, H = x.shape
     cout = P["decoder.weight"].shape[0]
@@ -346,7 +336,6 @@ def decoder_fwd(x: Tensor, P) -> Tensor:
 
 
 def decoder_bwd(x: Tensor, dy: Tensor, P, G) -> Tensor:
-    L = _lib.lib()
     x, dy = _f32c(x), _f32c(dy)
     B, F, T, H = x.shape
     cout = P["decoder.weight"].shape[0]
@@ -364,7 +353,6 @@ def _ll(v):
 
 def stft(x: Tensor, n_fft: int, hop: int) -> Tensor:
     """STFT.stft: [B,C,Ts] fp32 -> complex64 [B,C,F,T] (center, reflect, periodic Hann, onesided)."""
-    L = _lib.lib()
     x = _f32c(x)
     B, C, Ts = x.shape
     F, T = n_fft // 2 + 1, 1 + Ts // hop
@@ -377,7 +365,6 @@ def stft(x: Tensor, n_fft: int, hop: int) -> Tensor:
 
 def stft_norm_pack(x: Tensor, n_fft: int, hop: int, ref_channel: int, eps: float = 1e-6, want_xr: bool = False):
     """Fused stft + Norm(frequency, online) + pack: [B,C,Ts] -> (X [B,F,T,2C], XrMM [B,F,T], Xr [B,F,T] complex|None)."""
-    L = _lib.lib()
     x = _f32c(x)
     B, C, Ts = x.shape
     F, T = n_fft // 2 + 1, 1 + Ts // hop
@@ -393,7 +380,6 @@ def stft_norm_pack(x: Tensor, n_fft: int, hop: int, ref_channel: int, eps: float
 def istft_strided(real_view: Tensor, strides_bsft, scale: Optional[Tensor], B: int, S: int, F: int, T: int, n_fft: int,
                   hop: int, length: int) -> Tensor:
     """iSTFT of a complex tensor given as a float32 storage + (b,s,f,t) strides in floats (imag at +1)."""
-    L = _lib.lib()
     y = torch.empty(B, S, length, dtype=torch.float32, device=real_view.device)
     ib, is_, if_, it = strides_bsft
     st = _K("nbss_istft")(ptr(real_view), _ll(ib), _ll(is_), _ll(if_), _ll(it), ptr(scale), ptr(y), B, S, length, T, n_fft, hop,
@@ -403,7 +389,6 @@ def istft_strided(real_view: Tensor, strides_bsft, scale: Optional[Tensor], B: i
 
 
 def istft_bwd_strided(dy: Tensor, scale: Optional[Tensor], out: Tensor, strides_bsft, B, S, F, T, n_fft, hop) -> Tensor:
-    L = _lib.lib()
     dy = _f32c(dy)
     ib, is_, if_, it = strides_bsft
     st = _K("nbss_istft_bwd")(ptr(dy), ptr(scale), ptr(out), _ll(ib), _ll(is_), _ll(if_), _ll(it), B, S, dy.shape[-1], T, n_fft, hop,
@@ -416,7 +401,6 @@ def istft_bwd_strided(dy: Tensor, scale: Optional[Tensor], out: Tensor, strides_
 def ffn_bwd(x: Tensor, dy: Tensor, saves, gn_stats: Tensor, P, pre: str, img: Tensor, G, fmt_g: int = FMT_F16):
     """Backward of y = x + tconvffn(x).  saves = [a1, c1, c2, c3, ln_stats] from ffn_fwd(save=True).
     Returns dx; accumulates every tconvffn.* parameter gradient into G (fp32)."""
-    L = _lib.lib()
     x, dy = _f32c(x), _f32c(dy)
     B, F, T, H = x.shape
     n = B * F * T
@@ -446,7 +430,6 @@ def ffn_bwd(x: Tensor, dy: Tensor, saves, gn_stats: Tensor, P, pre: str, img: Te
 
 def mhsa_bwd(x: Tensor, dy: Tensor, msave, P, pre: str, img: Tensor, G, fmt_g: int = FMT_F16):
     """Backward of y = x + MHSA(LN(x)).  msave = (qkv, o, lse, ln_stats) from mhsa_fwd(save=True)."""
-    L = _lib.lib()
     x, dy = _f32c(x), _f32c(dy)
     B, F, T, H = x.shape
     n = B * F * T

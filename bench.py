@@ -94,7 +94,7 @@ def log(msg):
 def cpu_oracle_subprocess(threads, reps, timeout_s=420):
     """Runs cpu_oracle_step in a child process under a timeout so a slow host cannot stall the GPU bench line."""
     code = (f"import sys, json; sys.path.insert(0, {ROOT!r}); import bench; "
-            f"print(json.dumps(bench.cpu_oracle_step({threads}, 1, {reps})))")
+            f"print(json.dumps(bench.cpu_oracle_step({threads}, 4, {reps})))")
     try:
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=timeout_s)
         return tuple(json.loads(r.stdout.strip().splitlines()[-1]))
@@ -102,8 +102,11 @@ def cpu_oracle_subprocess(threads, reps, timeout_s=420):
         return None, None, f"cpu baseline unavailable: {type(e).__name__}"
 
 
-def cpu_oracle_step(threads, b=1, reps=2):
-    """One training pass of the same path through the oracle on the host cores (forward + autograd backward)."""
+def cpu_oracle_step(threads, b=4, reps=2):
+    """One training pass of the same path on the host cores through the reference's own op-set (oracle/eager_gpu.py: the
+    torch.nn.functional calls the reference's modules make, pinned to the oracle and the golden vectors by
+    tests/test_oracle_golden.py): forward + autograd backward, all host threads."""
+    from oracle import eager_gpu as E
     from oracle import spatialnet_oracle as O
     torch.set_num_threads(threads)
     P = O.synth_params(O.SMALL_CFG, 2)
@@ -116,8 +119,8 @@ def cpu_oracle_step(threads, b=1, reps=2):
     ts = []
     for i in range(reps + 1):
         t0 = time.perf_counter()
-        est = O.io_forward(Pl, x, O.SMALL_CFG, CFG["n_fft"], CFG["hop"], 0)
-        loss = O.neg_si_sdr_pit(est, tgt)[0]
+        est = E.io_forward(Pl, x, O.SMALL_CFG, CFG["n_fft"], CFG["hop"], 0)
+        loss = E.neg_si_sdr_pit2(est, tgt)
         loss.backward()
         ts.append(time.perf_counter() - t0)
         if sum(ts) > 120:  # bounded sample: stop once ~2 minutes of CPU work have been spent
@@ -125,7 +128,90 @@ def cpu_oracle_step(threads, b=1, reps=2):
     timed = ts[1:] if len(ts) > 1 else ts
     t = min(timed)
     note = f"1 warm-up + {len(ts) - 1} timed (best)" if len(ts) > 1 else "single cold pass (host too slow for a warm-up within the bound)"
-    return b * CFG["T"] / t, t, f"B={b} utterance(s) x T=250 frames, wave->wave fwd+bwd, {threads} threads, {note}"
+    return b * CFG["T"] / t, t, f"B={b} utterance(s) x T=250 frames, wave->wave fwd+bwd, reference op-set (torch CPU kernels), {threads} threads, {note}"
+
+
+def gpu_eager_baseline(dev, batch, steps=3, warmup=2):
+    """The reference's op-set in PyTorch eager on this GPU (oracle/eager_gpu.py: cuDNN / cuBLAS / SDPA / cuFFT calls in the
+    reference's module order), the same training step (wave -> wave, SI-SDR + PIT, backward, clip + Adam): fp32 with TF32
+    allowed (models/utils/base_cli.py:24-25) and bf16 autocast (Lightning 'bf16-mixed').  Largest batch <= `batch` that fits."""
+    from oracle import eager_gpu as E
+    from oracle import spatialnet_oracle as O
+
+    out = {}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        for mode in ("fp32_tf32", "bf16_autocast"):
+            b = batch
+            while b >= 1:
+                try:
+                    torch.manual_seed(2)
+                    P = O.synth_params(O.SMALL_CFG, 2)
+                    leaves, Pl = {}, {}
+                    for k, v in P.items():
+                        if id(v) not in leaves:
+                            leaves[id(v)] = v.to(dev).requires_grad_(True)
+                        Pl[k] = leaves[id(v)]
+                    params = list(leaves.values())
+                    opt = torch.optim.Adam(params, lr=1e-3, fused=True)
+                    x, y = (t.to(dev) for t in synth_batch(b, seed=777))
+
+                    def one():
+                        opt.zero_grad(set_to_none=True)
+                        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16_autocast")):
+                            est = E.io_forward(Pl, x, O.SMALL_CFG, CFG["n_fft"], CFG["hop"], 0)
+                        loss = E.neg_si_sdr_pit2(est.float(), y)
+                        loss.backward()
+                        torch.nn.utils.clip_grad_norm_(params, 5.0, foreach=True)
+                        opt.step()
+                        return loss
+
+                    for _ in range(warmup):
+                        one()
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(steps):
+                        loss = one()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / steps
+                    out[mode] = {"ms_per_step": round(ms, 2), "frames_per_s": round(b * CFG["T"] / (ms * 1e-3), 1), "batch": b,
+                                 "ms_per_step_scaled_to_batch": round(ms * batch / b, 2), "loss": float(loss),
+                                 "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1)}
+                    break
+                except torch.OutOfMemoryError:
+                    b //= 2
+                finally:
+                    Pl = leaves = params = opt = x = y = None
+                    import gc
+                    gc.collect()
+                    torch.cuda.empty_cache()
+                    torch.cuda.reset_peak_memory_stats(dev)
+            log(f"eager baseline {mode}: {out.get(mode)}")
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    out["what"] = ("reference op-set (oracle/eager_gpu.py: F.conv1d / F.multi_head_attention_forward (SDPA) / F.layer_norm / "
+                   "F.group_norm / torch.stft / torch.istft in the reference's module order), same training step, PyTorch eager")
+    return out
+
+
+def run_torch_gpu(args):
+    """--impl torch-gpu: the eager baseline as a bench line of its own (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    r = gpu_eager_baseline(dev, args.batch, steps=max(1, min(args.steps, 5)), warmup=max(2, min(args.warmup, 3)))
+    best = min((v for k, v in r.items() if isinstance(v, dict)), key=lambda v: v["ms_per_step_scaled_to_batch"])
+    _emit(json.dumps({
+        "impl": "torch-gpu", "metric": "T-F frames/sec (SpatialNet-small 6ch F=129, training step fwd+bwd incl. STFT/iSTFT)",
+        "value": best["frames_per_s"], "unit": "frames/s", "n_gpus": 1, "steps": max(1, min(args.steps, 5)), "warmup": max(2, min(args.warmup, 3)),
+        "ms_per_step": best["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "tf32 / bf16 autocast",
+        "data": "synthetic", "config": {"workload": "SpatialNet-small 6ch F=129 T=250 fwd+bwd, batch=32 (BASELINE configs[1])", "global_batch": best["batch"]},
+        "gpu_eager_baseline": r}))
 
 
 def run_reference(args):
@@ -134,16 +220,16 @@ def run_reference(args):
         return
     cores = min(os.cpu_count() or 1, 32)
     steps = max(1, min(args.steps, 3))
-    fps, t, sample = cpu_oracle_step(cores, b=1, reps=steps)
+    fps, t, sample = cpu_oracle_step(cores, b=4, reps=steps)
     _emit(json.dumps({
         "impl": "reference", "metric": "T-F frames/sec (SpatialNet-small 6ch F=129, training step fwd+bwd incl. STFT/iSTFT)",
         "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "SpatialNet-small 6ch F=129 T=250 fwd+bwd, batch=32 (BASELINE configs[1])", "global_batch": 32,
-                   "cpu_sample_batch": 1, "frames_per_utt": CFG["T"]},
+                   "cpu_sample_batch": 4, "frames_per_utt": CFG["T"]},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "rtf": t / (1 * TS / 8000.0),
+        "rtf": t / (4 * TS / 8000.0),
     }))
 
 
@@ -164,6 +250,7 @@ def main():
     ap.add_argument("--impl", default="nbss_b200")
     ap.add_argument("--torch-adam", action="store_true", help="clip_grad_norm_ + torch.optim.Adam(fused, capturable) instead of FlatClipAdam")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager reference op-set timed on this GPU")
     ap.add_argument("--batch", type=int, default=CFG["B"], help="global batch (utterances)")
     ap.add_argument("--profile", action="store_true", help="1 warm-up + 1 step only (for ncu); prints no bench line")
     ap.add_argument("--layers", type=int, default=CFG["L"], help="number of SpatialNet layers (profiling only; default 8)")
@@ -177,6 +264,8 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "torch-gpu":
+        return run_torch_gpu(args)
 
     import torch.distributed as dist
     from nbss_b200 import ops
@@ -195,6 +284,15 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert args.batch % world == 0
     b_local = args.batch // world
+
+    eager = None
+    if world == 1 and not args.no_eager_baseline and not args.profile:
+        # the kernel set to beat: timed first, in this process, then freed
+        try:
+            eager = gpu_eager_baseline(dev, args.batch)
+        except Exception as e:  # never let the baseline take the bench line down
+            eager = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+            log(f"eager baseline failed: {eager}")
 
     torch.manual_seed(2)  # configs/SpatialNet.yaml:1
     net = SpatialNet(dim_input=2 * CFG["C"], dim_output=2 * CFG["S"], dim_squeeze=8, num_layers=args.layers, num_freqs=CFG["F"],
@@ -398,6 +496,8 @@ def main():
         "gpu_launches": launches, "loss": loss_v, "rtf": ms_dev * 1e-3 / (args.batch * TS / 8000.0),
         "roofline": roof, "rooflines": rooflines, "kernels": kernels, "clocks": clocks,
     }
+    if eager is not None:
+        out["gpu_eager_baseline"] = eager
     if world == 1 and not args.no_cpu_baseline:
         cores = min(os.cpu_count() or 1, 32)
         log(f"cpu baseline on {cores} threads")

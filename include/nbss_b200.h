@@ -24,6 +24,10 @@ extern "C" {
 
 /* ---- weight images (pack.cu): UMMA B-operand tiles of one SpatialNetLayer's narrow-band weights ------------------- */
 unsigned int nbss_layer_image_bytes(void);
+/* ABI version (100 * round + revision) and the bytes of caller-owned scratch one SpatialNetLayer needs at [B,F,T]
+ * (training: activations saved for the backward + transient gradient operands; inference: 0). */
+int nbss_version(void);
+long long nbss_workspace_bytes(int B, int F, int T, int training);
 /* w1 = tconvffn.1.weight [192,96,1], wc{1,2,3} = tconvffn.{3,5,8}.weight [192,24,3], w2 = tconvffn.10.weight [96,192,1],
  * w_in = mhsa.in_proj_weight [288,96], w_out = mhsa.out_proj.weight [96,96]  (models/arch/SpatialNet.py:58,61-73) */
 int nbss_pack_layer_weights(const float* w1, const float* wc1, const float* wc2, const float* wc3, const float* w2,

@@ -10,7 +10,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnbss_b200.so")
+# NBSS_LIB selects another build of the same library (tools/phase_profile.py: lib/libnbss_b200_prof.so, `make prof`)
+LIB_PATH = os.environ.get("NBSS_LIB") or os.path.join(_HERE, "lib", "libnbss_b200.so")
 
 _lib = None
 _lock = threading.Lock()

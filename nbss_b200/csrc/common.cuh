@@ -17,6 +17,26 @@
         if (e__ != cudaSuccess) return (int)e__;  \
     } while (0)
 
+// Phase profiling (tools/phase_profile.py; `make prof` builds lib/libnbss_b200_prof.so with -DNBSS_PHASE_PROFILE): thread 0 of
+// CTA 0 stamps clock64() at the phase boundaries of its SECOND work item (steady state) into a device array that
+// nbss_debug_phases() copies out (one reader per .cu: nbss_debug_phases_<unit>).  Compiled out of the product library.
+#ifdef NBSS_PHASE_PROFILE
+static __device__ unsigned long long g_nbss_phase[4 * 64];  // one copy per translation unit: up to 4 kernels x 64 stamps
+#define NBSS_TICK(kid, idx, iter) \
+    do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (iter) == 1) g_nbss_phase[(kid) * 64 + (idx)] = clock64(); } while (0)
+// instantiate once per .cu that stamps phases: copies the unit's stamps to host memory and clears them
+#define NBSS_PHASE_READER(fn)                                                                        \
+    extern "C" int fn(unsigned long long* host_out) {                                                \
+        cudaError_t e = cudaMemcpyFromSymbol(host_out, g_nbss_phase, sizeof(unsigned long long) * 4 * 64); \
+        if (e != cudaSuccess) return (int)e;                                                         \
+        static unsigned long long zeros[4 * 64];                                                     \
+        return (int)cudaMemcpyToSymbol(g_nbss_phase, zeros, sizeof(zeros));                          \
+    }
+#else
+#define NBSS_TICK(kid, idx, iter) do { } while (0)
+#define NBSS_PHASE_READER(fn)
+#endif
+
 namespace nbss {
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -203,12 +203,15 @@ __global__ void __launch_bounds__(256, 2) fconv_tc_fwd_kernel(FcFwdArgs a) {
     const uint32_t lane_off = (uint32_t)(32 * (warp & 3)) << 16;
     uint32_t ph = 0;
     bool wready = false;
-    for (int grp = blockIdx.x; grp < g.ngroups; grp += gridDim.x) {
+    int it_ = 0;
+    for (int grp = blockIdx.x; grp < g.ngroups; grp += gridDim.x, ++it_) {
         const int b = grp / g.groups_per_b, t0 = (grp % g.groups_per_b) * g.nfr;
+        NBSS_TICK(0, 0, it_);
         fc_stage<FMT, 5>(g, a.x, b, t0, tile, cst, cst + 96, nullptr, warp, lane);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        NBSS_TICK(0, 1, it_);
         if (warp == 0) {
             tc_fence_after();
             if (!wready) mbar_wait(bar_w, 0, a.err);
@@ -221,6 +224,7 @@ __global__ void __launch_bounds__(256, 2) fconv_tc_fwd_kernel(FcFwdArgs a) {
         mbar_wait(bar_mma, ph, a.err);
         ph ^= 1;
         tc_fence_after();
+        NBSS_TICK(0, 2, it_);
         // epilogue 1: thread = one tile row (TMEM lane): PReLU(D + bias) -> 16-bit, written over the operand tile (dead
         // once every MMA of the group has completed) at the row's own slot.  warps 0-3 even tiles, warps 4-7 odd tiles.
         for (int m = warp >> 2; m < g.nt; m += 2) {
@@ -245,6 +249,7 @@ __global__ void __launch_bounds__(256, 2) fconv_tc_fwd_kernel(FcFwdArgs a) {
         }
         tc_fence_before();
         __syncthreads();
+        NBSS_TICK(0, 3, it_);
         // epilogue 2: eight lanes per (frame, f) row, coalesced: y = x + branch
         {
             constexpr int U = 5;
@@ -283,6 +288,7 @@ __global__ void __launch_bounds__(256, 2) fconv_tc_fwd_kernel(FcFwdArgs a) {
         }
         tc_fence_before();
         __syncthreads();
+        NBSS_TICK(0, 4, it_);
     }
     if (warp == 0) tmem_dealloc(tmem, ncols);
 }
@@ -344,14 +350,17 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         ph ^= 1;
         tc_fence_after();
     };
-    for (int grp = blockIdx.x; grp < g.ngroups; grp += gridDim.x) {
+    int it_ = 0;
+    for (int grp = blockIdx.x; grp < g.ngroups; grp += gridDim.x, ++it_) {
         const int b = grp / g.groups_per_b, t0 = (grp % g.groups_per_b) * g.nfr;
+        NBSS_TICK(1, 0, it_);
         if (tid == 0) load_image(wimg, a.img, FC_IMG_BYTES, bar_w);
         fc_stage<FMT, 5, NW>(g, a.x, b, t0, htile, cst, cst + 96, stats, warp, lane);
         fc_stage_plain<FMT, 5, NW>(g, a.dy, b, t0, gtile, warp, lane);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        NBSS_TICK(1, 1, it_);
         // ---- P1: recompute the conv
         if (warp == 0) {
             tc_fence_after();
@@ -362,6 +371,7 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         }
         ph_w ^= 1;
         wait_mma();
+        NBSS_TICK(1, 2, it_);
         if (tid == 0) load_image(wimg, a.img + FC_IMG_BYTES, FC_IMG_BYTES, bar_w);  // transposed image for the data gradient
         // ---- E-A: dc = dy * PReLU'(c), in place over the staged dy in gtile; column sums for dbias / dslope.
         //      work items (M-tile, 16-column block) are dealt to the four warp groups
@@ -401,6 +411,7 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        NBSS_TICK(1, 3, it_);
         // ---- P2: weight gradient  dW[co, ci, tap] += sum_q dc[q, co] * h[q + tap - 2, ci]   (MN-major x MN-major)
         if (warp == 0) {  // the whole warp runs the (uniform) descriptor arithmetic, one elected lane issues
             tc_fence_after();
@@ -417,6 +428,7 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
             if (leader) umma_commit(bar_mma);
         }
         wait_mma();
+        NBSS_TICK(1, 4, it_);
         if (q4 < 3) {
             // thread = out channel co (TMEM lane), taps dealt to the warp groups; it keeps the 12 in-channel columns
             // [12*(co/12), +12) of each tap.  tcgen05.ld takes ONE column address per warp, so every warp loads a uniform
@@ -444,6 +456,7 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         }
         tc_fence_before();
         __syncthreads();
+        NBSS_TICK(1, 5, it_);
         // ---- P3: data gradient of the conv
         if (warp == 0) {
             tc_fence_after();
@@ -454,6 +467,7 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         }
         ph_w ^= 1;
         wait_mma();
+        NBSS_TICK(1, 6, it_);
         // ---- E-B1: thread = tile row: d h (data gradient of the conv) -> 16-bit, over htile (dead after the weight
         //      gradient MMAs); gap rows are written as zeros so they keep acting as the next group's zero padding
 #pragma unroll 1
@@ -473,6 +487,7 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         }
         tc_fence_before();
         __syncthreads();
+        NBSS_TICK(1, 7, it_);
         // ---- E-B2: eight lanes per (frame, f) row, coalesced: LayerNorm backward + residual; d gamma / d beta per lane
         {
             constexpr int U = 3;
@@ -541,6 +556,7 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         }
         tc_fence_before();
         __syncthreads();
+        NBSS_TICK(1, 8, it_);
     }
     // ---- flush parameter gradients: one set of global atomics per CTA
     for (int i = tid; i < 96 * 60; i += NT) atomicAdd(a.dW + i, accdw[i]);
@@ -578,6 +594,8 @@ static bool fc_geom(FcGeom& g, int B, int F, int T, int max_tiles, int max_frame
 }
 
 }  // namespace nbss
+
+NBSS_PHASE_READER(nbss_debug_phases_fconv_tc)
 
 using namespace nbss;
 

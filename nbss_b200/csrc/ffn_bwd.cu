@@ -199,9 +199,11 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         }
     };
 
-    for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
+    int it_ = 0;
+    for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x, ++it_) {
         const size_t grow = (size_t)slab * T + t;
         const float* dys = a.dy + (size_t)slab * T * kH;
+        NBSS_TICK(0, 0, it_);
         if (tid == 0) {
             load_image(ws0, a.img + IMG_W2T, IMG_W1_BYTES, bar_w0);
             load_image(ws1, a.img + IMG_WC3T, IMG_WC_BYTES, bar_w1);
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         // ---- B0: dy -> G (chunks 0..11)
         stage_rows96<FMT, false, 2>(dys, T, hbuf, 1, nullptr, nullptr, warp, lane, nullptr, kFfnBwdThreads / 32);
         end_epilogue();
+        NBSS_TICK(0, 1, it_);
         // ---- B1: d s4 = dy W2
         if (warp == 0) {
             tc_fence_after();
@@ -221,11 +224,14 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         }
         ph_w0 ^= 1;
         wait_mma();
+        NBSS_TICK(0, 2, it_);
         if (tid == 0) load_image(ws0, a.img + IMG_WC2T, IMG_WC_BYTES, bar_w0);
         silu_epilogue(a.c3, a.g_c3, a.s4, slab);
         end_epilogue();
+        NBSS_TICK(0, 3, it_);
         // ---- B2: d s3 = conv3^T(g c3) ; E2: GroupNorm + SiLU backward
         convT_phase(w1a, bar_w1, ph_w1);
+        NBSS_TICK(0, 4, it_);
         if (tid == 0) load_image(ws1, a.img + IMG_WC1T, IMG_WC_BYTES, bar_w1);
         {
             const float* gst = a.gn_stats + (size_t)slab * 16;
@@ -303,15 +309,20 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
             }
         }
         end_epilogue();
+        NBSS_TICK(0, 5, it_);
         // ---- B3: d s2 = conv2^T(g c2)
         convT_phase(w0a, bar_w0, ph_w0);
+        NBSS_TICK(0, 6, it_);
         if (tid == 0) load_image(ws0, a.img + IMG_W1T, IMG_W2_BYTES, bar_w0);
         silu_epilogue(a.c1, a.g_c1, a.s2, slab);
         end_epilogue();
+        NBSS_TICK(0, 7, it_);
         // ---- B4: d s1 = conv1^T(g c1)
         convT_phase(w1a, bar_w1, ph_w1);
+        NBSS_TICK(0, 8, it_);
         silu_epilogue(a.a1, a.g_a1, a.s1, slab);
         end_epilogue();
+        NBSS_TICK(0, 9, it_);
         // ---- B5: d ln = g(a1) W1 ; E5: LayerNorm backward + residual
         if (warp == 0) {
             tc_fence_after();
@@ -324,6 +335,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         }
         ph_w0 ^= 1;
         wait_mma();
+        NBSS_TICK(0, 10, it_);
         {
             // E5a: thread = (frame, channel half): d ln (fp32) staged into the dead G tile with 4-float chunks
 #pragma unroll 1
@@ -339,6 +351,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
             }
             tc_fence_before();
             __syncthreads();
+            NBSS_TICK(0, 11, it_);
             // E5b: eight lanes per frame: LayerNorm backward + residual, coalesced; d gamma / d beta -> smem accumulators
             Oct12 dlng, dlnb;
             dlng.zero();
@@ -350,6 +363,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         }
         tc_fence_before();
         __syncthreads();
+        NBSS_TICK(0, 12, it_);
     }
     // flush the affine-parameter gradients
     for (int i = tid; i < 192; i += kFfnBwdThreads) { atomicAdd(a.d_gnw + i, acc[i]); atomicAdd(a.d_gnb + i, acc[192 + i]); }
@@ -358,6 +372,8 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
 }
 
 }  // namespace nbss
+
+NBSS_PHASE_READER(nbss_debug_phases_ffn_bwd)
 
 extern "C" int nbss_ffn_bwd(const float* x, const float* dy, float* dx, int nslab, int T, const float* ln_w,
                             const float* gn_w, const float* gn_b, const float* ln_stats, const float* gn_stats,

@@ -158,9 +158,11 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         }
     };
 
-    for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
+    int it_ = 0;
+    for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x, ++it_) {
         const float* xs = a.x + (size_t)slab * T * kH;
         const size_t grow = (size_t)slab * T + t;
+        NBSS_TICK(0, 0, it_);
         if (tid == 0) {
             load_image(ws0, a.img + IMG_W1, IMG_W1_BYTES, bar_w0);
             load_image(ws1, a.img + IMG_WC1, IMG_WC_BYTES, bar_w1);
@@ -168,6 +170,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         // ---- P0: LN(x) -> A0 (chunks 0..11 of H)
         stage_rows96<FMT, true>(xs, T, hbuf, 1, s_lng, s_lnb, warp, lane, a.ln_stats ? a.ln_stats + (size_t)slab * T * 2 : nullptr, kFfnThreads / 32);
         end_epilogue();
+        NBSS_TICK(0, 1, it_);
         // ---- P1: pw1
         if (warp == 0) {
             tc_fence_after();
@@ -183,17 +186,22 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         mbar_wait(m ? bar_mma1 : bar_mma, ph_mma, a.err);
         ph_mma ^= 1;
         tc_fence_after();
+        NBSS_TICK(0, 2, it_);
         if (tid == 0) load_image(ws0, a.img + IMG_WC2, IMG_WC_BYTES, bar_w0);
         // ---- E1: a1 = D + b1; H = SiLU(a1)
         act_epilogue(s_b1, a.save_a1, slab);
         end_epilogue();
+        NBSS_TICK(0, 3, it_);
         // ---- P2: conv1 ; E2: c1 = D + bc1; H = SiLU(c1)
         conv_phase(w1a, bar_w1, ph_w1);
+        NBSS_TICK(0, 4, it_);
         if (tid == 0) load_image(ws1, a.img + IMG_WC3, IMG_WC_BYTES, bar_w1);
         act_epilogue(s_bc, a.save_c1, slab);
         end_epilogue();
+        NBSS_TICK(0, 5, it_);
         // ---- P3: conv2 ; E3: c2 = D + bc2; GroupNorm over (24 ch x T) per group; H = SiLU(GN(c2))
         conv_phase(w0a, bar_w0, ph_w0);
+        NBSS_TICK(0, 6, it_);
         if (tid == 0) load_image(ws0, a.img + IMG_W2, IMG_W2_BYTES, bar_w0);
         {
             float* red_sum = red;       // [16 warps][8 groups] (a warp fills the 4 groups of its channel half)
@@ -270,10 +278,13 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
             }
         }
         end_epilogue();
+        NBSS_TICK(0, 7, it_);
         // ---- P4: conv3 ; E4: c3 = D + bc3; H = SiLU(c3)
         conv_phase(w1a, bar_w1, ph_w1);
+        NBSS_TICK(0, 8, it_);
         act_epilogue(s_bc + 384, a.save_c3, slab);
         end_epilogue();
+        NBSS_TICK(0, 9, it_);
         // ---- P5: pw2 ; E5: y = x + D + b2
         if (warp == 0) {
             tc_fence_after();
@@ -289,6 +300,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         mbar_wait(m ? bar_mma1 : bar_mma, ph_mma, a.err);
         ph_mma ^= 1;
         tc_fence_after();
+        NBSS_TICK(0, 10, it_);
         // E5a: thread = (frame, channel half): D + b2 -> fp32, staged into the (now dead) H tile with 4-float chunks at
         // the frame's row slot, so that E5b can do the residual add with coalesced warp-per-row global traffic
 #pragma unroll 1
@@ -308,15 +320,19 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         }
         tc_fence_before();
         __syncthreads();
+        NBSS_TICK(0, 11, it_);
         // E5b: eight lanes per frame: y = x + branch, coalesced
         add_rows(hbuf, kCS, 1, xs, a.y + (size_t)slab * T * kH, T, warp, lane, kFfnThreads / 32);
         tc_fence_before();
         __syncthreads();  // TMEM + H are reused by the next slab
+        NBSS_TICK(0, 12, it_);
     }
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace nbss
+
+NBSS_PHASE_READER(nbss_debug_phases_ffn_fwd)
 
 extern "C" int nbss_ffn_fwd(const float* x, float* y, int nslab, int T, const float* ln_w, const float* ln_b,
                             const float* b1, const float* bc1, const float* bc2, const float* bc3, const float* gn_w,

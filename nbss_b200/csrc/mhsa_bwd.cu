@@ -105,8 +105,10 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
         __syncthreads();
     };
 
-    for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
+    int it_ = 0;
+    for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x, ++it_) {
         const size_t row0 = (size_t)slab * T;
+        NBSS_TICK(0, 0, it_);
         if (tid == 0) load_image(pt, a.img + IMG_WOT, IMG_WQ_BYTES, bar_w);
         if (tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab)  // next slab's upstream gradient -> L2 (after the weight copy)
             l2_prefetch_slab(a.dy + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
         }
         stage_rows96<FMT_G, false>(a.dy + row0 * kH, T, dot, 0, nullptr, nullptr, warp, lane, nullptr, kMbThreads / 32);
         end_epilogue();
+        NBSS_TICK(0, 1, it_);
         // ---- M0: dO = dy Wo
         if (warp == 0) {
             tc_fence_after();
@@ -126,6 +129,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
         }
         ph_w ^= 1;
         wait_mma();
+        NBSS_TICK(0, 2, it_);
         // ---- E0: dO -> 16-bit tile (in place of dy), delta_h = sum_c dO O
         {
             const bool valid = t < T;
@@ -158,6 +162,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
             }
         }
         end_epilogue();
+        NBSS_TICK(0, 3, it_);
         // ---- heads
 #pragma unroll 1
         for (int h = 0; h < kNH; ++h) {
@@ -174,6 +179,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
             }
             ph_w ^= 1;
             end_epilogue();
+            NBSS_TICK(0, 4 + 12 * h, it_);
             // Software pipeline over the four 128x128 (query, key) blocks of the head: the S / dP MMAs of block b+1 are
             // issued together with the gradient MMAs of block b (different TMEM columns), so a block costs one
             // commit / wait round trip instead of two.
@@ -192,6 +198,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
             for (int blk = 0; blk < 4; ++blk) {
                 const int qb = blk >> 1, kb = blk & 1;
                 wait_mma();  // S, dP of this block (and the gradient MMAs of the previous one, which read the P / dS tiles)
+                NBSS_TICK(0, 5 + 12 * h + 2 * blk, it_);
                 // P and dS for this block: thread = (query row rt, key quarter kq: 32 of the 128 keys)
                 {
                     const int tq = 128 * qb + rt;
@@ -217,6 +224,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
                     }
                 }
                 end_epilogue();
+                NBSS_TICK(0, 6 + 12 * h + 2 * blk, it_);
                 if (warp == 0) {
                     tc_fence_after();
                     const bool leader = elect_one();
@@ -236,6 +244,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
                 }
             }
             wait_mma();  // the gradient MMAs of the last block
+            NBSS_TICK(0, 13 + 12 * h, it_);
             // read out dQ_h, dK_h, dV_h (thread = frame t of tile m) -> dQKV
             {
                 // tcgen05.ld is warp-collective: every lane issues it, only valid frames store
@@ -259,6 +268,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
             }
             tc_fence_before();
             __syncthreads();
+            NBSS_TICK(0, 14 + 12 * h, it_);
         }
     }
     if (warp == 0) tmem_dealloc(tmem, 512);
@@ -320,8 +330,10 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a
     const uint32_t id96 = make_idesc(FMT_G, 128, 96, 0, 0);
     uint32_t ph = 0, ph_ld = 0;
     bool wready = false;
-    for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
+    int it_ = 0;
+    for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x, ++it_) {
         const size_t row0 = (size_t)slab * T, grow = row0 + t;
+        NBSS_TICK(1, 0, it_);
         if (tid == 0) bulk_load_chunks(at, kCS, 0, a.dqkv + tile_off(slab, 36, T, 0, 0), 36, T, bar_ld);
         if (tid >= 32 && tid < 44) {  // this slab's x and dy rows (LayerNorm backward at the end of the iteration) -> L2
             const int i = tid - 32;
@@ -344,6 +356,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a
         mbar_wait(bar_mma, ph, a.err);
         ph ^= 1;
         tc_fence_after();
+        NBSS_TICK(1, 1, it_);
         // thread = (frame, channel half): d ln (fp32) staged into the dead dQKV tile (4-float chunks), then one warp per
         // frame does the LayerNorm backward + residual with coalesced global traffic (slab.cuh: ln_bwd_rows)
 #pragma unroll 1
@@ -359,6 +372,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a
         }
         tc_fence_before();
         __syncthreads();
+        NBSS_TICK(1, 2, it_);
         {
             Oct12 dlng, dlnb;
             dlng.zero();
@@ -370,12 +384,15 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a
         }
         tc_fence_before();
         __syncthreads();
+        NBSS_TICK(1, 3, it_);
     }
     for (int i = tid; i < 96; i += kMbThreads) { atomicAdd(a.d_lnw + i, acc[i]); atomicAdd(a.d_lnb + i, acc[96 + i]); }
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
 }  // namespace nbss
+
+NBSS_PHASE_READER(nbss_debug_phases_mhsa_bwd)
 
 // Backward of y = x + MHSA(LN(x)).  Writes dqkv (scratch, fmt_g [n,288], also consumed by nbss_mhsa_wgrad) and dx;
 // accumulates d_lnw / d_lnb.

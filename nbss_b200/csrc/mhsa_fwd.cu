@@ -109,13 +109,16 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         __syncthreads();
     };
 
-    for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x) {
+    int it_ = 0;
+    for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x, ++it_) {
         const float* xs = a.x + (size_t)slab * T * kH;
+        NBSS_TICK(0, 0, it_);
         if (tid == 0) load_image(wr, a.img + IMG_WKV, IMG_W1_BYTES, bar_w);
         if (tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab)  // next slab's input rows -> L2 (after the weight copy)
             l2_prefetch_slab(a.x + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
         stage_rows96<FMT, true>(xs, T, ao, 0, s_lng, s_lnb, warp, lane, a.ln_stats ? a.ln_stats + (size_t)slab * T * 2 : nullptr, kMhThreads / 32);
         end_epilogue();
+        NBSS_TICK(0, 1, it_);
         // ---- P1: K|V
         if (warp == 0) {
             tc_fence_after();
@@ -126,6 +129,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         }
         ph_w ^= 1;
         wait_mma();
+        NBSS_TICK(0, 2, it_);
         if (tid == 0) load_image(wr, a.img + IMG_WQ, IMG_WQ_BYTES, bar_w);
         {
             const bool valid = t < T;
@@ -160,6 +164,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
             }
         }
         end_epilogue();
+        NBSS_TICK(0, 3, it_);
         // ---- P2: Q (stays in TMEM cols 0..191)
         if (warp == 0) {
             tc_fence_after();
@@ -170,6 +175,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         }
         ph_w ^= 1;
         wait_mma();
+        NBSS_TICK(0, 4, it_);
         // ---- heads x query tiles
 #pragma unroll 1
         for (int hm = 0; hm < 2 * kNH; ++hm) {
@@ -194,6 +200,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
                 *reinterpret_cast<uint4*>(qs + 3 * kCSP + rt * 16) = make_uint4(0, 0, 0, 0);
             }
             end_epilogue();
+            NBSS_TICK(0, 8 + 5 * hm, it_);
             // S = Qs K_h^T
             if (warp == 0) {
                 tc_fence_after();
@@ -202,6 +209,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
                 if (leader) umma_commit(bar_mma);
             }
             wait_mma();
+            NBSS_TICK(0, 9 + 5 * hm, it_);
             // softmax: thread = (query row rt, key quarter kq): 64 of the 256 score columns
             const uint32_t ts = tmem + lane_off + 192 + 64 * kq;
             float mx = -INFINITY;
@@ -251,6 +259,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
                 }
                 tmem_st_wait();
                 end_epilogue();
+                NBSS_TICK(0, 10 + 5 * hm, it_);
                 if (warp == 0) {
                     tc_fence_after();
                     const bool leader = elect_one();
@@ -259,6 +268,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
                     if (leader) umma_commit(bar_mma);
                 }
                 wait_mma();
+                NBSS_TICK(0, 11 + 5 * hm, it_);
             } else {
             // O_h = P V_h, one key half at a time (the P tile holds 128 keys = two key quarters)
 #pragma unroll
@@ -301,6 +311,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
             }
             tc_fence_before();
             __syncthreads();
+            NBSS_TICK(0, 12 + 5 * hm, it_);
         }
         // ---- P3: out-proj + residual
         if (tid == 0) load_image(wr, a.img + IMG_WO, IMG_WQ_BYTES, bar_w);
@@ -314,6 +325,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         }
         ph_w ^= 1;
         wait_mma();
+        NBSS_TICK(0, 5, it_);
         {
             // thread = (frame, channel half): D + b_out -> fp32, staged into the dead K|V tiles at the frame's row slot (24
             // four-float chunks = the 12 K data chunks + V chunks 0..11; the zero pad chunks of K stay untouched:
@@ -336,15 +348,19 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
             }
             tc_fence_before();
             __syncthreads();
+            NBSS_TICK(0, 6, it_);
             add_rows<true>(kt, kCS, 0, xs, a.y + (size_t)slab * T * kH, T, warp, lane, kMhThreads / 32);
         }
         tc_fence_before();
         __syncthreads();
+        NBSS_TICK(0, 7, it_);
     }
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace nbss
+
+NBSS_PHASE_READER(nbss_debug_phases_mhsa_fwd)
 
 extern "C" int nbss_mhsa_fwd(const float* x, float* y, int nslab, int T, const float* ln_w, const float* ln_b,
                              const float* b_in, const float* b_out, const void* layer_img, void* save_qkv, void* save_o,

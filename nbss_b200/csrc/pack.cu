@@ -70,6 +70,26 @@ __global__ void pack_layer_kernel(PackArgs a) {
 
 extern "C" unsigned int nbss_layer_image_bytes() { return nbss::IMG_LAYER_BYTES; }
 
+// ABI version of this library: 100 * round + revision (nbss_version()).
+extern "C" int nbss_version() { return 200; }
+
+// Bytes of caller-owned scratch one SpatialNetLayer needs around its kernels at [B,F,T] (SURVEY.md §8b:
+// nbss_workspace_bytes()): training = activations saved by the forward for the backward kernels plus the transient
+// gradient-operand tensors of the backward; inference = 0 (every sub-block updates the stream in place).
+extern "C" long long nbss_workspace_bytes(int B, int F, int T, int training) {
+    if (B < 1 || F < 1 || T < 1) return -1;
+    if (!training) return 0;
+    const long long n = (long long)B * F * T, nslab = (long long)B * F;
+    const long long stream = n * 96 * 4;
+    long long saved = 5 * stream;                         // the five sub-block inputs (fp32 stream)
+    saved += n * (288 + 96) * 2 + nslab * 4 * T * 4;      // fp16 q|k|v, O, log2-sum-exp
+    saved += 4 * n * 192 * 2 + nslab * 16 * 4;            // fp16 T-ConvFFN pre-activations, GroupNorm statistics
+    saved += 2 * n * 2 * 4;                               // LayerNorm statistics of the two narrow-band sub-blocks
+    saved += 2 * (long long)B * T * 8 * F * 4;            // squeeze / full-band outputs [B,T,8,F]
+    const long long transient = 4 * n * 192 * 2 + n * 288 * 2 + 2 * stream;  // gradient operands + two stream gradients
+    return saved + transient;
+}
+
 extern "C" int nbss_pack_layer_weights(const float* w1, const float* wc1, const float* wc2, const float* wc3,
                                        const float* w2, const float* w_in, const float* w_out, void* img, int fwd_fmt,
                                        int bwd_fmt, void* stream) {

@@ -57,6 +57,10 @@ class NegSiSdrPitLoss(nn.Module):
     name = "neg_si_sdr"
     mask = None
 
+    def to_CC(self, out: Tensor, Xr: Tensor, stft, XrMM: Tensor):
+        """Loss.to_CC for a non-mask loss (models/io/loss.py:120-126): the network output is the estimate itself."""
+        return out, {"out": out, "Xr": Xr, "stft": stft, "XrMM": XrMM}
+
     def forward(self, yr_hat: Tensor, yr: Tensor, reorder: Optional[bool] = None, reduce_batch: bool = True, **kwargs):
         loss, loss_b, perms = neg_si_sdr_pit(yr_hat, yr)
         if reorder:

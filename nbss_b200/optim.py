@@ -43,6 +43,15 @@ class FlatClipAdam:
         flat = getattr(self.module, "_last_flat_grad", None)
         if flat is None or flat.numel() != self.n:
             raise _lib.NbssError("FlatClipAdam.step(): no flat gradient buffer (run a backward through nbss_b200.SpatialNet first)")
+        if not self.module.grads_alias_flat():
+            # gradient accumulation without zero_grad, a DDP bucket copy-back, user hooks ...: the p.grad tensors are the
+            # truth, so gather them into the flat buffer (one small copy per tensor) instead of stepping on a stale buffer
+            if any(p.grad is None for p in self._params):
+                raise _lib.NbssError("FlatClipAdam.step(): some parameters have no gradient")
+            off = 0
+            for p in self._params:
+                flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
+                off += p.numel()
         b1, b2 = self.betas
         _lib.check(ops._K("nbss_clip_adam")(_lib.ptr(self.ptrs), _lib.ptr(self.offsets), len(self._params), ctypes.c_longlong(self.n),
                                             _lib.ptr(flat), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(self.gnorm_sq),

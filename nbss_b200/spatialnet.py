@@ -13,6 +13,7 @@ accumulation in the narrow-band block.
 from __future__ import annotations
 
 import math
+import weakref
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -217,15 +218,23 @@ class _SpatialNetFn(torch.autograd.Function):
     @staticmethod
     def forward(fctx, module: "SpatialNet", x: Tensor, *params: Tensor):
         P = module._param_dict()
+        module._poll_device_errors()
         y, ctx, errs = module.engine.forward(P, x.detach().float(), save=True)
         fctx.module, fctx.ctx, fctx.errs = module, ctx, errs
+        module._live_graphs.add(fctx)  # weak: a graph that is dropped without a backward disappears by itself
         return y
 
     @staticmethod
     def backward(fctx, dy: Tensor):
         module = fctx.module
+        if fctx.ctx is None:
+            raise ops._lib.NbssError("nbss_b200.SpatialNet: backward through the same graph twice is not supported (the saved "
+                                     "activations are freed layer by layer during the first backward); re-run the forward")
         P = module._param_dict()
-        flat, G, views = module.make_flat_grads(dy.device)
+        # another forward of this module is still waiting for its backward (two forwards, one loss.backward()): its views
+        # of the persistent buffer may already sit in the autograd engine's input buffers, so this node gets a fresh buffer
+        fresh = any(c is not fctx and getattr(c, "ctx", None) is not None for c in module._live_graphs)
+        flat, G, views = module.make_flat_grads(dy.device, fresh=fresh)
         # fp16 gradient operands: the backward is linear in dy, so scale dy by a power of two that brings its largest
         # element to ~1 and undo it on the flat gradient buffer (exact loss scaling, no host synchronisation)
         dy = dy.contiguous().float()
@@ -239,6 +248,8 @@ class _SpatialNetFn(torch.autograd.Function):
         module._last_errs = fctx.errs + errs
         if _CHECK_EVERY_STEP:
             module.check_device_errors()
+        else:
+            module._post_device_error_check(dy.device)
         fctx.ctx = None
         return (None, None) + tuple(views)
 
@@ -272,6 +283,7 @@ class SpatialNet(nn.Module):
         self.layers = nn.ModuleList(layers)
         self.decoder = nn.Linear(dim_hidden, dim_output)
         self.engine = Engine(num_layers)
+        self._live_graphs = weakref.WeakSet()  # autograd contexts of forwards whose backward has not run yet
         self._aliases: Dict[str, List[str]] = {}
         self._build_aliases()
 
@@ -285,7 +297,7 @@ class SpatialNet(nn.Module):
                 self._aliases[name] = []
             self._aliases[first[id(p)]].append(name)
 
-    def make_flat_grads(self, device):
+    def make_flat_grads(self, device, fresh: bool = False):
         """One contiguous zero fp32 buffer holding every parameter gradient; returns (flat, name->view dict covering all
         state-dict aliases of shared tensors, list of views in parameter registration order).
 
@@ -295,7 +307,9 @@ class SpatialNet(nn.Module):
         uniq = self._unique_params()
         n = sum(p.numel() for _, p in uniq)
         flat = getattr(self, "_flat_grad_buf", None)
-        if flat is None or flat.device != torch.device(device) or flat.numel() != n:
+        if fresh:
+            flat = torch.zeros(n, dtype=torch.float32, device=device)
+        elif flat is None or flat.device != torch.device(device) or flat.numel() != n:
             flat = self._flat_grad_buf = torch.zeros(n, dtype=torch.float32, device=device)
         else:
             base = flat.untyped_storage().data_ptr()
@@ -325,18 +339,49 @@ class SpatialNet(nn.Module):
         return list(self.named_parameters())  # duplicates removed, registration order
 
     def _param_dict(self) -> Dict[str, Tensor]:
-        return {n: p.data for n, p in self.named_parameters(remove_duplicate=False)}
+        # p.detach() shares the parameter's version counter (p.data would start a fresh one): an in-place update by any
+        # torch optimizer, load_state_dict() or p.copy_() changes the keys of the cached weight images (Engine.images)
+        return {n: p.detach() for n, p in self.named_parameters(remove_duplicate=False)}
 
     def forward(self, x: Tensor, return_attn_score: bool = False):
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad:
             y = _SpatialNetFn.apply(self, x, *[p for _, p in self._unique_params()])
         else:
+            self._poll_device_errors()
             y, _, errs = self.engine.forward(self._param_dict(), x.detach().float().contiguous(), save=False)
             self._last_errs = errs
+            self._post_device_error_check(x.device)
         if return_attn_score:
             return y, [None] * len(self.layers)  # the reference also returns None here (SpatialNet.py:97 quirk)
         return y
+
+    def _post_device_error_check(self, device) -> None:
+        """Queues an asynchronous copy of the device error flag into pinned host memory (no host sync); the value is looked
+        at by the NEXT forward (`_poll_device_errors`), i.e. one step late, which keeps a timed-out barrier from silently
+        corrupting a whole run.  Skipped under CUDA-graph capture (replays cannot raise)."""
+        if torch.cuda.is_current_stream_capturing():
+            return
+        host = getattr(self, "_err_host", None)
+        if host is None:
+            host = self._err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._err_event = torch.cuda.Event()
+        host.copy_(ops.device_err_flag(torch.device(device)), non_blocking=True)
+        self._err_event.record()
+        self._err_posted = True
+
+    def _poll_device_errors(self) -> None:
+        if not getattr(self, "_err_posted", False) or torch.cuda.is_current_stream_capturing():
+            return
+        if not self._err_event.query():  # the copy has not finished yet: look again at the next call
+            return
+        self._err_posted = False
+        v = int(self._err_host.item())
+        if v != 0:
+            for f in list(ops._ERR_FLAGS.values()):
+                f.zero_()  # reset, so the caller can recover (e.g. re-run the step)
+            raise ops._lib.NbssError(f"nbss_b200 kernel: device-side error flag {v:#x} was raised during the previous step (an mbarrier "
+                                     "wait timed out: GPU time-slicing, preemption or a debugger); that step's results are invalid")
 
     def check_device_errors(self) -> None:
         """Raises if any tensor-core kernel launched so far reported an mbarrier time-out (host sync)."""

@@ -271,7 +271,7 @@ GRAD_TOL = {ops.FMT_BF16: 2e-2, ops.FMT_F16: 4e-3}  # 16-bit gradient operands (
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("fmt_g", [ops.FMT_F16, ops.FMT_BF16])
-@pytest.mark.parametrize("T", [250, 64])
+@pytest.mark.parametrize("T", [250, 251, 64])
 def test_ffn_bwd(T, fmt_g):
     GRAD_TOL_ = GRAD_TOL[fmt_g]
     P, Pd = _params()
@@ -301,7 +301,7 @@ def test_ffn_bwd(T, fmt_g):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("T", [250, 64])
+@pytest.mark.parametrize("T", [250, 251, 64])
 def test_mhsa_bwd(T):
     fmt_g = ops.FMT_F16  # q,k,v,O are saved in fp16 and one MMA cannot mix fp16 with bf16 operands
     GRAD_TOL_ = GRAD_TOL[fmt_g]

@@ -169,3 +169,36 @@ def test_oracle_si_sdr_pit_properties():
     # zero_mean=True is the plain formula on the centred signals, whatever DC offset they carry
     centred = O.si_sdr(est - est.mean(-1, keepdim=True), ref - ref.mean(-1, keepdim=True))
     assert torch.allclose(O.si_sdr(est + 0.3, ref - 0.1, zero_mean=True), centred, atol=1e-9)
+
+
+def test_eager_opset_restatement_matches_oracle():
+    """oracle/eager_gpu.py (the reference's op-set as torch.nn.functional calls: what bench.py times on the GPU as the
+    eager baseline and on the host cores as the CPU arm) computes the same function as the pinned oracle: identical in
+    fp64 (1e-10), and its fp32 gradients are within 5e-4 of fp64 autograd (the explicit-math oracle's own fp32 gradients are
+    only good to ~3e-3 on some tensors, which is why the GPU gradient tests compare against fp64)."""
+    from oracle import eager_gpu as E
+
+    cfg = dict(O.SMALL_CFG, num_layers=2)
+    g = torch.Generator().manual_seed(0)
+    x = 0.1 * torch.randn(2, 6, 128 * 20, generator=g)
+    tgt = 0.1 * torch.randn(2, 2, 128 * 20, generator=g)
+
+    def run(fwd, loss, dt):
+        P = O.synth_params(cfg, 3, dtype=dt)
+        seen, Pl = {}, {}
+        for k, v in P.items():
+            if id(v) not in seen:
+                seen[id(v)] = v.clone().requires_grad_(True)
+            Pl[k] = seen[id(v)]
+        est = fwd(Pl, x.to(dt), cfg)
+        loss(est, tgt.to(dt)).backward()
+        return est.detach(), {k: v.grad for k, v in Pl.items()}
+
+    o64, g_o64 = run(O.io_forward, lambda e, t: O.neg_si_sdr_pit(e, t)[0], torch.float64)
+    e64, g_e64 = run(E.io_forward, E.neg_si_sdr_pit2, torch.float64)
+    e32, g_e32 = run(E.io_forward, E.neg_si_sdr_pit2, torch.float32)
+    assert O.rel_l2(e64, o64) < 1e-10
+    for k in g_o64:
+        assert O.rel_l2(g_e64[k], g_o64[k]) < 1e-10, k
+        assert O.rel_l2(g_e32[k], g_o64[k]) < 5e-4, k
+    assert O.rel_l2(e32, o64) < 5e-5

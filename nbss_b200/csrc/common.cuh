@@ -50,9 +50,36 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// SiLU and its derivative (fp32, accurate exp: the parity budget is spent on 16-bit MMA operands, not here).
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// SiLU and its derivative (fp32).  The activation epilogues of the T-ConvFFN kernels are bound by the MUFU pipe (16 results
+// per clock per SM): 1 / (1 + exp(-x)) costs two MUFU operations per element (EX2, RCP).  sigmoid(x) = 0.5 + 0.5 tanh(x / 2)
+// costs ONE (MUFU.TANH, max relative error 2^-11, i.e. an absolute error <= 2.5e-4 on the sigmoid — the same size as the
+// rounding of the result to an fp16 MMA operand, which is where every one of these values goes next).
+// -DNBSS_SILU_EXACT selects the two-MUFU form (ex2.approx.ftz + rcp.approx.ftz: ~2 ulp) for A/B accuracy measurements.
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+#ifdef NBSS_SILU_EXACT
+__device__ __forceinline__ float sigmoidf_(float x) { return rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float silu(float x) { return x * sigmoidf_(x); }
+#else
+__device__ __forceinline__ float sigmoidf_(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
+__device__ __forceinline__ float silu(float x) {
+    const float h = 0.5f * x;
+    return fmaf(h, tanh_approx(h), h);
+}
+#endif
 __device__ __forceinline__ float silu_grad(float x) {
     float s = sigmoidf_(x);
     return s * (1.f + x * (1.f - s));

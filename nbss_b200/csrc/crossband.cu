@@ -5,6 +5,7 @@
 //   fullgemm           : u[b,t,g,:] = Wf[g] s[b,t,g,:] + bf  (LinearGroup, linear_group.py:29-34) + dgrad + wgrad
 //   unsqueeze_{fwd,bwd}: y = x + SiLU(Wun u + b)
 // These are 8 % of the layer FLOPs; they are HBM/L2-streaming kernels, fp32 end to end.
+#define NBSS_SILU_EXACT  // two-MUFU sigmoid (common.cuh): the fp32 cross-check kernels are held to 1e-5 by the tests
 #include <cstdlib>
 
 #include "common.cuh"

@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
     const int t = 128 * m + 32 * q + lane;
     const bool valid = t < T;
     const float vmask = valid ? 1.f : 0.f;
+    const bool wfull = 128 * m + 32 * q + 31 < T;  // warp-uniform: every frame of this warp is valid, no masking needed
     const uint32_t tacc = tmem + ((uint32_t)(32 * q) << 16) + m * 192;
     unsigned char* hrow = hbuf + (t + 1) * 16;
     const uint32_t hb = smem_u32(hbuf), w0a = smem_u32(ws0), w1a = smem_u32(ws1);
@@ -157,8 +158,12 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         for (int j = 0; j < 16; ++j) {
             const float cv = c[j];
             const float sg = sigmoidf_(cv);
-            g[j] = __uint_as_float(r[j]) * sg * (1.f + cv * (1.f - sg)) * vmask;
+            g[j] = __uint_as_float(r[j]) * sg * fmaf(cv, 1.f - sg, 1.f);
             c[j] = cv * sg;
+        }
+        if (!wfull) {  // frames >= T: zero gradient rows (they are the transposed conv's zero padding)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g[j] *= vmask;
         }
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
@@ -208,6 +213,11 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
             load_image(ws0, a.img + IMG_W2T, IMG_W1_BYTES, bar_w0);
             load_image(ws1, a.img + IMG_WC3T, IMG_WC_BYTES, bar_w1);
         }
+        if (tid >= 32 && tid < 44) {  // -> L2: this slab's x rows (LayerNorm backward at the end of the iteration), next slab's dy
+            const int i = tid - 32;
+            if (i < 6) l2_prefetch_slab(a.x + (size_t)slab * T * kH, T, i);
+            else if (slab + (int)gridDim.x < a.nslab) l2_prefetch_slab(a.dy + (size_t)(slab + gridDim.x) * T * kH, T, i - 6);
+        }
         // ---- B0: dy -> G (chunks 0..11)
         stage_rows96<FMT, false, 2>(dys, T, hbuf, 1, nullptr, nullptr, warp, lane, nullptr, kFfnBwdThreads / 32);
         end_epilogue();
@@ -234,37 +244,72 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         NBSS_TICK(0, 4, it_);
         if (tid == 0) load_image(ws1, a.img + IMG_WC1T, IMG_WC_BYTES, bar_w1);
         {
+            // GroupNorm + SiLU backward in two sweeps over the thread's 96 accumulator columns.  Both sweeps are software-
+            // pipelined (TMEM and global loads of the next 16 columns in flight while 16 are processed) and the second one
+            // needs NO global reads: sweep A parks the saved c2 bits in the G tile (dead after the conv^T MMAs) and writes
+            // dn = d s3 * SiLU'(n) back over the accumulator columns in tensor memory (fp32, tcgen05.st).
             const float* gst = a.gn_stats + (size_t)slab * 16;
-            // pass A: s3 out, dn -> G tile, group sums S1 = sum dn*gamma, S2 = sum dn*gamma*xhat
-#pragma unroll 1
-            for (int g = 4 * hf; g < 4 * hf + 4; ++g) {
-                const float mean = gst[2 * g], rstd = gst[2 * g + 1];
-                float s1 = 0.f, s2 = 0.f;
+            float gmean[4], grstd[4], s1g[4] = {0.f, 0.f, 0.f, 0.f}, s2g[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int c = kGC * g + 8 * k;
-                    uint32_t r[8];
-                    tmem_ld8(tacc + c, r);
-                    tmem_ld_wait();
-                    float cv[8], dn[8];
-                    if (valid) load_h16x8(a.c2, slab, T, t, c, cv);
+            for (int gl = 0; gl < 4; ++gl) { gmean[gl] = gst[2 * (4 * hf + gl)]; grstd[gl] = gst[2 * (4 * hf + gl) + 1]; }
+            // sweep A: s3 out, c2 -> G tile, dn -> TMEM, group sums S1 = sum dn*gamma, S2 = sum dn*gamma*xhat
+            auto sweepA16 = [&](const uint32_t (&r)[16], const uint4 (&cq)[2], int b) {  // b: compile-time after unrolling
+                const int c0 = cb + 16 * b;
+                float c[16];
+                uint32_t dn[16];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float xh = valid ? (cv[j] - mean) * rstd : 0.f;
-                        const float n = xh * s_gng[c + j] + s_gnb[c + j];
-                        const float sg = sigmoidf_(n);
-                        dn[j] = valid ? __uint_as_float(r[j]) * sg * (1.f + n * (1.f - sg)) : 0.f;
-                        cv[j] = n * sg;  // s3
-                        const float dxh = dn[j] * s_gng[c + j];
-                        s1 += dxh;
-                        s2 += dxh * xh;
-                    }
-                    if (valid) *reinterpret_cast<uint4*>(a.s3 + tile_off(slab, 24, T, c / 8, t)) = pack8<FMT>(cv);
-                    *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = pack8<FMT>(dn);
+                for (int cc = 0; cc < 2; ++cc) {
+                    unpack_f16x2(cq[cc].x, c[8 * cc + 0], c[8 * cc + 1]);
+                    unpack_f16x2(cq[cc].y, c[8 * cc + 2], c[8 * cc + 3]);
+                    unpack_f16x2(cq[cc].z, c[8 * cc + 4], c[8 * cc + 5]);
+                    unpack_f16x2(cq[cc].w, c[8 * cc + 6], c[8 * cc + 7]);
                 }
-                s1 = warp_sum(s1);
-                s2 = warp_sum(s2);
-                if (lane == 0) { red[(warp * 8 + g) * 2] = s1; red[(warp * 8 + g) * 2 + 1] = s2; }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int gl = (16 * b + j) / kGC;
+                    const float xh = (c[j] - gmean[gl]) * grstd[gl];
+                    const float n = fmaf(xh, s_gng[c0 + j], s_gnb[c0 + j]);
+                    const float sg = sigmoidf_(n);
+                    float d = __uint_as_float(r[j]) * sg * fmaf(n, 1.f - sg, 1.f);
+                    if (!wfull) d *= vmask;  // warp-uniform branch: frames >= T carry no gradient
+                    c[j] = n * sg;           // s3
+                    const float dxh = d * s_gng[c0 + j];
+                    s1g[gl] += dxh;
+                    s2g[gl] = fmaf(dxh, xh, s2g[gl]);
+                    dn[j] = __float_as_uint(d);
+                }
+                tmem_st16(tacc + c0, dn);
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    if (valid) *reinterpret_cast<uint4*>(a.s3 + tile_off(slab, 24, T, c0 / 8 + cc, t)) = pack8<FMT>(c + 8 * cc);
+                    *reinterpret_cast<uint4*>(hrow + (c0 / 8 + cc) * kCS) = cq[cc];
+                }
+            };
+            {
+                uint32_t ra[16], rb[16];
+                uint4 ca[2], cb2[2];
+                load_c(a.c2, slab, cb, ca);
+                tmem_ld16(tacc + cb, ra);
+                tmem_ld_wait();
+#pragma unroll
+                for (int b = 0; b < 6; b += 2) {
+                    tmem_ld16(tacc + cb + 16 * (b + 1), rb);
+                    load_c(a.c2, slab, cb + 16 * (b + 1), cb2);
+                    sweepA16(ra, ca, b);
+                    tmem_ld_wait();
+                    if (b + 2 < 6) {
+                        tmem_ld16(tacc + cb + 16 * (b + 2), ra);
+                        load_c(a.c2, slab, cb + 16 * (b + 2), ca);
+                    }
+                    sweepA16(rb, cb2, b + 1);
+                    tmem_ld_wait();
+                }
+                tmem_st_wait();
+            }
+#pragma unroll
+            for (int gl = 0; gl < 4; ++gl) {
+                const float s1 = warp_sum(s1g[gl]), s2 = warp_sum(s2g[gl]);
+                if (lane == 0) { red[(warp * 8 + 4 * hf + gl) * 2] = s1; red[(warp * 8 + 4 * hf + gl) * 2 + 1] = s2; }
             }
             __syncthreads();
             if (tid < 16) {
@@ -274,37 +319,53 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
                 gtot[tid] = s * inv_n;
             }
             __syncthreads();
-            // pass B: g(c2) = rstd * (dn*gamma - S1/N - xhat*S2/N) -> G tile + global; column sums for d_gnw, d_gnb
-#pragma unroll 1
-            for (int c0 = cb; c0 < cb + 96; c0 += 16) {
+            // sweep B: g(c2) = rstd * (dn*gamma - S1/N - xhat*S2/N) -> G tile + global; column sums for d_gnw, d_gnb
+            auto sweepB16 = [&](const uint32_t (&r)[16], int b) {
+                const int c0 = cb + 16 * b;
                 float dnv[16], dnx[16];
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
-                    const int c = c0 + 8 * cc, g = c / kGC;
-                    const float mean = gst[2 * g], rstd = gst[2 * g + 1], m1 = gtot[2 * g], m2 = gtot[2 * g + 1];
+                    const uint4 pk = *reinterpret_cast<const uint4*>(hrow + (c0 / 8 + cc) * kCS);  // the c2 bits parked by sweep A
                     float cv[8], gv[8];
-                    if (valid) load_h16x8(a.c2, slab, T, t, c, cv);
-                    const uint4 pk = *reinterpret_cast<const uint4*>(hrow + (c / 8) * kCS);
-                    float dn[8];
-                    unpack16<FMT>(pk.x, dn[0], dn[1]);
-                    unpack16<FMT>(pk.y, dn[2], dn[3]);
-                    unpack16<FMT>(pk.z, dn[4], dn[5]);
-                    unpack16<FMT>(pk.w, dn[6], dn[7]);
+                    unpack_f16x2(pk.x, cv[0], cv[1]);
+                    unpack_f16x2(pk.y, cv[2], cv[3]);
+                    unpack_f16x2(pk.z, cv[4], cv[5]);
+                    unpack_f16x2(pk.w, cv[6], cv[7]);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float xh = valid ? (cv[j] - mean) * rstd : 0.f;
-                        dnv[8 * cc + j] = dn[j];
-                        dnx[8 * cc + j] = dn[j] * xh;
-                        gv[j] = valid ? rstd * (dn[j] * s_gng[c + j] - m1 - xh * m2) : 0.f;
+                        const int gl = (16 * b + 8 * cc + j) / kGC, g = 4 * hf + gl;
+                        const float xh = (cv[j] - gmean[gl]) * grstd[gl];
+                        const float d = __uint_as_float(r[8 * cc + j]);  // 0 for frames >= T
+                        dnv[8 * cc + j] = d;
+                        dnx[8 * cc + j] = d * xh;
+                        gv[j] = grstd[gl] * (d * s_gng[c0 + 8 * cc + j] - gtot[2 * g] - xh * gtot[2 * g + 1]);
+                    }
+                    if (!wfull) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) gv[j] *= vmask;
                     }
                     const uint4 gp = pack8<FMT>(gv);
-                    if (valid) *reinterpret_cast<uint4*>(a.g_c2 + tile_off(slab, 24, T, c / 8, t)) = gp;
-                    *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = gp;
+                    if (valid) *reinterpret_cast<uint4*>(a.g_c2 + tile_off(slab, 24, T, c0 / 8 + cc, t)) = gp;
+                    *reinterpret_cast<uint4*>(hrow + (c0 / 8 + cc) * kCS) = gp;
                 }
                 const float sw = warp_colsum16(dnx, lane), sb = warp_colsum16(dnv, lane);
                 if (!(lane & 1)) {
                     atomicAdd(acc + c0 + (lane >> 1), sw);
                     atomicAdd(acc + 192 + c0 + (lane >> 1), sb);
+                }
+            };
+            {
+                uint32_t ra[16], rb[16];
+                tmem_ld16(tacc + cb, ra);
+                tmem_ld_wait();
+#pragma unroll
+                for (int b = 0; b < 6; b += 2) {
+                    tmem_ld16(tacc + cb + 16 * (b + 1), rb);
+                    sweepB16(ra, b);
+                    tmem_ld_wait();
+                    if (b + 2 < 6) tmem_ld16(tacc + cb + 16 * (b + 2), ra);
+                    sweepB16(rb, b + 1);
+                    tmem_ld_wait();
                 }
             }
         }

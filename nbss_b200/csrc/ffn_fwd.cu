@@ -31,9 +31,9 @@ constexpr uint32_t FF_HBUF = 0;
 constexpr uint32_t FF_WS0 = 24 * kCS;               // 101760
 constexpr uint32_t FF_WS1 = FF_WS0 + IMG_WC_BYTES;  // 157056
 constexpr uint32_t FF_CST = FF_WS1 + IMG_WC_BYTES;  // 212352
-constexpr uint32_t FF_NCST = 1440;                  // floats
-constexpr uint32_t FF_RED = FF_CST + FF_NCST * 4;   // 2 x [16 warps][8 groups] floats
-constexpr uint32_t FF_BAR = FF_RED + 1024;
+constexpr uint32_t FF_NCST = 1448;                  // floats (1440 parameters + 8 GroupNorm pivots)
+constexpr uint32_t FF_RED = FF_CST + FF_NCST * 4;   // 2 x [16 warps][8 groups] floats + [8][2] group (mean, rstd)
+constexpr uint32_t FF_BAR = FF_RED + 1024 + 64;
 constexpr int kFfnThreads = 512;  // 16 warps: warp w -> M-tile (w>>2)&1, TMEM lane quarter w&3, channel half w>>3
 constexpr uint32_t FF_SMEM = FF_BAR + 64;
 
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
     unsigned char* ws1 = smem + FF_WS1;
     float* cst = reinterpret_cast<float*>(smem + FF_CST);
     float *s_lng = cst, *s_lnb = cst + 96, *s_b1 = cst + 192, *s_bc = cst + 384, *s_gng = cst + 960, *s_gnb = cst + 1152,
-          *s_b2 = cst + 1344;
+          *s_b2 = cst + 1344, *s_piv = cst + 1440;
     float* red = reinterpret_cast<float*>(smem + FF_RED);
     uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + FF_BAR);
     uint64_t* bar_mma1 = bar_mma + 1;  // one commit barrier per M-tile: tile 0's epilogue warps start while tile 1's MMAs run
@@ -80,6 +80,11 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         s_b1[i] = a.b1[i]; s_bc[i] = a.bc1[i]; s_bc[192 + i] = a.bc2[i]; s_bc[384 + i] = a.bc3[i];
         s_gng[i] = a.gn_w[i]; s_gnb[i] = a.gn_b[i];
     }
+    if (tid < 8) {  // GroupNorm pivot of group tid: the mean of its conv2 biases
+        float p = 0.f;
+        for (int j = 0; j < kGC; ++j) p += a.bc2[kGC * tid + j];
+        s_piv[tid] = p * (1.f / kGC);
+    }
     for (int i = tid; i < (int)(24 * kCS / 16); i += kFfnThreads) reinterpret_cast<uint4*>(hbuf)[i] = make_uint4(0, 0, 0, 0);
     fence_async_smem();
     tc_fence_before();
@@ -91,7 +96,8 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
     const int cb = 96 * hf;                                     // first of this thread's 96 (of 192) channels
     const int t = 128 * m + 32 * q + lane;
     const bool valid = t < T;
-    const float vmask = valid ? 1.f : 0.f;  // frames >= T are written as zeros (conv zero padding) without branching
+    const float vmask = valid ? 1.f : 0.f;  // frames >= T are written as zeros (the conv's zero padding)
+    const bool wfull = 128 * m + 32 * q + 31 < T;  // warp-uniform: every frame of this warp is valid, no masking needed
     const uint32_t tacc = tmem + ((uint32_t)(32 * q) << 16) + m * 192;
     unsigned char* hrow = hbuf + (t + 1) * 16;
     const uint32_t hb = smem_u32(hbuf), w0a = smem_u32(ws0), w1a = smem_u32(ws1);
@@ -137,7 +143,11 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
             *reinterpret_cast<uint4*>(save + tile_off(slab, 24, T, c0 / 8 + 1, t)) = pack8<FMT_F16>(v + 8);
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = silu(v[j]) * vmask;  // branch-free: keeps the chains interleaved
+        for (int j = 0; j < 16; ++j) v[j] = silu(v[j]);
+        if (!wfull) {  // only the warp(s) that hold frames >= T pay for the mask
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] *= vmask;
+        }
         *reinterpret_cast<uint4*>(hrow + (c0 / 8) * kCS) = pack8<FMT>(v);
         *reinterpret_cast<uint4*>(hrow + (c0 / 8 + 1) * kCS) = pack8<FMT>(v + 8);
     };
@@ -167,6 +177,8 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
             load_image(ws0, a.img + IMG_W1, IMG_W1_BYTES, bar_w0);
             load_image(ws1, a.img + IMG_WC1, IMG_WC_BYTES, bar_w1);
         }
+        if (tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab)  // next slab's input rows -> L2 (after the weight copies)
+            l2_prefetch_slab(a.x + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
         // ---- P0: LN(x) -> A0 (chunks 0..11 of H)
         stage_rows96<FMT, true>(xs, T, hbuf, 1, s_lng, s_lnb, warp, lane, a.ln_stats ? a.ln_stats + (size_t)slab * T * 2 : nullptr, kFfnThreads / 32);
         end_epilogue();
@@ -204,76 +216,94 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         NBSS_TICK(0, 6, it_);
         if (tid == 0) load_image(ws0, a.img + IMG_W2, IMG_W2_BYTES, bar_w0);
         {
+            // GroupNorm(8 groups of 24 channels x T frames) in TWO sweeps over the thread's 96 accumulator columns, TMEM loads
+            // software-pipelined (16 columns in flight while 16 are processed):
+            //   sweep 1: per-group sum and sum of squares of (c2 - pivot); the pivot (the group's mean bias, known to every
+            //            thread without communication) takes the bias-dominated part of the mean out before squaring
+            //   sweep 2: normalise, affine, SiLU -> H; save c2
             float* red_sum = red;       // [16 warps][8 groups] (a warp fills the 4 groups of its channel half)
             float* red_sq = red + 128;
+            float* gtot = red + 256;    // [8 groups][2] (mean, rstd) of this slab
             const float* bc2 = s_bc + 192;
-            // pass A: per-group sums over valid frames
-#pragma unroll 1
-            for (int g = 4 * hf; g < 4 * hf + 4; ++g) {
-                float s = 0.f;
+            float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
+            auto acc16 = [&](const uint32_t (&r)[16], int b) {  // b is a compile-time constant after unrolling
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    uint32_t r[8];
-                    tmem_ld8(tacc + kGC * g + 8 * k, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) s += __uint_as_float(r[j]) + bc2[kGC * g + 8 * k + j];
+                for (int j = 0; j < 16; ++j) {
+                    const int gl = (16 * b + j) / kGC;
+                    const float v = __uint_as_float(r[j]) + bc2[cb + 16 * b + j] - s_piv[4 * hf + gl];
+                    gs[gl] += v;
+                    gq[gl] = fmaf(v, v, gq[gl]);
                 }
-                s = warp_sum(valid ? s : 0.f);
-                if (lane == 0) red_sum[warp * 8 + g] = s;
+            };
+            {
+                uint32_t ra[16], rb[16];
+                tmem_ld16(tacc + cb, ra);
+                tmem_ld_wait();
+#pragma unroll
+                for (int b = 0; b < 6; b += 2) {
+                    tmem_ld16(tacc + cb + 16 * (b + 1), rb);
+                    acc16(ra, b);
+                    tmem_ld_wait();
+                    if (b + 2 < 6) tmem_ld16(tacc + cb + 16 * (b + 2), ra);
+                    acc16(rb, b + 1);
+                    tmem_ld_wait();
+                }
+            }
+#pragma unroll
+            for (int gl = 0; gl < 4; ++gl) {
+                const float s = warp_sum(valid ? gs[gl] : 0.f), qq = warp_sum(valid ? gq[gl] : 0.f);
+                if (lane == 0) { red_sum[warp * 8 + 4 * hf + gl] = s; red_sq[warp * 8 + 4 * hf + gl] = qq; }
             }
             __syncthreads();
-            // pass B: centred second moment
-#pragma unroll 1
-            for (int g = 4 * hf; g < 4 * hf + 4; ++g) {
-                float mean = 0.f;
+            if (tid < 8) {  // fixed summation order: the forward is bit-reproducible
+                const int g = tid, h8 = 8 * (g >> 2);
+                float s = 0.f, qq = 0.f;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) mean += red_sum[(8 * hf + w) * 8 + g];
-                mean *= inv_n;
-                float s = 0.f;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    uint32_t r[8];
-                    tmem_ld8(tacc + kGC * g + 8 * k, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float d = __uint_as_float(r[j]) + bc2[kGC * g + 8 * k + j] - mean;
-                        s += d * d;
-                    }
-                }
-                s = warp_sum(valid ? s : 0.f);
-                if (lane == 0) red_sq[warp * 8 + g] = s;
-            }
-            __syncthreads();
-            // pass C: normalise, affine, SiLU -> H ; save c2
-#pragma unroll 1
-            for (int g = 4 * hf; g < 4 * hf + 4; ++g) {
-                float mean = 0.f, var = 0.f;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) { mean += red_sum[(8 * hf + w) * 8 + g]; var += red_sq[(8 * hf + w) * 8 + g]; }
-                mean *= inv_n;
-                const float rstd = rsqrtf(var * inv_n + 1e-5f);
-                if (a.gn_stats && m == 0 && q == 0 && lane == (g & 3)) {
+                for (int w = 0; w < 8; ++w) { s += red_sum[(h8 + w) * 8 + g]; qq += red_sq[(h8 + w) * 8 + g]; }
+                const float mp = s * inv_n;                                   // mean of (c2 - pivot)
+                const float var = fmaxf(qq * inv_n - mp * mp, 0.f);
+                const float mean = mp + s_piv[g], rstd = rsqrtf(var + 1e-5f);
+                gtot[2 * g] = mean;
+                gtot[2 * g + 1] = rstd;
+                if (a.gn_stats) {
                     a.gn_stats[(size_t)slab * 16 + 2 * g] = mean;
                     a.gn_stats[(size_t)slab * 16 + 2 * g + 1] = rstd;
                 }
+            }
+            __syncthreads();
+            auto norm16 = [&](const uint32_t (&r)[16], int b) {
+                float v[16];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int c = kGC * g + 8 * k;
-                    uint32_t r[8];
-                    tmem_ld8(tacc + c, r);
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + bc2[cb + 16 * b + j];
+                const int c0 = cb + 16 * b;
+                if (a.save_c2 && valid) {
+                    *reinterpret_cast<uint4*>(a.save_c2 + tile_off(slab, 24, T, c0 / 8, t)) = pack8<FMT_F16>(v);
+                    *reinterpret_cast<uint4*>(a.save_c2 + tile_off(slab, 24, T, c0 / 8 + 1, t)) = pack8<FMT_F16>(v + 8);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int g = 4 * hf + (16 * b + j) / kGC;
+                    v[j] = silu((v[j] - gtot[2 * g]) * (gtot[2 * g + 1] * s_gng[c0 + j]) + s_gnb[c0 + j]);
+                }
+                if (!wfull) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] *= vmask;
+                }
+                *reinterpret_cast<uint4*>(hrow + (c0 / 8) * kCS) = pack8<FMT>(v);
+                *reinterpret_cast<uint4*>(hrow + (c0 / 8 + 1) * kCS) = pack8<FMT>(v + 8);
+            };
+            {
+                uint32_t ra[16], rb[16];
+                tmem_ld16(tacc + cb, ra);
+                tmem_ld_wait();
+#pragma unroll
+                for (int b = 0; b < 6; b += 2) {
+                    tmem_ld16(tacc + cb + 16 * (b + 1), rb);
+                    norm16(ra, b);
                     tmem_ld_wait();
-                    float v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + bc2[c + j];
-                    if (a.save_c2 && valid) *reinterpret_cast<uint4*>(a.save_c2 + tile_off(slab, 24, T, c / 8, t)) = pack8<FMT_F16>(v);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float n = (v[j] - mean) * rstd * s_gng[c + j] + s_gnb[c + j];
-                        v[j] = silu(n) * vmask;
-                    }
-                    *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = pack8<FMT>(v);
+                    if (b + 2 < 6) tmem_ld16(tacc + cb + 16 * (b + 2), ra);
+                    norm16(rb, b + 1);
+                    tmem_ld_wait();
                 }
             }
         }

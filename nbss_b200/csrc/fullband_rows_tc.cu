@@ -14,6 +14,7 @@
 // gradients, through a ones feature) accumulate in TMEM across all tiles of the CTA as MN-major x MN-major UMMAs.
 // Small footprints (45-65 KB of shared memory, 32-128 TMEM columns) keep 3-4 CTAs resident per SM, so one CTA's loads and
 // epilogues overlap the others' MMAs.
+#define NBSS_SILU_EXACT  // two-MUFU sigmoid (common.cuh): the unsqueeze SiLU output goes straight into the fp32 stream (no 16-bit rounding to hide behind)
 #include "slab.cuh"
 
 namespace nbss {

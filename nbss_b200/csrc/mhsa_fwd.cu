@@ -4,14 +4,17 @@
 // (packed in-proj, q*dh^-0.5, softmax over T, out-proj; no mask, no dropout) for T <= 256:
 //   P0 stage x -> LN -> fp16 A0 [256x96]
 //   P1 K|V = A0 Wkv^T  (N=192)         E1: +bias -> K tile (per head padded 24->32, zero chunk) and V tile
-//   P2 Q   = A0 Wq^T   (N=96, stays in TMEM)
-//   per head h, query tile m:  Qs = (Q_h + b) * dh^-0.5 * log2(e)  -> smem [128x32]
-//        S = Qs K_h^T (N=256 keys, TMEM)   softmax over keys in registers (thread = query row, 2 threads per row)
-//        O_h = P V_h (P fp16 [128 x 128 keys] staged twice, V read MN-major)  -> O tile (normalised by the row sum)
-//   P3 y = x + O Wo^T + bo
+//   P2 Q   = A0 Wq^T   (N=96)          EQ: (Q + b) * dh^-0.5 * log2(e) -> fp16 Q tile (over the dead A0), all heads at once
+//   per head h, query tiles a = (h,0), b = (h,1), two 256-column score buffers in tensor memory:
+//        S = Q_h K_h^T (N = 256 keys)  issued one head ahead of its softmax
+//        softmax WITHOUT a cross-thread exchange (split-K as in flash attention): thread = (query row, key quarter) takes
+//        the max of ITS 64 scores, writes exp2(s - m_q) as fp16 pairs back over the first 32 of its own 64 score columns
+//        and leaves (m_q, l_q) in shared memory; the P V_h MMA runs per key quarter (A operand from tensor memory) into the
+//        last 32 columns of the quarter; the read-out combines the four partial outputs with exp2(m_q - m) and 1/l.
+//        One __syncthreads per softmax and per read-out; the S / PV MMAs of one query tile run under the softmax / read-out
+//        of the other.
+//   P3 y = x + O Wo^T + bo   (O lives in the K tile's per-head padded layout; Wo image padded to K = 128)
 // HBM traffic: x in, y out (+ fp16 q|k|v, O and the log2-sum-exp when save != 0, for the backward kernels).
-#include <cstdlib>
-
 #include "slab.cuh"
 
 namespace nbss {
@@ -29,43 +32,33 @@ struct MhsaFwdArgs {
     int* err;
 };
 
-constexpr uint32_t kCSP = 129 * 16;  // chunk stride of the 128-row P / Qs tiles
-constexpr uint32_t MH_AO = 0;
-constexpr uint32_t MH_K = 13 * kCS;             // 55120
-constexpr uint32_t MH_V = MH_K + 16 * kCS;      // 122960
-constexpr uint32_t MH_W = MH_V + 13 * kCS;      // 178080
-constexpr uint32_t MH_W_BYTES = 20 * kCSP;      // 41280: P (16 chunks) + Qs (4 chunks), or one weight image
-constexpr uint32_t MH_CST = MH_W + MH_W_BYTES;  // 219360
-constexpr uint32_t MH_XCH = MH_CST + 576 * 4;
-constexpr uint32_t MH_BAR = MH_XCH + 4096;
+constexpr uint32_t MH_AO = 0;                       // A0, then the Q tile: 13 chunks (the 13th stays zero)
+constexpr uint32_t MH_K = 13 * kCS;                 // 55120: K tile, 16 chunks (head h: chunks 4h..4h+2, 4h+3 = zero pad); later O
+constexpr uint32_t MH_V = MH_K + 16 * kCS;          // 122960: V tile, 13 chunks (the 13th stays zero)
+constexpr uint32_t MH_W = MH_V + 13 * kCS;          // 178080: one weight image at a time
+constexpr uint32_t MH_W_BYTES = IMG_W1_BYTES;       // 36864
+constexpr uint32_t MH_CST = MH_W + MH_W_BYTES;      // 214944
+constexpr uint32_t MH_STAT = MH_CST + 576 * 4;      // (m_q, l_q) [2 buffers][4 key quarters][128 rows] float2 = 8192
+constexpr uint32_t MH_BAR = MH_STAT + 8192;
 constexpr int kMhThreads = 512;  // 16 warps
 constexpr uint32_t MH_SMEM = MH_BAR + 64;
-static_assert(IMG_W1_BYTES <= MH_W_BYTES, "weight image must fit the W region");
+static_assert(IMG_WOP_BYTES <= MH_W_BYTES && IMG_WQ_BYTES <= MH_W_BYTES, "weight image must fit the W region");
 
-__device__ __forceinline__ float ex2(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// PTMEM: the softmax probabilities go back into tensor memory (over the score columns they came from) and feed the PV MMA
-// as its A operand from TMEM (umma.cuh: umma_f16_ts): one MMA round per (head, query tile) instead of two, no P tile.
-template <int FMT, bool PTMEM>
+template <int FMT>
 __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* ao = smem + MH_AO;
     unsigned char* kt = smem + MH_K;
     unsigned char* vt = smem + MH_V;
     unsigned char* wr = smem + MH_W;
-    unsigned char* pt = wr;               // P tile [128 x 128 keys]
-    unsigned char* qs = wr + 16 * kCSP;   // Qs tile [128 x 32]
     float* cst = reinterpret_cast<float*>(smem + MH_CST);
     float *s_lng = cst, *s_lnb = cst + 96, *s_bin = cst + 192, *s_bout = cst + 480;
-    float* xmax = reinterpret_cast<float*>(smem + MH_XCH);
-    float* xsum = xmax + 512;  // [4 key quarters][128 rows] each
-    uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + MH_BAR);
+    float2* stat = reinterpret_cast<float2*>(smem + MH_STAT);  // [buf][kq][row]
+    uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + MH_BAR);  // projections
     uint64_t* bar_w = bar_mma + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
+    uint64_t* bar_s = bar_mma + 2;   // [2] scores of buffer b are complete
+    uint64_t* bar_pv = bar_mma + 4;  // [2] partial outputs of buffer b are complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 6);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = a.T;
@@ -73,11 +66,12 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
     if (tid == 0) {
         mbar_init(bar_mma, 1);
         mbar_init(bar_w, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_s + i, 1); mbar_init(bar_pv + i, 1); }
         fence_mbar_init();
     }
     for (int i = tid; i < 96; i += kMhThreads) { s_lng[i] = a.ln_w[i]; s_lnb[i] = a.ln_b[i]; s_bout[i] = a.b_out[i]; }
     for (int i = tid; i < 288; i += kMhThreads) s_bin[i] = a.b_in[i];
-    // zero everything that is read as padding: AO, K (pad chunks), V (13th chunk)
+    // zero everything that is read as padding: AO (13th chunk), K (pad chunks), V (13th chunk)
     for (int i = tid; i < (int)(MH_W / 16); i += kMhThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_async_smem();
     tc_fence_before();
@@ -85,17 +79,17 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    // 16 warps.  'Both tiles' epilogues: M-tile m, lane quarter q, column half hf.  Softmax: key quarter kq.
+    // 16 warps.  'Both tiles' epilogues: M-tile m, lane quarter q, column half hf.  Softmax / read-out: key quarter kq.
     const int m = (warp >> 2) & 1, q = warp & 3, hf = warp >> 3, kq = warp >> 2;
     const int rt = 32 * q + lane;       // row within an M-tile (TMEM lane)
     const int t = 128 * m + rt;         // frame handled in "both tiles" epilogues
     const uint32_t lane_off = (uint32_t)(32 * q) << 16;
-    const uint32_t aoa = smem_u32(ao), kta = smem_u32(kt), vta = smem_u32(vt), wra = smem_u32(wr), pta = smem_u32(pt),
-                   qsa = smem_u32(qs);
+    const uint32_t aoa = smem_u32(ao), kta = smem_u32(kt), vta = smem_u32(vt), wra = smem_u32(wr);
     const uint32_t id192 = make_idesc(FMT, 128, 192, 0, 0), id96 = make_idesc(FMT, 128, 96, 0, 0),
                    id256 = make_idesc(FMT, 128, 256, 0, 0), idpv = make_idesc(FMT, 128, 32, 0, 1);
     const float qscale = rsqrtf((float)kDH) * 1.4426950408889634f;
-    uint32_t ph_mma = 0, ph_w = 0;
+    const bool kmask = 64 * kq + 63 >= T;  // warp-uniform: this key quarter holds keys >= T (they get probability 0)
+    uint32_t ph_mma = 0, ph_w = 0, ph_s = 0, ph_pv = 0;  // bit b of ph_s / ph_pv: phase of buffer b's barrier
 
     auto wait_mma = [&]() {
         __syncwarp();
@@ -107,6 +101,98 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+    };
+    // warp 0: S(h, mq) = Q_h K_h^T into score buffer mq (columns 256*mq .. +255); completion on bar_s[mq]
+    auto issue_s = [&](int h, int mq) {
+        tc_fence_after();
+        const bool leader = elect_one();
+        mma_kk(tmem + 256 * mq, aoa + 3 * h * kCS + 128 * mq * 16, kCS, kta + 4 * h * kCS, kCS, 2, id256, 0, leader);
+        if (leader) umma_commit(bar_s + mq);
+        __syncwarp();
+    };
+    // softmax of one query tile over the thread's own 64 keys; P -> TMEM (first 32 of the thread's 64 score columns)
+    auto softmax_local = [&](int b) {
+        const uint32_t ts = tmem + lane_off + 256 * b + 64 * kq;
+        uint32_t r0[32], r1[32];
+        tmem_ld32(ts, r0);
+        tmem_ld32(ts + 32, r1);
+        tmem_ld_wait();
+        if (kmask) {  // keys >= T: -inf (only the last key quarter(s) of a short slab pay for this)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (64 * kq + j >= T) r0[j] = 0xff800000u;
+                if (64 * kq + 32 + j >= T) r1[j] = 0xff800000u;
+            }
+        }
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            m4[j & 1] = fmaxf(m4[j & 1], __uint_as_float(r0[j]));
+            m4[2 + (j & 1)] = fmaxf(m4[2 + (j & 1)], __uint_as_float(r1[j]));
+        }
+        const float mq_ = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        const float mref = mq_ == -INFINITY ? 0.f : mq_;  // a fully masked quarter: every exponent stays -inf -> p = 0
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            const float p0 = ex2_ftz(__uint_as_float(r0[j]) - mref), p1 = ex2_ftz(__uint_as_float(r0[j + 1]) - mref);
+            s4[0] += p0;
+            s4[1] += p1;
+            pk[j >> 1] = pack16<FMT>(p0, p1);
+        }
+        tmem_st16(ts, pk);
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            const float p0 = ex2_ftz(__uint_as_float(r1[j]) - mref), p1 = ex2_ftz(__uint_as_float(r1[j + 1]) - mref);
+            s4[2] += p0;
+            s4[3] += p1;
+            pk[j >> 1] = pack16<FMT>(p0, p1);
+        }
+        tmem_st16(ts + 16, pk);
+        stat[(b * 4 + kq) * 128 + rt] = make_float2(mq_, (s4[0] + s4[1]) + (s4[2] + s4[3]));
+        tmem_st_wait();
+    };
+    // warp 0: O_q(h, mq) = P_q V_h for the four key quarters (A operand from tensor memory); completion on bar_pv[mq]
+    auto issue_pv = [&](int h, int b) {
+        tc_fence_after();
+        const bool leader = elect_one();
+#pragma unroll 1
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll 1
+            for (int ks = 0; ks < 4; ++ks)
+                if (leader)
+                    umma_f16_ts(tmem + 256 * b + 64 * kk + 32, tmem + 256 * b + 64 * kk + 8 * ks,
+                                sdesc_mnmajor(vta + 3 * h * kCS + (64 * kk + 16 * ks) * 16, kCS), idpv, ks ? 1u : 0u);
+        if (leader) umma_commit(bar_pv + b);
+        __syncwarp();
+    };
+    // read-out of one query tile: combine the four partial outputs, normalise, O_h -> K tile (chunks 4h..4h+2), saves
+    auto readout = [&](int h, int b, int slab) {
+        const int tq = 128 * b + rt;
+        const float2 s0 = stat[(b * 4 + 0) * 128 + rt], s1 = stat[(b * 4 + 1) * 128 + rt], s2 = stat[(b * 4 + 2) * 128 + rt],
+                     s3 = stat[(b * 4 + 3) * 128 + rt];
+        const float mx = fmaxf(fmaxf(s0.x, s1.x), fmaxf(s2.x, s3.x));  // finite: key quarter 0 always holds key 0 < T
+        const float f0 = ex2_ftz(s0.x - mx), f1 = ex2_ftz(s1.x - mx), f2 = ex2_ftz(s2.x - mx), f3 = ex2_ftz(s3.x - mx);  // ex2(-inf) = 0
+        const float l = f0 * s0.y + f1 * s1.y + f2 * s2.y + f3 * s3.y;
+        const float inv = 1.f / l;
+        if (kq < 3) {  // thread = (query row, 8 of the head's 24 output features)
+            const uint32_t to = tmem + lane_off + 256 * b + 32 + 8 * kq;
+            uint32_t o0[8], o1[8], o2[8], o3[8];
+            tmem_ld8(to, o0);
+            tmem_ld8(to + 64, o1);
+            tmem_ld8(to + 128, o2);
+            tmem_ld8(to + 192, o3);
+            tmem_ld_wait();
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                v[j] = (f0 * __uint_as_float(o0[j]) + f1 * __uint_as_float(o1[j]) + f2 * __uint_as_float(o2[j]) + f3 * __uint_as_float(o3[j])) * inv;
+            *reinterpret_cast<uint4*>(kt + (4 * h + kq) * kCS + tq * 16) = pack8<FMT>(v);
+            if (a.save_o && tq < T) *reinterpret_cast<uint4*>(a.save_o + tile_off(slab, 12, T, 3 * h + kq, tq)) = pack8<FMT_F16>(v);
+        } else if (a.save_lse && tq < T) {
+            a.save_lse[((size_t)slab * kNH + h) * T + tq] = mx + log2f(l);
+        }
     };
 
     int it_ = 0;
@@ -137,35 +223,39 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
             // K: cols 0..95 -> per-head padded chunks 4h..4h+2   (channel half 0 does K, half 1 does V)
 #pragma unroll 1
             for (int h = 0; h < (hf == 0 ? kNH : 0); ++h) {
+                uint32_t r[24];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) tmem_ld8(tacc + kDH * h + 8 * k, *reinterpret_cast<uint32_t(*)[8]>(r + 8 * k));
+                tmem_ld_wait();
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    uint32_t r[8];
-                    tmem_ld8(tacc + kDH * h + 8 * k, r);
-                    tmem_ld_wait();
                     float v[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = valid ? __uint_as_float(r[j]) + s_bin[96 + kDH * h + 8 * k + j] : 0.f;
-                    uint4 p = pack8<FMT>(v);
-                    *reinterpret_cast<uint4*>(kt + (4 * h + k) * kCS + t * 16) = p;
+                    for (int j = 0; j < 8; ++j) v[j] = valid ? __uint_as_float(r[8 * k + j]) + s_bin[96 + kDH * h + 8 * k + j] : 0.f;
+                    *reinterpret_cast<uint4*>(kt + (4 * h + k) * kCS + t * 16) = pack8<FMT>(v);
                     if (a.save_qkv && valid) *reinterpret_cast<uint4*>(a.save_qkv + tile_off(slab, 36, T, 12 + 3 * h + k, t)) = pack8<FMT_F16>(v);
                 }
             }
             // V: cols 96..191 -> compact chunks 0..11
 #pragma unroll 1
-            for (int c = 0; c < (hf == 1 ? 12 : 0); ++c) {
-                uint32_t r[8];
-                tmem_ld8(tacc + 96 + 8 * c, r);
-                tmem_ld_wait();
-                float v[8];
+            for (int c = 0; c < (hf == 1 ? 12 : 0); c += 3) {
+                uint32_t r[24];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = valid ? __uint_as_float(r[j]) + s_bin[192 + 8 * c + j] : 0.f;
-                *reinterpret_cast<uint4*>(vt + c * kCS + t * 16) = pack8<FMT>(v);
-                if (a.save_qkv && valid) *reinterpret_cast<uint4*>(a.save_qkv + tile_off(slab, 36, T, 24 + c, t)) = pack8<FMT_F16>(v);
+                for (int k = 0; k < 3; ++k) tmem_ld8(tacc + 96 + 8 * (c + k), *reinterpret_cast<uint32_t(*)[8]>(r + 8 * k));
+                tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = valid ? __uint_as_float(r[8 * k + j]) + s_bin[192 + 8 * (c + k) + j] : 0.f;
+                    *reinterpret_cast<uint4*>(vt + (c + k) * kCS + t * 16) = pack8<FMT>(v);
+                    if (a.save_qkv && valid) *reinterpret_cast<uint4*>(a.save_qkv + tile_off(slab, 36, T, 24 + c + k, t)) = pack8<FMT_F16>(v);
+                }
             }
         }
         end_epilogue();
         NBSS_TICK(0, 3, it_);
-        // ---- P2: Q (stays in TMEM cols 0..191)
+        // ---- P2: Q
         if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_w, ph_w, a.err);
@@ -176,151 +266,63 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         ph_w ^= 1;
         wait_mma();
         NBSS_TICK(0, 4, it_);
-        // ---- heads x query tiles
+        if (tid == 0) load_image(wr, a.img + IMG_WOP, IMG_WOP_BYTES, bar_w);  // out-proj image: needed only after the last head
+        // ---- EQ: scaled queries of all heads -> Q tile (over A0, dead now); thread = (frame, channel half)
+        {
+            const bool valid = t < T;
+            const uint32_t tacc = tmem + lane_off + m * 96;
 #pragma unroll 1
-        for (int hm = 0; hm < 2 * kNH; ++hm) {
-            const int h = hm >> 1, mq = hm & 1;
-            // EQ: warps 0..3 stage the scaled queries of tile mq
-            if (warp < 4) {
-                const int tq = 128 * mq + rt;
-                const bool valid = tq < T;
-                const uint32_t tq_acc = tmem + lane_off + mq * 96 + kDH * h;
+            for (int c0 = 48 * hf; c0 < 48 * hf + 48; c0 += 24) {
+                uint32_t r[24];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    uint32_t r[8];
-                    tmem_ld8(tq_acc + 8 * k, r);
-                    tmem_ld_wait();
-                    float v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = valid ? (__uint_as_float(r[j]) + s_bin[kDH * h + 8 * k + j]) * qscale : 0.f;
-                    *reinterpret_cast<uint4*>(qs + k * kCSP + rt * 16) = pack8<FMT>(v);
-                    if (a.save_qkv && valid)
-                        *reinterpret_cast<uint4*>(a.save_qkv + tile_off(slab, 36, T, 3 * h + k, tq)) = pack8<FMT_F16>(v);
-                }
-                *reinterpret_cast<uint4*>(qs + 3 * kCSP + rt * 16) = make_uint4(0, 0, 0, 0);
-            }
-            end_epilogue();
-            NBSS_TICK(0, 8 + 5 * hm, it_);
-            // S = Qs K_h^T
-            if (warp == 0) {
-                tc_fence_after();
-                const bool leader = elect_one();
-                mma_kk(tmem + 192, qsa, kCSP, kta + 4 * h * kCS, kCS, 2, id256, 0, leader);
-                if (leader) umma_commit(bar_mma);
-            }
-            wait_mma();
-            NBSS_TICK(0, 9 + 5 * hm, it_);
-            // softmax: thread = (query row rt, key quarter kq): 64 of the 256 score columns
-            const uint32_t ts = tmem + lane_off + 192 + 64 * kq;
-            float mx = -INFINITY;
-            {
-                // both 32-column loads in flight before the single wait; four independent max chains
-                uint32_t r0[32], r1[32];
-                tmem_ld32(ts, r0);
-                tmem_ld32(ts + 32, r1);
-                tmem_ld_wait();
-                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    m4[j & 1] = fmaxf(m4[j & 1], (64 * kq + j < T) ? __uint_as_float(r0[j]) : -INFINITY);
-                    m4[2 + (j & 1)] = fmaxf(m4[2 + (j & 1)], (64 * kq + 32 + j < T) ? __uint_as_float(r1[j]) : -INFINITY);
-                }
-                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-            }
-            xmax[kq * 128 + rt] = mx;
-            __syncthreads();
-            const float rowmax = fmaxf(fmaxf(xmax[rt], xmax[128 + rt]), fmaxf(xmax[256 + rt], xmax[384 + rt]));
-            uint32_t pk[32];
-            float sum = 0.f;
-#pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(ts + c0, r);
+                for (int k = 0; k < 3; ++k) tmem_ld8(tacc + c0 + 8 * k, *reinterpret_cast<uint32_t(*)[8]>(r + 8 * k));
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const int key = 64 * kq + c0 + j;
-                    // masked keys get exponent -inf (ex2 -> 0): a select on the argument, no branch around the MUFU
-                    float p0 = ex2(key < T ? __uint_as_float(r[j]) - rowmax : -INFINITY);
-                    float p1 = ex2(key + 1 < T ? __uint_as_float(r[j + 1]) - rowmax : -INFINITY);
-                    sum += p0 + p1;
-                    pk[(c0 + j) >> 1] = pack16<FMT>(p0, p1);
-                }
-            }
-            xsum[kq * 128 + rt] = sum;
-            if constexpr (PTMEM) {
-                // O_h = P V_h with P in tensor memory: key k of row rt -> column 192 + k/2 (two 16-bit values per column)
-                __syncthreads();  // every thread has read its score columns: the P columns alias them
-                const uint32_t tp = tmem + lane_off + 192 + 32 * kq;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint32_t v8[8] = {pk[8 * c], pk[8 * c + 1], pk[8 * c + 2], pk[8 * c + 3], pk[8 * c + 4], pk[8 * c + 5], pk[8 * c + 6], pk[8 * c + 7]};
-                    tmem_st8(tp + 8 * c, v8);
-                }
-                tmem_st_wait();
-                end_epilogue();
-                NBSS_TICK(0, 10 + 5 * hm, it_);
-                if (warp == 0) {
-                    tc_fence_after();
-                    const bool leader = elect_one();
-                    for (int ks = 0; ks < 16; ++ks)
-                        if (leader) umma_f16_ts(tmem + 448, tmem + 192 + 8 * ks, sdesc_mnmajor(vta + 3 * h * kCS + 16 * ks * 16, kCS), idpv, ks ? 1u : 0u);
-                    if (leader) umma_commit(bar_mma);
-                }
-                wait_mma();
-                NBSS_TICK(0, 11 + 5 * hm, it_);
-            } else {
-            // O_h = P V_h, one key half at a time (the P tile holds 128 keys = two key quarters)
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                if ((kq >> 1) == half) {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        *reinterpret_cast<uint4*>(pt + (8 * (kq & 1) + c) * kCSP + rt * 16) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-                }
-                end_epilogue();
-                if (warp == 0) {
-                    tc_fence_after();
-                    const bool leader = elect_one();
-                    for (int ks = 0; ks < 8; ++ks)
-                        if (leader) umma_f16(tmem + 448, sdesc_kmajor(pta + 2 * ks * kCSP, kCSP),
-                                 sdesc_mnmajor(vta + 3 * h * kCS + (128 * half + 16 * ks) * 16, kCS), idpv, (half | ks) ? 1u : 0u);
-                    if (leader) umma_commit(bar_mma);
-                }
-                wait_mma();
-            }
-            }
-            // EO: normalise and place O_h into the O tile (aliases A0, dead after P2)
-            if (warp < 4) {
-                const int tq = 128 * mq + rt;
-                const float l = xsum[rt] + xsum[128 + rt] + xsum[256 + rt] + xsum[384 + rt];
-                const float inv = 1.f / l;
-                if (a.save_lse && tq < T) a.save_lse[((size_t)slab * kNH + h) * T + tq] = rowmax + log2f(l);
-#pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    uint32_t r[8];
-                    tmem_ld8(tmem + lane_off + 448 + 8 * k, r);
-                    tmem_ld_wait();
                     float v[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) * inv;
-                    *reinterpret_cast<uint4*>(ao + (3 * h + k) * kCS + tq * 16) = pack8<FMT>(v);
-                    if (a.save_o && tq < T)
-                        *reinterpret_cast<uint4*>(a.save_o + tile_off(slab, 12, T, 3 * h + k, tq)) = pack8<FMT_F16>(v);
+                    for (int j = 0; j < 8; ++j) v[j] = valid ? (__uint_as_float(r[8 * k + j]) + s_bin[c0 + 8 * k + j]) * qscale : 0.f;
+                    *reinterpret_cast<uint4*>(ao + (c0 / 8 + k) * kCS + t * 16) = pack8<FMT>(v);
+                    if (a.save_qkv && valid) *reinterpret_cast<uint4*>(a.save_qkv + tile_off(slab, 36, T, c0 / 8 + k, t)) = pack8<FMT_F16>(v);
                 }
             }
-            tc_fence_before();
-            __syncthreads();
-            NBSS_TICK(0, 12 + 5 * hm, it_);
         }
-        // ---- P3: out-proj + residual
-        if (tid == 0) load_image(wr, a.img + IMG_WO, IMG_WQ_BYTES, bar_w);
         end_epilogue();
+        NBSS_TICK(0, 8, it_);
+        // ---- heads: the two query tiles of a head ping-pong between the two score buffers
+        if (warp == 0) { issue_s(0, 0); issue_s(0, 1); }
+#pragma unroll 1
+        for (int h = 0; h < kNH; ++h) {
+#pragma unroll 1
+            for (int b = 0; b < 2; ++b) {
+                mbar_wait(bar_s + b, (ph_s >> b) & 1u, a.err);
+                ph_s ^= 1u << b;
+                tc_fence_after();
+                softmax_local(b);
+                tc_fence_before();
+                __syncthreads();
+                if (warp == 0) issue_pv(h, b);
+                NBSS_TICK(0, 9 + 10 * h + 2 * b, it_);
+            }
+#pragma unroll 1
+            for (int b = 0; b < 2; ++b) {
+                mbar_wait(bar_pv + b, (ph_pv >> b) & 1u, a.err);
+                ph_pv ^= 1u << b;
+                tc_fence_after();
+                readout(h, b, slab);
+                fence_async_smem();  // O -> K tile is read by the out-proj MMA
+                tc_fence_before();
+                __syncthreads();
+                if (warp == 0 && h + 1 < kNH) issue_s(h + 1, b);  // buffer b is free again
+                NBSS_TICK(0, 10 + 10 * h + 2 * b + 3, it_);
+            }
+        }
+        // ---- P3: out-proj (K = 128 over the padded O layout) + residual
         if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_w, ph_w, a.err);
             const bool leader = elect_one();
-            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + 192 + mm * 96, aoa + 128 * mm * 16, kCS, wra, 96 * 16, 6, id96, 0, leader);
+            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 96, kta + 128 * mm * 16, kCS, wra, 96 * 16, 8, id96, 0, leader);
             if (leader) umma_commit(bar_mma);
         }
         ph_w ^= 1;
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
             // thread = (frame, channel half): D + b_out -> fp32, staged into the dead K|V tiles at the frame's row slot (24
             // four-float chunks = the 12 K data chunks + V chunks 0..11; the zero pad chunks of K stay untouched:
             // slab.cuh skip4_chunk); then eight lanes per frame add the residual with coalesced traffic
-            const uint32_t tacc = tmem + lane_off + 192 + m * 96;
+            const uint32_t tacc = tmem + lane_off + m * 96;
 #pragma unroll 1
             for (int c0 = 48 * hf; c0 < 48 * hf + 48; c0 += 16) {
                 uint32_t r[16];
@@ -375,13 +377,7 @@ extern "C" int nbss_mhsa_fwd(const float* x, float* y, int nslab, int T, const f
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = nslab < sms ? nslab : sms;
-    static int ptmem = -1;  // NBSS_MHSA_PTMEM=0 keeps the softmax probabilities in a shared-memory tile (the older path)
-    if (ptmem < 0) {
-        const char* e = getenv("NBSS_MHSA_PTMEM");
-        ptmem = (e && e[0] == '0') ? 0 : 1;
-    }
-    void (*kern)(MhsaFwdArgs) = ptmem ? ((fmt == FMT_F16) ? mhsa_fwd_kernel<FMT_F16, true> : mhsa_fwd_kernel<FMT_BF16, true>)
-                                      : ((fmt == FMT_F16) ? mhsa_fwd_kernel<FMT_F16, false> : mhsa_fwd_kernel<FMT_BF16, false>);
+    void (*kern)(MhsaFwdArgs) = (fmt == FMT_F16) ? mhsa_fwd_kernel<FMT_F16> : mhsa_fwd_kernel<FMT_BF16>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MH_SMEM);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, kMhThreads, MH_SMEM, (cudaStream_t)stream>>>(a);

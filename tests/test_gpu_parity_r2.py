@@ -54,27 +54,31 @@ def _family(name: str) -> str:
     return name.split(".")[0]
 
 
-# Gradient tolerances per parameter tensor (rel-L2 vs fp32 autograd of the oracle), 8 layers, fp16 operands.
-# What bounds them: every contraction reads operands rounded to 11 bits (2.8e-4 rms each), the backward re-evaluates
-# activation derivatives on those rounded forward values, and errors of all later layers flow into every earlier
-# parameter's gradient.  The F-conv / encoder families additionally see the PReLU slope decision (test below).
-GRAD_TOL_8L = {"decoder": 2e-3, "ffn": 6e-3, "mhsa": 6e-3, "full": 8e-3, "fconv": 2e-2, "encoder": 2e-2}
+# Gradient tolerances per parameter tensor (rel-L2 vs FP64 autograd of the oracle), 8 layers, fp16 operands.
+# Measured (r02a): decoder 7e-4; everything upstream of the last F-conv 1e-2 .. 4.8e-2.  What sets that level is NOT the
+# 16-bit rounding of the contractions (5e-3, second test) but the PReLU slope decision of the 16 F-conv sub-blocks: the
+# kernels evaluate PReLU'(c) on c computed from fp16 operands, so the ~0.4 % of pre-activations with |c| < ~2e-3 may take the
+# other slope, each F-conv adds ~5e-3 .. 1e-2 of relative error to the stream gradient that flows through it
+# (test_fconv_prelu_sign_claim), and 16 of them add up to ~3e-2 on every parameter upstream.  The kernels' gradient is the
+# exact gradient of the function the kernels compute; test_training_20_steps_loss_curve shows training is unaffected.
+GRAD_TOL_8L = {"decoder": 2e-3, "ffn": 5e-2, "mhsa": 5e-2, "full": 5e-2, "fconv": 7e-2, "encoder": 5e-2}
+GRAD_TOL_8L_SLOPE1 = {"decoder": 2e-3, "ffn": 8e-3, "mhsa": 8e-3, "full": 8e-3, "fconv": 8e-3, "encoder": 8e-3}
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("T", [250, 251])
-def test_bench_config_fwd_bwd(T):
-    """BASELINE configs[1]/[2] per utterance: 8 layers, 6ch, F=129, T=250 / 4 s (T=251), wave -> wave, SI-SDR + PIT loss,
-    backward through iSTFT, the network and nothing else (the input needs no gradient)."""
+def _bench_config_errors(T, B, seed, slope_one):
     cfg = O.SMALL_CFG
-    P = O.synth_params(cfg, 77)
+    P = O.synth_params(cfg, seed)
+    if slope_one:  # PReLU slope 1 = identity: the F-conv sub-block has no sign decision left
+        for k in P:
+            if k.endswith(".2.weight") and "fconv" in k:
+                P[k] = torch.ones_like(P[k])
     Pl = _leaf(P)
     net = _net(cfg, P)
     pipe = SeparationPipeline(net, 256, 128, channels=None, ref_channel=0)
     g = torch.Generator().manual_seed(1000 + T)
     Ts = 128 * (T - 1)
-    wave = 0.1 * torch.randn(2, 6, Ts, generator=g)
-    tgt = 0.1 * torch.randn(2, 2, Ts, generator=g)
+    wave = 0.1 * torch.randn(B, 6, Ts, generator=g)
+    tgt = 0.1 * torch.randn(B, 2, Ts, generator=g)
     est = pipe(wave.cuda())
     loss = neg_si_sdr_pit(est, tgt.cuda())[0]
     loss.backward()
@@ -84,17 +88,39 @@ def test_bench_config_fwd_bwd(T):
     loss_ref = O.neg_si_sdr_pit(est_ref, tgt.double())[0]
     loss_ref.backward()
     e_fwd = O.rel_l2(est.detach().cpu(), est_ref.detach())
-    assert e_fwd < 1e-3, f"forward rel-L2 {e_fwd:.3e}"
-    assert abs(loss.item() - loss_ref.item()) < 2e-3 * max(1.0, abs(loss_ref.item())), (loss.item(), loss_ref.item())
     errs = {n: O.rel_l2(p.grad.cpu().reshape(-1), Pl[n].grad.reshape(-1)) for n, p in net.named_parameters()}
     worst = {}
     for n, e in errs.items():
         f = _family(n)
         if f not in worst or e > worst[f][1]:
             worst[f] = (n, e)
-    print(f"[T={T}] forward {e_fwd:.2e}; worst gradient rel-L2 per family: " + ", ".join(f"{f}: {n} {e:.2e}" for f, (n, e) in sorted(worst.items())))
+    print(f"[T={T} slope_one={slope_one}] forward {e_fwd:.2e}; worst gradient rel-L2 per family: "
+          + ", ".join(f"{f}: {n} {e:.2e}" for f, (n, e) in sorted(worst.items())))
+    return e_fwd, loss.item(), loss_ref.item(), errs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T", [250, 251])
+def test_bench_config_fwd_bwd(T):
+    """BASELINE configs[1]/[2] per utterance: 8 layers, 6ch, F=129, T=250 / 4 s (T=251), wave -> wave, SI-SDR + PIT loss,
+    backward through iSTFT, the network and nothing else (the input needs no gradient)."""
+    e_fwd, loss, loss_ref, errs = _bench_config_errors(T, 2, 77, slope_one=False)
+    assert e_fwd < 1e-3, f"forward rel-L2 {e_fwd:.3e}"
+    assert abs(loss - loss_ref) < 2e-3 * max(1.0, abs(loss_ref)), (loss, loss_ref)
     bad = {n: f"{e:.2e}" for n, e in errs.items() if not e < GRAD_TOL_8L[_family(n)]}
     assert not bad, f"gradient rel-L2 over the family tolerance {GRAD_TOL_8L}: {bad}"
+
+
+@pytest.mark.gpu
+def test_bench_config_fwd_bwd_without_sign_decisions():
+    """The same 8-layer wave -> wave + loss + backward with every PReLU slope set to 1 (identity), i.e. with the only
+    discontinuous derivative of the network removed: what is left is the 16-bit operand rounding, and every parameter
+    gradient of the whole network is within 8e-3 of fp64 autograd — the proof that the 3e-2 of the test above is the
+    slope decision and not an error of the backward kernels."""
+    e_fwd, loss, loss_ref, errs = _bench_config_errors(250, 1, 78, slope_one=True)
+    assert e_fwd < 1e-3, f"forward rel-L2 {e_fwd:.3e}"
+    bad = {n: f"{e:.2e}" for n, e in errs.items() if not e < GRAD_TOL_8L_SLOPE1[_family(n)]}
+    assert not bad, f"gradient rel-L2 over the family tolerance {GRAD_TOL_8L_SLOPE1}: {bad}"
 
 
 @pytest.mark.gpu
@@ -181,25 +207,27 @@ def test_training_20_steps_loss_curve():
 @pytest.mark.gpu
 def test_fp16_range_guard_scaled_weights():
     """fp16 operands have a 65504 range.  Every 16-bit operand of the path is either the output of a LayerNorm / GroupNorm
-    (bounded by the affine gain) or at most three contractions away from one, so scaling EVERY weight matrix by 8 (a gain
-    of 8^3 = 512 on the widest un-normalised chain c2) must stay finite and on the oracle."""
+    (bounded by the affine gain) or at most three contractions away from one: the widest un-normalised chain is
+    a1 -> c1 -> c2 inside the T-ConvFFN.  Scaling every T-ConvFFN and F-conv weight matrix by 8 (a gain of 8^3 = 512 on c2,
+    64 on the sub-block outputs that are added to the fp32 stream) must stay finite and on the oracle.  (The attention
+    projections are left alone: multiplying q and k by 8 turns the softmax into an arg-max, an ill-conditioned function
+    that says nothing about range.)"""
     cfg = dict(O.SMALL_CFG, num_layers=3)
     P = O.synth_params(cfg, 61)
-    P8, done = {}, {}
-    for k, v in P.items():
-        if id(v) not in done:
-            done[id(v)] = v * 8.0 if (v.dim() >= 2 and "full" not in k) else v.clone()
-        P8[k] = done[id(v)]
+    P8 = {k: (v * 8.0 if (v.dim() >= 2 and ("tconvffn" in k or "fconv" in k)) else v.clone()) for k, v in P.items()}
+    for i in range(cfg["num_layers"]):  # keep the shared full-band tensors shared
+        for leaf in ("full.weight", "full.bias"):
+            P8[f"layers.{i}.{leaf}"] = P8[f"layers.0.{leaf}"]
     net = _net(cfg, P8).eval()
     x = torch.randn(1, 129, 250, 12, generator=torch.Generator().manual_seed(4))
     with torch.no_grad():
         y = net(x.cuda())
         net.check_device_errors()
-        ref = O.spatialnet_forward(P8, x, cfg)
+        ref = O.spatialnet_forward({k: v.double() for k, v in P8.items()}, x.double(), cfg)
     assert torch.isfinite(y).all()
     e = O.rel_l2(y.cpu(), ref)
-    print(f"weights x 8: forward rel-L2 {e:.2e}, |y| max {ref.abs().max().item():.1f}")
-    assert e < 3e-3, e  # softmax temperatures x 64 and gains x 8 amplify operand rounding; what matters is no overflow
+    print(f"T-ConvFFN / F-conv weights x 8: forward rel-L2 {e:.2e}, |y| max {ref.abs().max().item():.1f}")
+    assert e < 3e-3, e
 
 
 # ------------------------------------------------------------------------------------------------ ADVICE r1 regressions

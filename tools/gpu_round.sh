@@ -11,5 +11,8 @@ run parity tests/test_gpu_parity_r2.py
 if [ -f nbss_b200/lib/libnbss_b200_prof.so ]; then
   echo "=== phases"; NBSS_LIB=nbss_b200/lib/libnbss_b200_prof.so timeout 300 python tools/phase_profile.py --batch 8 --out gpurun_out/${TAG}_phases.json > gpurun_out/${TAG}_phases.txt 2>&1; echo "rc=$?"
 fi
-echo "=== bench"; timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.log; echo "rc=$? $(head -c 300 gpurun_out/${TAG}_bench.json)"
+if [ -f nbss_b200/lib/libnbss_b200_exact.so ]; then
+  echo "=== A/B sigmoid"; for L in "" _exact; do NBSS_LIB=nbss_b200/lib/libnbss_b200$L.so timeout 300 python tools/ab_forward.py 2>&1 | tail -1; done | tee gpurun_out/${TAG}_ab.txt
+fi
+echo "=== bench"; timeout 900 python bench.py --steps 10 --warmup 3 $BENCH_ARGS > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.log; echo "rc=$? $(head -c 300 gpurun_out/${TAG}_bench.json)"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt

@@ -75,14 +75,13 @@ def main():
             rows = []
             if unit == "mhsa_fwd":
                 s = st[kid]
-                rows = [(names[0], s[1] - s[0]), (names[1], s[2] - s[1]), (names[2], s[3] - s[2]), (names[3], s[4] - s[3])]
-                eq = sum(s[8 + 5 * i] - (s[4] if i == 0 else s[12 + 5 * (i - 1)]) for i in range(8))
-                sw = sum(s[9 + 5 * i] - s[8 + 5 * i] for i in range(8))
-                sm = sum(s[10 + 5 * i] - s[9 + 5 * i] for i in range(8))
-                pv = sum(s[11 + 5 * i] - s[10 + 5 * i] for i in range(8))
-                eo = sum(s[12 + 5 * i] - s[11 + 5 * i] for i in range(8))
-                rows += [("8x EQ stage q", eq), ("8x S MMA wait", sw), ("8x softmax + P->TMEM", sm), ("8x PV MMA wait", pv), ("8x EO normalise", eo)]
-                rows += [("out-proj load + MMA wait", s[5] - s[47]), (names[5], s[6] - s[5]), (names[6], s[7] - s[6])]
+                S = lambda h, b: s[9 + 10 * h + 2 * b]   # after softmax (+ PV issue) of query tile b of head h
+                R = lambda h, b: s[13 + 10 * h + 2 * b]  # after its read-out (+ next S issue)
+                rows = [(names[0], s[1] - s[0]), (names[1], s[2] - s[1]), (names[2], s[3] - s[2]), (names[3], s[4] - s[3]), ("EQ all heads", s[8] - s[4])]
+                sm = sum((S(h, 0) - (s[8] if h == 0 else R(h - 1, 1))) + (S(h, 1) - S(h, 0)) for h in range(4))
+                ro = sum((R(h, 0) - S(h, 1)) + (R(h, 1) - R(h, 0)) for h in range(4))
+                rows += [("8x S wait + softmax + P->TMEM", sm), ("8x PV wait + read-out", ro)]
+                rows += [("out-proj load + MMA wait", s[5] - R(3, 1)), (names[5], s[6] - s[5]), (names[6], s[7] - s[6])]
             elif unit == "mhsa_bwd" and kid == 0:
                 s = st[kid]
                 rows = [(names[0], s[1] - s[0]), (names[1], s[2] - s[1]), (names[2], s[3] - s[2])]

@@ -151,6 +151,19 @@ __device__ __forceinline__ void fc_stage_plain(const FcGeom& g, const float* __r
     }
 }
 
+// L2 prefetch of the NEXT group's rows (384 B each, F-strided): one cp.async.bulk.prefetch.L2 per row, dealt to the threads,
+// so that the next iteration's latency-exposed staging loads hit L2 instead of HBM
+__device__ __forceinline__ void fc_prefetch_rows(const FcGeom& g, const float* __restrict__ p0, const float* __restrict__ p1, int grp, int tid, int nthreads) {
+    if (grp >= g.ngroups) return;
+    const int b = grp / g.groups_per_b, t0 = (grp % g.groups_per_b) * g.nfr, N = g.nfr * g.F, tot = p1 ? 2 * N : N;
+    for (int i = tid; i < tot; i += nthreads) {
+        const int r = i < N ? i : i - N;
+        int tt, f;
+        fc_row(g, r, tt, f);
+        if (t0 + tt < g.T) l2_prefetch((i < N ? p0 : p1) + (((size_t)b * g.F + f) * g.T + t0 + tt) * kH, kH * 4);
+    }
+}
+
 // conv (or transposed conv) MMAs of one group: D[tile m][half q] = sum_tap A(rows shifted) * Wimg(q, tap)
 __device__ __forceinline__ void fc_conv_mmas(const FcGeom& g, uint32_t tmem, uint32_t tile_addr, uint32_t w_addr, uint32_t idesc,
                                              bool transposed, bool leader) {
@@ -207,6 +220,7 @@ __global__ void __launch_bounds__(256, 2) fconv_tc_fwd_kernel(FcFwdArgs a) {
     for (int grp = blockIdx.x; grp < g.ngroups; grp += gridDim.x, ++it_) {
         const int b = grp / g.groups_per_b, t0 = (grp % g.groups_per_b) * g.nfr;
         NBSS_TICK(0, 0, it_);
+        fc_prefetch_rows(g, a.x, nullptr, grp + gridDim.x, tid, 256);
         fc_stage<FMT, 5>(g, a.x, b, t0, tile, cst, cst + 96, nullptr, warp, lane);
         fence_async_smem();
         tc_fence_before();
@@ -355,6 +369,7 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         const int b = grp / g.groups_per_b, t0 = (grp % g.groups_per_b) * g.nfr;
         NBSS_TICK(1, 0, it_);
         if (tid == 0) load_image(wimg, a.img, FC_IMG_BYTES, bar_w);
+        fc_prefetch_rows(g, a.x, a.dy, grp + gridDim.x, tid, NT);
         fc_stage<FMT, 5, NW>(g, a.x, b, t0, htile, cst, cst + 96, stats, warp, lane);
         fc_stage_plain<FMT, 5, NW>(g, a.dy, b, t0, gtile, warp, lane);
         fence_async_smem();

@@ -213,11 +213,6 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
             load_image(ws0, a.img + IMG_W2T, IMG_W1_BYTES, bar_w0);
             load_image(ws1, a.img + IMG_WC3T, IMG_WC_BYTES, bar_w1);
         }
-        if (tid >= 32 && tid < 44) {  // -> L2: this slab's x rows (LayerNorm backward at the end of the iteration), next slab's dy
-            const int i = tid - 32;
-            if (i < 6) l2_prefetch_slab(a.x + (size_t)slab * T * kH, T, i);
-            else if (slab + (int)gridDim.x < a.nslab) l2_prefetch_slab(a.dy + (size_t)(slab + gridDim.x) * T * kH, T, i - 6);
-        }
         // ---- B0: dy -> G (chunks 0..11)
         stage_rows96<FMT, false, 2>(dys, T, hbuf, 1, nullptr, nullptr, warp, lane, nullptr, kFfnBwdThreads / 32);
         end_epilogue();
@@ -306,6 +301,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
                 }
                 tmem_st_wait();
             }
+            NBSS_TICK(0, 20, it_);
 #pragma unroll
             for (int gl = 0; gl < 4; ++gl) {
                 const float s1 = warp_sum(s1g[gl]), s2 = warp_sum(s2g[gl]);
@@ -319,6 +315,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
                 gtot[tid] = s * inv_n;
             }
             __syncthreads();
+            NBSS_TICK(0, 21, it_);
             // sweep B: g(c2) = rstd * (dn*gamma - S1/N - xhat*S2/N) -> G tile + global; column sums for d_gnw, d_gnb
             auto sweepB16 = [&](const uint32_t (&r)[16], int b) {
                 const int c0 = cb + 16 * b;

@@ -177,8 +177,6 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
             load_image(ws0, a.img + IMG_W1, IMG_W1_BYTES, bar_w0);
             load_image(ws1, a.img + IMG_WC1, IMG_WC_BYTES, bar_w1);
         }
-        if (tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab)  // next slab's input rows -> L2 (after the weight copies)
-            l2_prefetch_slab(a.x + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
         // ---- P0: LN(x) -> A0 (chunks 0..11 of H)
         stage_rows96<FMT, true>(xs, T, hbuf, 1, s_lng, s_lnb, warp, lane, a.ln_stats ? a.ln_stats + (size_t)slab * T * 2 : nullptr, kFfnThreads / 32);
         end_epilogue();
@@ -207,6 +205,8 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         // ---- P2: conv1 ; E2: c1 = D + bc1; H = SiLU(c1)
         conv_phase(w1a, bar_w1, ph_w1);
         NBSS_TICK(0, 4, it_);
+        // next slab's input rows -> L2, away from this slab's latency-exposed staging loads (E2..E4 read nothing from HBM)
+        if (tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab) l2_prefetch_slab(a.x + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
         if (tid == 0) load_image(ws1, a.img + IMG_WC3, IMG_WC_BYTES, bar_w1);
         act_epilogue(s_bc, a.save_c1, slab);
         end_epilogue();

@@ -28,10 +28,9 @@ struct MhsaBwdArgs {
 
 // smem map (bytes)
 constexpr uint32_t MB_DO = 0;                       // dO tile, 13 chunks x kCS (chunk 12 = zeros); first holds dy (12 chunks)
-constexpr uint32_t MB_Q = 13 * kCS;                 // per-head Qs tile [256 x 32] fp16, 4 chunks
-constexpr uint32_t MB_K = MB_Q + 4 * kCS;
-constexpr uint32_t MB_V = MB_K + 4 * kCS;
-constexpr uint32_t MB_P = MB_V + 4 * kCS;           // P tile [128 q x 128 keys], 16 chunks x kCSQ; aliases the WoT image
+constexpr uint32_t MB_Q = 13 * kCS;                 // per-head Qs | K | V tiles [256 x 32] fp16, 4 chunks each, TWO sets: the next head's
+constexpr uint32_t MB_QKV_SET = 12 * kCS;           // q,k,v arrive by TMA while the current head is processed
+constexpr uint32_t MB_P = MB_Q + 2 * MB_QKV_SET;    // P tile [128 q x 128 keys], 16 chunks x kCSQ; aliases the WoT image
 constexpr uint32_t MB_DS = MB_P + 16 * kCSQ;        // dS tile
 constexpr uint32_t MB_DELTA = MB_DS + 16 * kCSQ;    // delta [4][256] floats
 constexpr uint32_t MB_LSE = MB_DELTA + 4096;        // lse   [4][256] floats
@@ -49,22 +48,22 @@ template <int FMT_G>
 __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* dot = smem + MB_DO;
-    unsigned char* qt = smem + MB_Q;
-    unsigned char* kt = smem + MB_K;
-    unsigned char* vt = smem + MB_V;
     unsigned char* pt = smem + MB_P;
     unsigned char* dst = smem + MB_DS;
     float* s_delta = reinterpret_cast<float*>(smem + MB_DELTA);
     float* s_lse = reinterpret_cast<float*>(smem + MB_LSE);
     uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + MB_BAR);
     uint64_t* bar_w = bar_mma + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
+    uint64_t* bar_q = bar_mma + 2;  // [2] q,k,v of tile set s have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = a.T;
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
         mbar_init(bar_mma, 1);
         mbar_init(bar_w, 1);
+        mbar_init(bar_q, 1);
+        mbar_init(bar_q + 1, 1);
         fence_mbar_init();
     }
     for (int i = tid; i < (int)(MB_DELTA / 16); i += kMbThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -76,7 +75,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
 
     const int m = (warp >> 2) & 1, q = warp & 3, hf = warp >> 3, kq = warp >> 2, rt = 32 * q + lane, t = 128 * m + rt;
     const uint32_t lane_off = (uint32_t)(32 * q) << 16;
-    const uint32_t doa = smem_u32(dot), qa = smem_u32(qt), ka = smem_u32(kt), va = smem_u32(vt), pa = smem_u32(pt), dsa = smem_u32(dst);
+    const uint32_t doa = smem_u32(dot), pa = smem_u32(pt), dsa = smem_u32(dst);
     // instruction descriptors: (A fmt, B fmt, A major, B major, N)
     auto idesc = [](uint32_t fa, uint32_t fb, uint32_t amn, uint32_t bmn, uint32_t n) {
         return (1u << 4) | (fa << 7) | (fb << 10) | (amn << 15) | (bmn << 16) | ((n >> 3) << 17) | (8u << 24);
@@ -91,7 +90,17 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
     constexpr uint32_t C_S = 0, C_DP = 128, C_DQ = 256, C_DK = 320, C_DV = 384;  // dO (M0) uses 0..191
     const float kscale = 0.6931471805599453f;                   // dK was formed with log2e-scaled q
     const float qscale = rsqrtf((float)kDH);
-    uint32_t ph_mma = 0, ph_w = 0;
+    uint32_t ph_mma = 0, ph_w = 0, ph_q = 0;  // bit s of ph_q: phase of tile set s's barrier
+    // ONE thread: the head's Qs, K, V (fp16, 24 -> 32 features: the 4th chunk of every tile stays zero): three chunk columns each,
+    // straight TMA bulk copies out of the slab-tile tensor written by mhsa_fwd, into tile set h & 1
+    auto load_qkv = [&](int slab, int h) {
+        unsigned char* base = smem + MB_Q + (h & 1) * MB_QKV_SET;
+        uint64_t* bar = bar_q + (h & 1);
+        mbar_expect_tx(bar, (uint32_t)(9 * T * 16));
+        for (int which = 0; which < 3; ++which)
+            for (int c = 0; c < 3; ++c)
+                bulk_g2s(base + (4 * which + c) * kCS, a.qkv + tile_off(slab, 36, T, 12 * which + 3 * h + c, 0), (uint32_t)(T * 16), bar);
+    };
 
     auto wait_mma = [&]() {
         __syncwarp();
@@ -109,9 +118,10 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
     for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x, ++it_) {
         const size_t row0 = (size_t)slab * T;
         NBSS_TICK(0, 0, it_);
-        if (tid == 0) load_image(pt, a.img + IMG_WOT, IMG_WQ_BYTES, bar_w);
-        if (tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab)  // next slab's upstream gradient -> L2 (after the weight copy)
-            l2_prefetch_slab(a.dy + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
+        if (tid == 0) {
+            load_image(pt, a.img + IMG_WOT, IMG_WQ_BYTES, bar_w);
+            load_qkv(slab, 0);  // every MMA of the previous slab has completed: tile set 0 is free
+        }
         for (int i = tid; i < kNH * 256; i += kMbThreads) {
             const int h = i >> 8, tt = i & 255;
             s_lse[i] = tt < T ? a.lse[((size_t)slab * kNH + h) * T + tt] : 0.f;
@@ -163,22 +173,17 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
         }
         end_epilogue();
         NBSS_TICK(0, 3, it_);
+        // next slab's upstream gradient -> L2, issued after this slab's own staging loads are done
+        if (tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab) l2_prefetch_slab(a.dy + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
         // ---- heads
 #pragma unroll 1
         for (int h = 0; h < kNH; ++h) {
-            // the head's Qs, K, V (fp16, 24 -> 32 features: the 4th chunk stays zero): three chunk columns each, straight
-            // TMA bulk copies out of the slab-tile tensor written by mhsa_fwd
-            if (tid == 0) {
-                mbar_expect_tx(bar_w, (uint32_t)(9 * T * 16));
-                for (int which = 0; which < 3; ++which) {
-                    unsigned char* base = which == 0 ? qt : (which == 1 ? kt : vt);
-                    for (int c = 0; c < 3; ++c)
-                        bulk_g2s(base + c * kCS, a.qkv + tile_off(slab, 36, T, 12 * which + 3 * h + c, 0), (uint32_t)(T * 16), bar_w);
-                }
-                mbar_wait(bar_w, ph_w, a.err);
-            }
-            ph_w ^= 1;
-            end_epilogue();
+            // q,k,v of this head were requested one head ago (tile set h & 1); request the next head's into the other set,
+            // whose last readers (the MMAs of head h - 1) completed before that head's read-out
+            const uint32_t qa = smem_u32(smem + MB_Q + (h & 1) * MB_QKV_SET), ka = qa + 4 * kCS, va = qa + 8 * kCS;
+            if (tid == 0 && h + 1 < kNH) load_qkv(slab, h + 1);
+            mbar_wait(bar_q + (h & 1), (ph_q >> (h & 1)) & 1u, a.err);
+            ph_q ^= 1u << (h & 1);
             NBSS_TICK(0, 4 + 12 * h, it_);
             // Software pipeline over the four 128x128 (query, key) blocks of the head: the S / dP MMAs of block b+1 are
             // issued together with the gradient MMAs of block b (different TMEM columns), so a block costs one

@@ -200,8 +200,6 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         const float* xs = a.x + (size_t)slab * T * kH;
         NBSS_TICK(0, 0, it_);
         if (tid == 0) load_image(wr, a.img + IMG_WKV, IMG_W1_BYTES, bar_w);
-        if (tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab)  // next slab's input rows -> L2 (after the weight copy)
-            l2_prefetch_slab(a.x + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
         stage_rows96<FMT, true>(xs, T, ao, 0, s_lng, s_lnb, warp, lane, a.ln_stats ? a.ln_stats + (size_t)slab * T * 2 : nullptr, kMhThreads / 32);
         end_epilogue();
         NBSS_TICK(0, 1, it_);
@@ -267,6 +265,9 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         wait_mma();
         NBSS_TICK(0, 4, it_);
         if (tid == 0) load_image(wr, a.img + IMG_WOP, IMG_WOP_BYTES, bar_w);  // out-proj image: needed only after the last head
+        // next slab's input rows -> L2, issued HERE (not at the top of the slab, where it would compete with this slab's
+        // latency-exposed staging loads): the attention heads below need no HBM traffic at all
+        if (tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab) l2_prefetch_slab(a.x + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
         // ---- EQ: scaled queries of all heads -> Q tile (over A0, dead now); thread = (frame, channel half)
         {
             const bool valid = t < T;

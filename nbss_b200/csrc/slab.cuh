@@ -34,6 +34,10 @@ __device__ __forceinline__ void load_image(void* dst_smem, const void* src, uint
 // The persistent kernels issue it for the data their NEXT slab / row group will stage, so those latency-exposed loads
 // hit L2 instead of HBM.  No architectural side effects: a wrong address range would only waste bandwidth.
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+#ifdef NBSS_NO_L2_PREFETCH  // A/B build (`make nopf`): measures what the prefetches are worth
+    (void)p; (void)bytes;
+    return;
+#endif
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 // fp32 slab [T,96] (T*384 bytes) in 6 pieces; call with i = 0..5 from six different threads

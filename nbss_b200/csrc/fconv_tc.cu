@@ -369,7 +369,6 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         const int b = grp / g.groups_per_b, t0 = (grp % g.groups_per_b) * g.nfr;
         NBSS_TICK(1, 0, it_);
         if (tid == 0) load_image(wimg, a.img, FC_IMG_BYTES, bar_w);
-        fc_prefetch_rows(g, a.x, a.dy, grp + gridDim.x, tid, NT);
         fc_stage<FMT, 5, NW>(g, a.x, b, t0, htile, cst, cst + 96, stats, warp, lane);
         fc_stage_plain<FMT, 5, NW>(g, a.dy, b, t0, gtile, warp, lane);
         fence_async_smem();

@@ -239,74 +239,64 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         NBSS_TICK(0, 4, it_);
         if (tid == 0) load_image(ws1, a.img + IMG_WC1T, IMG_WC_BYTES, bar_w1);
         {
-            // GroupNorm + SiLU backward in two sweeps over the thread's 96 accumulator columns.  Both sweeps are software-
-            // pipelined (TMEM and global loads of the next 16 columns in flight while 16 are processed) and the second one
-            // needs NO global reads: sweep A parks the saved c2 bits in the G tile (dead after the conv^T MMAs) and writes
-            // dn = d s3 * SiLU'(n) back over the accumulator columns in tensor memory (fp32, tcgen05.st).
+            // GroupNorm + SiLU backward in two sweeps over the thread's 96 accumulator columns; the second sweep needs NO global
+            // reads: sweep A parks the saved c2 bits in the G tile (dead after the conv^T MMAs) and writes
+            // dn = d s3 * SiLU'(n) back over the accumulator columns in tensor memory (fp32, tcgen05.st).  Loops stay ROLLED:
+            // this kernel is far larger than the instruction cache and every warp walks the code once per slab, so
+            // straight-line unrolling costs more in instruction fetch than it saves (measured: 40k -> 57k cycles).
             const float* gst = a.gn_stats + (size_t)slab * 16;
-            float gmean[4], grstd[4], s1g[4] = {0.f, 0.f, 0.f, 0.f}, s2g[4] = {0.f, 0.f, 0.f, 0.f};
+            // sweep A, one group (24 channels) per iteration; the next group's saved c2 is requested one iteration ahead
+            uint4 cq[3], cqn[3];
 #pragma unroll
-            for (int gl = 0; gl < 4; ++gl) { gmean[gl] = gst[2 * (4 * hf + gl)]; grstd[gl] = gst[2 * (4 * hf + gl) + 1]; }
-            // sweep A: s3 out, c2 -> G tile, dn -> TMEM, group sums S1 = sum dn*gamma, S2 = sum dn*gamma*xhat
-            auto sweepA16 = [&](const uint32_t (&r)[16], const uint4 (&cq)[2], int b) {  // b: compile-time after unrolling
-                const int c0 = cb + 16 * b;
-                float c[16];
-                uint32_t dn[16];
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    unpack_f16x2(cq[cc].x, c[8 * cc + 0], c[8 * cc + 1]);
-                    unpack_f16x2(cq[cc].y, c[8 * cc + 2], c[8 * cc + 3]);
-                    unpack_f16x2(cq[cc].z, c[8 * cc + 4], c[8 * cc + 5]);
-                    unpack_f16x2(cq[cc].w, c[8 * cc + 6], c[8 * cc + 7]);
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int gl = (16 * b + j) / kGC;
-                    const float xh = (c[j] - gmean[gl]) * grstd[gl];
-                    const float n = fmaf(xh, s_gng[c0 + j], s_gnb[c0 + j]);
-                    const float sg = sigmoidf_(n);
-                    float d = __uint_as_float(r[j]) * sg * fmaf(n, 1.f - sg, 1.f);
-                    if (!wfull) d *= vmask;  // warp-uniform branch: frames >= T carry no gradient
-                    c[j] = n * sg;           // s3
-                    const float dxh = d * s_gng[c0 + j];
-                    s1g[gl] += dxh;
-                    s2g[gl] = fmaf(dxh, xh, s2g[gl]);
-                    dn[j] = __float_as_uint(d);
-                }
-                tmem_st16(tacc + c0, dn);
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    if (valid) *reinterpret_cast<uint4*>(a.s3 + tile_off(slab, 24, T, c0 / 8 + cc, t)) = pack8<FMT>(c + 8 * cc);
-                    *reinterpret_cast<uint4*>(hrow + (c0 / 8 + cc) * kCS) = cq[cc];
-                }
-            };
-            {
-                uint32_t ra[16], rb[16];
-                uint4 ca[2], cb2[2];
-                load_c(a.c2, slab, cb, ca);
-                tmem_ld16(tacc + cb, ra);
-                tmem_ld_wait();
-#pragma unroll
-                for (int b = 0; b < 6; b += 2) {
-                    tmem_ld16(tacc + cb + 16 * (b + 1), rb);
-                    load_c(a.c2, slab, cb + 16 * (b + 1), cb2);
-                    sweepA16(ra, ca, b);
-                    tmem_ld_wait();
-                    if (b + 2 < 6) {
-                        tmem_ld16(tacc + cb + 16 * (b + 2), ra);
-                        load_c(a.c2, slab, cb + 16 * (b + 2), ca);
-                    }
-                    sweepA16(rb, cb2, b + 1);
-                    tmem_ld_wait();
-                }
-                tmem_st_wait();
-            }
-            NBSS_TICK(0, 20, it_);
-#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                cq[k] = valid ? __ldg(reinterpret_cast<const uint4*>(a.c2 + tile_off(slab, 24, T, cb / 8 + k, t))) : make_uint4(0, 0, 0, 0);
+#pragma unroll 1
             for (int gl = 0; gl < 4; ++gl) {
-                const float s1 = warp_sum(s1g[gl]), s2 = warp_sum(s2g[gl]);
-                if (lane == 0) { red[(warp * 8 + 4 * hf + gl) * 2] = s1; red[(warp * 8 + 4 * hf + gl) * 2 + 1] = s2; }
+                const int g = 4 * hf + gl, c0 = kGC * g;
+                uint32_t r[24];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) tmem_ld8(tacc + c0 + 8 * k, *reinterpret_cast<uint32_t(*)[8]>(r + 8 * k));
+                if (gl < 3) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        cqn[k] = valid ? __ldg(reinterpret_cast<const uint4*>(a.c2 + tile_off(slab, 24, T, (c0 + kGC) / 8 + k, t))) : make_uint4(0, 0, 0, 0);
+                }
+                const float mean = __ldg(gst + 2 * g), rstd = __ldg(gst + 2 * g + 1);
+                tmem_ld_wait();
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int c = c0 + 8 * k;
+                    float cv[8];
+                    uint32_t dn[8];
+                    unpack_f16x2(cq[k].x, cv[0], cv[1]);
+                    unpack_f16x2(cq[k].y, cv[2], cv[3]);
+                    unpack_f16x2(cq[k].z, cv[4], cv[5]);
+                    unpack_f16x2(cq[k].w, cv[6], cv[7]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float xh = (cv[j] - mean) * rstd;
+                        const float n = fmaf(xh, s_gng[c + j], s_gnb[c + j]);
+                        const float sg = sigmoidf_(n);
+                        const float d = __uint_as_float(r[8 * k + j]) * sg * fmaf(n, 1.f - sg, 1.f) * vmask;  // frames >= T carry no gradient
+                        cv[j] = n * sg;  // s3
+                        const float dxh = d * s_gng[c + j];
+                        s1 += dxh;
+                        s2 = fmaf(dxh, xh, s2);
+                        dn[j] = __float_as_uint(d);
+                    }
+                    tmem_st8(tacc + c, dn);
+                    if (valid) *reinterpret_cast<uint4*>(a.s3 + tile_off(slab, 24, T, c / 8, t)) = pack8<FMT>(cv);
+                    *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = cq[k];
+                }
+                s1 = warp_sum(s1);
+                s2 = warp_sum(s2);
+                if (lane == 0) { red[(warp * 8 + g) * 2] = s1; red[(warp * 8 + g) * 2 + 1] = s2; }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) cq[k] = cqn[k];
             }
+            tmem_st_wait();
+            NBSS_TICK(0, 20, it_);
             __syncthreads();
             if (tid < 16) {
                 float s = 0.f;
@@ -317,52 +307,40 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
             __syncthreads();
             NBSS_TICK(0, 21, it_);
             // sweep B: g(c2) = rstd * (dn*gamma - S1/N - xhat*S2/N) -> G tile + global; column sums for d_gnw, d_gnb
-            auto sweepB16 = [&](const uint32_t (&r)[16], int b) {
-                const int c0 = cb + 16 * b;
+#pragma unroll 1
+            for (int c0 = cb; c0 < cb + 96; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tacc + c0, r);
                 float dnv[16], dnx[16];
+                uint4 pk[2];
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) pk[cc] = *reinterpret_cast<const uint4*>(hrow + (c0 / 8 + cc) * kCS);  // the c2 bits parked by sweep A
+                tmem_ld_wait();
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
-                    const uint4 pk = *reinterpret_cast<const uint4*>(hrow + (c0 / 8 + cc) * kCS);  // the c2 bits parked by sweep A
+                    const int c = c0 + 8 * cc, g = c / kGC;
+                    const float mean = __ldg(gst + 2 * g), rstd = __ldg(gst + 2 * g + 1), m1 = gtot[2 * g], m2 = gtot[2 * g + 1];
                     float cv[8], gv[8];
-                    unpack_f16x2(pk.x, cv[0], cv[1]);
-                    unpack_f16x2(pk.y, cv[2], cv[3]);
-                    unpack_f16x2(pk.z, cv[4], cv[5]);
-                    unpack_f16x2(pk.w, cv[6], cv[7]);
+                    unpack_f16x2(pk[cc].x, cv[0], cv[1]);
+                    unpack_f16x2(pk[cc].y, cv[2], cv[3]);
+                    unpack_f16x2(pk[cc].z, cv[4], cv[5]);
+                    unpack_f16x2(pk[cc].w, cv[6], cv[7]);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int gl = (16 * b + 8 * cc + j) / kGC, g = 4 * hf + gl;
-                        const float xh = (cv[j] - gmean[gl]) * grstd[gl];
+                        const float xh = (cv[j] - mean) * rstd;
                         const float d = __uint_as_float(r[8 * cc + j]);  // 0 for frames >= T
                         dnv[8 * cc + j] = d;
                         dnx[8 * cc + j] = d * xh;
-                        gv[j] = grstd[gl] * (d * s_gng[c0 + 8 * cc + j] - gtot[2 * g] - xh * gtot[2 * g + 1]);
-                    }
-                    if (!wfull) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) gv[j] *= vmask;
+                        gv[j] = rstd * (d * s_gng[c + j] - m1 - xh * m2) * vmask;
                     }
                     const uint4 gp = pack8<FMT>(gv);
-                    if (valid) *reinterpret_cast<uint4*>(a.g_c2 + tile_off(slab, 24, T, c0 / 8 + cc, t)) = gp;
-                    *reinterpret_cast<uint4*>(hrow + (c0 / 8 + cc) * kCS) = gp;
+                    if (valid) *reinterpret_cast<uint4*>(a.g_c2 + tile_off(slab, 24, T, c / 8, t)) = gp;
+                    *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = gp;
                 }
                 const float sw = warp_colsum16(dnx, lane), sb = warp_colsum16(dnv, lane);
                 if (!(lane & 1)) {
                     atomicAdd(acc + c0 + (lane >> 1), sw);
                     atomicAdd(acc + 192 + c0 + (lane >> 1), sb);
-                }
-            };
-            {
-                uint32_t ra[16], rb[16];
-                tmem_ld16(tacc + cb, ra);
-                tmem_ld_wait();
-#pragma unroll
-                for (int b = 0; b < 6; b += 2) {
-                    tmem_ld16(tacc + cb + 16 * (b + 1), rb);
-                    sweepB16(ra, b);
-                    tmem_ld_wait();
-                    if (b + 2 < 6) tmem_ld16(tacc + cb + 16 * (b + 2), ra);
-                    sweepB16(rb, b + 1);
-                    tmem_ld_wait();
                 }
             }
         }

@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         NBSS_TICK(0, 6, it_);
         if (tid == 0) load_image(ws0, a.img + IMG_W2, IMG_W2_BYTES, bar_w0);
         {
-            // GroupNorm(8 groups of 24 channels x T frames) in TWO sweeps over the thread's 96 accumulator columns, TMEM loads
-            // software-pipelined (16 columns in flight while 16 are processed):
+            // GroupNorm(8 groups of 24 channels x T frames) in TWO sweeps over the thread's 96 accumulator columns (one group of
+            // 24 columns = three TMEM loads in flight per iteration; loops stay rolled: the kernel exceeds the instruction cache):
             //   sweep 1: per-group sum and sum of squares of (c2 - pivot); the pivot (the group's mean bias, known to every
             //            thread without communication) takes the bias-dominated part of the mean out before squaring
             //   sweep 2: normalise, affine, SiLU -> H; save c2
@@ -225,34 +225,23 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
             float* red_sq = red + 128;
             float* gtot = red + 256;    // [8 groups][2] (mean, rstd) of this slab
             const float* bc2 = s_bc + 192;
-            float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
-            auto acc16 = [&](const uint32_t (&r)[16], int b) {  // b is a compile-time constant after unrolling
+#pragma unroll 1
+            for (int g = 4 * hf; g < 4 * hf + 4; ++g) {
+                uint32_t r[24];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int gl = (16 * b + j) / kGC;
-                    const float v = __uint_as_float(r[j]) + bc2[cb + 16 * b + j] - s_piv[4 * hf + gl];
-                    gs[gl] += v;
-                    gq[gl] = fmaf(v, v, gq[gl]);
-                }
-            };
-            {
-                uint32_t ra[16], rb[16];
-                tmem_ld16(tacc + cb, ra);
+                for (int k = 0; k < 3; ++k) tmem_ld8(tacc + kGC * g + 8 * k, *reinterpret_cast<uint32_t(*)[8]>(r + 8 * k));
+                const float piv = s_piv[g];
                 tmem_ld_wait();
+                float s = 0.f, qq = 0.f;
 #pragma unroll
-                for (int b = 0; b < 6; b += 2) {
-                    tmem_ld16(tacc + cb + 16 * (b + 1), rb);
-                    acc16(ra, b);
-                    tmem_ld_wait();
-                    if (b + 2 < 6) tmem_ld16(tacc + cb + 16 * (b + 2), ra);
-                    acc16(rb, b + 1);
-                    tmem_ld_wait();
+                for (int j = 0; j < 24; ++j) {
+                    const float v = __uint_as_float(r[j]) + bc2[kGC * g + j] - piv;
+                    s += v;
+                    qq = fmaf(v, v, qq);
                 }
-            }
-#pragma unroll
-            for (int gl = 0; gl < 4; ++gl) {
-                const float s = warp_sum(valid ? gs[gl] : 0.f), qq = warp_sum(valid ? gq[gl] : 0.f);
-                if (lane == 0) { red_sum[warp * 8 + 4 * hf + gl] = s; red_sq[warp * 8 + 4 * hf + gl] = qq; }
+                s = warp_sum(valid ? s : 0.f);
+                qq = warp_sum(valid ? qq : 0.f);
+                if (lane == 0) { red_sum[warp * 8 + g] = s; red_sq[warp * 8 + g] = qq; }
             }
             __syncthreads();
             if (tid < 8) {  // fixed summation order: the forward is bit-reproducible
@@ -271,39 +260,23 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
                 }
             }
             __syncthreads();
-            auto norm16 = [&](const uint32_t (&r)[16], int b) {
-                float v[16];
+#pragma unroll 1
+            for (int g = 4 * hf; g < 4 * hf + 4; ++g) {
+                uint32_t r[24];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + bc2[cb + 16 * b + j];
-                const int c0 = cb + 16 * b;
-                if (a.save_c2 && valid) {
-                    *reinterpret_cast<uint4*>(a.save_c2 + tile_off(slab, 24, T, c0 / 8, t)) = pack8<FMT_F16>(v);
-                    *reinterpret_cast<uint4*>(a.save_c2 + tile_off(slab, 24, T, c0 / 8 + 1, t)) = pack8<FMT_F16>(v + 8);
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int g = 4 * hf + (16 * b + j) / kGC;
-                    v[j] = silu((v[j] - gtot[2 * g]) * (gtot[2 * g + 1] * s_gng[c0 + j]) + s_gnb[c0 + j]);
-                }
-                if (!wfull) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] *= vmask;
-                }
-                *reinterpret_cast<uint4*>(hrow + (c0 / 8) * kCS) = pack8<FMT>(v);
-                *reinterpret_cast<uint4*>(hrow + (c0 / 8 + 1) * kCS) = pack8<FMT>(v + 8);
-            };
-            {
-                uint32_t ra[16], rb[16];
-                tmem_ld16(tacc + cb, ra);
+                for (int k = 0; k < 3; ++k) tmem_ld8(tacc + kGC * g + 8 * k, *reinterpret_cast<uint32_t(*)[8]>(r + 8 * k));
+                const float mean = gtot[2 * g], rstd = gtot[2 * g + 1];
                 tmem_ld_wait();
 #pragma unroll
-                for (int b = 0; b < 6; b += 2) {
-                    tmem_ld16(tacc + cb + 16 * (b + 1), rb);
-                    norm16(ra, b);
-                    tmem_ld_wait();
-                    if (b + 2 < 6) tmem_ld16(tacc + cb + 16 * (b + 2), ra);
-                    norm16(rb, b + 1);
-                    tmem_ld_wait();
+                for (int k = 0; k < 3; ++k) {
+                    const int c = kGC * g + 8 * k;
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * k + j]) + bc2[c + j];
+                    if (a.save_c2 && valid) *reinterpret_cast<uint4*>(a.save_c2 + tile_off(slab, 24, T, c / 8, t)) = pack8<FMT_F16>(v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = silu((v[j] - mean) * (rstd * s_gng[c + j]) + s_gnb[c + j]) * vmask;
+                    *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = pack8<FMT>(v);
                 }
             }
         }

@@ -44,9 +44,6 @@ constexpr uint32_t IMG_WO = IMG_WQ + IMG_WQ_BYTES;     // out_proj [N=96 x K=96]
 constexpr uint32_t IMG_WOT = IMG_WO + IMG_WQ_BYTES;    // dgrad out_proj: elem(n,k) = Wo[k,n]
 constexpr uint32_t IMG_WINT = IMG_WOT + IMG_WQ_BYTES;  // dgrad in_proj: [N=96 x K=288], elem(n,k) = Win[k,n]
 constexpr uint32_t IMG_WINT_BYTES = 36 * 96 * 16;      // 55296
-constexpr uint32_t IMG_WOP = IMG_WINT + IMG_WINT_BYTES;  // out_proj over the per-head PADDED feature axis (mhsa_fwd keeps O in the K tile's
-                                                         // layout, 24 -> 32 features per head): [N=96 x K=128], elem(n, 32h+j) = Wo[n, 24h+j], 0 for j >= 24
-constexpr uint32_t IMG_WOP_BYTES = 16 * 96 * 16;         // 24576
-constexpr uint32_t IMG_LAYER_BYTES = IMG_WOP + IMG_WOP_BYTES;  // 651264
+constexpr uint32_t IMG_LAYER_BYTES = IMG_WINT + IMG_WINT_BYTES;  // 626688
 
 }  // namespace nbss

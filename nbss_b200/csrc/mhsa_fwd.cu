@@ -13,7 +13,7 @@
 //        last 32 columns of the quarter; the read-out combines the four partial outputs with exp2(m_q - m) and 1/l.
 //        One __syncthreads per softmax and per read-out; the S / PV MMAs of one query tile run under the softmax / read-out
 //        of the other.
-//   P3 y = x + O Wo^T + bo   (O lives in the K tile's per-head padded layout; Wo image padded to K = 128)
+//   P3 y = x + O Wo^T + bo   (O_h(tile) overwrites Q_h(tile) in the Q tile once its scores are done)
 // HBM traffic: x in, y out (+ fp16 q|k|v, O and the log2-sum-exp when save != 0, for the backward kernels).
 #include "slab.cuh"
 
@@ -32,8 +32,8 @@ struct MhsaFwdArgs {
     int* err;
 };
 
-constexpr uint32_t MH_AO = 0;                       // A0, then the Q tile: 13 chunks (the 13th stays zero)
-constexpr uint32_t MH_K = 13 * kCS;                 // 55120: K tile, 16 chunks (head h: chunks 4h..4h+2, 4h+3 = zero pad); later O
+constexpr uint32_t MH_AO = 0;                       // A0, then the Q tile, then O: 13 chunks (the 13th stays zero)
+constexpr uint32_t MH_K = 13 * kCS;                 // 55120: K tile, 16 chunks (4 heads: head h = chunks 4h..4h+2, 4h+3 = zero pad; 2 heads: 6 chunks each)
 constexpr uint32_t MH_V = MH_K + 16 * kCS;          // 122960: V tile, 13 chunks (the 13th stays zero)
 constexpr uint32_t MH_W = MH_V + 13 * kCS;          // 178080: one weight image at a time
 constexpr uint32_t MH_W_BYTES = IMG_W1_BYTES;       // 36864
@@ -42,10 +42,20 @@ constexpr uint32_t MH_STAT = MH_CST + 576 * 4;      // (m_q, l_q) [2 buffers][4 
 constexpr uint32_t MH_BAR = MH_STAT + 8192;
 constexpr int kMhThreads = 512;  // 16 warps
 constexpr uint32_t MH_SMEM = MH_BAR + 64;
-static_assert(IMG_WOP_BYTES <= MH_W_BYTES && IMG_WQ_BYTES <= MH_W_BYTES, "weight image must fit the W region");
+static_assert(IMG_WQ_BYTES <= MH_W_BYTES, "weight image must fit the W region");
 
-template <int FMT>
+// NHEADS = 4 (SpatialNet-small: head dim 24, padded to 32 in the K / O tiles) or 2 (NBC2: head dim 48, no padding).
+// DBUF: the four partial-output accumulators of a query tile fit the spare columns of its score buffer (head dim <= 32), so two
+// score buffers ping-pong; otherwise (head dim 48) one score buffer [0,256) and the partial outputs at [256, 256 + 4*48).
+template <int FMT, int NHEADS>
 __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
+    constexpr int DH = kH / NHEADS;                 // 24 | 48
+    constexpr int KCH = DH / 8;                     // data chunks per head: 3 | 6
+    constexpr int HS = (DH % 16) ? KCH + 1 : KCH;   // chunk stride of a head in the K / O tile (one zero pad chunk if DH % 16): 4 | 6
+    constexpr int KKS = (DH + 15) / 16;             // k-steps of S = Q_h K_h^T: 2 | 3
+    constexpr int NPV = 16 * KKS;                   // N of the PV MMA: 32 | 48
+    constexpr bool DBUF = 4 * NPV <= 128;
+    constexpr int CPT = NPV == 32 ? 8 : 16;         // output features per read-out thread (3 threads per query row)
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* ao = smem + MH_AO;
     unsigned char* kt = smem + MH_K;
@@ -86,8 +96,10 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
     const uint32_t lane_off = (uint32_t)(32 * q) << 16;
     const uint32_t aoa = smem_u32(ao), kta = smem_u32(kt), vta = smem_u32(vt), wra = smem_u32(wr);
     const uint32_t id192 = make_idesc(FMT, 128, 192, 0, 0), id96 = make_idesc(FMT, 128, 96, 0, 0),
-                   id256 = make_idesc(FMT, 128, 256, 0, 0), idpv = make_idesc(FMT, 128, 32, 0, 1);
-    const float qscale = rsqrtf((float)kDH) * 1.4426950408889634f;
+                   id256 = make_idesc(FMT, 128, 256, 0, 0), idpv = make_idesc(FMT, 128, NPV, 0, 1);
+    const float qscale = rsqrtf((float)DH) * 1.4426950408889634f;
+    auto s_col = [&](int buf) -> uint32_t { return DBUF ? 256u * buf : 0u; };                          // score buffer
+    auto o_col = [&](int buf, int kk) -> uint32_t { return DBUF ? 256u * buf + 64u * kk + 32u : 256u + NPV * kk; };  // partial outputs
     const bool kmask = 64 * kq + 63 >= T;  // warp-uniform: this key quarter holds keys >= T (they get probability 0)
     uint32_t ph_mma = 0, ph_w = 0, ph_s = 0, ph_pv = 0;  // bit b of ph_s / ph_pv: phase of buffer b's barrier
 
@@ -102,17 +114,17 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         tc_fence_before();
         __syncthreads();
     };
-    // warp 0: S(h, mq) = Q_h K_h^T into score buffer mq (columns 256*mq .. +255); completion on bar_s[mq]
-    auto issue_s = [&](int h, int mq) {
+    // warp 0: S(h, mq) = Q_h K_h^T into score buffer `buf`; completion on bar_s[buf]
+    auto issue_s = [&](int h, int mq, int buf) {
         tc_fence_after();
         const bool leader = elect_one();
-        mma_kk(tmem + 256 * mq, aoa + 3 * h * kCS + 128 * mq * 16, kCS, kta + 4 * h * kCS, kCS, 2, id256, 0, leader);
-        if (leader) umma_commit(bar_s + mq);
+        mma_kk(tmem + s_col(buf), aoa + KCH * h * kCS + 128 * mq * 16, kCS, kta + HS * h * kCS, kCS, KKS, id256, 0, leader);
+        if (leader) umma_commit(bar_s + buf);
         __syncwarp();
     };
     // softmax of one query tile over the thread's own 64 keys; P -> TMEM (first 32 of the thread's 64 score columns)
     auto softmax_local = [&](int b) {
-        const uint32_t ts = tmem + lane_off + 256 * b + 64 * kq;
+        const uint32_t ts = tmem + lane_off + s_col(b) + 64 * kq;
         uint32_t r0[32], r1[32];
         tmem_ld32(ts, r0);
         tmem_ld32(ts + 32, r1);
@@ -162,36 +174,54 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
 #pragma unroll 1
             for (int ks = 0; ks < 4; ++ks)
                 if (leader)
-                    umma_f16_ts(tmem + 256 * b + 64 * kk + 32, tmem + 256 * b + 64 * kk + 8 * ks,
-                                sdesc_mnmajor(vta + 3 * h * kCS + (64 * kk + 16 * ks) * 16, kCS), idpv, ks ? 1u : 0u);
+                    umma_f16_ts(tmem + o_col(b, kk), tmem + s_col(b) + 64 * kk + 8 * ks,
+                                sdesc_mnmajor(vta + KCH * h * kCS + (64 * kk + 16 * ks) * 16, kCS), idpv, ks ? 1u : 0u);
         if (leader) umma_commit(bar_pv + b);
         __syncwarp();
     };
-    // read-out of one query tile: combine the four partial outputs, normalise, O_h -> K tile (chunks 4h..4h+2), saves
-    auto readout = [&](int h, int b, int slab) {
-        const int tq = 128 * b + rt;
+    // read-out of query tile mq (score buffer b): combine the four partial outputs, normalise, saves; O_h(tile mq) goes into the Q tile
+    // over Q_h(tile mq), which is dead once S(h, mq) has completed (the compact O tile is the out-proj's A operand)
+    auto readout = [&](int h, int mq, int b, int slab) {
+        const int tq = 128 * mq + rt;
         const float2 s0 = stat[(b * 4 + 0) * 128 + rt], s1 = stat[(b * 4 + 1) * 128 + rt], s2 = stat[(b * 4 + 2) * 128 + rt],
                      s3 = stat[(b * 4 + 3) * 128 + rt];
         const float mx = fmaxf(fmaxf(s0.x, s1.x), fmaxf(s2.x, s3.x));  // finite: key quarter 0 always holds key 0 < T
-        const float f0 = ex2_ftz(s0.x - mx), f1 = ex2_ftz(s1.x - mx), f2 = ex2_ftz(s2.x - mx), f3 = ex2_ftz(s3.x - mx);  // ex2(-inf) = 0
-        const float l = f0 * s0.y + f1 * s1.y + f2 * s2.y + f3 * s3.y;
+        const float f[4] = {ex2_ftz(s0.x - mx), ex2_ftz(s1.x - mx), ex2_ftz(s2.x - mx), ex2_ftz(s3.x - mx)};  // ex2(-inf) = 0
+        const float l = f[0] * s0.y + f[1] * s1.y + f[2] * s2.y + f[3] * s3.y;
         const float inv = 1.f / l;
-        if (kq < 3) {  // thread = (query row, 8 of the head's 24 output features)
-            const uint32_t to = tmem + lane_off + 256 * b + 32 + 8 * kq;
-            uint32_t o0[8], o1[8], o2[8], o3[8];
-            tmem_ld8(to, o0);
-            tmem_ld8(to + 64, o1);
-            tmem_ld8(to + 128, o2);
-            tmem_ld8(to + 192, o3);
-            tmem_ld_wait();
-            float v[8];
+        if (kq < 3) {  // thread = (query row, CPT of the head's output features)
+            float acc[CPT];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                v[j] = (f0 * __uint_as_float(o0[j]) + f1 * __uint_as_float(o1[j]) + f2 * __uint_as_float(o2[j]) + f3 * __uint_as_float(o3[j])) * inv;
-            *reinterpret_cast<uint4*>(kt + (4 * h + kq) * kCS + tq * 16) = pack8<FMT>(v);
-            if (a.save_o && tq < T) *reinterpret_cast<uint4*>(a.save_o + tile_off(slab, 12, T, 3 * h + kq, tq)) = pack8<FMT_F16>(v);
+            for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
+            if constexpr (CPT == 8) {
+                uint32_t o[4][8];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) tmem_ld8(tmem + lane_off + o_col(b, kk) + 8 * kq, o[kk]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[kk], __uint_as_float(o[kk][j]), acc[j]);
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    uint32_t o[16];
+                    tmem_ld16(tmem + lane_off + o_col(b, kk) + 16 * kq, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = fmaf(f[kk], __uint_as_float(o[j]), acc[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) acc[j] *= inv;
+#pragma unroll
+            for (int cc = 0; cc < CPT / 8; ++cc) {
+                *reinterpret_cast<uint4*>(ao + (KCH * h + (CPT / 8) * kq + cc) * kCS + tq * 16) = pack8<FMT>(acc + 8 * cc);
+                if (a.save_o && tq < T)
+                    *reinterpret_cast<uint4*>(a.save_o + tile_off(slab, 12, T, KCH * h + (CPT / 8) * kq + cc, tq)) = pack8<FMT_F16>(acc + 8 * cc);
+            }
         } else if (a.save_lse && tq < T) {
-            a.save_lse[((size_t)slab * kNH + h) * T + tq] = mx + log2f(l);
+            a.save_lse[((size_t)slab * NHEADS + h) * T + tq] = mx + log2f(l);
         }
     };
 
@@ -218,20 +248,21 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         {
             const bool valid = t < T;
             const uint32_t tacc = tmem + lane_off + m * 192;
-            // K: cols 0..95 -> per-head padded chunks 4h..4h+2   (channel half 0 does K, half 1 does V)
+            // K: cols 0..95 -> per-head chunks HS*h .. HS*h+KCH-1   (channel half 0 does K, half 1 does V)
 #pragma unroll 1
-            for (int h = 0; h < (hf == 0 ? kNH : 0); ++h) {
+            for (int c3 = 0; c3 < (hf == 0 ? 12 : 0); c3 += 3) {  // three compact chunks at a time (never straddles a head)
+                const int h = c3 / KCH, k0 = c3 % KCH;
                 uint32_t r[24];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) tmem_ld8(tacc + kDH * h + 8 * k, *reinterpret_cast<uint32_t(*)[8]>(r + 8 * k));
+                for (int k = 0; k < 3; ++k) tmem_ld8(tacc + 8 * (c3 + k), *reinterpret_cast<uint32_t(*)[8]>(r + 8 * k));
                 tmem_ld_wait();
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     float v[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = valid ? __uint_as_float(r[8 * k + j]) + s_bin[96 + kDH * h + 8 * k + j] : 0.f;
-                    *reinterpret_cast<uint4*>(kt + (4 * h + k) * kCS + t * 16) = pack8<FMT>(v);
-                    if (a.save_qkv && valid) *reinterpret_cast<uint4*>(a.save_qkv + tile_off(slab, 36, T, 12 + 3 * h + k, t)) = pack8<FMT_F16>(v);
+                    for (int j = 0; j < 8; ++j) v[j] = valid ? __uint_as_float(r[8 * k + j]) + s_bin[96 + 8 * (c3 + k) + j] : 0.f;
+                    *reinterpret_cast<uint4*>(kt + (HS * h + k0 + k) * kCS + t * 16) = pack8<FMT>(v);
+                    if (a.save_qkv && valid) *reinterpret_cast<uint4*>(a.save_qkv + tile_off(slab, 36, T, 12 + c3 + k, t)) = pack8<FMT_F16>(v);
                 }
             }
             // V: cols 96..191 -> compact chunks 0..11
@@ -264,7 +295,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         ph_w ^= 1;
         wait_mma();
         NBSS_TICK(0, 4, it_);
-        if (tid == 0) load_image(wr, a.img + IMG_WOP, IMG_WOP_BYTES, bar_w);  // out-proj image: needed only after the last head
+        if (tid == 0) load_image(wr, a.img + IMG_WO, IMG_WQ_BYTES, bar_w);  // out-proj image: needed only after the last head
         // next slab's input rows -> L2, issued HERE (not at the top of the slab, where it would compete with this slab's
         // latency-exposed staging loads): the attention heads below need no HBM traffic at all
         if (tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab) l2_prefetch_slab(a.x + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
@@ -290,40 +321,64 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         }
         end_epilogue();
         NBSS_TICK(0, 8, it_);
-        // ---- heads: the two query tiles of a head ping-pong between the two score buffers
-        if (warp == 0) { issue_s(0, 0); issue_s(0, 1); }
+        // ---- heads
+        if constexpr (DBUF) {
+            // the two query tiles of a head ping-pong between the two score buffers
+            if (warp == 0) { issue_s(0, 0, 0); issue_s(0, 1, 1); }
 #pragma unroll 1
-        for (int h = 0; h < kNH; ++h) {
+            for (int h = 0; h < NHEADS; ++h) {
 #pragma unroll 1
-            for (int b = 0; b < 2; ++b) {
-                mbar_wait(bar_s + b, (ph_s >> b) & 1u, a.err);
-                ph_s ^= 1u << b;
-                tc_fence_after();
-                softmax_local(b);
-                tc_fence_before();
-                __syncthreads();
-                if (warp == 0) issue_pv(h, b);
-                NBSS_TICK(0, 9 + 10 * h + 2 * b, it_);
+                for (int b = 0; b < 2; ++b) {
+                    mbar_wait(bar_s + b, (ph_s >> b) & 1u, a.err);
+                    ph_s ^= 1u << b;
+                    tc_fence_after();
+                    softmax_local(b);
+                    tc_fence_before();
+                    __syncthreads();
+                    if (warp == 0) issue_pv(h, b);
+                    NBSS_TICK(0, 9 + 10 * h + 2 * b, it_);
+                }
+#pragma unroll 1
+                for (int b = 0; b < 2; ++b) {
+                    mbar_wait(bar_pv + b, (ph_pv >> b) & 1u, a.err);
+                    ph_pv ^= 1u << b;
+                    tc_fence_after();
+                    readout(h, b, b, slab);
+                    fence_async_smem();  // O -> Q tile is read by the out-proj MMA
+                    tc_fence_before();
+                    __syncthreads();
+                    if (warp == 0 && h + 1 < NHEADS) issue_s(h + 1, b, b);  // buffer b is free again
+                    NBSS_TICK(0, 10 + 10 * h + 2 * b + 3, it_);
+                }
             }
+        } else {
+            // head dim 48: one score buffer; S -> softmax -> PV -> read-out in sequence (4 rounds per slab)
 #pragma unroll 1
-            for (int b = 0; b < 2; ++b) {
-                mbar_wait(bar_pv + b, (ph_pv >> b) & 1u, a.err);
-                ph_pv ^= 1u << b;
+            for (int hm = 0; hm < 2 * NHEADS; ++hm) {
+                const int h = hm >> 1, mq = hm & 1;
+                if (warp == 0) issue_s(h, mq, 0);
+                mbar_wait(bar_s, ph_s & 1u, a.err);
+                ph_s ^= 1u;
                 tc_fence_after();
-                readout(h, b, slab);
-                fence_async_smem();  // O -> K tile is read by the out-proj MMA
+                softmax_local(0);
                 tc_fence_before();
                 __syncthreads();
-                if (warp == 0 && h + 1 < kNH) issue_s(h + 1, b);  // buffer b is free again
-                NBSS_TICK(0, 10 + 10 * h + 2 * b + 3, it_);
+                if (warp == 0) issue_pv(h, 0);
+                mbar_wait(bar_pv, ph_pv & 1u, a.err);
+                ph_pv ^= 1u;
+                tc_fence_after();
+                readout(h, mq, 0, slab);
+                fence_async_smem();
+                tc_fence_before();
+                __syncthreads();
             }
         }
-        // ---- P3: out-proj (K = 128 over the padded O layout) + residual
+        // ---- P3: out-proj + residual
         if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_w, ph_w, a.err);
             const bool leader = elect_one();
-            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 96, kta + 128 * mm * 16, kCS, wra, 96 * 16, 8, id96, 0, leader);
+            for (int mm = 0; mm < 2; ++mm) mma_kk(tmem + mm * 96, aoa + 128 * mm * 16, kCS, wra, 96 * 16, 6, id96, 0, leader);
             if (leader) umma_commit(bar_mma);
         }
         ph_w ^= 1;
@@ -331,8 +386,8 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         NBSS_TICK(0, 5, it_);
         {
             // thread = (frame, channel half): D + b_out -> fp32, staged into the dead K|V tiles at the frame's row slot (24
-            // four-float chunks = the 12 K data chunks + V chunks 0..11; the zero pad chunks of K stay untouched:
-            // slab.cuh skip4_chunk); then eight lanes per frame add the residual with coalesced traffic
+            // four-float chunks; with per-head padding (HS != KCH) the zero pad chunks of K stay untouched: slab.cuh
+            // skip4_chunk); then eight lanes per frame add the residual with coalesced traffic
             const uint32_t tacc = tmem + lane_off + m * 96;
 #pragma unroll 1
             for (int c0 = 48 * hf; c0 < 48 * hf + 48; c0 += 16) {
@@ -346,13 +401,13 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
                     o.y = __uint_as_float(r[4 * j4 + 1]) + s_bout[c0 + 4 * j4 + 1];
                     o.z = __uint_as_float(r[4 * j4 + 2]) + s_bout[c0 + 4 * j4 + 2];
                     o.w = __uint_as_float(r[4 * j4 + 3]) + s_bout[c0 + 4 * j4 + 3];
-                    *reinterpret_cast<float4*>(kt + (size_t)skip4_chunk(c0 / 4 + j4) * kCS + t * 16) = o;
+                    *reinterpret_cast<float4*>(kt + (size_t)(HS != KCH ? skip4_chunk(c0 / 4 + j4) : c0 / 4 + j4) * kCS + t * 16) = o;
                 }
             }
             tc_fence_before();
             __syncthreads();
             NBSS_TICK(0, 6, it_);
-            add_rows<true>(kt, kCS, 0, xs, a.y + (size_t)slab * T * kH, T, warp, lane, kMhThreads / 32);
+            add_rows<(HS != KCH)>(kt, kCS, 0, xs, a.y + (size_t)slab * T * kH, T, warp, lane, kMhThreads / 32);
         }
         tc_fence_before();
         __syncthreads();
@@ -365,23 +420,31 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
 
 NBSS_PHASE_READER(nbss_debug_phases_mhsa_fwd)
 
-extern "C" int nbss_mhsa_fwd(const float* x, float* y, int nslab, int T, const float* ln_w, const float* ln_b,
-                             const float* b_in, const float* b_out, const void* layer_img, void* save_qkv, void* save_o,
-                             float* save_lse, float* ln_stats, int fmt, int* err, void* stream) {
+// num_heads = 4 (SpatialNet-small) or 2 (NBC2 small, models/arch/NBC2.py:294-311)
+extern "C" int nbss_mhsa_fwd_nh(const float* x, float* y, int nslab, int T, const float* ln_w, const float* ln_b,
+                                const float* b_in, const float* b_out, const void* layer_img, void* save_qkv, void* save_o,
+                                float* save_lse, float* ln_stats, int num_heads, int fmt, int* err, void* stream) {
     using namespace nbss;
     if (!x || !y || !layer_img || !ln_w || !ln_b || !b_in || !b_out) return NBSS_ERR_NULL;
     if (T < 1 || T > kTMax || nslab < 1) return NBSS_ERR_SHAPE;
-    if (fmt != FMT_F16 && fmt != FMT_BF16) return NBSS_ERR_UNSUPPORTED;
+    if ((fmt != FMT_F16 && fmt != FMT_BF16) || (num_heads != 4 && num_heads != 2)) return NBSS_ERR_UNSUPPORTED;
     MhsaFwdArgs a{x, y, nslab, T, ln_w, ln_b, b_in, b_out, (const unsigned char*)layer_img, (unsigned char*)save_qkv,
                   (unsigned char*)save_o, save_lse, ln_stats, err};
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = nslab < sms ? nslab : sms;
-    void (*kern)(MhsaFwdArgs) = (fmt == FMT_F16) ? mhsa_fwd_kernel<FMT_F16> : mhsa_fwd_kernel<FMT_BF16>;
+    void (*kern)(MhsaFwdArgs) = num_heads == 4 ? ((fmt == FMT_F16) ? mhsa_fwd_kernel<FMT_F16, 4> : mhsa_fwd_kernel<FMT_BF16, 4>)
+                                               : ((fmt == FMT_F16) ? mhsa_fwd_kernel<FMT_F16, 2> : mhsa_fwd_kernel<FMT_BF16, 2>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MH_SMEM);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, kMhThreads, MH_SMEM, (cudaStream_t)stream>>>(a);
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
+}
+
+extern "C" int nbss_mhsa_fwd(const float* x, float* y, int nslab, int T, const float* ln_w, const float* ln_b,
+                             const float* b_in, const float* b_out, const void* layer_img, void* save_qkv, void* save_o,
+                             float* save_lse, float* ln_stats, int fmt, int* err, void* stream) {
+    return nbss_mhsa_fwd_nh(x, y, nslab, T, ln_w, ln_b, b_in, b_out, layer_img, save_qkv, save_o, save_lse, ln_stats, 4, fmt, err, stream);
 }

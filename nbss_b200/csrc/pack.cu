@@ -59,8 +59,7 @@ __global__ void pack_layer_kernel(PackArgs a) {
     else if (byte < IMG_WO) plain(IMG_WQ, 96, [&](int n, int k) { return a.w_in[n * 96 + k]; });
     else if (byte < IMG_WOT) plain(IMG_WO, 96, [&](int n, int k) { return a.w_out[n * 96 + k]; });
     else if (byte < IMG_WINT) { fmt = a.bwd_fmt; plain(IMG_WOT, 96, [&](int n, int k) { return a.w_out[k * 96 + n]; }); }
-    else if (byte < IMG_WOP) { fmt = a.bwd_fmt; plain(IMG_WINT, 96, [&](int n, int k) { return a.w_in[k * 96 + n]; }); }
-    else plain(IMG_WOP, 96, [&](int n, int k) { return (k % 32) < kDH ? a.w_out[n * 96 + kDH * (k / 32) + (k % 32)] : 0.f; });
+    else { fmt = a.bwd_fmt; plain(IMG_WINT, 96, [&](int n, int k) { return a.w_in[k * 96 + n]; }); }
     uint4 q;
     if (fmt == FMT_F16) q = make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
     else q = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));

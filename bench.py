@@ -198,6 +198,65 @@ def gpu_eager_baseline(dev, batch, steps=3, warmup=2):
     return out
 
 
+def bench_nbc2(dev, steps=5, warmup=3, batch=64, eager=True):
+    """BASELINE configs[3]: NBC2 (models/arch/NBC2.py) small, 8-channel input (dim_input 16), F=257, T=250, inference, batch 64.
+    Device-resident and end-to-end (pinned host input copied in, output copied back) frames/s of nbss_b200.nbc2.NBC2, next to
+    the oracle's eager torch restatement of the reference on the same GPU (largest batch <= `batch` that fits)."""
+    from nbss_b200.nbc2 import NBC2
+    from oracle import nbc2_oracle as N2
+
+    B, F, T, Cin = batch, 257, 250, 16
+    cfg = N2.NBC2_SMALL
+    torch.manual_seed(2)
+    net = NBC2(dim_input=Cin, dim_output=4, n_layers=cfg["n_layers"], dim_hidden=96, dim_ffn=192, num_freqs=F).to(dev).eval()
+    g = torch.Generator().manual_seed(5)
+    x_host = torch.randn(B, F, T, Cin, generator=g).pin_memory()
+    x = x_host.to(dev)
+    y_host = torch.empty(B, F, T, 4).pin_memory()
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    ms = timed(lambda: net(x))
+
+    def e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        y_host.copy_(net(xd), non_blocking=True)
+
+    ms_e2e = timed(e2e)
+    net.check_device_errors()
+    out = {"workload": f"NBC2-small 8ch F=257 T=250 inference, batch={B} (BASELINE configs[3])", "ms_per_step": round(ms, 3),
+           "frames_per_s": round(B * T / (ms * 1e-3), 1), "e2e": {"ms_per_step": round(ms_e2e, 3), "frames_per_s": round(B * T / (ms_e2e * 1e-3), 1),
+                                                                  "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4},
+           "launches_per_step": 2 + 5 * cfg["n_layers"] + cfg["n_layers"]}
+    del net
+    if eager:
+        P = {k: v.to(dev) for k, v in N2.synth_params(cfg, 2).items()}
+        b = B
+        while b >= 1:
+            try:
+                xe = x[:b].contiguous()
+                with torch.no_grad():
+                    ms_e = timed(lambda: N2.nbc2_forward(P, xe, cfg))
+                out["gpu_eager_baseline"] = {"ms_per_step": round(ms_e, 2), "batch": b, "frames_per_s": round(b * T / (ms_e * 1e-3), 1),
+                                             "what": "oracle/nbc2_oracle.py (torch restatement of the reference's NBC2) in PyTorch eager, fp32"}
+                break
+            except torch.OutOfMemoryError:
+                b //= 2
+                torch.cuda.empty_cache()
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_torch_gpu(args):
     """--impl torch-gpu: the eager baseline as a bench line of its own (rank 0 only)."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -251,6 +310,7 @@ def main():
     ap.add_argument("--torch-adam", action="store_true", help="clip_grad_norm_ + torch.optim.Adam(fused, capturable) instead of FlatClipAdam")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager reference op-set timed on this GPU")
+    ap.add_argument("--no-nbc2", action="store_true", help="skip the NBC2 inference workload (BASELINE configs[3]) reported under 'extra_workloads'")
     ap.add_argument("--batch", type=int, default=CFG["B"], help="global batch (utterances)")
     ap.add_argument("--profile", action="store_true", help="1 warm-up + 1 step only (for ncu); prints no bench line")
     ap.add_argument("--layers", type=int, default=CFG["L"], help="number of SpatialNet layers (profiling only; default 8)")
@@ -498,6 +558,11 @@ def main():
     }
     if eager is not None:
         out["gpu_eager_baseline"] = eager
+    if world == 1 and not args.no_nbc2:
+        try:
+            out["extra_workloads"] = {"nbc2_inference": bench_nbc2(dev, eager=not args.no_eager_baseline)}
+        except Exception as e:
+            out["extra_workloads"] = {"nbc2_inference": {"unavailable": f"{type(e).__name__}: {e}"[:200]}}
     if world == 1 and not args.no_cpu_baseline:
         cores = min(os.cpu_count() or 1, 32)
         log(f"cpu baseline on {cores} threads")

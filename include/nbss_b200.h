@@ -46,6 +46,29 @@ int nbss_ffn_fwd(const float* x, float* y, int nslab, int T, const float* ln_w, 
                  const float* b2, const void* layer_img, void* save_a1, void* save_c1, void* save_c2, void* save_c3,
                  float* gn_stats, float* ln_stats, int fmt, int* err, void* stream);
 
+/* The same kernel for 4 heads (SpatialNet-small, head dim 24) or 2 heads (NBC2 small, head dim 48: models/arch/NBC2.py:294-311).
+ * row_part (nullable): [n,2] per output row (sum, sum of squares) over the 96 channels — the per-slab partials of NBC2's
+ * GroupBatchNorm norm2 (NBC2.py:111-145,170), reduced over the F slabs of an utterance by nbss_gbn_reduce. */
+int nbss_mhsa_fwd_nh(const float* x, float* y, int nslab, int T, const float* ln_w, const float* ln_b, const float* b_in,
+                     const float* b_out, const void* layer_img, void* save_qkv, void* save_o, float* save_lse,
+                     float* ln_stats, float* row_part, int num_heads, int fmt, int* err, void* stream);
+
+/* ---- NBC2 inference (BASELINE configs[3]; models/arch/NBC2.py:152-289) ------------------------------------------------ */
+/* GroupBatchNorm statistics (NBC2.py:118-128): part [B][NP][T][NQ][2] (sum, sum of squares) -> stats [B][T][2] (mean, rstd)
+ * over the NP*NQ partials of `count` elements in total (fp64 accumulation). */
+int nbss_gbn_reduce(const float* part, int B, int NP, int T, int NQ, long long count, float eps, float* stats, void* stream);
+/* NBC2Block._ff_block cut at its second GroupBatchNorm (conv.4), whose statistics span all F slabs of an utterance:
+ *   part A: c2 = conv.3(SiLU(conv.1(SiLU(linear1(GBN_norm2(x)))))) -> fp16 slab tiles [nslab][24][T][8] + partial sums
+ *           part [nslab][T][2][2]; row_stats = (mean, rstd) [B*T] of norm2, gbn_w/gbn_b = norm2.{weight,bias} [96]
+ *   part B: y = x + linear2(SiLU(conv.6(SiLU(GBN_conv4(c2))))); row_stats of conv.4, gbn_w/gbn_b = conv.4.{weight,bias} [192]
+ * layer_img: nbss_pack_layer_weights(linear1.weight, conv.1.weight, conv.3.weight, conv.6.weight, linear2.weight, in_proj, out_proj). */
+int nbss_nbc2_ffn_a(const float* x, int nslab, int T, int F, const float* row_stats, const float* gbn_w, const float* gbn_b,
+                    const float* b1, const float* bc1, const float* bc2, const void* layer_img, void* c2_out, float* part,
+                    int fmt, int* err, void* stream);
+int nbss_nbc2_ffn_b(const float* x, float* y, int nslab, int T, int F, const float* row_stats, const float* gbn_w,
+                    const float* gbn_b, const float* bc3, const float* b2, const void* layer_img, const void* c2_in, int fmt,
+                    int* err, void* stream);
+
 /* ---- narrow-band block, backward (tcgen05); autograd of the above -------------------------------- */
 int nbss_ffn_bwd(const float* x, const float* dy, float* dx, int nslab, int T, const float* ln_w, const float* gn_w,
                  const float* gn_b, const float* ln_stats, const float* gn_stats, const void* layer_img, const void* a1,

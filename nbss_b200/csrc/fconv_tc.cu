@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256, 2) fconv_tc_fwd_kernel(FcFwdArgs a) {
     uint64_t* bar_mma = reinterpret_cast<uint64_t*>(cst + 384);
     uint64_t* bar_w = bar_mma + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0) /* warp-uniform for ptxas: see umma.cuh elect_one */, lane = tid & 31;
     const uint32_t ncols = g.nt * 96 <= 256 ? 256u : 512u;  // 256 columns let two CTAs share an SM (one frame per group)
     if (warp == 0) tmem_alloc(tmem_slot, ncols);
     if (tid == 0) {
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
     uint64_t* bar_mma = reinterpret_cast<uint64_t*>(stats + g.rows);
     uint64_t* bar_w = bar_mma + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0) /* warp-uniform for ptxas: see umma.cuh elect_one */, lane = tid & 31;
     const int q4 = warp & 3, gq = warp >> 2;
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 0) {

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
     uint64_t* bar_w1 = bar_mma + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 4);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0) /* warp-uniform for ptxas: see umma.cuh elect_one */, lane = tid & 31;
     const int T = a.T;
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 0) {

@@ -24,6 +24,12 @@ struct FfnFwdArgs {
     unsigned char *save_a1, *save_c1, *save_c2, *save_c3;  // fp16 slab-tile [nslab][24][T][8] or null
     float* gn_stats;                                       // [nslab, 8, 2] (mean, rstd) or null
     float* ln_stats;                                       // [nslab*T, 2] (mean, rstd) of the LayerNorm or null
+    // NBC2's split T-ConvFFN (MODE 1 = part A, MODE 2 = part B; models/arch/NBC2.py:170-188,222-224): the two GroupBatchNorms take
+    // their statistics over all frequencies of a frame, so the sub-block is cut at the second one
+    const float2* row_stats;  // [B*T] (mean, rstd) per (b, t) of the GroupBatchNorm this part applies
+    int F;                    // slabs per utterance (b = slab / F)
+    unsigned char* c2_io;     // fp16 slab-tile [nslab][24][T][8]: conv2 output (+bias); part A writes it, part B reads it
+    float* part;              // part A out: [nslab][T][2][2] (sum, sum of squares) of c2 over each thread's 96 channels
     int* err;
 };
 
@@ -48,7 +54,10 @@ __device__ __forceinline__ void save_f16(unsigned char* base, int slab, int T, i
     for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(base + tile_off(slab, 24, T, c0 / 8 + cc, t)) = pack8<FMT_F16>(v + 8 * cc);
 }
 
-template <int FMT>
+// MODE 0: SpatialNet's T-ConvFFN (LayerNorm + GroupNorm, everything in one pass).
+// MODE 1: NBC2 part A: GroupBatchNorm(x) (statistics given) -> linear1 -> SiLU -> conv -> SiLU -> conv -> c2 (fp16) + partial sums.
+// MODE 2: NBC2 part B: SiLU(GroupBatchNorm(c2)) (statistics given) -> conv -> SiLU -> linear2 -> + x.
+template <int FMT, int MODE>
 __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* hbuf = smem + FF_HBUF;
@@ -63,8 +72,11 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
     uint64_t* bar_w0 = bar_mma + 2;
     uint64_t* bar_w1 = bar_mma + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 4);
+    uint64_t* bar_ld = bar_mma + 5;  // MODE 2: the c2 tile has landed
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the warp index through a shuffle: ptxas then KNOWS it is warp-uniform, keeps `if (warp == 0)` a uniform branch and the MMA
+    // descriptors in uniform registers (no R2UR.BROADCAST per tcgen05.mma operand)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int T = a.T;
 
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -73,6 +85,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         mbar_init(bar_mma1, 1);
         mbar_init(bar_w0, 1);
         mbar_init(bar_w1, 1);
+        mbar_init(bar_ld, 1);
         fence_mbar_init();
     }
     for (int i = tid; i < 96; i += kFfnThreads) { s_lng[i] = a.ln_w[i]; s_lnb[i] = a.ln_b[i]; s_b2[i] = a.b2[i]; }
@@ -103,7 +116,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
     const uint32_t hb = smem_u32(hbuf), w0a = smem_u32(ws0), w1a = smem_u32(ws1);
     const uint32_t id192 = make_idesc(FMT, 128, 192, 0, 0), id48 = make_idesc(FMT, 128, 48, 0, 0),
                    id96 = make_idesc(FMT, 128, 96, 0, 0);
-    uint32_t ph_mma = 0, ph_w0 = 0, ph_w1 = 0;
+    uint32_t ph_mma = 0, ph_w0 = 0, ph_w1 = 0, ph_ld = 0;
     const float inv_n = 1.f / (float)(kGC * T);
 
     auto conv_phase = [&](uint32_t wsa, uint64_t* bar_w, uint32_t& ph_w) {
@@ -173,110 +186,170 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         const float* xs = a.x + (size_t)slab * T * kH;
         const size_t grow = (size_t)slab * T + t;
         NBSS_TICK(0, 0, it_);
-        if (tid == 0) {
-            load_image(ws0, a.img + IMG_W1, IMG_W1_BYTES, bar_w0);
-            load_image(ws1, a.img + IMG_WC1, IMG_WC_BYTES, bar_w1);
-        }
-        // ---- P0: LN(x) -> A0 (chunks 0..11 of H)
-        stage_rows96<FMT, true>(xs, T, hbuf, 1, s_lng, s_lnb, warp, lane, a.ln_stats ? a.ln_stats + (size_t)slab * T * 2 : nullptr, kFfnThreads / 32);
-        end_epilogue();
-        NBSS_TICK(0, 1, it_);
-        // ---- P1: pw1
-        if (warp == 0) {
+        if constexpr (MODE != 2) {
+            if (tid == 0) {
+                load_image(ws0, a.img + IMG_W1, IMG_W1_BYTES, bar_w0);
+                load_image(ws1, a.img + IMG_WC1, IMG_WC_BYTES, bar_w1);
+            }
+            // ---- P0: LN(x) -> A0 (chunks 0..11 of H)
+            if constexpr (MODE == 1)
+                stage_rows96<FMT, true, 4, true>(xs, T, hbuf, 1, s_lng, s_lnb, warp, lane, nullptr, kFfnThreads / 32, a.row_stats + (size_t)(slab / a.F) * T);
+            else
+                stage_rows96<FMT, true>(xs, T, hbuf, 1, s_lng, s_lnb, warp, lane, a.ln_stats ? a.ln_stats + (size_t)slab * T * 2 : nullptr, kFfnThreads / 32);
+            end_epilogue();
+            NBSS_TICK(0, 1, it_);
+            // ---- P1: pw1
+            if (warp == 0) {
+                tc_fence_after();
+                mbar_wait(bar_w0, ph_w0, a.err);
+                const bool leader = elect_one();
+                for (int mm = 0; mm < 2; ++mm) {
+                    mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 192 * 16, 6, id192, 0, leader);
+                    if (leader) umma_commit(mm ? bar_mma1 : bar_mma);
+                }
+            }
+            __syncwarp();
+            ph_w0 ^= 1;
+            mbar_wait(m ? bar_mma1 : bar_mma, ph_mma, a.err);
+            ph_mma ^= 1;
             tc_fence_after();
-            mbar_wait(bar_w0, ph_w0, a.err);
-            const bool leader = elect_one();
-            for (int mm = 0; mm < 2; ++mm) {
-                mma_kk(tmem + mm * 192, hb + (128 * mm + 1) * 16, kCS, w0a, 192 * 16, 6, id192, 0, leader);
-                if (leader) umma_commit(mm ? bar_mma1 : bar_mma);
-            }
+            NBSS_TICK(0, 2, it_);
+            if (tid == 0) load_image(ws0, a.img + IMG_WC2, IMG_WC_BYTES, bar_w0);
+            // ---- E1: a1 = D + b1; H = SiLU(a1)
+            act_epilogue(s_b1, a.save_a1, slab);
+            end_epilogue();
+            NBSS_TICK(0, 3, it_);
+            // ---- P2: conv1 ; E2: c1 = D + bc1; H = SiLU(c1)
+            conv_phase(w1a, bar_w1, ph_w1);
+            NBSS_TICK(0, 4, it_);
+            // next slab's input rows -> L2, away from this slab's latency-exposed staging loads (E2..E4 read nothing from HBM)
+            if (tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab) l2_prefetch_slab(a.x + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
+            if (MODE == 0 && tid == 0) load_image(ws1, a.img + IMG_WC3, IMG_WC_BYTES, bar_w1);
+            act_epilogue(s_bc, a.save_c1, slab);
+            end_epilogue();
+            NBSS_TICK(0, 5, it_);
         }
-        __syncwarp();
-        ph_w0 ^= 1;
-        mbar_wait(m ? bar_mma1 : bar_mma, ph_mma, a.err);
-        ph_mma ^= 1;
-        tc_fence_after();
-        NBSS_TICK(0, 2, it_);
-        if (tid == 0) load_image(ws0, a.img + IMG_WC2, IMG_WC_BYTES, bar_w0);
-        // ---- E1: a1 = D + b1; H = SiLU(a1)
-        act_epilogue(s_b1, a.save_a1, slab);
-        end_epilogue();
-        NBSS_TICK(0, 3, it_);
-        // ---- P2: conv1 ; E2: c1 = D + bc1; H = SiLU(c1)
-        conv_phase(w1a, bar_w1, ph_w1);
-        NBSS_TICK(0, 4, it_);
-        // next slab's input rows -> L2, away from this slab's latency-exposed staging loads (E2..E4 read nothing from HBM)
-        if (tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab) l2_prefetch_slab(a.x + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
-        if (tid == 0) load_image(ws1, a.img + IMG_WC3, IMG_WC_BYTES, bar_w1);
-        act_epilogue(s_bc, a.save_c1, slab);
-        end_epilogue();
-        NBSS_TICK(0, 5, it_);
-        // ---- P3: conv2 ; E3: c2 = D + bc2; GroupNorm over (24 ch x T) per group; H = SiLU(GN(c2))
-        conv_phase(w0a, bar_w0, ph_w0);
-        NBSS_TICK(0, 6, it_);
-        if (tid == 0) load_image(ws0, a.img + IMG_W2, IMG_W2_BYTES, bar_w0);
-        {
-            // GroupNorm(8 groups of 24 channels x T frames) in TWO sweeps over the thread's 96 accumulator columns (one group of
-            // 24 columns = three TMEM loads in flight per iteration; loops stay rolled: the kernel exceeds the instruction cache):
-            //   sweep 1: per-group sum and sum of squares of (c2 - pivot); the pivot (the group's mean bias, known to every
-            //            thread without communication) takes the bias-dominated part of the mean out before squaring
-            //   sweep 2: normalise, affine, SiLU -> H; save c2
-            float* red_sum = red;       // [16 warps][8 groups] (a warp fills the 4 groups of its channel half)
-            float* red_sq = red + 128;
-            float* gtot = red + 256;    // [8 groups][2] (mean, rstd) of this slab
+        if constexpr (MODE == 1) {
+            // ---- P3: conv2 ; E3': c2 = D + bc2 -> fp16 slab-tile in HBM + per-thread (sum, sum of squares) over its 96 channels
+            conv_phase(w0a, bar_w0, ph_w0);
             const float* bc2 = s_bc + 192;
+            float ps = 0.f, pq = 0.f;
 #pragma unroll 1
             for (int g = 4 * hf; g < 4 * hf + 4; ++g) {
                 uint32_t r[24];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) tmem_ld8(tacc + kGC * g + 8 * k, *reinterpret_cast<uint32_t(*)[8]>(r + 8 * k));
-                const float piv = s_piv[g];
-                tmem_ld_wait();
-                float s = 0.f, qq = 0.f;
-#pragma unroll
-                for (int j = 0; j < 24; ++j) {
-                    const float v = __uint_as_float(r[j]) + bc2[kGC * g + j] - piv;
-                    s += v;
-                    qq = fmaf(v, v, qq);
-                }
-                s = warp_sum(valid ? s : 0.f);
-                qq = warp_sum(valid ? qq : 0.f);
-                if (lane == 0) { red_sum[warp * 8 + g] = s; red_sq[warp * 8 + g] = qq; }
-            }
-            __syncthreads();
-            if (tid < 8) {  // fixed summation order: the forward is bit-reproducible
-                const int g = tid, h8 = 8 * (g >> 2);
-                float s = 0.f, qq = 0.f;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) { s += red_sum[(h8 + w) * 8 + g]; qq += red_sq[(h8 + w) * 8 + g]; }
-                const float mp = s * inv_n;                                   // mean of (c2 - pivot)
-                const float var = fmaxf(qq * inv_n - mp * mp, 0.f);
-                const float mean = mp + s_piv[g], rstd = rsqrtf(var + 1e-5f);
-                gtot[2 * g] = mean;
-                gtot[2 * g + 1] = rstd;
-                if (a.gn_stats) {
-                    a.gn_stats[(size_t)slab * 16 + 2 * g] = mean;
-                    a.gn_stats[(size_t)slab * 16 + 2 * g + 1] = rstd;
-                }
-            }
-            __syncthreads();
-#pragma unroll 1
-            for (int g = 4 * hf; g < 4 * hf + 4; ++g) {
-                uint32_t r[24];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) tmem_ld8(tacc + kGC * g + 8 * k, *reinterpret_cast<uint32_t(*)[8]>(r + 8 * k));
-                const float mean = gtot[2 * g], rstd = gtot[2 * g + 1];
                 tmem_ld_wait();
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const int c = kGC * g + 8 * k;
                     float v[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * k + j]) + bc2[c + j];
-                    if (a.save_c2 && valid) *reinterpret_cast<uint4*>(a.save_c2 + tile_off(slab, 24, T, c / 8, t)) = pack8<FMT_F16>(v);
+                    for (int j = 0; j < 8; ++j) {
+                        v[j] = __uint_as_float(r[8 * k + j]) + bc2[c + j];
+                        ps += v[j];
+                        pq = fmaf(v[j], v[j], pq);
+                    }
+                    if (valid) *reinterpret_cast<uint4*>(a.c2_io + tile_off(slab, 24, T, c / 8, t)) = pack8<FMT_F16>(v);
+                }
+            }
+            if (valid) *reinterpret_cast<float2*>(a.part + (((size_t)slab * T + t) * 2 + hf) * 2) = make_float2(ps, pq);
+            tc_fence_before();
+            __syncthreads();  // TMEM + H are reused by the next slab
+            continue;
+        }
+        if constexpr (MODE == 2) {
+            // ---- part B: the c2 tile arrives by TMA straight into the H tile (same byte layout); every thread normalises its
+            //      frame's 96 channels in place: H = SiLU(GroupBatchNorm(c2)) with the (b, t) statistics reduced over all F and channels
+            if (tid == 0) {
+                load_image(ws1, a.img + IMG_WC3, IMG_WC_BYTES, bar_w1);
+                load_image(ws0, a.img + IMG_W2, IMG_W2_BYTES, bar_w0);
+                bulk_load_chunks(hbuf, kCS, 1, a.c2_io + tile_off(slab, 24, T, 0, 0), 24, T, bar_ld);
+            }
+            const float2 st = valid ? __ldg(a.row_stats + (size_t)(slab / a.F) * T + t) : make_float2(0.f, 0.f);
+            mbar_wait(bar_ld, ph_ld, a.err);
+            ph_ld ^= 1;
+#pragma unroll 1
+            for (int c = cb; c < cb + 96; c += 8) {
+                const uint4 pk = *reinterpret_cast<const uint4*>(hrow + (c / 8) * kCS);
+                float v[8];
+                unpack_f16x2(pk.x, v[0], v[1]);
+                unpack_f16x2(pk.y, v[2], v[3]);
+                unpack_f16x2(pk.z, v[4], v[5]);
+                unpack_f16x2(pk.w, v[6], v[7]);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = silu((v[j] - mean) * (rstd * s_gng[c + j]) + s_gnb[c + j]) * vmask;
-                    *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = pack8<FMT>(v);
+                for (int j = 0; j < 8; ++j) v[j] = silu((v[j] - st.x) * (st.y * s_gng[c + j]) + s_gnb[c + j]) * vmask;
+                *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = pack8<FMT>(v);
+            }
+        }
+        if constexpr (MODE == 0) {
+            // ---- P3: conv2 ; E3: c2 = D + bc2; GroupNorm over (24 ch x T) per group; H = SiLU(GN(c2))
+            conv_phase(w0a, bar_w0, ph_w0);
+            NBSS_TICK(0, 6, it_);
+            if (tid == 0) load_image(ws0, a.img + IMG_W2, IMG_W2_BYTES, bar_w0);
+            {
+                // GroupNorm(8 groups of 24 channels x T frames) in TWO sweeps over the thread's 96 accumulator columns (one group of
+                // 24 columns = three TMEM loads in flight per iteration; loops stay rolled: the kernel exceeds the instruction cache):
+                //   sweep 1: per-group sum and sum of squares of (c2 - pivot); the pivot (the group's mean bias, known to every
+                //            thread without communication) takes the bias-dominated part of the mean out before squaring
+                //   sweep 2: normalise, affine, SiLU -> H; save c2
+                float* red_sum = red;       // [16 warps][8 groups] (a warp fills the 4 groups of its channel half)
+                float* red_sq = red + 128;
+                float* gtot = red + 256;    // [8 groups][2] (mean, rstd) of this slab
+                const float* bc2 = s_bc + 192;
+    #pragma unroll 1
+                for (int g = 4 * hf; g < 4 * hf + 4; ++g) {
+                    uint32_t r[24];
+    #pragma unroll
+                    for (int k = 0; k < 3; ++k) tmem_ld8(tacc + kGC * g + 8 * k, *reinterpret_cast<uint32_t(*)[8]>(r + 8 * k));
+                    const float piv = s_piv[g];
+                    tmem_ld_wait();
+                    float s = 0.f, qq = 0.f;
+    #pragma unroll
+                    for (int j = 0; j < 24; ++j) {
+                        const float v = __uint_as_float(r[j]) + bc2[kGC * g + j] - piv;
+                        s += v;
+                        qq = fmaf(v, v, qq);
+                    }
+                    s = warp_sum(valid ? s : 0.f);
+                    qq = warp_sum(valid ? qq : 0.f);
+                    if (lane == 0) { red_sum[warp * 8 + g] = s; red_sq[warp * 8 + g] = qq; }
+                }
+                __syncthreads();
+                if (tid < 8) {  // fixed summation order: the forward is bit-reproducible
+                    const int g = tid, h8 = 8 * (g >> 2);
+                    float s = 0.f, qq = 0.f;
+    #pragma unroll
+                    for (int w = 0; w < 8; ++w) { s += red_sum[(h8 + w) * 8 + g]; qq += red_sq[(h8 + w) * 8 + g]; }
+                    const float mp = s * inv_n;                                   // mean of (c2 - pivot)
+                    const float var = fmaxf(qq * inv_n - mp * mp, 0.f);
+                    const float mean = mp + s_piv[g], rstd = rsqrtf(var + 1e-5f);
+                    gtot[2 * g] = mean;
+                    gtot[2 * g + 1] = rstd;
+                    if (a.gn_stats) {
+                        a.gn_stats[(size_t)slab * 16 + 2 * g] = mean;
+                        a.gn_stats[(size_t)slab * 16 + 2 * g + 1] = rstd;
+                    }
+                }
+                __syncthreads();
+    #pragma unroll 1
+                for (int g = 4 * hf; g < 4 * hf + 4; ++g) {
+                    uint32_t r[24];
+    #pragma unroll
+                    for (int k = 0; k < 3; ++k) tmem_ld8(tacc + kGC * g + 8 * k, *reinterpret_cast<uint32_t(*)[8]>(r + 8 * k));
+                    const float mean = gtot[2 * g], rstd = gtot[2 * g + 1];
+                    tmem_ld_wait();
+    #pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int c = kGC * g + 8 * k;
+                        float v[8];
+    #pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * k + j]) + bc2[c + j];
+                        if (a.save_c2 && valid) *reinterpret_cast<uint4*>(a.save_c2 + tile_off(slab, 24, T, c / 8, t)) = pack8<FMT_F16>(v);
+    #pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = silu((v[j] - mean) * (rstd * s_gng[c + j]) + s_gnb[c + j]) * vmask;
+                        *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = pack8<FMT>(v);
+                    }
                 }
             }
         }
@@ -346,15 +419,93 @@ extern "C" int nbss_ffn_fwd(const float* x, float* y, int nslab, int T, const fl
     if (T < 1 || T > kTMax || nslab < 1) return NBSS_ERR_SHAPE;
     if (fmt != FMT_F16 && fmt != FMT_BF16) return NBSS_ERR_UNSUPPORTED;
     FfnFwdArgs a{x, y, nslab, T, ln_w, ln_b, b1, bc1, bc2, bc3, gn_w, gn_b, b2, (const unsigned char*)layer_img,
-                 (unsigned char*)save_a1, (unsigned char*)save_c1, (unsigned char*)save_c2, (unsigned char*)save_c3, gn_stats, ln_stats, err};
+                 (unsigned char*)save_a1, (unsigned char*)save_c1, (unsigned char*)save_c2, (unsigned char*)save_c3, gn_stats, ln_stats, nullptr, 1, nullptr, nullptr, err};
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = nslab < sms ? nslab : sms;
-    auto kern = (fmt == FMT_F16) ? ffn_fwd_kernel<FMT_F16> : ffn_fwd_kernel<FMT_BF16>;
+    auto kern = (fmt == FMT_F16) ? ffn_fwd_kernel<FMT_F16, 0> : ffn_fwd_kernel<FMT_BF16, 0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, kFfnThreads, FF_SMEM, (cudaStream_t)stream>>>(a);
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ NBC2 (models/arch/NBC2.py)
+namespace nbss {
+// GroupBatchNorm statistics (NBC2.py:118-128): part [B][NP][T][NQ][2] (sum, sum of squares) -> stats [B][T] (mean, rstd) over
+// NP * NQ partials of `count` elements in total; one thread per (b, t), fp64 accumulation (the subtraction E[x^2] - mean^2 is
+// done where it cannot cancel).
+__global__ void gbn_reduce_kernel(const float* __restrict__ part, int B, int NP, int T, int NQ, double inv_count, float eps,
+                                  float2* __restrict__ stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * T) return;
+    const int b = i / T, t = i % T;
+    double s = 0.0, q = 0.0;
+    for (int p = 0; p < NP; ++p) {
+        const float* pp = part + ((((size_t)b * NP + p) * T + t) * NQ) * 2;
+        for (int k = 0; k < NQ; ++k) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(pp) + k);
+            s += v.x;
+            q += v.y;
+        }
+    }
+    const double mean = s * inv_count;
+    double var = q * inv_count - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    stats[i] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+}
+}  // namespace nbss
+
+extern "C" int nbss_gbn_reduce(const float* part, int B, int NP, int T, int NQ, long long count, float eps, float* stats, void* stream) {
+    using namespace nbss;
+    if (!part || !stats) return NBSS_ERR_NULL;
+    if (B < 1 || NP < 1 || T < 1 || NQ < 1 || count < 1) return NBSS_ERR_SHAPE;
+    const int n = B * T;
+    gbn_reduce_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(part, B, NP, T, NQ, 1.0 / (double)count, eps, reinterpret_cast<float2*>(stats));
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+
+static int nbc2_ffn_launch(nbss::FfnFwdArgs& a, int mode, int fmt, void* stream) {
+    using namespace nbss;
+    if (a.T < 1 || a.T > kTMax || a.nslab < 1 || a.F < 1 || a.nslab % a.F) return NBSS_ERR_SHAPE;
+    if (fmt != FMT_F16 && fmt != FMT_BF16) return NBSS_ERR_UNSUPPORTED;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = a.nslab < sms ? a.nslab : sms;
+    void (*kern)(FfnFwdArgs) = mode == 1 ? ((fmt == FMT_F16) ? ffn_fwd_kernel<FMT_F16, 1> : ffn_fwd_kernel<FMT_BF16, 1>)
+                                         : ((fmt == FMT_F16) ? ffn_fwd_kernel<FMT_F16, 2> : ffn_fwd_kernel<FMT_BF16, 2>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, kFfnThreads, FF_SMEM, (cudaStream_t)stream>>>(a);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+
+// NBC2Block._ff_block, first half (NBC2.py:170-184,222-224): c2 = conv.3(SiLU(conv.1(SiLU(linear1(GBN(x)))))) as fp16 slab tiles plus
+// the per-(slab, frame, channel half) partial sums of the second GroupBatchNorm.  row_stats: [B*T] (mean, rstd) of norm2.
+extern "C" int nbss_nbc2_ffn_a(const float* x, int nslab, int T, int F, const float* row_stats, const float* gbn_w, const float* gbn_b,
+                               const float* b1, const float* bc1, const float* bc2, const void* layer_img, void* c2_out, float* part,
+                               int fmt, int* err, void* stream) {
+    if (!x || !row_stats || !gbn_w || !gbn_b || !b1 || !bc1 || !bc2 || !layer_img || !c2_out || !part) return NBSS_ERR_NULL;
+    // slots the kernel prologue copies but this mode never uses get same-sized stand-ins (bc2: 192 floats, gbn_b: 96 floats)
+    nbss::FfnFwdArgs a{x, nullptr, nslab, T, gbn_w, gbn_b, b1, bc1, bc2, bc2, bc2, bc2, gbn_b, (const unsigned char*)layer_img,
+                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<const float2*>(row_stats), F,
+                       (unsigned char*)c2_out, part, err};
+    return nbc2_ffn_launch(a, 1, fmt, stream);
+}
+
+// second half (NBC2.py:185-188,224): y = x + linear2(SiLU(conv.6(SiLU(GBN(c2))))).  row_stats: [B*T] (mean, rstd) of conv.4.
+extern "C" int nbss_nbc2_ffn_b(const float* x, float* y, int nslab, int T, int F, const float* row_stats, const float* gbn_w,
+                               const float* gbn_b, const float* bc3, const float* b2, const void* layer_img, const void* c2_in,
+                               int fmt, int* err, void* stream) {
+    if (!x || !y || !row_stats || !gbn_w || !gbn_b || !bc3 || !b2 || !layer_img || !c2_in) return NBSS_ERR_NULL;
+    // the 192-wide affine of conv.4 travels in the gn_w / gn_b slots; ln_w / ln_b (96 floats each) are unused in this mode
+    nbss::FfnFwdArgs a{x, y, nslab, T, b2, b2, bc3, bc3, bc3, bc3, gbn_w, gbn_b, b2, (const unsigned char*)layer_img,
+                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<const float2*>(row_stats), F,
+                       (unsigned char*)c2_in, nullptr, err};
+    return nbc2_ffn_launch(a, 2, fmt, stream);
 }

@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(256, 3) squeeze_fwd_tc_kernel(RtArgs a) {
     long long* rowq = rowx + kRtRows;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SQF_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0) /* warp-uniform for ptxas: see umma.cuh elect_one */, lane = tid & 31;
     if (warp == 0) tmem_alloc(tmem_slot, 32);
     if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     for (int i = tid; i < 96; i += 256) { cst[i] = a.lnw[i]; cst[96 + i] = a.lnb[i]; }
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(256, 3) unsqueeze_fwd_tc_kernel(RtArgs a) {
     long long* rowq = rowx + kRtRows;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + UNF_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0) /* warp-uniform for ptxas: see umma.cuh elect_one */, lane = tid & 31;
     if (warp == 0) tmem_alloc(tmem_slot, 128);
     if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     for (int i = tid; i < 96; i += 256) cst[i] = a.bias[i];
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(256, 4) unsqueeze_bwd_tc_kernel(RtArgs a) {
     long long* rowq = rowx + kRtRows;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + UNB_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0) /* warp-uniform for ptxas: see umma.cuh elect_one */, lane = tid & 31;
     if (warp == 0) tmem_alloc(tmem_slot, 128);
     if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     for (int i = tid; i < 96; i += 256) cst[i] = a.bias[i];
@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(256, 2) squeeze_bwd_tc_kernel(RtArgs a) {
     long long* rowq = rowx + kRtRows;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SQB_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0) /* warp-uniform for ptxas: see umma.cuh elect_one */, lane = tid & 31;
     if (warp == 0) tmem_alloc(tmem_slot, 128);
     if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     for (int i = tid; i < 96; i += 256) { cst[i] = a.lnw[i]; cst[96 + i] = a.lnb[i]; }

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256, 2) lg_tc_kernel(LgArgs a) {
     uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + ((body + 15) / 16) * 16);
     uint64_t* bar_w = bar_mma + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0) /* warp-uniform for ptxas: see umma.cuh elect_one */, lane = tid & 31;
     const int m0 = blockIdx.x * kLgRows, grp = blockIdx.y;
     if (warp == 0) tmem_alloc(tmem_slot, 256);
     if (tid == 0) {
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256, 2) lg_wgrad_kernel(LgWgArgs a) {
     unsigned char* st = smem + (size_t)ach * kLgCsA;
     uint64_t* bar_mma = reinterpret_cast<uint64_t*>(st + (size_t)g.nch * kLgCsA);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0) /* warp-uniform for ptxas: see umma.cuh elect_one */, lane = tid & 31;
     const int grp = blockIdx.y;
     if (warp == 0) tmem_alloc(tmem_slot, 256);
     if (tid == 0) {

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
     uint64_t* bar_q = bar_mma + 2;  // [2] q,k,v of tile set s have landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 4);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = a.T;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0) /* warp-uniform for ptxas: see umma.cuh elect_one */, lane = tid & 31, T = a.T;
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
         mbar_init(bar_mma, 1);
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a
     uint64_t* bar_w = bar_mma + 1;
     uint64_t* bar_ld = bar_mma + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 3);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = a.T;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0) /* warp-uniform for ptxas: see umma.cuh elect_one */, lane = tid & 31, T = a.T;
     if (warp == 0) tmem_alloc(tmem_slot, 256);
     if (tid == 0) {
         mbar_init(bar_mma, 1);

@@ -29,6 +29,7 @@ struct MhsaFwdArgs {
     unsigned char* save_o;    // fp16 slab-tile [nslab][12][T][8] or null
     float* save_lse;          // [nslab, 4, T] log2-domain logsumexp or null
     float* ln_stats;          // [nslab*T, 2] (mean, rstd) of the LayerNorm or null
+    float* row_part;          // [nslab*T, 2] (sum, sum of squares) over the channels of every output row, or null (NBC2 GroupBatchNorm)
     int* err;
 };
 
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
     uint64_t* bar_pv = bar_mma + 4;  // [2] partial outputs of buffer b are complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 6);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0) /* warp-uniform for ptxas: see umma.cuh elect_one */, lane = tid & 31;
     const int T = a.T;
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
@@ -407,7 +408,8 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
             tc_fence_before();
             __syncthreads();
             NBSS_TICK(0, 6, it_);
-            add_rows<(HS != KCH)>(kt, kCS, 0, xs, a.y + (size_t)slab * T * kH, T, warp, lane, kMhThreads / 32);
+            add_rows<(HS != KCH)>(kt, kCS, 0, xs, a.y + (size_t)slab * T * kH, T, warp, lane, kMhThreads / 32,
+                                  a.row_part ? a.row_part + (size_t)slab * T * 2 : nullptr);
         }
         tc_fence_before();
         __syncthreads();
@@ -420,16 +422,17 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
 
 NBSS_PHASE_READER(nbss_debug_phases_mhsa_fwd)
 
-// num_heads = 4 (SpatialNet-small) or 2 (NBC2 small, models/arch/NBC2.py:294-311)
+// num_heads = 4 (SpatialNet-small) or 2 (NBC2 small, models/arch/NBC2.py:294-311); row_part (nullable): per-row (sum, sum of
+// squares) of the output over the 96 channels, the per-slab partials of NBC2's GroupBatchNorm (norm2, NBC2.py:170)
 extern "C" int nbss_mhsa_fwd_nh(const float* x, float* y, int nslab, int T, const float* ln_w, const float* ln_b,
                                 const float* b_in, const float* b_out, const void* layer_img, void* save_qkv, void* save_o,
-                                float* save_lse, float* ln_stats, int num_heads, int fmt, int* err, void* stream) {
+                                float* save_lse, float* ln_stats, float* row_part, int num_heads, int fmt, int* err, void* stream) {
     using namespace nbss;
     if (!x || !y || !layer_img || !ln_w || !ln_b || !b_in || !b_out) return NBSS_ERR_NULL;
     if (T < 1 || T > kTMax || nslab < 1) return NBSS_ERR_SHAPE;
     if ((fmt != FMT_F16 && fmt != FMT_BF16) || (num_heads != 4 && num_heads != 2)) return NBSS_ERR_UNSUPPORTED;
     MhsaFwdArgs a{x, y, nslab, T, ln_w, ln_b, b_in, b_out, (const unsigned char*)layer_img, (unsigned char*)save_qkv,
-                  (unsigned char*)save_o, save_lse, ln_stats, err};
+                  (unsigned char*)save_o, save_lse, ln_stats, row_part, err};
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -446,5 +449,5 @@ extern "C" int nbss_mhsa_fwd_nh(const float* x, float* y, int nslab, int T, cons
 extern "C" int nbss_mhsa_fwd(const float* x, float* y, int nslab, int T, const float* ln_w, const float* ln_b,
                              const float* b_in, const float* b_out, const void* layer_img, void* save_qkv, void* save_o,
                              float* save_lse, float* ln_stats, int fmt, int* err, void* stream) {
-    return nbss_mhsa_fwd_nh(x, y, nslab, T, ln_w, ln_b, b_in, b_out, layer_img, save_qkv, save_o, save_lse, ln_stats, 4, fmt, err, stream);
+    return nbss_mhsa_fwd_nh(x, y, nslab, T, ln_w, ln_b, b_in, b_out, layer_img, save_qkv, save_o, save_lse, ln_stats, nullptr, 4, fmt, err, stream);
 }

@@ -133,11 +133,13 @@ struct Oct12 {
 // Writes rows [row_off, row_off+256) of the tile; rows t >= T are written as zeros.  gamma/beta in shared memory.
 // Each warp takes 16-row blocks; one load/store instruction covers rows R + 4*sub + u (u = 0..3 unrolled), which spreads
 // the 8-byte tile stores of a warp over all 32 banks twice (the minimum for 256 bytes).
-template <int FMT, bool LN, int U = 4>
+// EXT: the row statistics come from `ext` ([T] (mean, rstd) of this slab's frames) instead of the row itself — GroupBatchNorm of
+// NBC2 (models/arch/NBC2.py:111-145), whose statistics span all frequencies of a frame and are reduced by another kernel.
+template <int FMT, bool LN, int U = 4, bool EXT = false>
 __device__ __forceinline__ void stage_rows96(const float* __restrict__ xslab, int T, unsigned char* tile, int row_off,
                                              const float* s_gamma, const float* s_beta, int warp, int lane,
                                              float* stats_out = nullptr /* [T,2] (mean, rstd) of this slab */,
-                                             int nwarps = 8) {
+                                             int nwarps = 8, const float2* __restrict__ ext = nullptr) {
     const int sub = lane >> 3, l8 = lane & 7;
     Oct12 g, be;
     if (LN) { g.load(s_gamma, l8); be.load(s_beta, l8); }
@@ -158,14 +160,23 @@ __device__ __forceinline__ void stage_rows96(const float* __restrict__ xslab, in
             const int r = R + U * sub + u;
             const bool ok = r < T;
             if (LN) {
-                const float mean = oct_sum(f4_hsum(v[u][0]) + f4_hsum(v[u][1]) + f4_hsum(v[u][2])) * (1.f / kH);
-                float q = 0.f;
+                float mean, rstd;
+                if constexpr (EXT) {
+                    const float2 st = ok ? __ldg(ext + r) : make_float2(0.f, 0.f);
+                    mean = st.x;
+                    rstd = st.y;
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    v[u][j] = make_float4(v[u][j].x - mean, v[u][j].y - mean, v[u][j].z - mean, v[u][j].w - mean);
-                    q += f4_dot(v[u][j], v[u][j]);
+                    for (int j = 0; j < 3; ++j) v[u][j] = make_float4(v[u][j].x - mean, v[u][j].y - mean, v[u][j].z - mean, v[u][j].w - mean);
+                } else {
+                    mean = oct_sum(f4_hsum(v[u][0]) + f4_hsum(v[u][1]) + f4_hsum(v[u][2])) * (1.f / kH);
+                    float q = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        v[u][j] = make_float4(v[u][j].x - mean, v[u][j].y - mean, v[u][j].z - mean, v[u][j].w - mean);
+                        q += f4_dot(v[u][j], v[u][j]);
+                    }
+                    rstd = rsqrtf(oct_sum(q) * (1.f / kH) + 1e-5f);
                 }
-                const float rstd = rsqrtf(oct_sum(q) * (1.f / kH) + 1e-5f);
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
                     v[u][j] = make_float4(v[u][j].x * rstd * g.v[j].x + be.v[j].x, v[u][j].y * rstd * g.v[j].y + be.v[j].y,
@@ -276,9 +287,11 @@ __device__ __forceinline__ void ln_bwd_rows(const unsigned char* tile, uint32_t 
 // SKIP4: the staging area is a tile whose every 4th chunk among the first 16 must stay untouched (zero padding of the
 // per-head K tile in mhsa_fwd): four-float chunk c lives at tile chunk skip4_chunk(c).
 __device__ __forceinline__ int skip4_chunk(int c) { return c + (c < 12 ? c / 3 : 4); }
+// row_part (nullable): [T][2] (sum, sum of squares) over the 96 channels of every OUTPUT row — the per-slab partials of NBC2's
+// GroupBatchNorm, reduced over the frequencies of a frame by gbn_reduce (ffn_fwd.cu).
 template <bool SKIP4 = false>
 __device__ __forceinline__ void add_rows(const unsigned char* tile, uint32_t cs, int row_off, const float* __restrict__ xs,
-                                         float* __restrict__ ys, int T, int warp, int lane, int nwarps) {
+                                         float* __restrict__ ys, int T, int warp, int lane, int nwarps, float* __restrict__ row_part = nullptr) {
     const int sub = lane >> 3, l8 = lane & 7;
     const unsigned char* tl = tile + (size_t)row_off * 16;
 #pragma unroll 1
@@ -294,14 +307,22 @@ __device__ __forceinline__ void add_rows(const unsigned char* tile, uint32_t cs,
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int r = R + 4 * sub + u;
+            float ps = 0.f, pq = 0.f;
             if (r < T) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     const int ch = SKIP4 ? skip4_chunk(l8 + 8 * j) : l8 + 8 * j;
                     const float4 v = *reinterpret_cast<const float4*>(tl + (size_t)ch * cs + r * 16);
-                    reinterpret_cast<float4*>(ys + (size_t)r * kH)[l8 + 8 * j] =
-                        make_float4(xv[u][j].x + v.x, xv[u][j].y + v.y, xv[u][j].z + v.z, xv[u][j].w + v.w);
+                    const float4 o = make_float4(xv[u][j].x + v.x, xv[u][j].y + v.y, xv[u][j].z + v.z, xv[u][j].w + v.w);
+                    reinterpret_cast<float4*>(ys + (size_t)r * kH)[l8 + 8 * j] = o;
+                    ps += f4_hsum(o);
+                    pq += f4_dot(o, o);
                 }
+            }
+            if (row_part) {  // uniform across the block
+                ps = oct_sum(ps);
+                pq = oct_sum(pq);
+                if (l8 == 0 && r < T) *reinterpret_cast<float2*>(row_part + 2 * r) = make_float2(ps, pq);
             }
         }
     }

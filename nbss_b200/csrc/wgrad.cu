@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(WgArgs args) {
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float s_ln[192];
     const WgJob& J = args.job[blockIdx.y];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = args.T;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0) /* warp-uniform for ptxas: see umma.cuh elect_one */, lane = tid & 31, T = args.T;
     unsigned char* gt = smem;
     unsigned char* at = smem + (size_t)J.g_alloc * kCS;
     const int a_alloc = J.a_chunks + 2;

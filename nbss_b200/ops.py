@@ -20,7 +20,7 @@ Tensor = torch.Tensor
 # every C-ABI call is bracketed by CUDA events on the launching (current) stream.
 LAUNCHES = 0
 TIMING = None
-_NLAUNCH = {"nbss_full_fwd": 3, "nbss_full_bwd": 4, "nbss_full_fwd_tc": 3, "nbss_full_bwd_tc": 4, "nbss_ffn_wgrad": 3, "nbss_mhsa_bwd": 2, "nbss_istft": 2, "nbss_sisdr_pit_fwd": 2, "nbss_clip_adam": 2}
+_NLAUNCH = {"nbss_nbc2_block": 5, "nbss_full_fwd": 3, "nbss_full_bwd": 4, "nbss_full_fwd_tc": 3, "nbss_full_bwd_tc": 4, "nbss_ffn_wgrad": 3, "nbss_mhsa_bwd": 2, "nbss_istft": 2, "nbss_sisdr_pit_fwd": 2, "nbss_clip_adam": 2}
 
 
 _KCACHE = {}
@@ -152,6 +152,59 @@ def ffn_fwd(x: Tensor, P: Dict[str, Tensor], pre: str, img: Tensor, save: bool =
     if save:
         return y, saves + [ln_stats], stats, err
     return y, err
+
+
+def nbc2_pack_block(P: Dict[str, Tensor], pre: str, img: Optional[Tensor] = None, fmt: int = FMT_F16) -> Tensor:
+    """UMMA weight images of one NBC2Block (models/arch/NBC2.py:152-194): the same image layout as a SpatialNet layer's
+    narrow-band block (linear1 / conv.{1,3,6} / linear2 / self_attn take the places of tconvffn.{1,3,5,8,10} / mhsa)."""
+    dev = P[pre + "linear1.weight"].device
+    if img is None:
+        img = torch.empty(layer_image_bytes(), dtype=torch.uint8, device=dev)
+    st = _K("nbss_pack_layer_weights")(
+        ptr(_f32c(P[pre + "linear1.weight"])), ptr(_f32c(P[pre + "conv.1.weight"])), ptr(_f32c(P[pre + "conv.3.weight"])),
+        ptr(_f32c(P[pre + "conv.6.weight"])), ptr(_f32c(P[pre + "linear2.weight"])), ptr(_f32c(P[pre + "self_attn.in_proj_weight"])),
+        ptr(_f32c(P[pre + "self_attn.out_proj.weight"])), ptr(img), fmt, fmt, stream_ptr())
+    check(st, "nbss_pack_layer_weights")
+    return img
+
+
+def nbc2_block_fwd(x: Tensor, P: Dict[str, Tensor], pre: str, img: Tensor, num_heads: int = 2, fmt: int = FMT_F16,
+                   ws: Optional[dict] = None) -> Tensor:
+    """One NBC2Block in place on the stream x [B,F,T,96] (inference): x += MHSA(LN(x)); x += FF(GBN(x)) (NBC2.py:196-225).
+    Five launches: attention (+ GroupBatchNorm partials), statistics, T-ConvFFN part A, statistics, part B.  `ws` caches the
+    scratch tensors across blocks."""
+    x = _f32c(x)
+    B, F, T, H = x.shape
+    assert H == 96
+    n, nslab = B * F * T, B * F
+    ws = {} if ws is None else ws
+    key = (B, F, T, x.device)
+    if ws.get("key") != key:
+        ws.clear()
+        ws.update(key=key, part1=torch.empty(n, 2, dtype=torch.float32, device=x.device),
+                  part2=torch.empty(n, 2, 2, dtype=torch.float32, device=x.device),
+                  stats=torch.empty(B * T, 2, dtype=torch.float32, device=x.device),
+                  c2=torch.empty(n, 192, dtype=torch.float16, device=x.device))
+    err = device_err_flag(x.device)
+    st = _K("nbss_mhsa_fwd_nh")(
+        ptr(x), ptr(x), nslab, T, ptr(_f32c(P[pre + "norm1.weight"])), ptr(_f32c(P[pre + "norm1.bias"])),
+        ptr(_f32c(P[pre + "self_attn.in_proj_bias"])), ptr(_f32c(P[pre + "self_attn.out_proj.bias"])), ptr(img), ptr(None), ptr(None),
+        ptr(None), ptr(None), ptr(ws["part1"]), num_heads, fmt, ptr(err), stream_ptr())
+    check(st, "nbss_mhsa_fwd_nh")
+    check(_K("nbss_gbn_reduce")(ptr(ws["part1"]), B, F, T, 1, ctypes.c_longlong(F * 96), ctypes.c_float(1e-5), ptr(ws["stats"]), stream_ptr()),
+          "nbss_gbn_reduce")
+    st = _K("nbss_nbc2_ffn_a")(
+        ptr(x), nslab, T, F, ptr(ws["stats"]), ptr(_f32c(P[pre + "norm2.weight"])), ptr(_f32c(P[pre + "norm2.bias"])),
+        ptr(_f32c(P[pre + "linear1.bias"])), ptr(_f32c(P[pre + "conv.1.bias"])), ptr(_f32c(P[pre + "conv.3.bias"])), ptr(img),
+        ptr(ws["c2"]), ptr(ws["part2"]), fmt, ptr(err), stream_ptr())
+    check(st, "nbss_nbc2_ffn_a")
+    check(_K("nbss_gbn_reduce")(ptr(ws["part2"]), B, F, T, 2, ctypes.c_longlong(F * 192), ctypes.c_float(1e-5), ptr(ws["stats"]), stream_ptr()),
+          "nbss_gbn_reduce")
+    st = _K("nbss_nbc2_ffn_b")(
+        ptr(x), ptr(x), nslab, T, F, ptr(ws["stats"]), ptr(_f32c(P[pre + "conv.4.weight"])), ptr(_f32c(P[pre + "conv.4.bias"])),
+        ptr(_f32c(P[pre + "conv.6.bias"])), ptr(_f32c(P[pre + "linear2.bias"])), ptr(img), ptr(ws["c2"]), fmt, ptr(err), stream_ptr())
+    check(st, "nbss_nbc2_ffn_b")
+    return x
 
 
 def mhsa_fwd(x: Tensor, P: Dict[str, Tensor], pre: str, img: Tensor, save: bool = False, fmt: int = FMT_F16,

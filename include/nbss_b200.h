@@ -53,6 +53,12 @@ int nbss_mhsa_fwd_nh(const float* x, float* y, int nslab, int T, const float* ln
                      const float* b_out, const void* layer_img, void* save_qkv, void* save_o, float* save_lse,
                      float* ln_stats, float* row_part, int num_heads, int fmt, int* err, void* stream);
 
+/* ---- predict / test post-processing (predict.cu): recover_scale (models/utils/metrics.py:192-218, scale_src_together=False) and
+ * the peak normalisation of SharedTrainer.py:301-305.  preds [B,S,Ts] (S <= 4), mixture [B,Ts] (reference channel), out may
+ * alias preds; ws_sums: 14*B doubles, ws_peak: B*S uints (scratch, zeroed inside); scale_out (nullable) [B,S]. */
+int nbss_predict_post(const float* preds, const float* mixture, float* out, int B, int S, long long Ts, int recover,
+                      int norm_if_exceed_1, double* ws_sums, unsigned int* ws_peak, float* scale_out, void* stream);
+
 /* ---- NBC2 inference (BASELINE configs[3]; models/arch/NBC2.py:152-289) ------------------------------------------------ */
 /* GroupBatchNorm statistics (NBC2.py:118-128): part [B][NP][T][NQ][2] (sum, sum of squares) -> stats [B][T][2] (mean, rstd)
  * over the NP*NQ partials of `count` elements in total (fp64 accumulation). */

@@ -387,6 +387,9 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         wait_mma();
         NBSS_TICK(1, 2, it_);
         if (tid == 0) load_image(wimg, a.img + FC_IMG_BYTES, FC_IMG_BYTES, bar_w);  // transposed image for the data gradient
+        // next group's x / dy rows -> L2, issued after this group's own staging loads have landed (at the top of the group the
+        // prefetch competed with them and cost 5 %)
+        fc_prefetch_rows(g, a.x, a.dy, grp + gridDim.x, tid, NT);
         // ---- E-A: dc = dy * PReLU'(c), in place over the staged dy in gtile; column sums for dbias / dslope.
         //      work items (M-tile, 16-column block) are dealt to the four warp groups
 #pragma unroll 1

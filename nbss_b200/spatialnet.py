@@ -146,8 +146,11 @@ class Engine:
             raise ops._lib.NbssError("nbss_b200.SpatialNet runs on CUDA tensors only (there is no CPU path)")
         imgs = self.images(P)
         fimgs = self.fconv_images(P)
-        limgs = self.lg_images(P) if self.full_tc else None
-        ctx = {"x_in": x, "layers": []} if save else None
+        # the tensor-core LinearGroup holds one F x F weight per CTA with N = F <= 256 (UMMA limit); wider bands (16 kHz: F = 257,
+        # models/io/stft.py:8-12) run the full-band sub-block on the fp32 CUDA-core kernels (crossband.cu), 7 % of a layer
+        full_tc = self.full_tc and x.shape[1] <= 256
+        limgs = self.lg_images(P) if full_tc else None
+        ctx = {"x_in": x, "layers": [], "full_tc": full_tc} if save else None
         errs = []
         h = ops.encoder_fwd(x, P)
         for i in range(self.L):
@@ -155,7 +158,7 @@ class Engine:
             if save:
                 lc = {"x0": h}
                 h1, e3 = ops.fconv_tc_fwd(h, P, pre + "fconv1", fimgs[i][0], fmt=self.fwd_fmt)
-                h2, s, u = (ops.full_fwd_tc(h1, P, pre, limgs[i], fmt=self.fwd_fmt) if self.full_tc else ops.full_fwd(h1, P, pre))
+                h2, s, u = (ops.full_fwd_tc(h1, P, pre, limgs[i], fmt=self.fwd_fmt) if full_tc else ops.full_fwd(h1, P, pre))
                 h3, e4 = ops.fconv_tc_fwd(h2, P, pre + "fconv2", fimgs[i][1], fmt=self.fwd_fmt)
                 h4, msave, e1 = ops.mhsa_fwd(h3, P, pre, imgs[i], save=True, fmt=self.fwd_fmt)
                 h5, fsave, gstats, e2 = ops.ffn_fwd(h4, P, pre, imgs[i], save=True, fmt=self.fwd_fmt)
@@ -165,7 +168,7 @@ class Engine:
             else:
                 # inference: every sub-block updates the stream in place (each kernel reads a row before writing it)
                 h, e3 = ops.fconv_tc_fwd(h, P, pre + "fconv1", fimgs[i][0], out=h, fmt=self.fwd_fmt)
-                h, _, _ = (ops.full_fwd_tc(h, P, pre, limgs[i], out=h, fmt=self.fwd_fmt) if self.full_tc else ops.full_fwd(h, P, pre, out=h))
+                h, _, _ = (ops.full_fwd_tc(h, P, pre, limgs[i], out=h, fmt=self.fwd_fmt) if full_tc else ops.full_fwd(h, P, pre, out=h))
                 h, e4 = ops.fconv_tc_fwd(h, P, pre + "fconv2", fimgs[i][1], out=h, fmt=self.fwd_fmt)
                 h, e1 = ops.mhsa_fwd(h, P, pre, imgs[i], fmt=self.fwd_fmt, out=h)
                 h, e2 = ops.ffn_fwd(h, P, pre, imgs[i], fmt=self.fwd_fmt, out=h)
@@ -180,7 +183,7 @@ class Engine:
         (SharedTrainer.py:113-120: X comes from the STFT of the data)."""
         imgs = self.images(P)
         fimgs = self.fconv_images(P)
-        limgs = self.lg_images(P) if self.full_tc else None
+        limgs = self.lg_images(P) if ctx["full_tc"] else None
         errs = []
         if self.use_side and self._side is None:
             self._side = torch.cuda.Stream(device=dy.device)
@@ -203,7 +206,7 @@ class Engine:
             d, e1 = ops.ffn_bwd(lc["x4"], d, lc["fsave"], lc["gstats"], P, pre, imgs[i], G, fmt_g=self.grad_fmt)
             d, e2 = ops.mhsa_bwd(lc["x3"], d, lc["msave"], P, pre, imgs[i], G, fmt_g=self.grad_fmt)
             d, e3 = ops.fconv_tc_bwd(lc["x2"], d, P, pre + "fconv2", fimgs[i][1], G, fmt=self.grad_fmt)
-            d = (ops.full_bwd_tc(lc["x1"], d, lc["s"], lc["u"], P, pre, limgs[i], G, fmt=self.fwd_fmt) if self.full_tc
+            d = (ops.full_bwd_tc(lc["x1"], d, lc["s"], lc["u"], P, pre, limgs[i], G, fmt=self.fwd_fmt) if ctx["full_tc"]
                  else ops.full_bwd(lc["x1"], d, lc["s"], lc["u"], P, pre, G))
             d, e4 = ops.fconv_tc_bwd(lc["x0"], d, P, pre + "fconv1", fimgs[i][0], G, fmt=self.grad_fmt)
             errs += [e1, e2, e3, e4]

@@ -54,6 +54,34 @@ def test_cfg1_small_2ch_f65_t64():
 
 
 @pytest.mark.gpu
+def test_forward_backward_16khz_f257():
+    """The reference's 16 kHz framing (n_fft 512, F = 257; models/io/stft.py:8-12): forward 1e-3, parameter gradients of a
+    2-layer network against fp64 autograd (the full-band LinearGroup runs on the fp32 kernels for F > 256)."""
+    cfg = dict(O.SMALL_CFG, num_layers=2, num_freqs=257)
+    P = O.synth_params(cfg, 35)
+    Pl = {}
+    seen = {}
+    for k, v in P.items():
+        if id(v) not in seen:
+            seen[id(v)] = v.double().requires_grad_(True)
+        Pl[k] = seen[id(v)]
+    net = _net(cfg, P)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(1, 257, 60, 12, generator=g)
+    dy = torch.randn(1, 257, 60, 4, generator=g)
+    y = net(x.cuda())
+    y.backward(dy.cuda())
+    torch.cuda.synchronize()
+    net.check_device_errors()
+    ref = O.spatialnet_forward(Pl, x.double(), cfg)
+    ref.backward(dy.double())
+    assert O.rel_l2(y.detach().cpu(), ref.detach()) < 1e-3
+    errs = {n: O.rel_l2(p.grad.cpu().reshape(-1), Pl[n].grad.reshape(-1)) for n, p in net.named_parameters()}
+    bad = {k: f"{v:.2e}" for k, v in errs.items() if not v < 3e-2}
+    assert not bad, bad
+
+
+@pytest.mark.gpu
 def test_forward_backward_grads():
     cfg = dict(O.SMALL_CFG, num_layers=3)
     P = O.synth_params(cfg, 33)

@@ -490,19 +490,20 @@ __global__ void __launch_bounds__(256) unsqueeze_bwd_kernel(const float* __restr
 // ------------------------------------------------------------------------------------------------ LinearGroup
 // rows r = (frame m, group g) of a [M*8, F] matrix.  out[m,g,k] = sum_f in[m,g,f] * Wf[g,k,f] (+ bf[g,k])   (trans=0)
 //                                                    out[m,g,f] = sum_k in[m,g,k] * Wf[g,k,f]                (trans=1)
-// CTA: 64 frames x one group; the group's F x F weight sits in smem (padded rows), 256 threads x (1 frame, F/4 outs).
+// CTA: 64 frames x one group x one block of OB outputs (blockIdx.z); the block's OB x F weight rows sit in smem (padded rows),
+// 256 threads x (1 frame, OB/4 outs).  OB = F for F <= 190 (one block); wider bands (16 kHz: F = 257) take two blocks.
 __global__ void __launch_bounds__(256) fullgemm_kernel(const float* __restrict__ in, float* __restrict__ out, int M, int F,
-                                                       const float* __restrict__ Wf, const float* __restrict__ bf, int trans) {
+                                                       const float* __restrict__ Wf, const float* __restrict__ bf, int trans, int OB) {
     extern __shared__ __align__(16) float sm[];
     const int FP = F + 1;
-    float* ws = sm;               // [F][FP]   ws[o][i] = weight(out o, in i)
-    float* as = sm + F * FP;      // [64][FP]
+    float* ws = sm;               // [OB][FP]   ws[o][i] = weight(out o0 + o, in i)
+    float* as = sm + OB * FP;     // [64][FP]
     const int g = blockIdx.y, m0 = blockIdx.x * 64, tid = threadIdx.x;
+    const int o0 = blockIdx.z * OB, on = min(OB, F - o0);
     const float* wg = Wf + (size_t)g * F * F;
-    for (int i = tid; i < F * F; i += 256) {
-        const int r = i / F, c = i % F;  // wg[r][c] = W[k=r][f=c]
-        if (!trans) ws[r * FP + c] = wg[i];
-        else ws[c * FP + r] = wg[i];
+    for (int i = tid; i < on * F; i += 256) {
+        const int r = i / F, c = i % F;  // W[k][f]: out = k (forward) or out = f (data gradient)
+        ws[r * FP + c] = !trans ? wg[(size_t)(o0 + r) * F + c] : wg[(size_t)c * F + o0 + r];
     }
     for (int i = tid; i < 64 * F; i += 256) {
         const int fr = i / F, c = i % F;
@@ -510,7 +511,7 @@ __global__ void __launch_bounds__(256) fullgemm_kernel(const float* __restrict__
     }
     __syncthreads();
     const int fr = tid >> 2, oq = tid & 3;
-    constexpr int MAXO = 65;  // supports F <= 260
+    constexpr int MAXO = 48;  // supports OB <= 192
     float acc[MAXO];
 #pragma unroll
     for (int j = 0; j < MAXO; ++j) acc[j] = 0.f;
@@ -520,16 +521,21 @@ __global__ void __launch_bounds__(256) fullgemm_kernel(const float* __restrict__
 #pragma unroll
         for (int j = 0; j < MAXO; ++j) {
             const int o = oq + 4 * j;
-            if (o < F) acc[j] = fmaf(a, ws[o * FP + i], acc[j]);
+            if (o < on) acc[j] = fmaf(a, ws[o * FP + i], acc[j]);
         }
     }
     if (m0 + fr < M) {
 #pragma unroll
         for (int j = 0; j < MAXO; ++j) {
             const int o = oq + 4 * j;
-            if (o < F) out[((size_t)(m0 + fr) * kHS + g) * F + o] = acc[j] + ((bf && !trans) ? bf[g * F + o] : 0.f);
+            if (o < on) out[((size_t)(m0 + fr) * kHS + g) * F + o0 + o] = acc[j] + ((bf && !trans) ? bf[g * F + o0 + o] : 0.f);
         }
     }
+}
+static inline int fullgemm_ob(int F) {  // outputs per CTA: everything when the whole weight fits, else the fewest equal blocks <= 192
+    if ((size_t)(F + 64) * (F + 1) * 4 <= 200 * 1024 && F <= 192) return F;
+    const int nb = (F + 131) / 132;
+    return (F + nb - 1) / nb;
 }
 
 // dWf[g,k,f] += sum_m du[m,g,k] * s[m,g,f];  dbf[g,k] += sum_m du[m,g,k].   grid (chunks, 8 groups, kblk*fblk)
@@ -650,18 +656,19 @@ extern "C" int nbss_full_fwd(const float* x, float* y, float* s_out, float* u_ou
                              const float* Wun, const float* bun, void* stream) {
     if (!x || !y || !s_out || !u_out || !lnw || !lnb || !Wsq || !bsq || !Wf || !bf || !Wun || !bun) return NBSS_ERR_NULL;
     if (B < 1 || F < 1 || T < 1) return NBSS_ERR_SHAPE;
-    if ((size_t)(F + 64) * (F + 1) * 4 > 227 * 1024) return NBSS_ERR_UNSUPPORTED;
+    const int OB = fullgemm_ob(F);
+    if ((size_t)(OB + 64) * (F + 1) * 4 > 227 * 1024) return NBSS_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const int tiles = B * ((T + kSQT - 1) / kSQT);
     const size_t sm_sq = (size_t)(kHS * kH + kSQT * kHS * F) * 4;
     const int fsplit = f_split(tiles, F);
     squeeze_fwd_kernel<<<dim3(tiles, fsplit), 256, sm_sq, st>>>(x, s_out, B, F, T, lnw, lnb, Wsq, bsq);
     NBSS_LAUNCH_CHECK();
-    const size_t sm_g = (size_t)(F + 64) * (F + 1) * 4;
+    const size_t sm_g = (size_t)(OB + 64) * (F + 1) * 4;
     cudaError_t e = cudaFuncSetAttribute(fullgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_g);
     if (e != cudaSuccess) return (int)e;
     const int M = B * T;
-    fullgemm_kernel<<<dim3((M + 63) / 64, kHS), 256, sm_g, st>>>(s_out, u_out, M, F, Wf, bf, 0);
+    fullgemm_kernel<<<dim3((M + 63) / 64, kHS, (F + OB - 1) / OB), 256, sm_g, st>>>(s_out, u_out, M, F, Wf, bf, 0, OB);
     NBSS_LAUNCH_CHECK();
     unsqueeze_fwd_kernel<<<dim3(tiles, fsplit), 256, (size_t)kSQT * kHS * F * 4, st>>>(x, u_out, y, B, F, T, Wun, bun);
     NBSS_LAUNCH_CHECK();
@@ -675,7 +682,8 @@ extern "C" int nbss_full_bwd(const float* x, const float* dy, float* dx, const f
                              float* dbsq, float* dWf, float* dbf, float* dWun, float* dbun, void* stream) {
     if (!x || !dy || !dx || !s || !u || !ws) return NBSS_ERR_NULL;
     if (B < 1 || F < 1 || T < 1) return NBSS_ERR_SHAPE;
-    if ((size_t)(F + 64) * (F + 1) * 4 > 227 * 1024) return NBSS_ERR_UNSUPPORTED;
+    const int OB = fullgemm_ob(F);
+    if ((size_t)(OB + 64) * (F + 1) * 4 > 227 * 1024) return NBSS_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const int sms = num_sms();
     const int tiles = B * ((T + kSQT - 1) / kSQT), M = B * T;
@@ -686,10 +694,10 @@ extern "C" int nbss_full_bwd(const float* x, const float* dy, float* dx, const f
     cudaFuncSetAttribute(unsqueeze_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(2 * kSQT * kHS * F + 1024) * 4));
     unsqueeze_bwd_kernel<<<pg, 256, (size_t)(2 * kSQT * kHS * F + 1024) * 4, st>>>(dy, u, du, B, F, T, Wun, bun, dWun, dbun, fsplit);
     NBSS_LAUNCH_CHECK();
-    const size_t sm_g = (size_t)(F + 64) * (F + 1) * 4;
+    const size_t sm_g = (size_t)(OB + 64) * (F + 1) * 4;
     cudaError_t e = cudaFuncSetAttribute(fullgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_g);
     if (e != cudaSuccess) return (int)e;
-    fullgemm_kernel<<<dim3((M + 63) / 64, kHS), 256, sm_g, st>>>(du, ds, M, F, Wf, nullptr, 1);
+    fullgemm_kernel<<<dim3((M + 63) / 64, kHS, (F + OB - 1) / OB), 256, sm_g, st>>>(du, ds, M, F, Wf, nullptr, 1, OB);
     NBSS_LAUNCH_CHECK();
     const int chunks = M < 32 * 32 ? (M + 31) / 32 : 32;
     const int nkb = (F + 143) / 144, nfb = (F + 1 + 143) / 144;

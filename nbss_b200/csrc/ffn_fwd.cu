@@ -278,8 +278,10 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
                 unpack_f16x2(pk.z, v[4], v[5]);
                 unpack_f16x2(pk.w, v[6], v[7]);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = silu((v[j] - st.x) * (st.y * s_gng[c + j]) + s_gnb[c + j]) * vmask;
-                *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = pack8<FMT>(v);
+                for (int j = 0; j < 8; ++j) v[j] = silu((v[j] - st.x) * (st.y * s_gng[c + j]) + s_gnb[c + j]);
+                // frames >= T: the TMA copy did not touch these rows, they still hold the previous slab's fp32 staging bytes
+                // (possibly NaN patterns when read as fp16): select zeros, do not multiply
+                *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = valid ? pack8<FMT>(v) : make_uint4(0u, 0u, 0u, 0u);
             }
         }
         if constexpr (MODE == 0) {

@@ -6,7 +6,7 @@ PAT=${1:-ffn_bwd_kernel}
 BATCH=${2:-32}
 TAG=${3:-r01}
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
-    --log-file gpurun_out/launches_$TAG.csv python bench.py --profile --batch $BATCH > gpurun_out/prof_launch.log 2>&1
+    --log-file gpurun_out/launches_$TAG.csv python bench.py --profile --batch ${LBATCH:-$BATCH} > gpurun_out/prof_launch.log 2>&1
 echo "launch list rc=$?"
 # full captures on a ONE-layer network: one step then holds exactly one launch of every kernel (fwd and bwd)
 timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"$PAT" -c 24 \

@@ -521,11 +521,13 @@ def main():
         if k in FLOP_PER_POINT:
             ent["tflops"] = round(FLOP_PER_POINT[k] * npts / (ms * 1e-3) / 1e12, 2)
         kernels[k] = ent
-    # DRAM bytes per call from the committed ncu capture (tools/traffic_from_ncu.py), scaled linearly to this batch
-    traffic = {}
+    # DRAM bytes per call from the committed ncu capture of the r02 build (tools/profile.sh + tools/traffic_from_ncu.py;
+    # profiles/r02_traffic.json names its commit and command), scaled linearly to this batch (one slab = one unit of traffic)
+    traffic, traffic_src = {}, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         traffic = {k: v * b_local / tj["batch_per_gpu"] for k, v in tj["dram_bytes_per_call"].items()}
+        traffic_src = f"profiles/r02_traffic.json (ncu --set full, commit {tj.get('commit')}, batch {tj['batch_per_gpu']} scaled to {b_local})"
     except Exception:
         pass
 
@@ -536,9 +538,9 @@ def main():
         # roofline side: arithmetic intensity of the ALGORITHMIC work against the machine balance of the measured peaks
         if FLOP_PER_POINT[k] / BYTES_PER_POINT[k] >= peak_tf * 1e12 / (peak_bw * 1e9):
             return {"kernel": k, "bound": "tensor", "achieved": round(tf, 2), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(tf / peak_tf, 4),
-                    "traffic": traffic.get(k), "also_hbm_gbs": round(gb, 1), "peak_source": peak_src}
+                    "traffic": traffic.get(k), "traffic_source": traffic_src, "also_hbm_gbs": round(gb, 1), "peak_source": peak_src}
         return {"kernel": k, "bound": "hbm", "achieved": round(gb, 1), "peak": peak_bw, "unit": "GB/s", "frac": round(gb / peak_bw, 4),
-                "traffic": traffic.get(k), "also_tflops": round(tf, 2), "peak_source": peak_src}
+                "traffic": traffic.get(k), "traffic_source": traffic_src, "also_tflops": round(tf, 2), "peak_source": peak_src}
     cands = [k for k in kernels if k in FLOP_PER_POINT and k in BYTES_PER_POINT]
     top = max(cands, key=lambda k: kernels[k]["ms_per_step"])
     rooflines = sorted((dict(roof(k), ms_per_step=kernels[k]["ms_per_step"]) for k in cands), key=lambda r: -r["ms_per_step"])

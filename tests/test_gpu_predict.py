@@ -41,6 +41,9 @@ def test_predict_step_order_of_operations():
     x = src.sum(1, keepdim=True).repeat(1, C, 1) + 0.01 * torch.randn(B, C, Ts, generator=g)
     fake_est = torch.stack([src[:, 1] * 0.01, src[:, 0] * 50.0], 1)  # swapped speakers, wrong scales
 
+    from nbss_b200.loss import neg_si_sdr_pit
+    rec_dbg = recover_scale(fake_est.cuda(), x[:, 0].cuda(), norm_if_exceed_1=False)
+    print("debug: PIT of the recovered estimates:", neg_si_sdr_pit(rec_dbg, src.cuda()))
     out = predict_step(lambda w: fake_est.cuda(), x.cuda(), yr=src.cuda(), ref_channel=0, norm_if_exceed_1=True)
     ref, _ = _ref_recover(fake_est, x[:, 0], False)
     ref = ref[:, [1, 0]]                                             # PIT against the targets undoes the swap

@@ -257,6 +257,51 @@ def bench_nbc2(dev, steps=5, warmup=3, batch=64, eager=True):
     return out
 
 
+def bench_online(dev, frames=1000, batches=(1, 8, 64)):
+    """BASELINE configs[4]: online (causal) SpatialNet, 6 channels, F=129, one 16 ms frame (hop 128 at 8 kHz) per call through
+    nbss_b200.online.OnlineSpatialNet.step, the whole step replayed as one CUDA graph.  Latency = host wall clock from handing a
+    pinned host frame to having the output frame back on the host (H2D copy + graph + D2H copy + stream sync), p50 / p95 over
+    `frames` consecutive frames of one stream (B=1); throughput = frames/s of B parallel streams (device time)."""
+    from nbss_b200.online import OnlineSpatialNet
+
+    torch.manual_seed(2)
+    net = OnlineSpatialNet(dim_input=12, dim_output=4, num_layers=8, dim_squeeze=8, num_freqs=129, dim_hidden=96, dim_ffn=192, num_heads=4,
+                           attention="mhsa(251)").to(dev).eval()
+    out = {"workload": "OnlineSpatialNet mhsa(251) 6ch F=129, 8 layers, one 16 ms frame per call (BASELINE configs[4])", "hop_ms": 16.0, "streams": {}}
+    for B in batches:
+        state = net.init_state(B)
+        x_host = torch.randn(B, 129, 12).pin_memory()
+        y_host = torch.empty(B, 129, 4).pin_memory()
+        x_dev = x_host.to(dev)
+        for _ in range(3):  # warm-up (packs the weights, fills caches)
+            net.step(x_dev, state)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            y_dev = net.step(x_dev, state)
+        torch.cuda.synchronize()
+        lat = []
+        n = frames if B == 1 else max(100, frames // 5)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            t0 = time.perf_counter()
+            x_dev.copy_(x_host, non_blocking=True)
+            g.replay()
+            y_host.copy_(y_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            lat.append((time.perf_counter() - t0) * 1e3)
+        e1.record()
+        torch.cuda.synchronize()
+        lat.sort()
+        dev_ms = e0.elapsed_time(e1) / n
+        out["streams"][str(B)] = {"latency_ms_p50": round(lat[len(lat) // 2], 4), "latency_ms_p95": round(lat[int(len(lat) * 0.95)], 4),
+                                  "frames": n, "ms_per_frame_wall": round(dev_ms, 4), "frames_per_s": round(B / (dev_ms * 1e-3), 1),
+                                  "real_time_factor": round(dev_ms / 16.0, 5), "state_mb": round(sum(t.numel() * 4 for t in state.kcache + state.vcache) / 2**20, 1)}
+    net.check_device_errors()
+    return out
+
+
 def run_torch_gpu(args):
     """--impl torch-gpu: the eager baseline as a bench line of its own (rank 0 only)."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -310,7 +355,7 @@ def main():
     ap.add_argument("--torch-adam", action="store_true", help="clip_grad_norm_ + torch.optim.Adam(fused, capturable) instead of FlatClipAdam")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager reference op-set timed on this GPU")
-    ap.add_argument("--no-nbc2", action="store_true", help="skip the NBC2 inference workload (BASELINE configs[3]) reported under 'extra_workloads'")
+    ap.add_argument("--no-nbc2", action="store_true", help="skip the extra workloads (NBC2 inference = BASELINE configs[3], online streaming = configs[4]) reported under 'extra_workloads'")
     ap.add_argument("--batch", type=int, default=CFG["B"], help="global batch (utterances)")
     ap.add_argument("--profile", action="store_true", help="1 warm-up + 1 step only (for ncu); prints no bench line")
     ap.add_argument("--layers", type=int, default=CFG["L"], help="number of SpatialNet layers (profiling only; default 8)")
@@ -561,10 +606,12 @@ def main():
     if eager is not None:
         out["gpu_eager_baseline"] = eager
     if world == 1 and not args.no_nbc2:
-        try:
-            out["extra_workloads"] = {"nbc2_inference": bench_nbc2(dev, eager=not args.no_eager_baseline)}
-        except Exception as e:
-            out["extra_workloads"] = {"nbc2_inference": {"unavailable": f"{type(e).__name__}: {e}"[:200]}}
+        out["extra_workloads"] = {}
+        for name, fn in (("nbc2_inference", lambda: bench_nbc2(dev, eager=not args.no_eager_baseline)), ("online_streaming", lambda: bench_online(dev))):
+            try:
+                out["extra_workloads"][name] = fn()
+            except Exception as e:
+                out["extra_workloads"][name] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     if world == 1 and not args.no_cpu_baseline:
         cores = min(os.cpu_count() or 1, 32)
         log(f"cpu baseline on {cores} threads")

@@ -202,3 +202,20 @@ def test_eager_opset_restatement_matches_oracle():
         assert O.rel_l2(g_e64[k], g_o64[k]) < 1e-10, k
         assert O.rel_l2(g_e32[k], g_o64[k]) < 5e-4, k
     assert O.rel_l2(e32, o64) < 5e-5
+
+
+def test_online_oracle_matches_reference():
+    """oracle/online_oracle.py (BASELINE configs[4]) against the unmodified reference OnlineSpatialNet
+    (attention='mhsa(251)', T = 270): the executed function is causal attention over all past frames (torch drops the window mask
+    for need_weights=False, see the oracle's header); the windowed restatement agrees on the first 251 frames."""
+    from oracle import online_oracle as OO
+
+    z = np.load(os.path.join(G, "online_f9_t270.npz"))
+    P = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("P.")}
+    cfg = dict(O.SMALL_CFG, num_layers=2, num_freqs=9)
+    x, y = torch.from_numpy(z["x"]), torch.from_numpy(z["y"])
+    with torch.no_grad():
+        assert O.rel_l2(OO.online_forward(P, x, cfg), y) < 2e-6
+        assert O.rel_l2(OO.online_forward(P, x[:, :, :251], cfg, scope=251), y[:, :, :251]) < 2e-6
+        yw = OO.online_forward(P, x, cfg, scope=251)
+        assert O.rel_l2(yw[:, :, :251], y[:, :, :251]) < 2e-6 and O.rel_l2(yw, y) > 1e-4  # the window matters beyond frame 251

@@ -74,7 +74,9 @@ __global__ void sisdr_finalize_kernel(const double* __restrict__ sums, int B, lo
             for (int j = 0; j < 2; ++j) {
                 const double alpha = (C[i][j] + e) / (T[j] + e);
                 const double S = alpha * alpha * T[j];
-                const double N = S - 2.0 * alpha * C[i][j] + P[i];
+                // |alpha t - p|^2 from the Gram sums; >= 0 in exact arithmetic, but an estimate that is an exact scaled copy
+                // of the target cancels to -1e-12-ish, and log() of that would make the permutation compare with NaN
+                const double N = fmax(S - 2.0 * alpha * C[i][j] + P[i], 0.0);
                 val[i][j] = K * (log(S + e) - log(N + e));
                 // d val / d p_n = K * (a1 t_n + a2 p_n)
                 const double a1 = 2.0 * alpha * T[j] / ((T[j] + e) * (S + e)) - ((2.0 * alpha * T[j] - 2.0 * C[i][j]) / (T[j] + e) - 2.0 * alpha) / (N + e);

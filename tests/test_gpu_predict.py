@@ -41,9 +41,8 @@ def test_predict_step_order_of_operations():
     x = src.sum(1, keepdim=True).repeat(1, C, 1) + 0.01 * torch.randn(B, C, Ts, generator=g)
     fake_est = torch.stack([src[:, 1] * 0.01, src[:, 0] * 50.0], 1)  # swapped speakers, wrong scales
 
-    from nbss_b200.loss import neg_si_sdr_pit
-    rec_dbg = recover_scale(fake_est.cuda(), x[:, 0].cuda(), norm_if_exceed_1=False)
-    print("debug: PIT of the recovered estimates:", neg_si_sdr_pit(rec_dbg, src.cuda()))
+    # the estimates are exact scaled copies of the targets: |alpha t - p|^2 cancels to ~0 (or just below) in the Gram-sum form
+    # of the loss kernel — the permutation must still come out right (regression: NaN compare kept the identity)
     out = predict_step(lambda w: fake_est.cuda(), x.cuda(), yr=src.cuda(), ref_channel=0, norm_if_exceed_1=True)
     ref, _ = _ref_recover(fake_est, x[:, 0], False)
     ref = ref[:, [1, 0]]                                             # PIT against the targets undoes the swap

@@ -46,6 +46,7 @@ class OnlineState:
         self.st = [[z(R, 2, 192) for _ in range(3)] for _ in range(L)]
         self.h = z(batch, F, 1, 96)
         self.c2, self.part, self.stats = z(R, 192), z(R, 8, 2), z(batch, 8, 2)
+        self.graph, self.x_in, self.y_out = None, None, None  # set by OnlineSpatialNet.capture_step
 
 
 class OnlineSpatialNet(nn.Module):
@@ -116,10 +117,34 @@ class OnlineSpatialNet(nn.Module):
         return OnlineState(self, batch, device, scope if scope is not None else self.attn_scope)
 
     @torch.no_grad()
+    def capture_step(self, state: OnlineState) -> OnlineState:
+        """Records the ~60 launches of one step of this stream into a CUDA graph (every pointer of a step is fixed: the state, the
+        ring position lives on the device); afterwards `step` copies the frame into the graph's input and replays.  The returned
+        frame is then a static buffer, overwritten by the next step.  Capturing executes nothing: the state is not advanced."""
+        dev = state.h.device
+        self._pack(self._params())
+        ops.device_err_flag(dev)
+        state.x_in = torch.zeros(state.batch, self.num_freqs, self.dim_input, dtype=torch.float32, device=dev)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            state.y_out = self._step_launches(state.x_in, state)
+        state.graph = g
+        return state
+
+    @torch.no_grad()
     def step(self, x_t: Tensor, state: OnlineState) -> Tensor:
         """One frame: x_t [B,F,Cin] -> y_t [B,F,Cout]; `state` is updated in place."""
         B, F, Cin = x_t.shape
         assert B == state.batch and F == self.num_freqs and Cin == self.dim_input, (x_t.shape, state.batch)
+        if state.graph is not None:
+            state.x_in.copy_(x_t, non_blocking=True)
+            state.graph.replay()
+            return state.y_out
+        return self._step_launches(x_t, state)
+
+    def _step_launches(self, x_t: Tensor, state: OnlineState) -> Tensor:
+        B, F, Cin = x_t.shape
         P = self._params()
         W = self._pack(P)
         R, h, sp = state.R, state.h, stream_ptr

@@ -61,7 +61,8 @@ int nbss_predict_post(const float* preds, const float* mixture, float* out, int 
 
 /* ---- online / causal SpatialNet, one frame per call (online.cu; models/arch/OnlineSpatialNet.py with attention='mhsa(N)') ------
  * R = B*F rows of one frame, fp32 [R,96] stream updated in place; `pos` = device int, frames consumed so far (nbss_online_advance
- * increments it, so a captured CUDA graph of the whole step replays unchanged); weights marked T are [in][out] (nbss_transpose). */
+ * increments it, so a captured CUDA graph of the whole step replays unchanged); weights marked T are [in][out] (nbss_transpose;
+ * the grouped T-conv weights [192][24][3] are passed as their transpose [72][192]).  A CTA owns 1 row (R <= 600) or 4 rows. */
 int nbss_transpose(const float* in, float* out, int rows, int cols, void* stream);
 int nbss_online_pack_encoder(const float* W /*[96][Cin][5]*/, float* Wt /*[5*Cin][96]*/, int Cin, void* stream);
 int nbss_online_encoder_step(const float* xt /*[R,Cin]*/, float* state /*[R,4,Cin]*/, const float* Wt, const float* bias, float* h,
@@ -70,11 +71,11 @@ int nbss_online_attn_step(float* x, int R, const float* ln_w, const float* ln_b,
                           const float* WoT, const float* b_out, float* kcache /*[R,scope,96]*/, float* vcache, const int* pos,
                           int scope, void* stream);
 int nbss_online_ffn_a_step(const float* x, int R, const float* ln_w, const float* ln_b, const float* W1T, const float* b1,
-                           const float* Wc1, const float* bc1, const float* Wc2, const float* bc2, float* st1 /*[R,2,192]*/,
+                           const float* Wc1T /*[72][192]*/, const float* bc1, const float* Wc2T, const float* bc2, float* st1 /*[R,2,192]*/,
                            float* st2, float* c2 /*[R,192]*/, float* part /*[R,8,2]*/, void* stream);
 int nbss_online_gn_stats(const float* part, int B, int F, float* stats /*[B,8,2]*/, void* stream);
 int nbss_online_ffn_b_step(float* x, int R, int F, const float* c2, const float* stats, const float* gn_w, const float* gn_b,
-                           const float* Wc3, const float* bc3, const float* W2T, const float* b2, float* st3, void* stream);
+                           const float* Wc3T, const float* bc3, const float* W2T, const float* b2, float* st3, void* stream);
 int nbss_online_advance(int* pos, void* stream);
 
 /* ---- NBC2 inference (BASELINE configs[3]; models/arch/NBC2.py:152-289) ------------------------------------------------ */

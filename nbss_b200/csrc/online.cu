@@ -8,7 +8,8 @@
 //   * the four previous input frames of the causal encoder conv (k=5).
 // The cross-band sub-blocks act on one frame by construction and reuse the tensor-core kernels of fconv_tc.cu / fullband_*.cu
 // with T = 1.  One new frame is R = B*F rows x 96 channels — 355 kFLOP per row and layer: far too little for tcgen05 tiles, so
-// these kernels are one CTA per row, weights streamed from L2 in [in][out] order (coalesced across the output threads), fp32
+// these kernels are one CTA per row (one stream) or per 4 rows (many streams: each weight loaded from L2 feeds 4 rows), weights
+// streamed from L2 in [in][out] order (coalesced across the output threads), fp32
 // throughout (parity with the oracle 1e-5 on the narrow-band part).  `pos` is a device-side frame counter so that a captured
 // CUDA graph of the step can be replayed without host arguments changing.
 //   nbss_online_encoder_step   Conv1d(k=5) over [x_{t-4} .. x_t]                                   OnlineSpatialNet.py:333,358
@@ -22,28 +23,7 @@
 namespace nbss {
 
 constexpr int kOH = 96, kOHf = 192, kONH = 4, kODH = 24, kOG = 8, kOGC = 24;
-
-__device__ __forceinline__ float block_reduce_sum(float v, float* red, int tid, int nthreads) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((tid & 31) == 0) red[tid >> 5] = v;
-    __syncthreads();
-    float s = 0.f;
-    for (int w = 0; w < nthreads / 32; ++w) s += red[w];
-    return s;
-}
-
-// LayerNorm of one 96-channel row held in smem row[96] -> ln[96]; all threads of the block call it
-__device__ __forceinline__ void row_layernorm(const float* row, const float* __restrict__ g, const float* __restrict__ b, float* ln, float* red,
-                                              int tid, int nthreads) {
-    const float v = tid < kOH ? row[tid] : 0.f;
-    const float mean = block_reduce_sum(v, red, tid, nthreads) * (1.f / kOH);
-    const float d = tid < kOH ? v - mean : 0.f;
-    const float var = block_reduce_sum(d * d, red, tid, nthreads) * (1.f / kOH);
-    const float rstd = rsqrtf(var + 1e-5f);
-    if (tid < kOH) ln[tid] = d * rstd * g[tid] + b[tid];
-    __syncthreads();
-}
+constexpr int kOnFewRows = 600;  // up to ~2 CTAs per SM of single rows: below this, do not block rows
 
 // ---------------------------------------------------------------------------------------------------- encoder
 // x_t [R, Cin], state [R, 4, Cin] (oldest first), Wt [5*Cin][96] (Wt[(k*Cin + c)][o] = W[o][c][k]) -> h [R, 96]; state shifts
@@ -60,6 +40,9 @@ __global__ void __launch_bounds__(96) online_encoder_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------- attention
+// Row blocking: a CTA owns RB consecutive rows and keeps RB accumulators per weight it loads, so the projection weights (147 KB
+// per layer) are read from L2 once per RB rows; with many streams the kernel is then bound by the HBM read of the rings
+// (2 x scope x 96 fp32 per row).  RB = 1 when there are too few rows to fill the GPU (one stream): shortest dependent chains.
 struct OnAttnArgs {
     float* x;               // [R, 96] in / out (residual added in place)
     const float *ln_w, *ln_b;
@@ -69,72 +52,141 @@ struct OnAttnArgs {
     const float* b_out;
     float *kcache, *vcache; // [R][scope][96]
     const int* pos;         // frames consumed so far
-    int scope;
+    int scope, R;
 };
-constexpr int kOnAttnThreads = 128;
-constexpr int kOnMaxScope = 2048;  // 32 KB of scores in shared memory
+constexpr int kOnAttnThreads = 384;
+constexpr int kOnMaxScope = 2048;  // 32 KB of scores in shared memory (RB rows x 4 heads x scope <= 8192 floats)
 
+// LayerNorm of row r (global, 96 channels) by one warp -> ln[96] (smem); rows beyond R give zeros
+__device__ __forceinline__ void warp_layernorm(const float* __restrict__ x, int r, int R, const float* __restrict__ g, const float* __restrict__ b,
+                                               float* ln, float* raw, int lane) {
+    float v[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = r < R ? x[(size_t)r * kOH + lane + 32 * k] : 0.f;
+    const float mean = warp_sum(v[0] + v[1] + v[2]) * (1.f / kOH);
+    float d[3], q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { d[k] = v[k] - mean; q = fmaf(d[k], d[k], q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / kOH) + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int c = lane + 32 * k;
+        ln[c] = r < R ? d[k] * rstd * g[c] + b[c] : 0.f;
+        if (raw) raw[c] = v[k];
+    }
+}
+
+template <int RB>
 __global__ void __launch_bounds__(kOnAttnThreads) online_attn_kernel(OnAttnArgs a) {
-    __shared__ float row[kOH], ln[kOH], q[kOH], o[kOH], red[8];
-    __shared__ float p[kONH][kOnMaxScope];
-    __shared__ float hmax[kONH], hsum[kONH];
-    const int r = blockIdx.x, tid = threadIdx.x, t = *a.pos;
-    if (tid < kOH) row[tid] = a.x[(size_t)r * kOH + tid];
+    constexpr int KS = 4 / RB;            // key splits of the P.V sum per row
+    constexpr int PS = kOnMaxScope / RB;  // score slots per (row, head)
+    __shared__ float row[RB][kOH], ln[RB][kOH], q[RB][kOH], o[RB][kOH];
+    __shared__ float po[4][kOH];
+    __shared__ float p[RB][kONH][PS];
+    __shared__ float hsum[RB][kONH];
+    const int r0 = blockIdx.x * RB, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, t = *a.pos;
+    for (int j = warp; j < RB; j += kOnAttnThreads / 32) warp_layernorm(a.x, r0 + j, a.R, a.ln_w, a.ln_b, ln[j], row[j], lane);
     __syncthreads();
-    row_layernorm(row, a.ln_w, a.ln_b, ln, red, tid, kOnAttnThreads);
-    // q | k | v = Win ln + b: 288 outputs over 128 threads
     const int slot = t % a.scope, n = min(t + 1, a.scope);
-    float* kc = a.kcache + (size_t)r * a.scope * kOH;
-    float* vc = a.vcache + (size_t)r * a.scope * kOH;
-    for (int oi = tid; oi < 3 * kOH; oi += kOnAttnThreads) {
-        float acc = a.b_in[oi];
+    const size_t ring = (size_t)a.scope * kOH;
+    // q | k | v = Win ln + b: one output per thread, RB rows each
+    if (tid < 3 * kOH) {
+        float acc[RB];
+#pragma unroll
+        for (int j = 0; j < RB; ++j) acc[j] = a.b_in[tid];
 #pragma unroll 8
-        for (int i = 0; i < kOH; ++i) acc = fmaf(ln[i], a.WinT[i * 3 * kOH + oi], acc);
-        if (oi < kOH) q[oi] = acc * rsqrtf((float)kODH);
-        else if (oi < 2 * kOH) kc[(size_t)slot * kOH + oi - kOH] = acc;
-        else vc[(size_t)slot * kOH + oi - 2 * kOH] = acc;
+        for (int i = 0; i < kOH; ++i) {
+            const float w = a.WinT[i * 3 * kOH + tid];
+#pragma unroll
+            for (int j = 0; j < RB; ++j) acc[j] = fmaf(ln[j][i], w, acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+            if (tid < kOH) q[j][tid] = acc[j] * rsqrtf((float)kODH);
+            else if (r0 + j < a.R) {
+                if (tid < 2 * kOH) a.kcache[(size_t)(r0 + j) * ring + (size_t)slot * kOH + tid - kOH] = acc[j];
+                else a.vcache[(size_t)(r0 + j) * ring + (size_t)slot * kOH + tid - 2 * kOH] = acc[j];
+            }
+        }
     }
     __syncthreads();  // also orders the ring writes of this block before its reads below (same block, global memory)
-    // scores of the n cached keys, 4 heads each
-    for (int j = tid; j < n; j += kOnAttnThreads) {
-        const float* kj = kc + (size_t)j * kOH;
+    // scores of the n cached keys of every row, 4 heads each
+    for (int idx = tid; idx < RB * n; idx += kOnAttnThreads) {
+        const int j = idx / n, key = idx - j * n;
+        if (r0 + j >= a.R) { for (int h = 0; h < kONH; ++h) p[j][h][key] = 0.f; continue; }
+        const float4* kj = reinterpret_cast<const float4*>(a.kcache + (size_t)(r0 + j) * ring + (size_t)key * kOH);
 #pragma unroll
         for (int h = 0; h < kONH; ++h) {
-            float s = 0.f;
+            float sc = 0.f;
 #pragma unroll
-            for (int c = 0; c < kODH; ++c) s = fmaf(q[kODH * h + c], kj[kODH * h + c], s);
-            p[h][j] = s;
+            for (int c = 0; c < kODH / 4; ++c) {
+                const float4 kv = kj[(kODH / 4) * h + c];
+                const float* qq = &q[j][kODH * h + 4 * c];
+                sc = fmaf(qq[0], kv.x, sc); sc = fmaf(qq[1], kv.y, sc); sc = fmaf(qq[2], kv.z, sc); sc = fmaf(qq[3], kv.w, sc);
+            }
+            p[j][h][key] = sc;
         }
     }
     __syncthreads();
-    // softmax per head: warp h reduces head h
-    {
-        const int h = tid >> 5, lane = tid & 31;
+    // softmax per (row, head): one warp each
+    for (int pr = warp; pr < RB * kONH; pr += kOnAttnThreads / 32) {
+        float* ph = p[pr / kONH][pr % kONH];
         float mx = -INFINITY;
-        for (int j = lane; j < n; j += 32) mx = fmaxf(mx, p[h][j]);
+        for (int jj = lane; jj < n; jj += 32) mx = fmaxf(mx, ph[jj]);
         mx = warp_max(mx);
         float sm = 0.f;
-        for (int j = lane; j < n; j += 32) {
-            const float e = __expf(p[h][j] - mx);
-            p[h][j] = e;
+        for (int jj = lane; jj < n; jj += 32) {
+            const float e = __expf(ph[jj] - mx);
+            ph[jj] = e;
             sm += e;
         }
         sm = warp_sum(sm);
-        if (lane == 0) { hmax[h] = mx; hsum[h] = sm; }
+        if (lane == 0) hsum[pr / kONH][pr % kONH] = sm;
     }
     __syncthreads();
-    if (tid < kOH) {
-        const int h = tid / kODH;
+    // P.V: thread (grp, c): row grp / KS, keys grp % KS, +KS, ...
+    {
+        const int grp = tid / kOH, c = tid % kOH, j = grp / KS, ks = grp % KS, h = c / kODH;
         float acc = 0.f;
-        for (int j = 0; j < n; ++j) acc = fmaf(p[h][j], vc[(size_t)j * kOH + tid], acc);
-        o[tid] = acc / hsum[h];
+        if (r0 + j < a.R) {
+            const float* vc = a.vcache + (size_t)(r0 + j) * ring + c;
+            const float* ph = p[j][h];
+#pragma unroll 4
+            for (int key = ks; key < n; key += KS) acc = fmaf(ph[key], vc[(size_t)key * kOH], acc);
+        }
+        po[grp][c] = acc;
     }
     __syncthreads();
-    if (tid < kOH) {
-        float acc = a.b_out[tid];
+    if (tid < RB * kOH) {
+        const int j = tid / kOH, c = tid % kOH;
+        float acc = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) acc += po[j * KS + ks][c];
+        o[j][c] = acc / hsum[j][c / kODH];
+    }
+    __syncthreads();
+    // out-proj: thread (kq, c) sums a quarter of the inputs for RB rows
+    {
+        const int kq = tid / kOH, c = tid % kOH;
+        float acc[RB];
+#pragma unroll
+        for (int j = 0; j < RB; ++j) acc[j] = 0.f;
 #pragma unroll 8
-        for (int i = 0; i < kOH; ++i) acc = fmaf(o[i], a.WoT[i * kOH + tid], acc);
-        a.x[(size_t)r * kOH + tid] = row[tid] + acc;
+        for (int i = 24 * kq; i < 24 * kq + 24; ++i) {
+            const float w = a.WoT[i * kOH + c];
+#pragma unroll
+            for (int j = 0; j < RB; ++j) acc[j] = fmaf(o[j][i], w, acc[j]);
+        }
+        __syncthreads();  // p is dead: reuse its first RB*4*96 floats for the partial sums
+        float* part = &p[0][0][0];
+#pragma unroll
+        for (int j = 0; j < RB; ++j) part[(j * 4 + kq) * kOH + c] = acc[j];
+    }
+    __syncthreads();
+    if (tid < RB * kOH) {
+        const int j = tid / kOH, c = tid % kOH;
+        const float* part = &p[0][0][0] + (size_t)j * 4 * kOH + c;
+        if (r0 + j < a.R) a.x[(size_t)(r0 + j) * kOH + c] = row[j][c] + a.b_out[c] + ((part[0] + part[kOH]) + (part[2 * kOH] + part[3 * kOH]));
     }
 }
 
@@ -144,78 +196,115 @@ struct OnFfnAArgs {
     const float *ln_w, *ln_b;
     const float* W1T;        // [96][192]
     const float* b1;
-    const float *Wc1, *bc1, *Wc2, *bc2;  // grouped conv weights as stored by the reference: [192][24][3]
+    const float *Wc1T, *bc1, *Wc2T, *bc2;  // grouped conv weights transposed: WcT[(i*3 + tap)][o] = W[o][i][tap]  ([72][192])
     float *st1, *st2;        // [R][2][192]: SiLU outputs of the two previous frames feeding conv1 / conv2 (older first)
     float* c2;               // [R][192] out
     float* part;             // [R][8][2] (sum, sum of squares) of c2 per conv group
+    int R;
 };
-__device__ __forceinline__ float cconv3(const float* prev2, const float* prev1, const float* cur, const float* __restrict__ W, int o) {
-    // out[o] = sum_i sum_tap W[o][i][tap] * in_{t-2+tap}[24*(o/24) + i]
+// out[j][o] = bias[o] + sum_i sum_tap W[o][i][tap] * in_j[tap][24*(o/24) + i]   (tap 2 = the current frame)
+template <int RB>
+__device__ __forceinline__ void cconv3(const float (*s)[3][kOHf], const float* __restrict__ WT, float bias, int o, float* acc) {
     const int g0 = kOGC * (o / kOGC);
-    const float* w = W + (size_t)o * kOGC * 3;
-    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < RB; ++j) acc[j] = bias;
 #pragma unroll 8
-    for (int i = 0; i < kOGC; ++i)
-        acc = fmaf(w[3 * i + 2], cur[g0 + i], fmaf(w[3 * i + 1], prev1[g0 + i], fmaf(w[3 * i], prev2[g0 + i], acc)));
-    return acc;
+    for (int i = 0; i < kOGC; ++i) {
+#pragma unroll
+        for (int tap = 0; tap < 3; ++tap) {
+            const float w = WT[(i * 3 + tap) * kOHf + o];
+#pragma unroll
+            for (int j = 0; j < RB; ++j) acc[j] = fmaf(w, s[j][tap][g0 + i], acc[j]);
+        }
+    }
 }
+__device__ __forceinline__ float silu_exact(float v) { return v / (1.f + __expf(-v)); }
+
+template <int RB>
 __global__ void __launch_bounds__(192) online_ffn_a_kernel(OnFfnAArgs a) {
-    __shared__ float row[kOH], ln[kOH], s1[3][kOHf], s2[3][kOHf], red[8];
-    const int r = blockIdx.x, tid = threadIdx.x;
-    if (tid < kOH) row[tid] = a.x[(size_t)r * kOH + tid];
-    s1[0][tid] = a.st1[((size_t)r * 2 + 0) * kOHf + tid];
-    s1[1][tid] = a.st1[((size_t)r * 2 + 1) * kOHf + tid];
-    s2[0][tid] = a.st2[((size_t)r * 2 + 0) * kOHf + tid];
-    s2[1][tid] = a.st2[((size_t)r * 2 + 1) * kOHf + tid];
+    __shared__ float ln[RB][kOH], s1[RB][3][kOHf], s2[RB][3][kOHf];
+    const int r0 = blockIdx.x * RB, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int j = 0; j < RB; ++j) {
+        const bool ok = r0 + j < a.R;
+        const size_t base = (size_t)(r0 + j) * 2 * kOHf + tid;
+        s1[j][0][tid] = ok ? a.st1[base] : 0.f;
+        s1[j][1][tid] = ok ? a.st1[base + kOHf] : 0.f;
+        s2[j][0][tid] = ok ? a.st2[base] : 0.f;
+        s2[j][1][tid] = ok ? a.st2[base + kOHf] : 0.f;
+    }
+    for (int j = warp; j < RB; j += 6) warp_layernorm(a.x, r0 + j, a.R, a.ln_w, a.ln_b, ln[j], nullptr, lane);
     __syncthreads();
-    row_layernorm(row, a.ln_w, a.ln_b, ln, red, tid, 192);
-    {
-        float acc = a.b1[tid];
+    float acc[RB];
+#pragma unroll
+    for (int j = 0; j < RB; ++j) acc[j] = a.b1[tid];
 #pragma unroll 8
-        for (int i = 0; i < kOH; ++i) acc = fmaf(ln[i], a.W1T[i * kOHf + tid], acc);
-        s1[2][tid] = acc / (1.f + __expf(-acc));
+    for (int i = 0; i < kOH; ++i) {
+        const float w = a.W1T[i * kOHf + tid];
+#pragma unroll
+        for (int j = 0; j < RB; ++j) acc[j] = fmaf(ln[j][i], w, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < RB; ++j) s1[j][2][tid] = silu_exact(acc[j]);
+    __syncthreads();
+    cconv3<RB>(s1, a.Wc1T, a.bc1[tid], tid, acc);
+#pragma unroll
+    for (int j = 0; j < RB; ++j) s2[j][2][tid] = silu_exact(acc[j]);
+    __syncthreads();
+    cconv3<RB>(s2, a.Wc2T, a.bc2[tid], tid, acc);
+    // GroupNorm partials: 24 consecutive threads form a group (not warp-aligned): through smem
+    __shared__ float gs[RB][kOHf];
+#pragma unroll
+    for (int j = 0; j < RB; ++j) {
+        gs[j][tid] = acc[j];
+        if (r0 + j < a.R) a.c2[(size_t)(r0 + j) * kOHf + tid] = acc[j];
     }
     __syncthreads();
-    {
-        const float c1 = cconv3(s1[0], s1[1], s1[2], a.Wc1, tid) + a.bc1[tid];
-        s2[2][tid] = c1 / (1.f + __expf(-c1));
-    }
-    __syncthreads();
-    const float c2 = cconv3(s2[0], s2[1], s2[2], a.Wc2, tid) + a.bc2[tid];
-    a.c2[(size_t)r * kOHf + tid] = c2;
-    // GroupNorm partials: 24 consecutive threads form a group (not warp-aligned): smem tree per group
-    __shared__ float gs[kOHf], gq[kOHf];
-    gs[tid] = c2;
-    gq[tid] = c2 * c2;
-    __syncthreads();
-    if (tid < kOG) {
-        float s = 0.f, qq = 0.f;
-        for (int i = 0; i < kOGC; ++i) { s += gs[kOGC * tid + i]; qq += gq[kOGC * tid + i]; }
-        a.part[((size_t)r * kOG + tid) * 2] = s;
-        a.part[((size_t)r * kOG + tid) * 2 + 1] = qq;
+    if (tid < RB * kOG) {
+        const int j = tid / kOG, g = tid % kOG;
+        float sm = 0.f, qq = 0.f;
+        for (int i = 0; i < kOGC; ++i) { const float v = gs[j][kOGC * g + i]; sm += v; qq = fmaf(v, v, qq); }
+        if (r0 + j < a.R) {
+            a.part[((size_t)(r0 + j) * kOG + g) * 2] = sm;
+            a.part[((size_t)(r0 + j) * kOG + g) * 2 + 1] = qq;
+        }
     }
     // shift the conv states
-    a.st1[((size_t)r * 2 + 0) * kOHf + tid] = s1[1][tid];
-    a.st1[((size_t)r * 2 + 1) * kOHf + tid] = s1[2][tid];
-    a.st2[((size_t)r * 2 + 0) * kOHf + tid] = s2[1][tid];
-    a.st2[((size_t)r * 2 + 1) * kOHf + tid] = s2[2][tid];
+#pragma unroll
+    for (int j = 0; j < RB; ++j) {
+        if (r0 + j >= a.R) break;
+        const size_t base = (size_t)(r0 + j) * 2 * kOHf + tid;
+        a.st1[base] = s1[j][1][tid];
+        a.st1[base + kOHf] = s1[j][2][tid];
+        a.st2[base] = s2[j][1][tid];
+        a.st2[base + kOHf] = s2[j][2][tid];
+    }
 }
 
-// (b, group) statistics over the F rows of the frame: part [B][F][8][2] -> stats [B][8][2] (mean, rstd), fp64 accumulation
+// (b, group) statistics over the F rows of the frame: part [B][F][8][2] -> stats [B][8][2] (mean, rstd); one warp per (b, group),
+// fp64 accumulation
 __global__ void online_gn_stats_kernel(const float* __restrict__ part, int B, int F, float* stats) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= B * kOG) return;
     const int b = i / kOG, g = i % kOG;
     double s = 0.0, q = 0.0;
-    for (int f = 0; f < F; ++f) {
-        s += (double)part[(((size_t)b * F + f) * kOG + g) * 2];
-        q += (double)part[(((size_t)b * F + f) * kOG + g) * 2 + 1];
+    for (int f = lane; f < F; f += 32) {
+        const float2 v = *reinterpret_cast<const float2*>(part + (((size_t)b * F + f) * kOG + g) * 2);
+        s += (double)v.x;
+        q += (double)v.y;
     }
-    const double n = (double)F * kOGC, mean = s / n;
-    double var = q / n - mean * mean;
-    var = var > 0.0 ? var : 0.0;
-    stats[2 * i] = (float)mean;
-    stats[2 * i + 1] = (float)(1.0 / sqrt(var + 1e-5));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+        const double n = (double)F * kOGC, mean = s / n;
+        double var = q / n - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        stats[2 * i] = (float)mean;
+        stats[2 * i + 1] = (float)(1.0 / sqrt(var + 1e-5));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------- T-ConvFFN, part B
@@ -224,32 +313,66 @@ struct OnFfnBArgs {
     const float* c2;        // [R][192]
     const float* stats;     // [B][8][2]
     const float *gn_w, *gn_b;
-    const float *Wc3, *bc3;
+    const float *Wc3T, *bc3;  // [72][192], see OnFfnAArgs
     const float* W2T;       // [192][96]
     const float* b2;
     float* st3;             // [R][2][192]
-    int F;
+    int F, R;
 };
+template <int RB>
 __global__ void __launch_bounds__(192) online_ffn_b_kernel(OnFfnBArgs a) {
-    __shared__ float s3[3][kOHf], s4[kOHf];
-    const int r = blockIdx.x, tid = threadIdx.x, b = r / a.F, g = tid / kOGC;
-    s3[0][tid] = a.st3[((size_t)r * 2 + 0) * kOHf + tid];
-    s3[1][tid] = a.st3[((size_t)r * 2 + 1) * kOHf + tid];
-    const float mean = a.stats[((size_t)b * kOG + g) * 2], rstd = a.stats[((size_t)b * kOG + g) * 2 + 1];
-    const float nrm = (a.c2[(size_t)r * kOHf + tid] - mean) * rstd * a.gn_w[tid] + a.gn_b[tid];
-    s3[2][tid] = nrm / (1.f + __expf(-nrm));
-    __syncthreads();
-    const float c3 = cconv3(s3[0], s3[1], s3[2], a.Wc3, tid) + a.bc3[tid];
-    s4[tid] = c3 / (1.f + __expf(-c3));
-    __syncthreads();
-    if (tid < kOH) {
-        float acc = a.b2[tid];
-#pragma unroll 8
-        for (int i = 0; i < kOHf; ++i) acc = fmaf(s4[i], a.W2T[i * kOH + tid], acc);
-        a.x[(size_t)r * kOH + tid] += acc;
+    __shared__ float s3[RB][3][kOHf], s4[RB][kOHf], half[RB][kOH];
+    const int r0 = blockIdx.x * RB, tid = threadIdx.x, g = tid / kOGC;
+    const float gw = a.gn_w[tid], gb = a.gn_b[tid];
+#pragma unroll
+    for (int j = 0; j < RB; ++j) {
+        const int r = r0 + j;
+        const bool ok = r < a.R;
+        const size_t base = (size_t)r * 2 * kOHf + tid;
+        s3[j][0][tid] = ok ? a.st3[base] : 0.f;
+        s3[j][1][tid] = ok ? a.st3[base + kOHf] : 0.f;
+        float v = 0.f;
+        if (ok) {
+            const int b = r / a.F;
+            const float mean = a.stats[((size_t)b * kOG + g) * 2], rstd = a.stats[((size_t)b * kOG + g) * 2 + 1];
+            v = silu_exact((a.c2[(size_t)r * kOHf + tid] - mean) * rstd * gw + gb);
+        }
+        s3[j][2][tid] = v;
     }
-    a.st3[((size_t)r * 2 + 0) * kOHf + tid] = s3[1][tid];
-    a.st3[((size_t)r * 2 + 1) * kOHf + tid] = s3[2][tid];
+    __syncthreads();
+    float acc[RB];
+    cconv3<RB>(s3, a.Wc3T, a.bc3[tid], tid, acc);
+#pragma unroll
+    for (int j = 0; j < RB; ++j) s4[j][tid] = silu_exact(acc[j]);
+    __syncthreads();
+    // pw2: thread (kh, c) sums half of the 192 inputs
+    const int kh = tid / kOH, c = tid % kOH;
+#pragma unroll
+    for (int j = 0; j < RB; ++j) acc[j] = 0.f;
+#pragma unroll 8
+    for (int i = kOH * kh; i < kOH * kh + kOH; ++i) {
+        const float w = a.W2T[i * kOH + c];
+#pragma unroll
+        for (int j = 0; j < RB; ++j) acc[j] = fmaf(s4[j][i], w, acc[j]);
+    }
+    if (kh == 1) {
+#pragma unroll
+        for (int j = 0; j < RB; ++j) half[j][c] = acc[j];
+    }
+    __syncthreads();
+    if (kh == 0) {
+        const float b2 = a.b2[c];
+#pragma unroll
+        for (int j = 0; j < RB; ++j)
+            if (r0 + j < a.R) a.x[(size_t)(r0 + j) * kOH + c] += b2 + (acc[j] + half[j][c]);
+    }
+#pragma unroll
+    for (int j = 0; j < RB; ++j) {
+        if (r0 + j >= a.R) break;
+        const size_t base = (size_t)(r0 + j) * 2 * kOHf + tid;
+        a.st3[base] = s3[j][1][tid];
+        a.st3[base + kOHf] = s3[j][2][tid];
+    }
 }
 
 __global__ void online_advance_kernel(int* pos) { *pos += 1; }
@@ -304,8 +427,12 @@ extern "C" int nbss_online_attn_step(float* x, int R, const float* ln_w, const f
                                      void* stream) {
     if (!x || !ln_w || !ln_b || !WinT || !b_in || !WoT || !b_out || !kcache || !vcache || !pos) return NBSS_ERR_NULL;
     if (R < 1 || scope < 1 || scope > kOnMaxScope) return NBSS_ERR_SHAPE;
-    OnAttnArgs a{x, ln_w, ln_b, WinT, b_in, WoT, b_out, kcache, vcache, pos, scope};
-    online_attn_kernel<<<R, kOnAttnThreads, 0, (cudaStream_t)stream>>>(a);
+    OnAttnArgs a{x, ln_w, ln_b, WinT, b_in, WoT, b_out, kcache, vcache, pos, scope, R};
+    // few rows (one stream): one row per CTA, shortest chains; many rows: 4 (or 2 for long rings: RB * scope <= 2048) rows per CTA
+    const int rb = R <= kOnFewRows ? 1 : (scope <= kOnMaxScope / 4 ? 4 : (scope <= kOnMaxScope / 2 ? 2 : 1));
+    if (rb == 4) online_attn_kernel<4><<<(R + 3) / 4, kOnAttnThreads, 0, (cudaStream_t)stream>>>(a);
+    else if (rb == 2) online_attn_kernel<2><<<(R + 1) / 2, kOnAttnThreads, 0, (cudaStream_t)stream>>>(a);
+    else online_attn_kernel<1><<<R, kOnAttnThreads, 0, (cudaStream_t)stream>>>(a);
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
 }
@@ -315,8 +442,9 @@ extern "C" int nbss_online_ffn_a_step(const float* x, int R, const float* ln_w, 
                                       float* c2, float* part, void* stream) {
     if (!x || !ln_w || !ln_b || !W1T || !b1 || !Wc1 || !bc1 || !Wc2 || !bc2 || !st1 || !st2 || !c2 || !part) return NBSS_ERR_NULL;
     if (R < 1) return NBSS_ERR_SHAPE;
-    OnFfnAArgs a{x, ln_w, ln_b, W1T, b1, Wc1, bc1, Wc2, bc2, st1, st2, c2, part};
-    online_ffn_a_kernel<<<R, 192, 0, (cudaStream_t)stream>>>(a);
+    OnFfnAArgs a{x, ln_w, ln_b, W1T, b1, Wc1, bc1, Wc2, bc2, st1, st2, c2, part, R};
+    if (R <= kOnFewRows) online_ffn_a_kernel<1><<<R, 192, 0, (cudaStream_t)stream>>>(a);
+    else online_ffn_a_kernel<4><<<(R + 3) / 4, 192, 0, (cudaStream_t)stream>>>(a);
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
 }
@@ -324,7 +452,7 @@ extern "C" int nbss_online_ffn_a_step(const float* x, int R, const float* ln_w, 
 extern "C" int nbss_online_gn_stats(const float* part, int B, int F, float* stats, void* stream) {
     if (!part || !stats) return NBSS_ERR_NULL;
     if (B < 1 || F < 1) return NBSS_ERR_SHAPE;
-    online_gn_stats_kernel<<<(B * kOG + 63) / 64, 64, 0, (cudaStream_t)stream>>>(part, B, F, stats);
+    online_gn_stats_kernel<<<(B * kOG + 3) / 4, 128, 0, (cudaStream_t)stream>>>(part, B, F, stats);
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
 }
@@ -333,8 +461,9 @@ extern "C" int nbss_online_ffn_b_step(float* x, int R, int F, const float* c2, c
                                       const float* Wc3, const float* bc3, const float* W2T, const float* b2, float* st3, void* stream) {
     if (!x || !c2 || !stats || !gn_w || !gn_b || !Wc3 || !bc3 || !W2T || !b2 || !st3) return NBSS_ERR_NULL;
     if (R < 1 || F < 1 || R % F) return NBSS_ERR_SHAPE;
-    OnFfnBArgs a{x, c2, stats, gn_w, gn_b, Wc3, bc3, W2T, b2, st3, F};
-    online_ffn_b_kernel<<<R, 192, 0, (cudaStream_t)stream>>>(a);
+    OnFfnBArgs a{x, c2, stats, gn_w, gn_b, Wc3, bc3, W2T, b2, st3, F, R};
+    if (R <= kOnFewRows) online_ffn_b_kernel<1><<<R, 192, 0, (cudaStream_t)stream>>>(a);
+    else online_ffn_b_kernel<4><<<(R + 3) / 4, 192, 0, (cudaStream_t)stream>>>(a);
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
 }

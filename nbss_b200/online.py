@@ -104,6 +104,7 @@ class OnlineSpatialNet(nn.Module):
             pre = f"layers.{i}."
             layers.append(dict(WinT=tr(P[pre + "mhsa.in_proj_weight"]), WoT=tr(P[pre + "mhsa.out_proj.weight"]),
                                W1T=tr(P[pre + "tconvffn.1.weight"]), W2T=tr(P[pre + "tconvffn.10.weight"]),
+                               Wc1T=tr(P[pre + "tconvffn.3.weight"]), Wc2T=tr(P[pre + "tconvffn.5.weight"]), Wc3T=tr(P[pre + "tconvffn.8.weight"]),
                                f1=ops.fconv_pack(P[pre + "fconv1.1.weight"]), f2=ops.fconv_pack(P[pre + "fconv2.1.weight"]),
                                lg=ops.lg_pack(P[pre + "full.weight"])))
         self._packed, self._packed_key = dict(enc=enc, layers=layers), key
@@ -162,12 +163,12 @@ class OnlineSpatialNet(nn.Module):
                                                   ptr(state.pos), state.scope, sp()), "nbss_online_attn_step")
             t = pre + "tconvffn."
             check(ops._K("nbss_online_ffn_a_step")(ptr(h), R, ptr(ops._f32c(P[t + "0.weight"])), ptr(ops._f32c(P[t + "0.bias"])), ptr(Wl["W1T"]),
-                                                   ptr(ops._f32c(P[t + "1.bias"])), ptr(ops._f32c(P[t + "3.weight"])), ptr(ops._f32c(P[t + "3.bias"])),
-                                                   ptr(ops._f32c(P[t + "5.weight"])), ptr(ops._f32c(P[t + "5.bias"])), ptr(state.st[i][0]),
+                                                   ptr(ops._f32c(P[t + "1.bias"])), ptr(Wl["Wc1T"]), ptr(ops._f32c(P[t + "3.bias"])),
+                                                   ptr(Wl["Wc2T"]), ptr(ops._f32c(P[t + "5.bias"])), ptr(state.st[i][0]),
                                                    ptr(state.st[i][1]), ptr(state.c2), ptr(state.part), sp()), "nbss_online_ffn_a_step")
             check(ops._K("nbss_online_gn_stats")(ptr(state.part), B, F, ptr(state.stats), sp()), "nbss_online_gn_stats")
             check(ops._K("nbss_online_ffn_b_step")(ptr(h), R, F, ptr(state.c2), ptr(state.stats), ptr(ops._f32c(P[t + "6.weight"])),
-                                                   ptr(ops._f32c(P[t + "6.bias"])), ptr(ops._f32c(P[t + "8.weight"])), ptr(ops._f32c(P[t + "8.bias"])),
+                                                   ptr(ops._f32c(P[t + "6.bias"])), ptr(Wl["Wc3T"]), ptr(ops._f32c(P[t + "8.bias"])),
                                                    ptr(Wl["W2T"]), ptr(ops._f32c(P[t + "10.bias"])), ptr(state.st[i][2]), sp()), "nbss_online_ffn_b_step")
         y = ops.decoder_fwd(h, P)  # [B,F,1,Cout]
         check(ops._K("nbss_online_advance")(ptr(state.pos), sp()), "nbss_online_advance")

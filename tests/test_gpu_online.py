@@ -75,6 +75,31 @@ def test_online_streaming_state_and_f129():
     assert int(sa.pos.item()) == 20 and sa.kcache[0].shape == (129, 251, 96)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("scope", [251, 600, 2048])
+def test_online_many_streams_row_blocked_kernels(scope):
+    """More than 600 rows: the kernels that give one CTA 4 rows (2 / 1 for longer rings), with a ragged last CTA (645 % 4 = 1);
+    the step replayed from a CUDA graph (capture_step) gives the same numbers as the plain launches."""
+    cfg = dict(O.SMALL_CFG, num_layers=2, num_freqs=129)
+    P = O.synth_params(cfg, 17)
+    net = _net(cfg, P)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(5, 129, 10, 12, generator=g)
+    with torch.no_grad():
+        ref = OO.online_forward({k: v.double() for k, v in P.items()}, x.double(), cfg)
+    st, stg = net.init_state(5, scope=scope), net.capture_step(net.init_state(5, scope=scope))
+    assert stg.graph is not None and int(stg.pos.item()) == 0  # capturing advanced nothing
+    ys, yg = [], []
+    for t in range(10):
+        ys.append(net.step(x[:, :, t].cuda(), st).clone())
+        yg.append(net.step(x[:, :, t].cuda(), stg).clone())
+    torch.cuda.synchronize()
+    net.check_device_errors()
+    y, y2 = torch.stack(ys, 2), torch.stack(yg, 2)
+    assert O.rel_l2(y.cpu(), ref) < 1e-3
+    assert torch.equal(y, y2)
+
+
 def test_online_state_dict_matches_reference_names():
     cfg = dict(O.SMALL_CFG, num_layers=2, num_freqs=9)
     net = OnlineSpatialNet(dim_input=12, dim_output=4, num_layers=2, dim_squeeze=8, num_freqs=9, dim_hidden=96, dim_ffn=192, num_heads=4)

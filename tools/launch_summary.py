@@ -1,5 +1,6 @@
 """Per-kernel totals of an ncu `--metrics gpu__time_duration.sum --csv` launch list:  python tools/launch_summary.py file.csv"""
-import csv, sys, collections, re
+import csv, sys, collections, re, signal
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 rows = []
 with open(sys.argv[1]) as f:
     lines = [l for l in f if not l.startswith("==")]

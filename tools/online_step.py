@@ -13,6 +13,7 @@ state = net.init_state(B)
 x = torch.randn(B, 129, 12, device=dev)
 for _ in range(3):
     net.step(x, state)
+state.pos.fill_(4 * state.scope)  # full ring: steady state of a long stream
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
 net.step(x, state)

@@ -206,20 +206,28 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
                 NBSS_TICK(0, 5 + 12 * h + 2 * blk, it_);
                 // P and dS for this block: thread = (query row rt, key quarter kq: 32 of the 128 keys)
                 {
-                    const int tq = 128 * qb + rt;
-                    const float lse = s_lse[h * 256 + tq], dl = s_delta[h * 256 + tq];
-                    const bool qok = tq < T;
+                    const int tq = 128 * qb + rt, key0 = 128 * kb + 32 * kq;
+                    // a query row beyond T gets lse = +inf: every P of the row is ex2(-inf) = 0 without a per-element select
+                    const float lse = tq < T ? s_lse[h * 256 + tq] : INFINITY, dl = s_delta[h * 256 + tq];
                     uint32_t rs[32], rp[32];
                     tmem_ld32(tmem + lane_off + C_S + 32 * kq, rs);
                     tmem_ld32(tmem + lane_off + C_DP + 32 * kq, rp);
                     tmem_ld_wait();
                     float p[32], ds[32];
+                    if (key0 + 32 <= T) {  // warp-uniform: all 32 keys of this quarter exist (every quarter but the slab's last)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int key = 128 * kb + 32 * kq + j;
-                        const float pv = ex2f((qok && key < T) ? __uint_as_float(rs[j]) - lse : -INFINITY);
-                        p[j] = pv;
-                        ds[j] = pv * (__uint_as_float(rp[j]) - dl);
+                        for (int j = 0; j < 32; ++j) {
+                            const float pv = ex2f(__uint_as_float(rs[j]) - lse);
+                            p[j] = pv;
+                            ds[j] = pv * (__uint_as_float(rp[j]) - dl);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float pv = ex2f(key0 + j < T ? __uint_as_float(rs[j]) - lse : -INFINITY);
+                            p[j] = pv;
+                            ds[j] = pv * (__uint_as_float(rp[j]) - dl);
+                        }
                     }
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {

@@ -278,7 +278,9 @@ def test_two_forwards_one_backward_and_retain_graph():
     ((ya * da).sum() + (yb * db).sum()).backward()
     torch.cuda.synchronize()
     for p, ga, gb in zip(net.parameters(), *grads):
-        assert O.rel_l2(p.grad.cpu(), (ga + gb).cpu()) < 1e-5  # atomics: summation order differs, nothing else
+        # atomics: summation order differs, nothing else; the two terms may cancel (decoder bias: -54.60 + 55.16), so the
+        # error is measured against the size of the terms, not of their sum
+        assert (p.grad - (ga + gb)).norm().item() <= 1e-5 * (ga.norm() + gb.norm()).item()
     # a second backward through the same graph is refused with a clear message (activations are freed)
     y = net(xa)
     y.backward(da, retain_graph=True)

@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(256, 2) fconv_tc_fwd_kernel(FcFwdArgs a) {
     const uint32_t lane_off = (uint32_t)(32 * (warp & 3)) << 16;
     uint32_t ph = 0;
     bool wready = false;
+    stagger_start(17000);  // cycles per work item (profiles/r02e_phases.txt)
     int it_ = 0;
     for (int grp = blockIdx.x; grp < g.ngroups; grp += gridDim.x, ++it_) {
         const int b = grp / g.groups_per_b, t0 = (grp % g.groups_per_b) * g.nfr;
@@ -364,17 +365,22 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         ph ^= 1;
         tc_fence_after();
     };
+    stagger_start(60000);  // cycles per work item (profiles/r02e_phases.txt)
     int it_ = 0;
     for (int grp = blockIdx.x; grp < g.ngroups; grp += gridDim.x, ++it_) {
         const int b = grp / g.groups_per_b, t0 = (grp % g.groups_per_b) * g.nfr;
         NBSS_TICK(1, 0, it_);
         if (tid == 0) load_image(wimg, a.img, FC_IMG_BYTES, bar_w);
-        fc_stage<FMT, 5, NW>(g, a.x, b, t0, htile, cst, cst + 96, stats, warp, lane);
+        // dy first, LN(x) second: whichever staging pass comes first waits ~7-11 k cycles for the memory pipeline to drain the
+        // previous group's dx stores; the LayerNorm arithmetic of the x pass then overlaps the tail of the dy loads
+        // (measured: 14.7 k -> 13.3 k cycles for the two passes, profiles/r02n_fconv_stage_order.txt)
         fc_stage_plain<FMT, 5, NW>(g, a.dy, b, t0, gtile, warp, lane);
+        NBSS_TICK(1, 1, it_);
+        fc_stage<FMT, 5, NW>(g, a.x, b, t0, htile, cst, cst + 96, stats, warp, lane);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        NBSS_TICK(1, 1, it_);
+        NBSS_TICK(1, 2, it_);
         // ---- P1: recompute the conv
         if (warp == 0) {
             tc_fence_after();
@@ -385,7 +391,7 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         }
         ph_w ^= 1;
         wait_mma();
-        NBSS_TICK(1, 2, it_);
+        NBSS_TICK(1, 3, it_);
         if (tid == 0) load_image(wimg, a.img + FC_IMG_BYTES, FC_IMG_BYTES, bar_w);  // transposed image for the data gradient
         // next group's x / dy rows -> L2, issued after this group's own staging loads have landed (at the top of the group the
         // prefetch competed with them and cost 5 %)
@@ -428,7 +434,7 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        NBSS_TICK(1, 3, it_);
+        NBSS_TICK(1, 4, it_);
         // ---- P2: weight gradient  dW[co, ci, tap] += sum_q dc[q, co] * h[q + tap - 2, ci]   (MN-major x MN-major)
         if (warp == 0) {  // the whole warp runs the (uniform) descriptor arithmetic, one elected lane issues
             tc_fence_after();
@@ -445,7 +451,7 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
             if (leader) umma_commit(bar_mma);
         }
         wait_mma();
-        NBSS_TICK(1, 4, it_);
+        NBSS_TICK(1, 5, it_);
         if (q4 < 3) {
             // thread = out channel co (TMEM lane), taps dealt to the warp groups; it keeps the 12 in-channel columns
             // [12*(co/12), +12) of each tap.  tcgen05.ld takes ONE column address per warp, so every warp loads a uniform
@@ -473,7 +479,7 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         }
         tc_fence_before();
         __syncthreads();
-        NBSS_TICK(1, 5, it_);
+        NBSS_TICK(1, 6, it_);
         // ---- P3: data gradient of the conv
         if (warp == 0) {
             tc_fence_after();
@@ -484,7 +490,7 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         }
         ph_w ^= 1;
         wait_mma();
-        NBSS_TICK(1, 6, it_);
+        NBSS_TICK(1, 7, it_);
         // ---- E-B1: thread = tile row: d h (data gradient of the conv) -> 16-bit, over htile (dead after the weight
         //      gradient MMAs); gap rows are written as zeros so they keep acting as the next group's zero padding
 #pragma unroll 1
@@ -504,7 +510,7 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         }
         tc_fence_before();
         __syncthreads();
-        NBSS_TICK(1, 7, it_);
+        NBSS_TICK(1, 8, it_);
         // ---- E-B2: eight lanes per (frame, f) row, coalesced: LayerNorm backward + residual; d gamma / d beta per lane
         {
             constexpr int U = 3;
@@ -573,7 +579,7 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         }
         tc_fence_before();
         __syncthreads();
-        NBSS_TICK(1, 8, it_);
+        NBSS_TICK(1, 9, it_);
     }
     // ---- flush parameter gradients: one set of global atomics per CTA
     for (int i = tid; i < 96 * 60; i += NT) atomicAdd(a.dW + i, accdw[i]);

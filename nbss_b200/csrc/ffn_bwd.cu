@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         }
     };
 
+    stagger_start(112000);  // cycles per work item (profiles/r02e_phases.txt)
     int it_ = 0;
     for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x, ++it_) {
         const size_t grow = (size_t)slab * T + t;

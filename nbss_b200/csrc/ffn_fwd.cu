@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         }
     };
 
+    stagger_start(58000);  // cycles per work item (profiles/r02e_phases.txt)
     int it_ = 0;
     for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x, ++it_) {
         const float* xs = a.x + (size_t)slab * T * kH;

@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_core_kernel(MhsaBwdArg
         __syncthreads();
     };
 
+    stagger_start(78000);  // cycles per work item (profiles/r02e_phases.txt)
     int it_ = 0;
     for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x, ++it_) {
         const size_t row0 = (size_t)slab * T;
@@ -343,6 +344,7 @@ __global__ void __launch_bounds__(kMbThreads, 1) mhsa_bwd_ln_kernel(MhsaLnArgs a
     const uint32_t id96 = make_idesc(FMT_G, 128, 96, 0, 0);
     uint32_t ph = 0, ph_ld = 0;
     bool wready = false;
+    stagger_start(26000);  // cycles per work item (profiles/r02e_phases.txt)
     int it_ = 0;
     for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x, ++it_) {
         const size_t row0 = (size_t)slab * T, grow = row0 + t;

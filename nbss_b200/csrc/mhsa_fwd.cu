@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         }
     };
 
+    stagger_start(59000);  // cycles per work item (profiles/r02e_phases.txt)
     int it_ = 0;
     for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x, ++it_) {
         const float* xs = a.x + (size_t)slab * T * kH;

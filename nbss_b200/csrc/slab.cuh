@@ -45,6 +45,28 @@ __device__ __forceinline__ void l2_prefetch_slab(const float* slab, int T, int i
     l2_prefetch(reinterpret_cast<const unsigned char*>(slab) + (size_t)i * T * 64, (uint32_t)(T * 64));
 }
 
+// ---------------------------------------------------------------- de-phasing the persistent CTAs
+// All CTAs of a persistent kernel start together and do identical work, so they walk their phases in lockstep: every SM stages
+// its inputs from HBM in the same few microseconds (a chip-wide burst at the full 6.5 TB/s) and then every SM computes while
+// HBM idles.  Delaying CTA i by (i mod K) / K of one work item's duration makes the bursts of one part of the chip fall into the
+// compute phases of the rest.  `period` = cycles per work item (from the phase profile); K = NBSS_STAGGER (0 = off).
+// MEASURED (profiles/r02n_fconv_stage_order.txt): K = 2 and K = 4 make every slab kernel 1-4 % SLOWER - the CTAs are not limited
+// by chip-wide bursts, the delay is pure cost - so the product build keeps it off; the hook stays for re-measuring.
+#ifndef NBSS_STAGGER
+#define NBSS_STAGGER 0
+#endif
+__device__ __forceinline__ void stagger_start(int period) {
+#if NBSS_STAGGER > 1
+    const int k = blockIdx.x % NBSS_STAGGER;
+    if (k) {
+        const long long t0 = clock64(), d = (long long)period * k / NBSS_STAGGER;
+        while (clock64() - t0 < d) __nanosleep(256);
+    }
+#else
+    (void)period;
+#endif
+}
+
 // ---------------------------------------------------------------- 16-bit intermediates in HBM: "slab tile" layout
 // Every 16-bit tensor that only travels between these kernels (saved pre-activations, q|k|v, O, gradient operands) is
 // stored as [slab][C/8 chunks][T rows][8 elements]: the byte image of the smem operand tile.  A thread-per-frame

@@ -472,11 +472,23 @@ __global__ void __launch_bounds__(192) encoder_wgrad_kernel(const float* __restr
             }
         }
     }
+    // the two frame halves of a channel are summed through shared memory first: one atomic per (CTA, weight); the weights of
+    // this layer sit in 183 L2 lines, so every lane-level atomic saved shortens the serialised tail of the launch
+    __shared__ float s_half[kH * (CIN * K + 1)];
+    __syncthreads();
+    if (half == 1) {
 #pragma unroll
-    for (int ci = 0; ci < CIN; ++ci)
+        for (int i = 0; i < CIN * K; ++i) s_half[i * kH + co] = dw[i];
+        s_half[CIN * K * kH + co] = db;
+    }
+    __syncthreads();
+    if (half == 0) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) atomicAdd(dW + (co * CIN + ci) * K + k, dw[k * CIN + ci]);
-    atomicAdd(dbias + co, db);
+        for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+            for (int k = 0; k < K; ++k) atomicAdd(dW + (co * CIN + ci) * K + k, dw[k * CIN + ci] + s_half[(k * CIN + ci) * kH + co]);
+        atomicAdd(dbias + co, db + s_half[CIN * K * kH + co]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ decoder
@@ -539,14 +551,22 @@ __global__ void __launch_bounds__(256) decoder_bwd_kernel(const float* __restric
             if (act && r < n) st_f4(dx + r * kH + 4 * lane, d);
         }
     }
+    // the CTA's eight warps are summed through shared memory: one atomic per (CTA, weight) instead of one per warp — the
+    // whole layer is COUT*96 + COUT floats (13 L2 lines for COUT = 4), and lane-level atomics on so few lines serialise
+    __shared__ float s_red[8][COUT * kH + COUT];
+    const int w8 = threadIdx.x >> 5;
     if (act) {
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) {
-            atomicAdd(dW + o * kH + 4 * lane + 0, dw[o].x); atomicAdd(dW + o * kH + 4 * lane + 1, dw[o].y);
-            atomicAdd(dW + o * kH + 4 * lane + 2, dw[o].z); atomicAdd(dW + o * kH + 4 * lane + 3, dw[o].w);
-        }
+        for (int o = 0; o < COUT; ++o) *reinterpret_cast<float4*>(&s_red[w8][o * kH + 4 * lane]) = dw[o];
     }
-    if (lane < COUT) atomicAdd(dbias + lane, db);
+    if (lane < COUT) s_red[w8][COUT * kH + lane] = db;
+    __syncthreads();
+    for (int i = threadIdx.x; i < COUT * kH + COUT; i += 256) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_red[w][i];
+        atomicAdd(i < COUT * kH ? dW + i : dbias + (i - COUT * kH), t);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ Norm (standalone)
@@ -730,7 +750,7 @@ extern "C" int nbss_decoder_bwd(const float* x, const float* dy, float* dx, long
                                 float* dbias, void* stream) {
     if (!x || !dy || !dx || !W || !dW || !dbias) return NBSS_ERR_NULL;
     if (n < 1) return NBSS_ERR_SHAPE;
-    const int grid = 4 * io_num_sms();
+    const int grid = 2 * io_num_sms();
     cudaStream_t st = (cudaStream_t)stream;
     switch (cout) {
         case 2: decoder_bwd_kernel<2><<<grid, 256, 0, st>>>(x, dy, dx, (size_t)n, W, dW, dbias); break;

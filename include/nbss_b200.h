@@ -59,6 +59,19 @@ int nbss_mhsa_fwd_nh(const float* x, float* y, int nslab, int T, const float* ln
 int nbss_predict_post(const float* preds, const float* mixture, float* out, int B, int S, long long Ts, int recover,
                       int norm_if_exceed_1, double* ws_sums, unsigned int* ws_peak, float* scale_out, void* stream);
 
+/* ---- T > 256, inference only (validation / test utterances are longer than the 4 s training crops; SharedTrainer.py:134-189) -----
+ * Same layer image and parameters as nbss_mhsa_fwd / nbss_ffn_fwd; 256 < T <= 65536; fmt = 0 (fp16).  In place (y == x) is allowed.
+ * nbss_mhsa_fwd_long: kv_ws = fp16 [nslab][36][T][8] (576*T bytes per slab): pass 1 writes k | v of all frames, pass 2 attends per
+ *   256-frame query chunk over the slab's key blocks (flash-style running softmax), out-proj + residual.
+ * nbss_ffn_fwd_long: the T-ConvFFN cut at its GroupNorm and tiled over T with halo rows; c2_ws fp16 [nslab][24][T][8] (384*T bytes
+ *   per slab), part_ws [nslab][nbss_ffn_long_chunks(T,0)][8][2] floats, stats_ws [nslab][8][2] floats. */
+int nbss_mhsa_fwd_long(const float* x, float* y, int nslab, int T, const float* ln_w, const float* ln_b, const float* b_in,
+                       const float* b_out, const void* layer_img, void* kv_ws, int fmt, int* err, void* stream);
+long long nbss_ffn_long_chunks(int T, int part);
+int nbss_ffn_fwd_long(const float* x, float* y, int nslab, int T, const float* ln_w, const float* ln_b, const float* b1,
+                      const float* bc1, const float* bc2, const float* bc3, const float* gn_w, const float* gn_b, const float* b2,
+                      const void* layer_img, void* c2_ws, float* part_ws, float* stats_ws, int fmt, int* err, void* stream);
+
 /* ---- online / causal SpatialNet, one frame per call (online.cu; models/arch/OnlineSpatialNet.py with attention='mhsa(N)') ------
  * R = B*F rows of one frame, fp32 [R,96] stream updated in place; `pos` = device int, frames consumed so far (nbss_online_advance
  * increments it, so a captured CUDA graph of the whole step replays unchanged); weights marked T are [in][out] (nbss_transpose;

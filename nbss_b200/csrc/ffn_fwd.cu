@@ -57,6 +57,13 @@ __device__ __forceinline__ void save_f16(unsigned char* base, int slab, int T, i
 // MODE 0: SpatialNet's T-ConvFFN (LayerNorm + GroupNorm, everything in one pass).
 // MODE 1: NBC2 part A: GroupBatchNorm(x) (statistics given) -> linear1 -> SiLU -> conv -> SiLU -> conv -> c2 (fp16) + partial sums.
 // MODE 2: NBC2 part B: SiLU(GroupBatchNorm(c2)) (statistics given) -> conv -> SiLU -> linear2 -> + x.
+// MODE 3 / 4: SpatialNet's T-ConvFFN for T > 256 (inference), cut at the GroupNorm like NBC2's and tiled over T with halos:
+//   MODE 3 work item = (slab, chunk j): frames [252 j, 252 j + 256) in, LN .. conv2; c2 of the frames whose two conv inputs were all
+//          inside the tile (local rows 2 .. 253; from row 0 in the first chunk, to the last row in the last one) -> fp16 c2_io, and
+//          the chunk's per-group (sum, sum of squares) of (c2 - pivot) over those frames -> part [nslab][nch][8][2];
+//   (nbss_ffn_long_gn_reduce: per (slab, group) mean / rstd over all T frames -> gn_stats, fp64)
+//   MODE 4 work item = (slab, chunk j): c2 frames [254 j, 254 j + 256) by TMA, GroupNorm + SiLU, conv3, SiLU, pw2, + x for local rows
+//          1 .. 254 (again from row 0 / to the last row at the ends of the slab).
 template <int FMT, int MODE>
 __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -108,9 +115,11 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
     const int m = (warp >> 2) & 1, q = warp & 3, hf = warp >> 3;  // two threads per frame: channel halves
     const int cb = 96 * hf;                                     // first of this thread's 96 (of 192) channels
     const int t = 128 * m + 32 * q + lane;
-    const bool valid = t < T;
-    const float vmask = valid ? 1.f : 0.f;  // frames >= T are written as zeros (the conv's zero padding)
-    const bool wfull = 128 * m + 32 * q + 31 < T;  // warp-uniform: every frame of this warp is valid, no masking needed
+    constexpr bool LONG = MODE >= 3;
+    // (modes 0-2: constants of the launch; LONG: set per work item to the chunk's frame count Tc)
+    bool valid = t < T;
+    float vmask = valid ? 1.f : 0.f;  // frames >= T are written as zeros (the conv's zero padding)
+    bool wfull = 128 * m + 32 * q + 31 < T;  // warp-uniform: every frame of this warp is valid, no masking needed
     const uint32_t tacc = tmem + ((uint32_t)(32 * q) << 16) + m * 192;
     unsigned char* hrow = hbuf + (t + 1) * 16;
     const uint32_t hb = smem_u32(hbuf), w0a = smem_u32(ws0), w1a = smem_u32(ws1);
@@ -183,11 +192,23 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
 
     stagger_start(58000);  // cycles per work item (profiles/r02e_phases.txt)
     int it_ = 0;
-    for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x, ++it_) {
-        const float* xs = a.x + (size_t)slab * T * kH;
-        const size_t grow = (size_t)slab * T + t;
+    // LONG: chunk stride = 256 - (halo rows at both ends): two convs before the cut (MODE 3), one after it (MODE 4)
+    constexpr int HALO = MODE == 3 ? 2 : 1, STRIDE = 256 - 2 * HALO;
+    const int nch = LONG ? (T <= 256 ? 1 : (T - 256 + STRIDE - 1) / STRIDE + 1) : 1;
+    for (int item = blockIdx.x; item < a.nslab * nch; item += gridDim.x, ++it_) {
+        const int slab = LONG ? item / nch : item, jch = LONG ? item - slab * nch : 0;
+        const int f0 = STRIDE * jch;                                    // first frame of the tile
+        const int Tc = LONG ? min(256, T - f0) : T;                     // frames in the tile
+        const int lo = (LONG && jch) ? HALO : 0;                        // local rows [lo, hi) are this item's outputs
+        const int hi = (LONG && f0 + 256 < T) ? 256 - HALO : Tc;
+        if constexpr (LONG) {
+            valid = t < Tc;
+            vmask = valid ? 1.f : 0.f;
+            wfull = 128 * m + 32 * q + 31 < Tc;
+        }
+        const float* xs = a.x + ((size_t)slab * T + f0) * kH;
         NBSS_TICK(0, 0, it_);
-        if constexpr (MODE != 2) {
+        if constexpr (MODE != 2 && MODE != 4) {
             if (tid == 0) {
                 load_image(ws0, a.img + IMG_W1, IMG_W1_BYTES, bar_w0);
                 load_image(ws1, a.img + IMG_WC1, IMG_WC_BYTES, bar_w1);
@@ -196,7 +217,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
             if constexpr (MODE == 1)
                 stage_rows96<FMT, true, 4, true>(xs, T, hbuf, 1, s_lng, s_lnb, warp, lane, nullptr, kFfnThreads / 32, a.row_stats + (size_t)(slab / a.F) * T);
             else
-                stage_rows96<FMT, true>(xs, T, hbuf, 1, s_lng, s_lnb, warp, lane, a.ln_stats ? a.ln_stats + (size_t)slab * T * 2 : nullptr, kFfnThreads / 32);
+                stage_rows96<FMT, true>(xs, Tc, hbuf, 1, s_lng, s_lnb, warp, lane, (!LONG && a.ln_stats) ? a.ln_stats + (size_t)slab * T * 2 : nullptr, kFfnThreads / 32);
             end_epilogue();
             NBSS_TICK(0, 1, it_);
             // ---- P1: pw1
@@ -224,7 +245,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
             conv_phase(w1a, bar_w1, ph_w1);
             NBSS_TICK(0, 4, it_);
             // next slab's input rows -> L2, away from this slab's latency-exposed staging loads (E2..E4 read nothing from HBM)
-            if (tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab) l2_prefetch_slab(a.x + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
+            if (!LONG && tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab) l2_prefetch_slab(a.x + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
             if (MODE == 0 && tid == 0) load_image(ws1, a.img + IMG_WC3, IMG_WC_BYTES, bar_w1);
             act_epilogue(s_bc, a.save_c1, slab);
             end_epilogue();
@@ -258,6 +279,78 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
             tc_fence_before();
             __syncthreads();  // TMEM + H are reused by the next slab
             continue;
+        }
+        if constexpr (MODE == 3) {
+            // ---- P3: conv2 ; c2 = D + bc2 of the output rows -> fp16 slab-tile (frame f0 + t); per-group sums of (c2 - pivot) over them
+            conv_phase(w0a, bar_w0, ph_w0);
+            float* red_sum = red;
+            float* red_sq = red + 128;
+            const float* bc2 = s_bc + 192;
+            const bool mine = t >= lo && t < hi;
+#pragma unroll 1
+            for (int g = 4 * hf; g < 4 * hf + 4; ++g) {
+                uint32_t r[24];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) tmem_ld8(tacc + kGC * g + 8 * k, *reinterpret_cast<uint32_t(*)[8]>(r + 8 * k));
+                const float piv = s_piv[g];
+                tmem_ld_wait();
+                float sg = 0.f, qg = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int c = kGC * g + 8 * k;
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v[j] = __uint_as_float(r[8 * k + j]) + bc2[c + j];
+                        const float d = v[j] - piv;
+                        sg += d;
+                        qg = fmaf(d, d, qg);
+                    }
+                    if (mine) *reinterpret_cast<uint4*>(a.c2_io + tile_off(slab, 24, T, c / 8, f0 + t)) = pack8<FMT_F16>(v);
+                }
+                sg = warp_sum(mine ? sg : 0.f);
+                qg = warp_sum(mine ? qg : 0.f);
+                if (lane == 0) { red_sum[warp * 8 + g] = sg; red_sq[warp * 8 + g] = qg; }
+            }
+            tc_fence_before();
+            __syncthreads();
+            if (tid < 8) {
+                const int g = tid, h8 = 8 * (g >> 2);
+                float sg = 0.f, qg = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { sg += red_sum[(h8 + w) * 8 + g]; qg += red_sq[(h8 + w) * 8 + g]; }
+                *reinterpret_cast<float2*>(a.part + ((size_t)item * 8 + g) * 2) = make_float2(sg, qg);
+            }
+            __syncthreads();  // red, TMEM and H are reused by the next item
+            continue;
+        }
+        if constexpr (MODE == 4) {
+            // ---- part B of the long sequence: c2 frames [f0, f0 + Tc) by TMA into the H tile; GroupNorm with the slab's statistics
+            float* gtot = red + 256;
+            if (tid == 0) {
+                load_image(ws1, a.img + IMG_WC3, IMG_WC_BYTES, bar_w1);
+                load_image(ws0, a.img + IMG_W2, IMG_W2_BYTES, bar_w0);
+                mbar_expect_tx(bar_ld, (uint32_t)(24 * Tc * 16));
+                for (int c = 0; c < 24; ++c) bulk_g2s(hbuf + (size_t)c * kCS + 16, a.c2_io + tile_off(slab, 24, T, c, f0), (uint32_t)(Tc * 16), bar_ld);
+            }
+            if (tid < 16) gtot[tid] = a.gn_stats[(size_t)slab * 16 + tid];
+            __syncthreads();
+            mbar_wait(bar_ld, ph_ld, a.err);
+            ph_ld ^= 1;
+#pragma unroll 1
+            for (int c = cb; c < cb + 96; c += 8) {
+                const float mean = gtot[2 * (c / kGC)], rstd = gtot[2 * (c / kGC) + 1];
+                const uint4 pk = *reinterpret_cast<const uint4*>(hrow + (c / 8) * kCS);
+                float v[8];
+                unpack_f16x2(pk.x, v[0], v[1]);
+                unpack_f16x2(pk.y, v[2], v[3]);
+                unpack_f16x2(pk.z, v[4], v[5]);
+                unpack_f16x2(pk.w, v[6], v[7]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = silu((v[j] - mean) * (rstd * s_gng[c + j]) + s_gnb[c + j]);
+                // frames >= Tc: not touched by the TMA copy (stale bytes, possibly NaN patterns): select zeros, do not multiply
+                *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = valid ? pack8<FMT>(v) : make_uint4(0u, 0u, 0u, 0u);
+            }
         }
         if constexpr (MODE == 2) {
             // ---- part B: the c2 tile arrives by TMA straight into the H tile (same byte layout); every thread normalises its
@@ -401,7 +494,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_fwd_kernel(FfnFwdArgs a) {
         __syncthreads();
         NBSS_TICK(0, 11, it_);
         // E5b: eight lanes per frame: y = x + branch, coalesced
-        add_rows(hbuf, kCS, 1, xs, a.y + (size_t)slab * T * kH, T, warp, lane, kFfnThreads / 32);
+        add_rows(hbuf, kCS, 1 + lo, xs + (size_t)lo * kH, a.y + ((size_t)slab * T + f0 + lo) * kH, hi - lo, warp, lane, kFfnThreads / 32);
         tc_fence_before();
         __syncthreads();  // TMEM + H are reused by the next slab
         NBSS_TICK(0, 12, it_);
@@ -431,6 +524,72 @@ extern "C" int nbss_ffn_fwd(const float* x, float* y, int nslab, int T, const fl
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, kFfnThreads, FF_SMEM, (cudaStream_t)stream>>>(a);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ T > 256 (inference)
+namespace nbss {
+// GroupNorm statistics of a long slab: part [nslab][nch][8][2] = (sum, sum of squares) of (c2 - pivot_g) over the chunk's frames ->
+// gn_stats [nslab][8][2] (mean, rstd) over 24 channels x T frames; pivot_g = mean of the group's conv2 biases (as in the kernel)
+__global__ void ffn_long_gn_reduce_kernel(const float* __restrict__ part, int nslab, int nch, int T, const float* __restrict__ bc2,
+                                          float* __restrict__ gn_stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslab * 8) return;
+    const int slab = i >> 3, g = i & 7;
+    float piv = 0.f;
+    for (int j = 0; j < kGC; ++j) piv += bc2[kGC * g + j];
+    piv *= (1.f / kGC);
+    double sg = 0.0, qg = 0.0;
+    for (int c = 0; c < nch; ++c) {
+        const float2 v = *reinterpret_cast<const float2*>(part + (((size_t)slab * nch + c) * 8 + g) * 2);
+        sg += (double)v.x;
+        qg += (double)v.y;
+    }
+    const double n = (double)kGC * (double)T, mp = sg / n;
+    double var = qg / n - mp * mp;
+    var = var > 0.0 ? var : 0.0;
+    gn_stats[2 * i] = (float)((double)piv + mp);
+    gn_stats[2 * i + 1] = (float)(1.0 / sqrt(var + 1e-5));
+}
+}  // namespace nbss
+
+extern "C" long long nbss_ffn_long_chunks(int T, int part) {  // work items per slab of part A (0) / part B (1)
+    const int stride = part ? 254 : 252;
+    return T <= 256 ? 1 : (T - 256 + stride - 1) / stride + 1;
+}
+
+// SpatialNet's T-ConvFFN + residual for T > 256, inference only (header of ffn_fwd_kernel, MODE 3 / 4).  Workspaces: c2_ws fp16
+// [nslab][24][T][8] (384 T bytes per slab), part_ws [nslab][nbss_ffn_long_chunks(T, 0)][8][2] floats, stats_ws [nslab][8][2] floats.
+extern "C" int nbss_ffn_fwd_long(const float* x, float* y, int nslab, int T, const float* ln_w, const float* ln_b, const float* b1,
+                                 const float* bc1, const float* bc2, const float* bc3, const float* gn_w, const float* gn_b,
+                                 const float* b2, const void* layer_img, void* c2_ws, float* part_ws, float* stats_ws, int fmt,
+                                 int* err, void* stream) {
+    using namespace nbss;
+    if (!x || !y || !layer_img || !ln_w || !ln_b || !b1 || !bc1 || !bc2 || !bc3 || !gn_w || !gn_b || !b2 || !c2_ws || !part_ws || !stats_ws)
+        return NBSS_ERR_NULL;
+    if (T <= kTMax || T > 65536 || nslab < 1) return NBSS_ERR_SHAPE;
+    if (fmt != FMT_F16) return NBSS_ERR_UNSUPPORTED;
+    FfnFwdArgs a{x, y, nslab, T, ln_w, ln_b, b1, bc1, bc2, bc3, gn_w, gn_b, b2, (const unsigned char*)layer_img,
+                 nullptr, nullptr, nullptr, nullptr, stats_ws, nullptr, nullptr, 1, (unsigned char*)c2_ws, part_ws, err};
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ncha = (int)nbss_ffn_long_chunks(T, 0), nchb = (int)nbss_ffn_long_chunks(T, 1);
+    void (*ka)(FfnFwdArgs) = ffn_fwd_kernel<FMT_F16, 3>;
+    void (*kb)(FfnFwdArgs) = ffn_fwd_kernel<FMT_F16, 4>;
+    cudaError_t e = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    long long items = (long long)nslab * ncha;
+    ka<<<items < sms ? (int)items : sms, kFfnThreads, FF_SMEM, st>>>(a);
+    NBSS_LAUNCH_CHECK();
+    ffn_long_gn_reduce_kernel<<<(nslab * 8 + 127) / 128, 128, 0, st>>>(part_ws, nslab, ncha, T, bc2, stats_ws);
+    NBSS_LAUNCH_CHECK();
+    items = (long long)nslab * nchb;
+    kb<<<items < sms ? (int)items : sms, kFfnThreads, FF_SMEM, st>>>(a);
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
 }

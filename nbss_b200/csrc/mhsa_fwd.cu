@@ -15,6 +15,14 @@
 //        of the other.
 //   P3 y = x + O Wo^T + bo   (O_h(tile) overwrites Q_h(tile) in the Q tile once its scores are done)
 // HBM traffic: x in, y out (+ fp16 q|k|v, O and the log2-sum-exp when save != 0, for the backward kernels).
+//
+// T > 256 (inference; SURVEY.md §8 f4: validation / test utterances are longer than the 4 s training crops) runs as two passes of
+// the same kernel over work items (slab, 256-frame chunk):
+//   LONG = 1  P0, P1, E1 only: K | V of every chunk -> the fp16 slab-tile tensor [nslab][36][T][8] (the training path's save layout)
+//   LONG = 2  P0, P2, EQ for the chunk's queries, then flash-style attention over the key blocks of the slab: step n = (head h, key
+//             block kb) loads K_h[kb], V_h[kb] by TMA (two tile sets, one step ahead) and runs the SAME S / split-K softmax / P.V
+//             machinery on the chunk's two query tiles; the read-out folds each block into a running (max, sum, output) per thread
+//             and writes O_h over Q_h after the head's last block; P3 as before.
 #include "slab.cuh"
 
 namespace nbss {
@@ -25,7 +33,7 @@ struct MhsaFwdArgs {
     int nslab, T;
     const float *ln_w, *ln_b, *b_in, *b_out;
     const unsigned char* img;
-    unsigned char* save_qkv;  // fp16 slab-tile [nslab][36][T][8]: (scaled q | k | v) or null
+    unsigned char* save_qkv;  // fp16 slab-tile [nslab][36][T][8]: (scaled q | k | v) or null; LONG: the k | v exchange tensor
     unsigned char* save_o;    // fp16 slab-tile [nslab][12][T][8] or null
     float* save_lse;          // [nslab, 4, T] log2-domain logsumexp or null
     float* ln_stats;          // [nslab*T, 2] (mean, rstd) of the LayerNorm or null
@@ -42,14 +50,15 @@ constexpr uint32_t MH_CST = MH_W + MH_W_BYTES;      // 214944
 constexpr uint32_t MH_STAT = MH_CST + 576 * 4;      // (m_q, l_q) [2 buffers][4 key quarters][128 rows] float2 = 8192
 constexpr uint32_t MH_BAR = MH_STAT + 8192;
 constexpr int kMhThreads = 512;  // 16 warps
-constexpr uint32_t MH_SMEM = MH_BAR + 64;
+constexpr uint32_t MH_SMEM = MH_BAR + 96;  // 7 barriers + the TMEM slot (+ 2 K/V-set barriers of the long-sequence mode)
 static_assert(IMG_WQ_BYTES <= MH_W_BYTES, "weight image must fit the W region");
 
 // NHEADS = 4 (SpatialNet-small: head dim 24, padded to 32 in the K / O tiles) or 2 (NBC2: head dim 48, no padding).
 // DBUF: the four partial-output accumulators of a query tile fit the spare columns of its score buffer (head dim <= 32), so two
 // score buffers ping-pong; otherwise (head dim 48) one score buffer [0,256) and the partial outputs at [256, 256 + 4*48).
-template <int FMT, int NHEADS>
+template <int FMT, int NHEADS, int LONG = 0>
 __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) {
+    static_assert(LONG == 0 || NHEADS == 4, "the long-sequence passes exist for the 4-head layer only");
     constexpr int DH = kH / NHEADS;                 // 24 | 48
     constexpr int KCH = DH / 8;                     // data chunks per head: 3 | 6
     constexpr int HS = (DH % 16) ? KCH + 1 : KCH;   // chunk stride of a head in the K / O tile (one zero pad chunk if DH % 16): 4 | 6
@@ -70,6 +79,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
     uint64_t* bar_s = bar_mma + 2;   // [2] scores of buffer b are complete
     uint64_t* bar_pv = bar_mma + 4;  // [2] partial outputs of buffer b are complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 6);
+    uint64_t* bar_kv = bar_mma + 7;  // [2] LONG = 2: K_h / V_h block of tile set s has landed
 
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0) /* warp-uniform for ptxas: see umma.cuh elect_one */, lane = tid & 31;
     const int T = a.T;
@@ -77,7 +87,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
     if (tid == 0) {
         mbar_init(bar_mma, 1);
         mbar_init(bar_w, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_s + i, 1); mbar_init(bar_pv + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_s + i, 1); mbar_init(bar_pv + i, 1); mbar_init(bar_kv + i, 1); }
         fence_mbar_init();
     }
     for (int i = tid; i < 96; i += kMhThreads) { s_lng[i] = a.ln_w[i]; s_lnb[i] = a.ln_b[i]; s_bout[i] = a.b_out[i]; }
@@ -101,8 +111,9 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
     const float qscale = rsqrtf((float)DH) * 1.4426950408889634f;
     auto s_col = [&](int buf) -> uint32_t { return DBUF ? 256u * buf : 0u; };                          // score buffer
     auto o_col = [&](int buf, int kk) -> uint32_t { return DBUF ? 256u * buf + 64u * kk + 32u : 256u + NPV * kk; };  // partial outputs
-    const bool kmask = 64 * kq + 63 >= T;  // warp-uniform: this key quarter holds keys >= T (they get probability 0)
     uint32_t ph_mma = 0, ph_w = 0, ph_s = 0, ph_pv = 0;  // bit b of ph_s / ph_pv: phase of buffer b's barrier
+    int Tc = T, t0 = 0;  // LONG: frames of this work item's chunk, its first frame
+    uint32_t ph_kv = 0;  // LONG = 2: bit s = phase of tile set s's barrier (only warp 0 waits on it)
 
     auto wait_mma = [&]() {
         __syncwarp();
@@ -124,7 +135,8 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         __syncwarp();
     };
     // softmax of one query tile over the thread's own 64 keys; P -> TMEM (first 32 of the thread's 64 score columns)
-    auto softmax_local = [&](int b) {
+    auto softmax_local = [&](int b, int tk) {
+        const bool kmask = 64 * kq + 63 >= tk;  // warp-uniform: this key quarter holds keys >= tk (they get probability 0)
         const uint32_t ts = tmem + lane_off + s_col(b) + 64 * kq;
         uint32_t r0[32], r1[32];
         tmem_ld32(ts, r0);
@@ -133,8 +145,8 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         if (kmask) {  // keys >= T: -inf (only the last key quarter(s) of a short slab pay for this)
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                if (64 * kq + j >= T) r0[j] = 0xff800000u;
-                if (64 * kq + 32 + j >= T) r1[j] = 0xff800000u;
+                if (64 * kq + j >= tk) r0[j] = 0xff800000u;
+                if (64 * kq + 32 + j >= tk) r1[j] = 0xff800000u;
             }
         }
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -228,14 +240,27 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
 
     stagger_start(59000);  // cycles per work item (profiles/r02e_phases.txt)
     int it_ = 0;
-    for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x, ++it_) {
-        const float* xs = a.x + (size_t)slab * T * kH;
+    const int nch = LONG ? (T + 255) / 256 : 1;  // work items per slab
+    for (int item = blockIdx.x; item < a.nslab * nch; item += gridDim.x, ++it_) {
+        const int slab = LONG ? item / nch : item;
+        if constexpr (LONG != 0) { t0 = 256 * (item % nch); Tc = min(256, T - t0); }
+        const float* xs = a.x + ((size_t)slab * T + t0) * kH;
         NBSS_TICK(0, 0, it_);
-        if (tid == 0) load_image(wr, a.img + IMG_WKV, IMG_W1_BYTES, bar_w);
-        stage_rows96<FMT, true>(xs, T, ao, 0, s_lng, s_lnb, warp, lane, a.ln_stats ? a.ln_stats + (size_t)slab * T * 2 : nullptr, kMhThreads / 32);
+        if (tid == 0) load_image(wr, a.img + (LONG == 2 ? IMG_WQ : IMG_WKV), LONG == 2 ? IMG_WQ_BYTES : IMG_W1_BYTES, bar_w);
+        if constexpr (LONG == 2) {
+            // rows of the V tile sets beyond the slab's last (partial) key block must be finite: P = 0 there, but 0 x NaN is NaN, and
+            // the previous item's fp32 out-proj staging left arbitrary bits.  (Full blocks overwrite them with real values later.)
+            const int tl = T - 256 * ((T - 1) / 256);
+            for (int i = tid; i < 8 * (256 - tl); i += kMhThreads) {
+                const int c = i / (256 - tl), r = tl + i % (256 - tl);
+                *reinterpret_cast<uint4*>(vt + (size_t)c * kCS + r * 16) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        stage_rows96<FMT, true>(xs, Tc, ao, 0, s_lng, s_lnb, warp, lane, (LONG == 0 && a.ln_stats) ? a.ln_stats + (size_t)slab * T * 2 : nullptr, kMhThreads / 32);
         end_epilogue();
         NBSS_TICK(0, 1, it_);
         // ---- P1: K|V
+        if constexpr (LONG != 2) {
         if (warp == 0) {
             tc_fence_after();
             mbar_wait(bar_w, ph_w, a.err);
@@ -246,9 +271,9 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         ph_w ^= 1;
         wait_mma();
         NBSS_TICK(0, 2, it_);
-        if (tid == 0) load_image(wr, a.img + IMG_WQ, IMG_WQ_BYTES, bar_w);
+        if (LONG == 0 && tid == 0) load_image(wr, a.img + IMG_WQ, IMG_WQ_BYTES, bar_w);
         {
-            const bool valid = t < T;
+            const bool valid = t < Tc;
             const uint32_t tacc = tmem + lane_off + m * 192;
             // K: cols 0..95 -> per-head chunks HS*h .. HS*h+KCH-1   (channel half 0 does K, half 1 does V)
 #pragma unroll 1
@@ -264,7 +289,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = valid ? __uint_as_float(r[8 * k + j]) + s_bin[96 + 8 * (c3 + k) + j] : 0.f;
                     *reinterpret_cast<uint4*>(kt + (HS * h + k0 + k) * kCS + t * 16) = pack8<FMT>(v);
-                    if (a.save_qkv && valid) *reinterpret_cast<uint4*>(a.save_qkv + tile_off(slab, 36, T, 12 + c3 + k, t)) = pack8<FMT_F16>(v);
+                    if (a.save_qkv && valid) *reinterpret_cast<uint4*>(a.save_qkv + tile_off(slab, 36, T, 12 + c3 + k, t0 + t)) = pack8<FMT_F16>(v);
                 }
             }
             // V: cols 96..191 -> compact chunks 0..11
@@ -280,12 +305,14 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = valid ? __uint_as_float(r[8 * k + j]) + s_bin[192 + 8 * (c + k) + j] : 0.f;
                     *reinterpret_cast<uint4*>(vt + (c + k) * kCS + t * 16) = pack8<FMT>(v);
-                    if (a.save_qkv && valid) *reinterpret_cast<uint4*>(a.save_qkv + tile_off(slab, 36, T, 24 + c + k, t)) = pack8<FMT_F16>(v);
+                    if (a.save_qkv && valid) *reinterpret_cast<uint4*>(a.save_qkv + tile_off(slab, 36, T, 24 + c + k, t0 + t)) = pack8<FMT_F16>(v);
                 }
             }
         }
         end_epilogue();
         NBSS_TICK(0, 3, it_);
+        if constexpr (LONG == 1) continue;  // K | V pass: TMEM and the tiles are reused by the next item
+        }  // LONG != 2
         // ---- P2: Q
         if (warp == 0) {
             tc_fence_after();
@@ -300,10 +327,10 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
         if (tid == 0) load_image(wr, a.img + IMG_WO, IMG_WQ_BYTES, bar_w);  // out-proj image: needed only after the last head
         // next slab's input rows -> L2, issued HERE (not at the top of the slab, where it would compete with this slab's
         // latency-exposed staging loads): the attention heads below need no HBM traffic at all
-        if (tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab) l2_prefetch_slab(a.x + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
+        if (LONG == 0 && tid >= 32 && tid < 38 && slab + (int)gridDim.x < a.nslab) l2_prefetch_slab(a.x + (size_t)(slab + gridDim.x) * T * kH, T, tid - 32);
         // ---- EQ: scaled queries of all heads -> Q tile (over A0, dead now); thread = (frame, channel half)
         {
-            const bool valid = t < T;
+            const bool valid = t < Tc;
             const uint32_t tacc = tmem + lane_off + m * 96;
 #pragma unroll 1
             for (int c0 = 48 * hf; c0 < 48 * hf + 48; c0 += 24) {
@@ -317,14 +344,130 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = valid ? (__uint_as_float(r[8 * k + j]) + s_bin[c0 + 8 * k + j]) * qscale : 0.f;
                     *reinterpret_cast<uint4*>(ao + (c0 / 8 + k) * kCS + t * 16) = pack8<FMT>(v);
-                    if (a.save_qkv && valid) *reinterpret_cast<uint4*>(a.save_qkv + tile_off(slab, 36, T, c0 / 8 + k, t)) = pack8<FMT_F16>(v);
+                    if (LONG == 0 && a.save_qkv && valid) *reinterpret_cast<uint4*>(a.save_qkv + tile_off(slab, 36, T, c0 / 8 + k, t)) = pack8<FMT_F16>(v);
                 }
             }
         }
         end_epilogue();
         NBSS_TICK(0, 8, it_);
         // ---- heads
-        if constexpr (DBUF) {
+        if constexpr (LONG == 2) {
+            const int nkb = nch, nsteps = NHEADS * nkb;
+            // ONE thread: K_h, V_h of key block kb (three chunk columns each) -> tile set `set` (K: chunks 4 set .. +2, the 4th stays the
+            // zero pad of the S MMA's second k-step; V: chunks 4 set .. +2)
+            auto load_kv = [&](int n, int set) {
+                const int h = n / nkb, kb = n % nkb, tk = min(256, T - 256 * kb);
+                mbar_expect_tx(bar_kv + set, (uint32_t)(6 * tk * 16));
+                for (int c = 0; c < 3; ++c) {
+                    bulk_g2s(kt + (size_t)(4 * set + c) * kCS, a.save_qkv + tile_off(slab, 36, T, 12 + 3 * h + c, 256 * kb), (uint32_t)(tk * 16), bar_kv + set);
+                    bulk_g2s(vt + (size_t)(4 * set + c) * kCS, a.save_qkv + tile_off(slab, 36, T, 24 + 3 * h + c, 256 * kb), (uint32_t)(tk * 16), bar_kv + set);
+                }
+            };
+            // warp 0: S of query tile b against the key block in tile set `set`
+            auto issue_s_l = [&](int h, int b, int set) {
+                tc_fence_after();
+                const bool leader = elect_one();
+                mma_kk(tmem + s_col(b), aoa + KCH * h * kCS + 128 * b * 16, kCS, kta + 4 * set * kCS, kCS, KKS, id256, 0, leader);
+                if (leader) umma_commit(bar_s + b);
+                __syncwarp();
+            };
+            auto issue_pv_l = [&](int set, int b) {
+                tc_fence_after();
+                const bool leader = elect_one();
+#pragma unroll 1
+                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll 1
+                    for (int ks = 0; ks < 4; ++ks)
+                        if (leader)
+                            umma_f16_ts(tmem + o_col(b, kk), tmem + s_col(b) + 64 * kk + 8 * ks,
+                                        sdesc_mnmajor(vta + 4 * set * kCS + (64 * kk + 16 * ks) * 16, kCS), idpv, ks ? 1u : 0u);
+                if (leader) umma_commit(bar_pv + b);
+                __syncwarp();
+            };
+            if (tid == 0) {
+                load_kv(0, 0);
+                if (nsteps > 1) load_kv(1, 1);
+            }
+            if (warp == 0) {
+                mbar_wait(bar_kv, ph_kv & 1u, a.err);
+                ph_kv ^= 1u;
+                issue_s_l(0, 0, 0);
+                issue_s_l(0, 1, 0);
+            }
+            // running (max, sum, output) of the two query tiles; the read-out threads (kq < 3) own 8 output features each
+            float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f}, acc_run[2][8];
+#pragma unroll 1
+            for (int n = 0; n < nsteps; ++n) {
+                const int h = n / nkb, kb = n - h * nkb, set = n & 1, tk = min(256, T - 256 * kb);
+                if (kb == 0) {
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        m_run[b] = -INFINITY;
+                        l_run[b] = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc_run[b][j] = 0.f;
+                    }
+                }
+#pragma unroll 1
+                for (int b = 0; b < 2; ++b) {
+                    mbar_wait(bar_s + b, (ph_s >> b) & 1u, a.err);
+                    ph_s ^= 1u << b;
+                    tc_fence_after();
+                    softmax_local(b, tk);
+                    tc_fence_before();
+                    __syncthreads();
+                    if (warp == 0) issue_pv_l(set, b);
+                }
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    mbar_wait(bar_pv + b, (ph_pv >> b) & 1u, a.err);
+                    ph_pv ^= 1u << b;
+                    tc_fence_after();
+                    {
+                        const float2 s0 = stat[(b * 4 + 0) * 128 + rt], s1 = stat[(b * 4 + 1) * 128 + rt], s2 = stat[(b * 4 + 2) * 128 + rt],
+                                     s3 = stat[(b * 4 + 3) * 128 + rt];
+                        const float mx = fmaxf(fmaxf(s0.x, s1.x), fmaxf(s2.x, s3.x));  // finite: key quarter 0 holds the block's first key
+                        const float mn = fmaxf(m_run[b], mx);
+                        const float fr = ex2_ftz(m_run[b] - mn);                       // 0 on the first block (m_run = -inf)
+                        const float f[4] = {ex2_ftz(s0.x - mn), ex2_ftz(s1.x - mn), ex2_ftz(s2.x - mn), ex2_ftz(s3.x - mn)};
+                        l_run[b] = l_run[b] * fr + (f[0] * s0.y + f[1] * s1.y + f[2] * s2.y + f[3] * s3.y);
+                        m_run[b] = mn;
+                        if (kq < 3) {
+                            uint32_t o[4][8];
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) tmem_ld8(tmem + lane_off + o_col(b, kk) + 8 * kq, o[kk]);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float v = acc_run[b][j] * fr;
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) v = fmaf(f[kk], __uint_as_float(o[kk][j]), v);
+                                acc_run[b][j] = v;
+                            }
+                            if (kb == nkb - 1) {  // the head's last key block: O_h(tile b) over Q_h(tile b), whose scores are all done
+                                const float inv = 1.f / l_run[b];
+                                float ov[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) ov[j] = acc_run[b][j] * inv;
+                                *reinterpret_cast<uint4*>(ao + (KCH * h + kq) * kCS + (128 * b + rt) * 16) = pack8<FMT>(ov);
+                            }
+                        }
+                    }
+                    fence_async_smem();
+                    tc_fence_before();
+                    __syncthreads();
+                    if (warp == 0 && n + 1 < nsteps) {
+                        if (b == 0) {  // the next step's K_h / V_h block (requested one step ago)
+                            mbar_wait(bar_kv + ((n + 1) & 1), (ph_kv >> ((n + 1) & 1)) & 1u, a.err);
+                            ph_kv ^= 1u << ((n + 1) & 1);
+                        }
+                        issue_s_l((n + 1) / nkb, b, (n + 1) & 1);
+                    }
+                }
+                // every MMA that read tile set n & 1 has completed (both bar_pv waits above): request step n + 2 into it
+                if (tid == 0 && n + 2 < nsteps) load_kv(n + 2, set);
+            }
+        } else if constexpr (DBUF) {
             // the two query tiles of a head ping-pong between the two score buffers
             if (warp == 0) { issue_s(0, 0, 0); issue_s(0, 1, 1); }
 #pragma unroll 1
@@ -334,7 +477,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
                     mbar_wait(bar_s + b, (ph_s >> b) & 1u, a.err);
                     ph_s ^= 1u << b;
                     tc_fence_after();
-                    softmax_local(b);
+                    softmax_local(b, T);
                     tc_fence_before();
                     __syncthreads();
                     if (warp == 0) issue_pv(h, b);
@@ -362,7 +505,7 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
                 mbar_wait(bar_s, ph_s & 1u, a.err);
                 ph_s ^= 1u;
                 tc_fence_after();
-                softmax_local(0);
+                softmax_local(0, T);
                 tc_fence_before();
                 __syncthreads();
                 if (warp == 0) issue_pv(h, 0);
@@ -409,8 +552,8 @@ __global__ void __launch_bounds__(kMhThreads, 1) mhsa_fwd_kernel(MhsaFwdArgs a) 
             tc_fence_before();
             __syncthreads();
             NBSS_TICK(0, 6, it_);
-            add_rows<(HS != KCH)>(kt, kCS, 0, xs, a.y + (size_t)slab * T * kH, T, warp, lane, kMhThreads / 32,
-                                  a.row_part ? a.row_part + (size_t)slab * T * 2 : nullptr);
+            add_rows<(HS != KCH)>(kt, kCS, 0, xs, a.y + ((size_t)slab * T + t0) * kH, Tc, warp, lane, kMhThreads / 32,
+                                  (LONG == 0 && a.row_part) ? a.row_part + (size_t)slab * T * 2 : nullptr);
         }
         tc_fence_before();
         __syncthreads();
@@ -443,6 +586,33 @@ extern "C" int nbss_mhsa_fwd_nh(const float* x, float* y, int nslab, int T, cons
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MH_SMEM);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, kMhThreads, MH_SMEM, (cudaStream_t)stream>>>(a);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+
+// T > 256, inference only (no saves): pass 1 writes k | v of all frames to kv_ws (fp16 [nslab][36][T][8], 576 T bytes per slab), pass 2
+// attends chunk by chunk (see the header).  T <= 65536.
+extern "C" int nbss_mhsa_fwd_long(const float* x, float* y, int nslab, int T, const float* ln_w, const float* ln_b, const float* b_in,
+                                  const float* b_out, const void* layer_img, void* kv_ws, int fmt, int* err, void* stream) {
+    using namespace nbss;
+    if (!x || !y || !layer_img || !ln_w || !ln_b || !b_in || !b_out || !kv_ws) return NBSS_ERR_NULL;
+    if (T <= kTMax || T > 65536 || nslab < 1) return NBSS_ERR_SHAPE;
+    if (fmt != FMT_F16) return NBSS_ERR_UNSUPPORTED;
+    MhsaFwdArgs a{x, y, nslab, T, ln_w, ln_b, b_in, b_out, (const unsigned char*)layer_img, (unsigned char*)kv_ws, nullptr, nullptr, nullptr, nullptr, err};
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long items = (long long)nslab * ((T + 255) / 256);
+    const int grid = items < sms ? (int)items : sms;
+    void (*k1)(MhsaFwdArgs) = mhsa_fwd_kernel<FMT_F16, 4, 1>;
+    void (*k2)(MhsaFwdArgs) = mhsa_fwd_kernel<FMT_F16, 4, 2>;
+    cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MH_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MH_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    k1<<<grid, kMhThreads, MH_SMEM, (cudaStream_t)stream>>>(a);
+    NBSS_LAUNCH_CHECK();
+    k2<<<grid, kMhThreads, MH_SMEM, (cudaStream_t)stream>>>(a);
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
 }

@@ -20,7 +20,8 @@ Tensor = torch.Tensor
 # every C-ABI call is bracketed by CUDA events on the launching (current) stream.
 LAUNCHES = 0
 TIMING = None
-_NLAUNCH = {"nbss_nbc2_block": 5, "nbss_full_fwd": 3, "nbss_full_bwd": 4, "nbss_full_fwd_tc": 3, "nbss_full_bwd_tc": 4, "nbss_ffn_wgrad": 3, "nbss_mhsa_bwd": 2, "nbss_istft": 2, "nbss_sisdr_pit_fwd": 2, "nbss_clip_adam": 2}
+_NLAUNCH = {"nbss_nbc2_block": 5, "nbss_full_fwd": 3, "nbss_full_bwd": 4, "nbss_full_fwd_tc": 3, "nbss_full_bwd_tc": 4, "nbss_ffn_wgrad": 3, "nbss_mhsa_bwd": 2, "nbss_istft": 2, "nbss_sisdr_pit_fwd": 2, "nbss_clip_adam": 2,
+            "nbss_mhsa_fwd_long": 2, "nbss_ffn_fwd_long": 3}
 
 
 _KCACHE = {}
@@ -138,11 +139,27 @@ def ffn_fwd(x: Tensor, P: Dict[str, Tensor], pre: str, img: Tensor, save: bool =
     assert H == 96
     y = torch.empty_like(x) if out is None else out
     n = B * F * T
+    t = pre + "tconvffn."
+    if T > 256:  # inference on long utterances: the sub-block cut at its GroupNorm and tiled over T (ffn_fwd.cu MODE 3 / 4)
+        if save:
+            raise NotImplementedError("nbss_b200: training needs T <= 256 frames per utterance (the backward kernels hold one (b,f) "
+                                      "slab per CTA); longer inputs run in inference mode (torch.no_grad())")
+        if fmt != FMT_F16:
+            raise NotImplementedError("the long-sequence kernels are built for fp16 operands")
+        c2 = torch.empty(B * F * 24 * T * 8, dtype=torch.float16, device=x.device)
+        part = torch.empty(B * F * int(_lib.lib().nbss_ffn_long_chunks(T, 0)) * 16, dtype=torch.float32, device=x.device)
+        stats = torch.empty(B * F * 16, dtype=torch.float32, device=x.device)
+        err = device_err_flag(x.device)
+        check(_K("nbss_ffn_fwd_long")(
+            ptr(x), ptr(y), B * F, T, ptr(_f32c(P[t + "0.weight"])), ptr(_f32c(P[t + "0.bias"])), ptr(_f32c(P[t + "1.bias"])),
+            ptr(_f32c(P[t + "3.bias"])), ptr(_f32c(P[t + "5.bias"])), ptr(_f32c(P[t + "8.bias"])), ptr(_f32c(P[t + "6.weight"])),
+            ptr(_f32c(P[t + "6.bias"])), ptr(_f32c(P[t + "10.bias"])), ptr(img), ptr(c2), ptr(part), ptr(stats), fmt, ptr(err),
+            stream_ptr()), "nbss_ffn_fwd_long")
+        return y, err
     saves = [torch.empty(n, 192, dtype=torch.float16, device=x.device) for _ in range(4)] if save else [None] * 4
     stats = torch.empty(B * F, 8, 2, dtype=torch.float32, device=x.device) if save else None
     ln_stats = torch.empty(n, 2, dtype=torch.float32, device=x.device) if save else None
     err = device_err_flag(x.device)
-    t = pre + "tconvffn."
     st = _K("nbss_ffn_fwd")(
         ptr(x), ptr(y), B * F, T, ptr(_f32c(P[t + "0.weight"])), ptr(_f32c(P[t + "0.bias"])), ptr(_f32c(P[t + "1.bias"])),
         ptr(_f32c(P[t + "3.bias"])), ptr(_f32c(P[t + "5.bias"])), ptr(_f32c(P[t + "8.bias"])), ptr(_f32c(P[t + "6.weight"])),
@@ -216,6 +233,19 @@ def mhsa_fwd(x: Tensor, P: Dict[str, Tensor], pre: str, img: Tensor, save: bool 
     assert H == 96
     y = torch.empty_like(x) if out is None else out
     n = B * F * T
+    if T > 256:  # inference on long utterances: K | V pass + chunked flash-style attention (mhsa_fwd.cu LONG = 1 / 2)
+        if save:
+            raise NotImplementedError("nbss_b200: training needs T <= 256 frames per utterance (the backward kernels hold one (b,f) "
+                                      "slab per CTA); longer inputs run in inference mode (torch.no_grad())")
+        if fmt != FMT_F16:
+            raise NotImplementedError("the long-sequence kernels are built for fp16 operands")
+        kv = torch.empty(n, 288, dtype=torch.float16, device=x.device)
+        err = device_err_flag(x.device)
+        check(_K("nbss_mhsa_fwd_long")(
+            ptr(x), ptr(y), B * F, T, ptr(_f32c(P[pre + "norm_mhsa.weight"])), ptr(_f32c(P[pre + "norm_mhsa.bias"])),
+            ptr(_f32c(P[pre + "mhsa.in_proj_bias"])), ptr(_f32c(P[pre + "mhsa.out_proj.bias"])), ptr(img), ptr(kv), fmt, ptr(err),
+            stream_ptr()), "nbss_mhsa_fwd_long")
+        return y, err
     qkv = torch.empty(n, 288, dtype=torch.float16, device=x.device) if save else None
     o = torch.empty(n, 96, dtype=torch.float16, device=x.device) if save else None
     lse = torch.empty(B * F, 4, T, dtype=torch.float32, device=x.device) if save else None

@@ -259,7 +259,9 @@ class _SpatialNetFn(torch.autograd.Function):
 
 class SpatialNet(nn.Module):
     """See module docstring.  Tensor-core path supports the reference's small configuration (dim_hidden 96, dim_ffn
-    192, 4 heads, conv_groups (8,8), kernel_size (5,3), LN/GN norms, zero padding, no dropout) and T <= 256 frames."""
+    192, 4 heads, conv_groups (8,8), kernel_size (5,3), LN/GN norms, zero padding, no dropout).  Training: T <= 256 frames (the 4 s
+    crops of the reference's configs); inference (torch.no_grad()) takes any T up to 65536 (ops.mhsa_fwd / ops.ffn_fwd switch to the
+    chunked long-sequence kernels above 256 frames)."""
 
     def __init__(self, dim_input: int, dim_output: int, dim_squeeze: int, num_layers: int, num_freqs: int,
                  encoder_kernel_size: int = 5, dim_hidden: int = 192, dim_ffn: int = 384, num_heads: int = 2,

@@ -257,6 +257,71 @@ def bench_nbc2(dev, steps=5, warmup=3, batch=64, eager=True):
     return out
 
 
+def bench_long(dev, seconds=32, steps=3, warmup=2, eager=True):
+    """Validation / test-time inference on a whole utterance (SharedTrainer.py:134-189: no 4 s crop): one 32 s, 8 kHz, 6-channel
+    recording = T = 2001 STFT frames, wave -> wave through nbss_b200.SeparationPipeline under torch.no_grad() — the chunked
+    long-sequence kernels (mhsa_fwd.cu LONG 1/2, ffn_fwd.cu MODE 3/4).  Device-resident and end to end (pinned host wave in, host
+    estimates out); next to it the reference's op-set in PyTorch eager on the same GPU (forward only)."""
+    from nbss_b200.io import SeparationPipeline
+    from nbss_b200.spatialnet import SpatialNet
+    from oracle import eager_gpu as E
+    from oracle import spatialnet_oracle as O
+
+    Ts = CFG["hop"] * (seconds * 8000 // CFG["hop"])
+    T = Ts // CFG["hop"] + 1
+    torch.manual_seed(2)
+    net = SpatialNet(dim_input=2 * CFG["C"], dim_output=2 * CFG["S"], dim_squeeze=8, num_layers=CFG["L"], num_freqs=CFG["F"], dim_hidden=96,
+                     dim_ffn=192, num_heads=4).to(dev).eval()
+    pipe = SeparationPipeline(net, CFG["n_fft"], CFG["hop"], channels=None, ref_channel=0)
+    x_host = (0.1 * torch.randn(1, CFG["C"], Ts, generator=torch.Generator().manual_seed(9))).pin_memory()
+    y_host = torch.empty(1, CFG["S"], Ts).pin_memory()
+    x = x_host.to(dev)
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    with torch.no_grad():
+        ms = timed(lambda: pipe(x))
+
+        def e2e():
+            y_host.copy_(pipe(x_host.to(dev, non_blocking=True)), non_blocking=True)
+
+        ms_e2e = timed(e2e)
+    net.check_device_errors()
+    out = {"workload": f"SpatialNet-small 6ch F=129, one {seconds} s utterance (T={T} frames), inference wave->wave", "ms_per_utt": round(ms, 2),
+           "frames_per_s": round(T / (ms * 1e-3), 1), "real_time_factor": round(ms * 1e-3 / seconds, 5),
+           "e2e": {"ms_per_utt": round(ms_e2e, 2), "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4}}
+    if eager:
+        P = {k: v.to(dev) for k, v in O.synth_params(O.SMALL_CFG, 2).items()}
+        old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+        try:
+            eg = {}
+            for mode in ("fp32_tf32", "bf16_autocast"):
+                def one():
+                    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16_autocast")):
+                        return E.io_forward(P, x, O.SMALL_CFG, CFG["n_fft"], CFG["hop"], 0)
+                try:
+                    eg[mode] = {"ms_per_utt": round(timed(one), 2)}
+                except torch.OutOfMemoryError:
+                    eg[mode] = {"unavailable": "out of memory"}
+                    torch.cuda.empty_cache()
+            out["gpu_eager_baseline"] = eg
+        finally:
+            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    return out
+
+
 def bench_online(dev, frames=1000, batches=(1, 8, 64)):
     """BASELINE configs[4]: online (causal) SpatialNet, 6 channels, F=129, one 16 ms frame (hop 128 at 8 kHz) per call through
     nbss_b200.online.OnlineSpatialNet.step, the whole step replayed as one CUDA graph.  Latency = host wall clock from handing a
@@ -608,7 +673,8 @@ def main():
         out["gpu_eager_baseline"] = eager
     if world == 1 and not args.no_nbc2:
         out["extra_workloads"] = {}
-        for name, fn in (("nbc2_inference", lambda: bench_nbc2(dev, eager=not args.no_eager_baseline)), ("online_streaming", lambda: bench_online(dev))):
+        for name, fn in (("nbc2_inference", lambda: bench_nbc2(dev, eager=not args.no_eager_baseline)), ("online_streaming", lambda: bench_online(dev)),
+                         ("long_utterance_inference", lambda: bench_long(dev, eager=not args.no_eager_baseline))):
             try:
                 out["extra_workloads"][name] = fn()
             except Exception as e:

@@ -88,7 +88,7 @@ def test_long_path_error_level_matches_one_slab_kernels():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("T", [300, 777])
+@pytest.mark.parametrize("T", [300, 777, 2001])
 def test_network_forward_long_and_training_refuses(T):
     cfg = dict(CFG, num_layers=2)
     P = O.synth_params(cfg, 23)
@@ -104,3 +104,22 @@ def test_network_forward_long_and_training_refuses(T):
     assert e < 1e-3
     with pytest.raises(NotImplementedError):
         net(x.cuda())  # grad mode on: the training path saves for backward, and the backward kernels hold T <= 256
+
+
+@pytest.mark.gpu
+def test_pipeline_wave_to_wave_long():
+    """STFT -> norm -> network -> inverse norm -> iSTFT on a 6.4 s recording (T = 401 frames) under no_grad, against the oracle."""
+    from nbss_b200.io import SeparationPipeline
+
+    cfg = dict(CFG, num_layers=2)
+    P = O.synth_params(cfg, 29)
+    net = SpatialNet(dim_input=12, dim_output=4, dim_squeeze=8, num_layers=2, num_freqs=129, dim_hidden=96, dim_ffn=192, num_heads=4).cuda()
+    net.load_state_dict({k: v.clone() for k, v in P.items()})
+    pipe = SeparationPipeline(net, 256, 128, channels=None, ref_channel=0)
+    x = 0.1 * torch.randn(1, 6, 128 * 400, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        ref = O.io_forward(P, x, cfg, 256, 128, 0)
+        y = pipe(x.cuda())
+    torch.cuda.synchronize()
+    assert y.shape == ref.shape
+    assert O.rel_l2(y.cpu(), ref) < 1e-3

@@ -59,6 +59,12 @@ int nbss_mhsa_fwd_nh(const float* x, float* y, int nslab, int T, const float* ln
 int nbss_predict_post(const float* preds, const float* mixture, float* out, int B, int S, long long Ts, int recover,
                       int norm_if_exceed_1, double* ws_sums, unsigned int* ws_peak, float* scale_out, void* stream);
 
+/* ---- exact loss scaling of the upstream gradient (loss.cu): dy_scaled = dy * s with s = 2^-round(log2 max|dy|) (1 if dy == 0); the
+ * backward kernels are linear in dy, nbss_grad_unscale multiplies the flat gradient buffer by 1/s.  ws: 1 uint, scale: 2 floats (s, 1/s);
+ * everything stays on the device (no host synchronisation, graph-capturable). */
+int nbss_grad_prescale(const float* dy, long long n, float* dy_scaled, unsigned int* ws, float* scale, void* stream);
+int nbss_grad_unscale(float* flat, long long n, const float* scale, void* stream);
+
 /* ---- T > 256, inference only (validation / test utterances are longer than the 4 s training crops; SharedTrainer.py:134-189) -----
  * Same layer image and parameters as nbss_mhsa_fwd / nbss_ffn_fwd; 256 < T <= 65536; fmt = 0 (fp16).  In place (y == x) is allowed.
  * nbss_mhsa_fwd_long: kv_ws = fp16 [nslab][36][T][8] (576*T bytes per slab): pass 1 writes k | v of all frames, pass 2 attends per

@@ -233,3 +233,58 @@ extern "C" int nbss_clip_adam(float* const* params, const long long* offsets, in
     NBSS_LAUNCH_CHECK();
     return NBSS_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ exact loss scaling of dy
+// The backward kernels carry 16-bit gradient operands and are linear in the upstream gradient: dy is multiplied by the power of two
+// that brings its largest element to ~1 and the flat gradient buffer is multiplied back (spatialnet.py _SpatialNetFn.backward).
+// No host synchronisation: the scale lives on the device.   ws: one zeroed uint (bit pattern of max |dy|), scale: [2] = (s, 1/s).
+namespace nbss {
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, long long n, unsigned int* amax_bits) {
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) m = fmaxf(m, fabsf(x[i]));
+    m = warp_max(m);
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+        atomicMax(amax_bits, __float_as_uint(m));  // non-negative floats order like their bit patterns (NaN sorts above everything)
+    }
+}
+__device__ __forceinline__ float pow2_scale(unsigned int amax_bits) {
+    const float amax = __uint_as_float(amax_bits);
+    return (amax > 0.f && amax < INFINITY) ? exp2f(-rintf(log2f(fmaxf(amax, 1e-30f)))) : 1.f;
+}
+__global__ void __launch_bounds__(256) prescale_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
+                                                       const unsigned int* __restrict__ amax_bits, float* scale) {
+    const float s = pow2_scale(*amax_bits);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { scale[0] = s; scale[1] = 1.f / s; }
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) y[i] = x[i] * s;
+}
+__global__ void __launch_bounds__(256) unscale_kernel(float* __restrict__ g, long long n, const float* __restrict__ scale) {
+    const float r = scale[1];
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) g[i] *= r;
+}
+}  // namespace nbss
+
+extern "C" int nbss_grad_prescale(const float* dy, long long n, float* dy_scaled, unsigned int* ws, float* scale, void* stream) {
+    if (!dy || !dy_scaled || !ws || !scale) return NBSS_ERR_NULL;
+    if (n < 1) return NBSS_ERR_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return (int)e;
+    nbss::absmax_kernel<<<grid, 256, 0, st>>>(dy, n, ws);
+    NBSS_LAUNCH_CHECK();
+    nbss::prescale_kernel<<<grid, 256, 0, st>>>(dy, dy_scaled, n, ws, scale);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}
+extern "C" int nbss_grad_unscale(float* flat, long long n, const float* scale, void* stream) {
+    if (!flat || !scale) return NBSS_ERR_NULL;
+    if (n < 1) return NBSS_ERR_SHAPE;
+    const int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    nbss::unscale_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(flat, n, scale);
+    NBSS_LAUNCH_CHECK();
+    return NBSS_OK;
+}

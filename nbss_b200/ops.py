@@ -21,7 +21,7 @@ Tensor = torch.Tensor
 LAUNCHES = 0
 TIMING = None
 _NLAUNCH = {"nbss_nbc2_block": 5, "nbss_full_fwd": 3, "nbss_full_bwd": 4, "nbss_full_fwd_tc": 3, "nbss_full_bwd_tc": 4, "nbss_ffn_wgrad": 3, "nbss_mhsa_bwd": 2, "nbss_istft": 2, "nbss_sisdr_pit_fwd": 2, "nbss_clip_adam": 2,
-            "nbss_mhsa_fwd_long": 2, "nbss_ffn_fwd_long": 3}
+            "nbss_mhsa_fwd_long": 2, "nbss_ffn_fwd_long": 3, "nbss_grad_prescale": 2}
 
 
 _KCACHE = {}

@@ -16,6 +16,8 @@ import math
 import weakref
 from typing import Dict, List, Optional, Tuple
 
+import ctypes
+
 import torch
 import torch.nn as nn
 from torch import Tensor
@@ -241,10 +243,12 @@ class _SpatialNetFn(torch.autograd.Function):
         # fp16 gradient operands: the backward is linear in dy, so scale dy by a power of two that brings its largest
         # element to ~1 and undo it on the flat gradient buffer (exact loss scaling, no host synchronisation)
         dy = dy.contiguous().float()
-        amax = dy.abs().amax()
-        scale = torch.where(amax > 0, torch.exp2(-torch.round(torch.log2(amax.clamp_min(1e-30)))), torch.ones_like(amax))
-        errs = module.engine.backward(P, fctx.ctx, dy * scale, G)
-        flat.mul_(1.0 / scale)
+        dys = torch.empty_like(dy)
+        ws = torch.empty(4, dtype=torch.float32, device=dy.device)  # [0]: bits of max |dy|, [2:4]: scale, 1 / scale
+        ops.check(ops._K("nbss_grad_prescale")(ops.ptr(dy), ctypes.c_longlong(dy.numel()), ops.ptr(dys), ops.ptr(ws), ops.ptr(ws[2:]),
+                                               ops.stream_ptr()), "nbss_grad_prescale")
+        errs = module.engine.backward(P, fctx.ctx, dys, G)
+        ops.check(ops._K("nbss_grad_unscale")(ops.ptr(flat), ctypes.c_longlong(flat.numel()), ops.ptr(ws[2:]), ops.stream_ptr()), "nbss_grad_unscale")
         module._last_flat_grad = flat  # one contiguous buffer: a single NCCL all-reduce covers every gradient
         # The device error flag is sticky and shared by all launches; reading it needs a host sync, so the hot path does
         # it only on request (NBSS_CHECK_EVERY_STEP=1) — `SpatialNet.check_device_errors()` reads it at any time.

@@ -638,7 +638,8 @@ def main():
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         traffic = {k: v * b_local / tj["batch_per_gpu"] for k, v in tj["dram_bytes_per_call"].items()}
-        traffic_src = f"profiles/r02_traffic.json (ncu --set full, commit {tj.get('commit')}, batch {tj['batch_per_gpu']} scaled to {b_local})"
+        traffic_src = (f"profiles/r02_traffic.json (ncu --set full, commit {tj.get('commit')}, batch {tj['batch_per_gpu']}"
+                       + ("" if tj["batch_per_gpu"] == b_local else f" scaled to {b_local}") + ")")
     except Exception:
         pass
 

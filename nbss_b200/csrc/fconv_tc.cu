@@ -371,12 +371,11 @@ __global__ void __launch_bounds__(kFcBwdThreads, 1) fconv_tc_bwd_kernel(FcBwdArg
         const int b = grp / g.groups_per_b, t0 = (grp % g.groups_per_b) * g.nfr;
         NBSS_TICK(1, 0, it_);
         if (tid == 0) load_image(wimg, a.img, FC_IMG_BYTES, bar_w);
-        // dy first, LN(x) second: whichever staging pass comes first waits ~7-11 k cycles for the memory pipeline to drain the
-        // previous group's dx stores; the LayerNorm arithmetic of the x pass then overlaps the tail of the dy loads
-        // (measured: 14.7 k -> 13.3 k cycles for the two passes, profiles/r02n_fconv_stage_order.txt)
-        fc_stage_plain<FMT, 5, NW>(g, a.dy, b, t0, gtile, warp, lane);
-        NBSS_TICK(1, 1, it_);
+        // (staging dy first moves ~1.4 k cycles from the staging passes into E-A: the item's total is unchanged, see
+        // profiles/r02n_fconv_stage_order.txt)
         fc_stage<FMT, 5, NW>(g, a.x, b, t0, htile, cst, cst + 96, stats, warp, lane);
+        NBSS_TICK(1, 1, it_);
+        fc_stage_plain<FMT, 5, NW>(g, a.dy, b, t0, gtile, warp, lane);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();

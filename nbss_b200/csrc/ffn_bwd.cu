@@ -204,6 +204,13 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         }
     };
 
+    // L2 prefetch of one saved fp16 pre-activation tensor of a slab (slab-tile layout: 24 T 16 contiguous bytes), six threads of warp 1.
+    // The activation epilogues keep only one 16-column block (32 B per thread, 16 KB per SM) of these loads in flight — the kernel
+    // is at 128 registers — so out of HBM they run at ~11 B/clk; issued one phase ahead they are L2 hits.
+    auto prefetch_saved = [&](const unsigned char* base, int slab) {
+        if (tid >= 32 && tid < 38 && slab < a.nslab)
+            l2_prefetch(base + tile_off(slab, 24, T, 0, 0) + (size_t)(tid - 32) * T * 64, (uint32_t)(T * 64));
+    };
     stagger_start(112000);  // cycles per work item (profiles/r02e_phases.txt)
     int it_ = 0;
     for (int slab = blockIdx.x; slab < a.nslab; slab += gridDim.x, ++it_) {
@@ -232,6 +239,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         wait_mma();
         NBSS_TICK(0, 2, it_);
         if (tid == 0) load_image(ws0, a.img + IMG_WC2T, IMG_WC_BYTES, bar_w0);
+        prefetch_saved(a.c2, slab);  // needed by E2, one MMA phase from now
         silu_epilogue(a.c3, a.g_c3, a.s4, slab);
         end_epilogue();
         NBSS_TICK(0, 3, it_);
@@ -239,6 +247,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         convT_phase(w1a, bar_w1, ph_w1);
         NBSS_TICK(0, 4, it_);
         if (tid == 0) load_image(ws1, a.img + IMG_WC1T, IMG_WC_BYTES, bar_w1);
+        prefetch_saved(a.c1, slab);  // E3
         {
             // GroupNorm + SiLU backward in two sweeps over the thread's 96 accumulator columns; the second sweep needs NO global
             // reads: sweep A parks the saved c2 bits in the G tile (dead after the conv^T MMAs) and writes
@@ -350,6 +359,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         // ---- B3: d s2 = conv2^T(g c2)
         convT_phase(w0a, bar_w0, ph_w0);
         NBSS_TICK(0, 6, it_);
+        prefetch_saved(a.a1, slab);  // E4
         if (tid == 0) load_image(ws0, a.img + IMG_W1T, IMG_W2_BYTES, bar_w0);
         silu_epilogue(a.c1, a.g_c1, a.s2, slab);
         end_epilogue();
@@ -357,6 +367,10 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         // ---- B4: d s1 = conv1^T(g c1)
         convT_phase(w1a, bar_w1, ph_w1);
         NBSS_TICK(0, 8, it_);
+        // E5b of this slab reads x (fp32); the next slab starts with dy and its E1 reads c3
+        if (tid >= 38 && tid < 44) l2_prefetch_slab(a.x + (size_t)slab * T * kH, T, tid - 38);
+        if (tid >= 44 && tid < 50 && slab + (int)gridDim.x < a.nslab) l2_prefetch_slab(a.dy + (size_t)(slab + gridDim.x) * T * kH, T, tid - 44);
+        prefetch_saved(a.c3, slab + gridDim.x);
         silu_epilogue(a.a1, a.g_a1, a.s1, slab);
         end_epilogue();
         NBSS_TICK(0, 9, it_);

@@ -31,7 +31,7 @@ NAMES = {
     "mhsa_fwd": {0: ["stage LN(x)", "KV MMA wait", "E1 K|V out", "Q MMA wait", "(heads)", "out-proj D->smem", "residual out"]},
     "mhsa_bwd": {0: ["stage dy", "dO MMA wait", "E0 dO, delta"], 1: ["dQKV load + MMA wait", "D->smem", "LN bwd + out"]},
     "fconv_tc": {0: ["stage LN(x)", "conv MMA wait", "E1 PReLU", "E2 residual out"],
-                 1: ["stage dy (warp 0)", "stage LN(x) + sync", "conv MMA wait", "E-A dc", "wgrad MMA wait", "wgrad read-out", "dgrad MMA wait", "E-B1 dh", "E-B2 LN bwd + out"]},
+                 1: ["stage LN(x) (warp 0)", "stage dy + sync", "conv MMA wait", "E-A dc", "wgrad MMA wait", "wgrad read-out", "dgrad MMA wait", "E-B1 dh", "E-B2 LN bwd + out"]},
 }
 
 

@@ -116,14 +116,15 @@ int nbss_nbc2_ffn_b(const float* x, float* y, int nslab, int T, int F, const flo
 /* ---- narrow-band block, backward (tcgen05); autograd of the above -------------------------------- */
 int nbss_ffn_bwd(const float* x, const float* dy, float* dx, int nslab, int T, const float* ln_w, const float* gn_w,
                  const float* gn_b, const float* ln_stats, const float* gn_stats, const void* layer_img, const void* a1,
-                 const void* c1, const void* c2, const void* c3, void* g_a1, void* g_c1, void* g_c2, void* g_c3, void* s1,
-                 void* s2, void* s3, void* s4, float* d_lnw, float* d_lnb, float* d_gnw, float* d_gnb, int fmt, int* err,
-                 void* stream);
+                 const void* c1, const void* c2, const void* c3, void* g_a1, void* g_c1, void* g_c2, void* g_c3,
+                 float* d_lnw, float* d_lnb, float* d_gnw, float* d_gnb, int fmt, int* err, void* stream);
+/* a1, c1, c2, c3: the forward's saved fp16 pre-activations; the activation operands SiLU(.) / SiLU(GroupNorm(c2)) of the weight
+ * gradients are recomputed from them inside the kernel (gn_stats [nslab,8,2], gn_w / gn_b [192]) */
 int nbss_ffn_wgrad(const float* x, const float* dy, int nslab, int T, const float* ln_w, const float* ln_b,
-                   const void* g_a1, const void* g_c1, const void* g_c2, const void* g_c3, const void* s1, const void* s2,
-                   const void* s3, const void* s4, float* dW1, float* db1, float* dWc1, float* dbc1, float* dWc2,
-                   float* dbc2, float* dWc3, float* dbc3, float* dW2, float* db2, int fmt_g, int fmt_a, int* err,
-                   void* stream);
+                   const void* g_a1, const void* g_c1, const void* g_c2, const void* g_c3, const void* a1, const void* c1,
+                   const void* c2, const void* c3, const float* gn_stats, const float* gn_w, const float* gn_b, float* dW1,
+                   float* db1, float* dWc1, float* dbc1, float* dWc2, float* dbc2, float* dWc3, float* dbc3, float* dW2,
+                   float* db2, int fmt_g, int fmt_a, int* err, void* stream);
 int nbss_mhsa_bwd(const float* x, const float* dy, float* dx, int nslab, int T, const float* ln_w, const float* ln_stats,
                   const void* layer_img, const void* qkv, const void* o, const float* lse, void* dqkv, float* d_lnw,
                   float* d_lnb, int fmt_g, int* err, void* stream);

@@ -8,8 +8,9 @@
 //   B3 d s2 = conv2^T(g c2)                           E4 g(a1) = D * SiLU'(a1)              -> G
 //   B4 d s1 = conv1^T(g c1)                           E5 LayerNorm backward, dx = dy + ...
 //   B5 d ln = g(a1) W1      (K=192, N=96)
-// Every E-phase also streams out, for the weight-gradient kernels (wgrad.cu), the gradient operand g(.) and the
-// recomputed activation operand s(.) = SiLU(.) as 16-bit [n,192] tensors.  Column sums needed for the affine
+// Every E-phase also streams out, for the weight-gradient kernels (wgrad.cu), the gradient operand g(.) as a 16-bit [n,192]
+// tensor; the activation operand s(.) = SiLU(.) is recomputed by wgrad from the forward's saved pre-activation (it used to be
+// written here too: 1.6 GB of the kernel's 6.3 GB of HBM traffic per launch).  Column sums needed for the affine
 // parameters of LN / GN are formed with warp transposing reductions and accumulated in shared memory.
 #include "slab.cuh"
 
@@ -26,7 +27,6 @@ struct FfnBwdArgs {
     const unsigned char* img;
     const unsigned char *a1, *c1, *c2, *c3;   // fp16 [n,192]
     unsigned char *g_a1, *g_c1, *g_c2, *g_c3;  // 16-bit (FMT) [n,192] gradients wrt the pre-activations
-    unsigned char *s1, *s2, *s3, *s4;          // 16-bit (FMT) [n,192] activations SiLU(.) (wgrad operands)
     float *d_lnw, *d_lnb, *d_gnw, *d_gnb;      // accumulated with atomics
     int* err;
 };
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
     };
     // g = D * SiLU'(c), s = SiLU(c): the three plain activation epilogues
     // one 16-column block: g = D * SiLU'(c) -> G tile + global, s = SiLU(c) -> global
-    auto silu_block = [&](const uint32_t (&r)[16], const uint4 (&cq)[2], int c0, unsigned char* gout, unsigned char* sout, int slab) {
+    auto silu_block = [&](const uint32_t (&r)[16], const uint4 (&cq)[2], int c0, unsigned char* gout, int slab) {
         float c[16], g[16];
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
@@ -159,7 +159,6 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
             const float cv = c[j];
             const float sg = sigmoidf_(cv);
             g[j] = __uint_as_float(r[j]) * sg * fmaf(cv, 1.f - sg, 1.f);
-            c[j] = cv * sg;
         }
         if (!wfull) {  // frames >= T: zero gradient rows (they are the transposed conv's zero padding)
 #pragma unroll
@@ -168,10 +167,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
             const uint4 gp = pack8<FMT>(g + 8 * cc);
-            if (valid) {
-                *reinterpret_cast<uint4*>(sout + tile_off(slab, 24, T, c0 / 8 + cc, t)) = pack8<FMT>(c + 8 * cc);
-                *reinterpret_cast<uint4*>(gout + tile_off(slab, 24, T, c0 / 8 + cc, t)) = gp;
-            }
+            if (valid) *reinterpret_cast<uint4*>(gout + tile_off(slab, 24, T, c0 / 8 + cc, t)) = gp;
             *reinterpret_cast<uint4*>(hrow + (c0 / 8 + cc) * kCS) = gp;
         }
     };
@@ -183,7 +179,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
     };
     // the three plain activation epilogues: TMEM loads and the global loads of the saved pre-activations are both
     // software-pipelined over two register buffers (the global loads are issued one 16-column block ahead)
-    auto silu_epilogue = [&](const unsigned char* csave, unsigned char* gout, unsigned char* sout, int slab) {
+    auto silu_epilogue = [&](const unsigned char* csave, unsigned char* gout, int slab) {
         uint32_t ra[16], rb[16];
         uint4 ca[2], cb2[2];
         load_c(csave, slab, cb, ca);
@@ -193,13 +189,13 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         for (int c0 = cb; c0 < cb + 96; c0 += 32) {
             tmem_ld16(tacc + c0 + 16, rb);
             load_c(csave, slab, c0 + 16, cb2);
-            silu_block(ra, ca, c0, gout, sout, slab);
+            silu_block(ra, ca, c0, gout, slab);
             tmem_ld_wait();
             if (c0 + 32 < cb + 96) {
                 tmem_ld16(tacc + c0 + 32, ra);
                 load_c(csave, slab, c0 + 32, ca);
             }
-            silu_block(rb, cb2, c0 + 16, gout, sout, slab);
+            silu_block(rb, cb2, c0 + 16, gout, slab);
             tmem_ld_wait();
         }
     };
@@ -240,7 +236,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         NBSS_TICK(0, 2, it_);
         if (tid == 0) load_image(ws0, a.img + IMG_WC2T, IMG_WC_BYTES, bar_w0);
         prefetch_saved(a.c2, slab);  // needed by E2, one MMA phase from now
-        silu_epilogue(a.c3, a.g_c3, a.s4, slab);
+        silu_epilogue(a.c3, a.g_c3, slab);
         end_epilogue();
         NBSS_TICK(0, 3, it_);
         // ---- B2: d s3 = conv3^T(g c3) ; E2: GroupNorm + SiLU backward
@@ -289,14 +285,12 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
                         const float n = fmaf(xh, s_gng[c + j], s_gnb[c + j]);
                         const float sg = sigmoidf_(n);
                         const float d = __uint_as_float(r[8 * k + j]) * sg * fmaf(n, 1.f - sg, 1.f) * vmask;  // frames >= T carry no gradient
-                        cv[j] = n * sg;  // s3
                         const float dxh = d * s_gng[c + j];
                         s1 += dxh;
                         s2 = fmaf(dxh, xh, s2);
                         dn[j] = __float_as_uint(d);
                     }
                     tmem_st8(tacc + c, dn);
-                    if (valid) *reinterpret_cast<uint4*>(a.s3 + tile_off(slab, 24, T, c / 8, t)) = pack8<FMT>(cv);
                     *reinterpret_cast<uint4*>(hrow + (c / 8) * kCS) = cq[k];
                 }
                 s1 = warp_sum(s1);
@@ -361,7 +355,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         NBSS_TICK(0, 6, it_);
         prefetch_saved(a.a1, slab);  // E4
         if (tid == 0) load_image(ws0, a.img + IMG_W1T, IMG_W2_BYTES, bar_w0);
-        silu_epilogue(a.c1, a.g_c1, a.s2, slab);
+        silu_epilogue(a.c1, a.g_c1, slab);
         end_epilogue();
         NBSS_TICK(0, 7, it_);
         // ---- B4: d s1 = conv1^T(g c1)
@@ -371,7 +365,7 @@ __global__ void __launch_bounds__(kFfnBwdThreads, 1) ffn_bwd_kernel(FfnBwdArgs a
         if (tid >= 38 && tid < 44) l2_prefetch_slab(a.x + (size_t)slab * T * kH, T, tid - 38);
         if (tid >= 44 && tid < 50 && slab + (int)gridDim.x < a.nslab) l2_prefetch_slab(a.dy + (size_t)(slab + gridDim.x) * T * kH, T, tid - 44);
         prefetch_saved(a.c3, slab + gridDim.x);
-        silu_epilogue(a.a1, a.g_a1, a.s1, slab);
+        silu_epilogue(a.a1, a.g_a1, slab);
         end_epilogue();
         NBSS_TICK(0, 9, it_);
         // ---- B5: d ln = g(a1) W1 ; E5: LayerNorm backward + residual
@@ -429,18 +423,18 @@ NBSS_PHASE_READER(nbss_debug_phases_ffn_bwd)
 extern "C" int nbss_ffn_bwd(const float* x, const float* dy, float* dx, int nslab, int T, const float* ln_w,
                             const float* gn_w, const float* gn_b, const float* ln_stats, const float* gn_stats,
                             const void* layer_img, const void* a1, const void* c1, const void* c2, const void* c3,
-                            void* g_a1, void* g_c1, void* g_c2, void* g_c3, void* s1, void* s2, void* s3, void* s4,
+                            void* g_a1, void* g_c1, void* g_c2, void* g_c3,
                             float* d_lnw, float* d_lnb, float* d_gnw, float* d_gnb, int fmt, int* err, void* stream) {
     using namespace nbss;
     if (!x || !dy || !dx || !ln_w || !gn_w || !gn_b || !ln_stats || !gn_stats || !layer_img || !a1 || !c1 || !c2 || !c3 ||
-        !g_a1 || !g_c1 || !g_c2 || !g_c3 || !s1 || !s2 || !s3 || !s4 || !d_lnw || !d_lnb || !d_gnw || !d_gnb)
+        !g_a1 || !g_c1 || !g_c2 || !g_c3 || !d_lnw || !d_lnb || !d_gnw || !d_gnb)
         return NBSS_ERR_NULL;
     if (T < 1 || T > kTMax || nslab < 1) return NBSS_ERR_SHAPE;
     if (fmt != FMT_F16 && fmt != FMT_BF16) return NBSS_ERR_UNSUPPORTED;
     FfnBwdArgs a{x, dy, dx, nslab, T, ln_w, gn_w, gn_b, ln_stats, gn_stats, (const unsigned char*)layer_img,
                  (const unsigned char*)a1, (const unsigned char*)c1, (const unsigned char*)c2, (const unsigned char*)c3,
                  (unsigned char*)g_a1, (unsigned char*)g_c1, (unsigned char*)g_c2, (unsigned char*)g_c3,
-                 (unsigned char*)s1, (unsigned char*)s2, (unsigned char*)s3, (unsigned char*)s4, d_lnw, d_lnb, d_gnw, d_gnb, err};
+                 d_lnw, d_lnb, d_gnw, d_gnb, err};
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -23,6 +23,9 @@ struct WgJob {
     int g_fp32, g_cols, g_c0, g_chunks, g_alloc;  // g_fp32: fp32 [n,96]; else 16-bit [n,g_cols], features [g_c0, g_c0+8*g_chunks)
     int a_ln, a_cols, a_c0, a_chunks, a_row_off;  // a_ln: fp32 x [n,96] through LayerNorm; ones chunks at [a_chunks, a_chunks+2)
     int dbl;                                      // both operands arrive by TMA: two tile sets, loads of slab i+1 overlap MMAs of slab i
+    int a_silu;                                   // the activation operand is RECOMPUTED from the forward's saved fp16 pre-activation (act points at
+                                                  // it): 1 = SiLU(.), 2 = SiLU(GroupNorm(.)); the tile is transformed in place after its TMA copy
+    const float *gn_stats, *gn_w, *gn_b;          // a_silu == 2: [nslab][8][2] (mean, rstd), affine [192]
     int nmma, nout;
     WgMma mma[6];
     WgOut out[8];
@@ -34,6 +37,38 @@ struct WgArgs {
 };
 
 constexpr int kWgThreads = 512;  // 16 warps: the fp32 operands of the pointwise jobs are staged by all of them
+
+// In-place transform of a landed activation tile: saved pre-activation (fp16) -> s = SiLU(.) resp. SiLU(GroupNorm(.)) in FMT_A, with
+// exactly the arithmetic ffn_bwd uses for its gradient (same sigmoid, same rounding points).  ffn_bwd therefore does not write the
+// s1..s4 operand tensors any more (1.6 GB less HBM traffic per launch at batch 32).  Threads tidx of nthr walk 16-byte pieces, rows
+// fastest (conflict-free shared-memory accesses).
+template <int FMT_A>
+__device__ __forceinline__ void wg_silu_tile(unsigned char* at, const WgJob& J, int slab, int T, int tidx, int nthr) {
+    const int total = J.a_chunks << 8;  // pieces indexed (chunk, row) with 256 row slots per chunk: no division
+    for (int i = tidx; i < total; i += nthr) {
+        const int c = i >> 8, r = i & 255;
+        if (r >= T) continue;
+        uint4* p = reinterpret_cast<uint4*>(at + (size_t)c * kCS + (size_t)(J.a_row_off + r) * 16);
+        const uint4 q = *p;
+        float v[8];
+        unpack_f16x2(q.x, v[0], v[1]);
+        unpack_f16x2(q.y, v[2], v[3]);
+        unpack_f16x2(q.z, v[4], v[5]);
+        unpack_f16x2(q.w, v[6], v[7]);
+        if (J.a_silu == 2) {
+            const int ch = J.a_c0 + 8 * c, g = ch / kGC;  // a 16-byte piece never straddles a group (24 = 3 x 8)
+            const float2 st = __ldg(reinterpret_cast<const float2*>(J.gn_stats + (size_t)slab * 16) + g);  // (mean, rstd)
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(J.gn_w + ch)), w1 = __ldg(reinterpret_cast<const float4*>(J.gn_w + ch) + 1);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(J.gn_b + ch)), b1 = __ldg(reinterpret_cast<const float4*>(J.gn_b + ch) + 1);
+            const float gw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w}, gb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf((v[j] - st.x) * st.y, gw[j], gb[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = v[j] * sigmoidf_(v[j]);
+        *p = pack8<FMT_A>(v);
+    }
+}
 
 template <int FMT_G, int FMT_A>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(WgArgs args) {
@@ -91,7 +126,50 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(WgArgs args) {
             }
         }
     };
-    if (J.dbl) {
+    if (J.dbl && J.a_silu) {
+        // ---- pipelined path with a recomputed activation operand: warp 0 drives loads and MMAs as below; the other 15 warps turn the
+        //      landed pre-activation tile into the operand while the previous slab's MMAs and the next slab's copies are in flight
+        const bool leader = warp == 0 && elect_one();
+        auto issue_loads = [&](int slab, int set) {
+            unsigned char* g0 = smem + (size_t)set * set_bytes;
+            uint64_t* bar = set ? &bar_ld2 : &bar_ld;
+            bulk_load_chunks(g0, kCS, 0, reinterpret_cast<const unsigned char*>(J.g) + tile_off(slab, J.g_cols / 8, T, J.g_c0 / 8, 0),
+                             J.g_chunks, T, bar);
+            bulk_load_chunks(g0 + (size_t)J.g_alloc * kCS, kCS, J.a_row_off,
+                             reinterpret_cast<const unsigned char*>(J.act) + tile_off(slab, J.a_cols / 8, T, J.a_c0 / 8, 0), J.a_chunks, T, bar);
+        };
+        uint32_t phl = 0;  // bit s: phase of tile set s's load barrier
+        int k = 0;
+        if (leader && (int)blockIdx.x < args.nslab) issue_loads(blockIdx.x, 0);
+        for (int slab = blockIdx.x; slab < args.nslab; slab += gridDim.x, ++k) {
+            const int set = k & 1, nxt = slab + gridDim.x;
+            if (warp == 0) {
+                if (k >= 1) {  // MMAs of the previous slab (other tile set) are done: its tiles may be overwritten
+                    mbar_wait(&bar_mma, ph, args.err);
+                    ph ^= 1;
+                }
+                if (leader && nxt < args.nslab) issue_loads(nxt, set ^ 1);
+            }
+            mbar_wait(set ? &bar_ld2 : &bar_ld, (phl >> set) & 1u, args.err);
+            phl ^= 1u << set;
+            if (warp != 0)
+                wg_silu_tile<FMT_A>(smem + (size_t)set * set_bytes + (size_t)J.g_alloc * kCS, J, slab, T, tid - 32, kWgThreads - 32);
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (warp == 0) {
+                tc_fence_after();
+                const uint32_t ga = gta + set * set_bytes;
+                issue_mmas(ga, ga + J.g_alloc * kCS, k == 0, leader);
+                if (leader) umma_commit(&bar_mma);
+                __syncwarp();
+            }
+        }
+        if (warp == 0 && k >= 1) mbar_wait(&bar_mma, ph, args.err);
+        first = k == 0;
+        __syncthreads();
+        tc_fence_after();
+    } else if (J.dbl) {
         // ---- pipelined path (both operands by TMA): warp 0 drives loads and MMAs (one elected lane issues), two tile sets
         if (warp == 0) {
             const bool leader = elect_one();
@@ -142,12 +220,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(WgArgs args) {
         }
         if (J.g_fp32) stage_rows96<FMT_G, false>(reinterpret_cast<const float*>(J.g) + row0 * kH, T, gt, 0, nullptr, nullptr, warp, lane, nullptr, kWgThreads / 32);
         if (J.a_ln) stage_rows96<FMT_A, true>(reinterpret_cast<const float*>(J.act) + row0 * kH, T, at, J.a_row_off, s_ln, s_ln + 96, warp, lane, nullptr, kWgThreads / 32);
+        if (J.a_silu) {  // every thread waits for the copies, then the pre-activation tile becomes the operand in place
+            mbar_wait(&bar_ld, ph_ld, args.err);
+            ph_ld ^= 1;
+            wg_silu_tile<FMT_A>(at, J, slab, T, tid, kWgThreads);
+        }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
         if (warp == 0) {
             tc_fence_after();
-            if (n_bulk > 0) { mbar_wait(&bar_ld, ph_ld, args.err); ph_ld ^= 1; }
+            if (n_bulk > 0 && !J.a_silu) { mbar_wait(&bar_ld, ph_ld, args.err); ph_ld ^= 1; }
             const bool leader = elect_one();
             issue_mmas(gta, ata, first, leader);
             if (leader) umma_commit(&bar_mma);
@@ -230,15 +313,18 @@ static void add_out(WgJob& j, float* dst, int col, int lane0, int nl, int nc, in
 
 using namespace nbss;
 
-// T-ConvFFN weight gradients.  g_* / s_*: 16-bit [n,192] tensors written by nbss_ffn_bwd (formats fmt_g / fmt_a).
+// T-ConvFFN weight gradients.  g_*: 16-bit [n,192] gradient operands written by nbss_ffn_bwd (fmt_g); the activation operands
+// s1 = SiLU(a1), s2 = SiLU(c1), s3 = SiLU(GroupNorm(c2)), s4 = SiLU(c3) are recomputed (fmt_a) from the forward's saved fp16
+// pre-activations a1, c1, c2, c3 and the GroupNorm statistics / affine (wg_silu_tile).
 // Accumulates into dW1 [192,96], db1, dWc{1,2,3} [192,24,3], dbc{1,2,3}, dW2 [96,192], db2 (all fp32, += semantics).
 extern "C" int nbss_ffn_wgrad(const float* x, const float* dy, int nslab, int T, const float* ln_w, const float* ln_b,
-                              const void* g_a1, const void* g_c1, const void* g_c2, const void* g_c3, const void* s1,
-                              const void* s2, const void* s3, const void* s4, float* dW1, float* db1, float* dWc1,
+                              const void* g_a1, const void* g_c1, const void* g_c2, const void* g_c3, const void* a1,
+                              const void* c1, const void* c2, const void* c3, const float* gn_stats, const float* gn_w,
+                              const float* gn_b, float* dW1, float* db1, float* dWc1,
                               float* dbc1, float* dWc2, float* dbc2, float* dWc3, float* dbc3, float* dW2, float* db2,
                               int fmt_g, int fmt_a, int* err, void* stream) {
-    if (!x || !dy || !ln_w || !ln_b || !g_a1 || !g_c1 || !g_c2 || !g_c3 || !s1 || !s2 || !s3 || !s4 || !dW1 || !db1 || !dWc1 ||
-        !dbc1 || !dWc2 || !dbc2 || !dWc3 || !dbc3 || !dW2 || !db2)
+    if (!x || !dy || !ln_w || !ln_b || !g_a1 || !g_c1 || !g_c2 || !g_c3 || !a1 || !c1 || !c2 || !c3 || !gn_stats || !gn_w || !gn_b ||
+        !dW1 || !db1 || !dWc1 || !dbc1 || !dWc2 || !dbc2 || !dWc3 || !dbc3 || !dW2 || !db2)
         return NBSS_ERR_NULL;
     if (T < 1 || T > kTMax || nslab < 1) return NBSS_ERR_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -249,7 +335,7 @@ extern "C" int nbss_ffn_wgrad(const float* x, const float* dy, int nslab, int T,
         // pw2: dW2[o<96, i<192] = dy^T s4
         WgJob& j = a.job[0];
         j.g = dy; j.g_fp32 = 1; j.g_alloc = 16;
-        j.act = s4; j.a_cols = 192; j.a_c0 = 0; j.a_chunks = 24; j.a_row_off = 0;
+        j.act = c3; j.a_silu = 1; j.a_cols = 192; j.a_c0 = 0; j.a_chunks = 24; j.a_row_off = 0;
         add_mma(j, 0, 0, 192, 0, 0);
         add_mma(j, 0, 24, 16, 192, 0);
         add_out(j, dW2, 0, 0, 96, 192, 0, 192, 0);
@@ -271,7 +357,7 @@ extern "C" int nbss_ffn_wgrad(const float* x, const float* dy, int nslab, int T,
     }
     // ---- launches 2,3: the three grouped convs, two channel halves each (3 jobs per launch)
     const void* gs[3] = {g_c1, g_c2, g_c3};
-    const void* as[3] = {s1, s2, s3};
+    const void* as[3] = {a1, c1, c2};
     float* dWs[3] = {dWc1, dWc2, dWc3};
     float* dbs[3] = {dbc1, dbc2, dbc3};
     for (int half = 0; half < 2; ++half) {
@@ -282,6 +368,8 @@ extern "C" int nbss_ffn_wgrad(const float* x, const float* dy, int nslab, int T,
             j.g = gs[c]; j.g_fp32 = 0; j.g_cols = 192; j.g_c0 = 96 * half; j.g_chunks = 12; j.g_alloc = 12;  // M window rows 0..95
             j.dbl = 1;
             j.act = as[c]; j.a_cols = 192; j.a_c0 = 96 * half; j.a_chunks = 12; j.a_row_off = 1;
+            j.a_silu = c == 2 ? 2 : 1;
+            j.gn_stats = gn_stats; j.gn_w = gn_w; j.gn_b = gn_b;
             const int l0 = 0;  // TMEM lane of output channel 96*half (window starts at the half's first channel)
             for (int tap = 0; tap < 3; ++tap) {
                 add_mma(j, 0, 0, 96, 96 * tap, tap);

@@ -490,20 +490,21 @@ def ffn_bwd(x: Tensor, dy: Tensor, saves, gn_stats: Tensor, P, pre: str, img: Te
     a1, c1, c2, c3, ln_stats = saves
     dt = torch.bfloat16 if fmt_g == FMT_BF16 else torch.float16
     gbuf = [torch.empty(n, 192, dtype=dt, device=x.device) for _ in range(4)]  # g_a1, g_c1, g_c2, g_c3
-    sbuf = [torch.empty(n, 192, dtype=dt, device=x.device) for _ in range(4)]  # s1..s4
     dx = torch.empty_like(x)
     err = device_err_flag(x.device)
     t = pre + "tconvffn."
     st = _K("nbss_ffn_bwd")(
         ptr(x), ptr(dy), ptr(dx), B * F, T, ptr(_f32c(P[t + "0.weight"])), ptr(_f32c(P[t + "6.weight"])), ptr(_f32c(P[t + "6.bias"])),
         ptr(ln_stats), ptr(gn_stats), ptr(img), ptr(a1), ptr(c1), ptr(c2), ptr(c3), ptr(gbuf[0]), ptr(gbuf[1]), ptr(gbuf[2]),
-        ptr(gbuf[3]), ptr(sbuf[0]), ptr(sbuf[1]), ptr(sbuf[2]), ptr(sbuf[3]), ptr(G[t + "0.weight"]), ptr(G[t + "0.bias"]),
-        ptr(G[t + "6.weight"]), ptr(G[t + "6.bias"]), fmt_g, ptr(err), stream_ptr())
+        ptr(gbuf[3]), ptr(G[t + "0.weight"]), ptr(G[t + "0.bias"]), ptr(G[t + "6.weight"]), ptr(G[t + "6.bias"]), fmt_g, ptr(err),
+        stream_ptr())
     check(st, "nbss_ffn_bwd")
-    with _side_stream((x, dy, gbuf, sbuf)):
+    # the weight gradients recompute their activation operands SiLU(.) from the saved pre-activations (kept alive for the side stream)
+    with _side_stream((x, dy, gbuf, (a1, c1, c2, c3), gn_stats)):
         st = _K("nbss_ffn_wgrad")(
             ptr(x), ptr(dy), B * F, T, ptr(_f32c(P[t + "0.weight"])), ptr(_f32c(P[t + "0.bias"])), ptr(gbuf[0]), ptr(gbuf[1]),
-            ptr(gbuf[2]), ptr(gbuf[3]), ptr(sbuf[0]), ptr(sbuf[1]), ptr(sbuf[2]), ptr(sbuf[3]), ptr(G[t + "1.weight"]),
+            ptr(gbuf[2]), ptr(gbuf[3]), ptr(a1), ptr(c1), ptr(c2), ptr(c3), ptr(gn_stats), ptr(_f32c(P[t + "6.weight"])),
+            ptr(_f32c(P[t + "6.bias"])), ptr(G[t + "1.weight"]),
             ptr(G[t + "1.bias"]), ptr(G[t + "3.weight"]), ptr(G[t + "3.bias"]), ptr(G[t + "5.weight"]), ptr(G[t + "5.bias"]),
             ptr(G[t + "8.weight"]), ptr(G[t + "8.bias"]), ptr(G[t + "10.weight"]), ptr(G[t + "10.bias"]), fmt_g, fmt_g, ptr(err),
             stream_ptr())

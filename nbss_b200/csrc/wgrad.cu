@@ -150,10 +150,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(WgArgs args) {
                 }
                 if (leader && nxt < args.nslab) issue_loads(nxt, set ^ 1);
             }
-            mbar_wait(set ? &bar_ld2 : &bar_ld, (phl >> set) & 1u, args.err);
+            // ONE warp (warp 1: another scheduler than the issuing warp 0) polls the copy's mbarrier and releases the other transform
+            // warps through a named hardware barrier, so that 15 spinning warps do not compete with warp 0's long serial TMA / MMA
+            // issue sequences.  (Measured: the all-warp loop costs +0.05 ms per launch against the warp-0-only loop even with an EMPTY
+            // transform, the arithmetic another +0.045 ms; polling by one warp instead of fifteen recovers 0.005 ms of it.)
+            if (warp == 1) mbar_wait(set ? &bar_ld2 : &bar_ld, (phl >> set) & 1u, args.err);
             phl ^= 1u << set;
-            if (warp != 0)
+            if (warp != 0) {
+                asm volatile("bar.sync 1, %0;" ::"n"(kWgThreads - 32) : "memory");
                 wg_silu_tile<FMT_A>(smem + (size_t)set * set_bytes + (size_t)J.g_alloc * kCS, J, slab, T, tid - 32, kWgThreads - 32);
+            }
             fence_async_smem();
             tc_fence_before();
             __syncthreads();

@@ -355,8 +355,13 @@ def rel_l2(a: Tensor, b: Tensor) -> float:
 # ----------------------------------------------------------------------------------------------------------------------
 # loss next to the path.  models/io/loss.py:21-29 (neg_si_sdr) and :95-118 (Loss.forward with pit)
 # call torchmetrics.functional.audio (scale_invariant_signal_distortion_ratio, permutation_invariant_training), a
-# third-party dependency that is absent from /root/reference and unpinned (requirements.txt:2).  Restated from the
-# published torchmetrics algorithm; PARITY UNPINNED (no golden vector of the reference exists for it).
+# third-party dependency that is absent from /root/reference and not version-pinned there (requirements.txt:2,
+# `torchmetrics[audio]`).  Restated from the published torchmetrics algorithm (functional/audio/sdr.py: alpha =
+# (<p,t> + eps) / (<t,t> + eps), 10 log10((|alpha t|^2 + eps) / (|alpha t - p|^2 + eps)), eps = finfo(dtype).eps;
+# functional/audio/pit.py: permutation-wise search, eval_func min/max over the mean metric of each permutation;
+# functional/audio/snr.py).  PINNED to the known-answer vectors torchmetrics publishes in the doctests of those three
+# functions (tests/golden/torchmetrics_kat.json, tests/test_oracle_golden.py::test_loss_oracle_torchmetrics_known_answers);
+# the reference itself holds no test or vector for its loss module.
 # ----------------------------------------------------------------------------------------------------------------------
 def si_sdr(preds: Tensor, target: Tensor, zero_mean: bool = False) -> Tensor:
     eps = torch.finfo(preds.dtype).eps
@@ -367,6 +372,16 @@ def si_sdr(preds: Tensor, target: Tensor, zero_mean: bool = False) -> Tensor:
     ts = alpha * target
     noise = ts - preds
     return 10 * torch.log10(((ts * ts).sum(-1) + eps) / ((noise * noise).sum(-1) + eps))
+
+
+def snr(preds: Tensor, target: Tensor, zero_mean: bool = False) -> Tensor:
+    """torchmetrics signal_noise_ratio (what models/io/loss.py:32-41 neg_snr negates): 10 log10((|t|^2 + eps) / (|t - p|^2 + eps))."""
+    eps = torch.finfo(preds.dtype).eps
+    if zero_mean:
+        preds = preds - preds.mean(-1, keepdim=True)
+        target = target - target.mean(-1, keepdim=True)
+    noise = target - preds
+    return 10 * torch.log10(((target * target).sum(-1) + eps) / ((noise * noise).sum(-1) + eps))
 
 
 def neg_si_sdr_pit(est: Tensor, ref: Tensor, zero_mean: bool = False):

@@ -171,6 +171,23 @@ def test_si_sdr_pit_loss(B, Ts, zero_mean):
 
 
 @pytest.mark.gpu
+def test_si_sdr_pit_loss_torchmetrics_known_answer():
+    """csrc/loss.cu on the vector torchmetrics publishes in the doctest of permutation_invariant_training (the library
+    models/io/loss.py:5-9 calls): best SI-SDR -5.1091 dB with the identity permutation (tests/golden/torchmetrics_kat.json)."""
+    import json
+    import os
+
+    from nbss_b200.loss import neg_si_sdr_pit
+
+    k = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "torchmetrics_kat.json")))["pit_si_sdr_max"]
+    loss, loss_b, perms = neg_si_sdr_pit(torch.tensor(k["preds"]).cuda(), torch.tensor(k["target"]).cuda())
+    torch.cuda.synchronize()
+    assert abs(loss.item() + k["best_metric"][0]) < 2e-4
+    assert abs(loss_b.cpu()[0].item() + k["best_metric"][0]) < 2e-4
+    assert perms.cpu().tolist() == k["best_perm"]
+
+
+@pytest.mark.gpu
 def test_flat_clip_adam_matches_torch():
     """nbss_clip_adam (two launches over the flat gradient buffer) against clip_grad_norm_(5) + torch.optim.Adam(1e-3) fed
     with the SAME gradients (Adam's first steps are sign-like, so independently computed gradients would not do)."""

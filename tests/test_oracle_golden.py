@@ -171,6 +171,25 @@ def test_oracle_si_sdr_pit_properties():
     assert torch.allclose(O.si_sdr(est + 0.3, ref - 0.1, zero_mean=True), centred, atol=1e-9)
 
 
+def test_loss_oracle_torchmetrics_known_answers():
+    """Pins the loss restatement (oracle si_sdr / snr / neg_si_sdr_pit) to the known-answer vectors torchmetrics publishes in
+    the doctests of the three functions models/io/loss.py:5-9 imports (tests/golden/torchmetrics_kat.json; 4 printed decimals)."""
+    import json
+    import os
+
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "torchmetrics_kat.json")))
+    k = kat["si_sdr"]
+    assert abs(O.si_sdr(torch.tensor(k["preds"]), torch.tensor(k["target"])).item() - k["value"]) < 5e-5
+    k = kat["snr"]
+    assert abs(O.snr(torch.tensor(k["preds"]), torch.tensor(k["target"])).item() - k["value"]) < 5e-5
+    k = kat["pit_si_sdr_max"]
+    # torchmetrics maximises si_sdr over the permutations; the reference minimises neg_si_sdr (loss.py:109-110): same optimum
+    loss, loss_b, perms = O.neg_si_sdr_pit(torch.tensor(k["preds"]), torch.tensor(k["target"]))
+    assert torch.allclose(-loss_b, torch.tensor(k["best_metric"]), atol=5e-5)
+    assert perms.tolist() == k["best_perm"]
+    assert abs(loss.item() + k["best_metric"][0]) < 5e-5
+
+
 def test_eager_opset_restatement_matches_oracle():
     """oracle/eager_gpu.py (the reference's op-set as torch.nn.functional calls: what bench.py times on the GPU as the
     eager baseline and on the host cores as the CPU arm) computes the same function as the pinned oracle: identical in

@@ -58,3 +58,16 @@ def stream_ptr() -> ctypes.c_void_p:
     import torch
 
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def device_of(t):
+    """Context: make the CUDA device of tensor `t` current for the enclosed launches (the wrappers take the stream of the
+    CURRENT device, so a module called with tensors of another device must switch first; a no-op when it already is, and for
+    CPU tensors, which the wrappers reject themselves)."""
+    import contextlib
+
+    import torch
+
+    if t is not None and getattr(t, "is_cuda", False) and t.device.index != torch.cuda.current_device():
+        return torch.cuda.device(t.device)
+    return contextlib.nullcontext()

@@ -107,11 +107,12 @@ class NBC2(nn.Module):
         if F != self.num_freqs:
             raise ValueError(f"NBC2 was built for num_freqs={self.num_freqs} (GroupBatchNorm group size), got F={F}")
         P = {n: p.detach() for n, p in self.named_parameters()}
-        imgs = self._images(P)
-        h = ops.encoder_fwd(x.detach().float().contiguous(), P)
-        for i in range(len(self.sa_layers)):
-            h = ops.nbc2_block_fwd(h, P, f"sa_layers.{i}.", imgs[i], num_heads=self.n_heads, ws=self._ws)
-        return ops.decoder_fwd(h, P)
+        with ops._lib.device_of(x):
+            imgs = self._images(P)
+            h = ops.encoder_fwd(x.detach().float().contiguous(), P)
+            for i in range(len(self.sa_layers)):
+                h = ops.nbc2_block_fwd(h, P, f"sa_layers.{i}.", imgs[i], num_heads=self.n_heads, ws=self._ws)
+            return ops.decoder_fwd(h, P)
 
     def check_device_errors(self) -> None:
         for f in ops._ERR_FLAGS.values():

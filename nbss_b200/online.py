@@ -138,11 +138,12 @@ class OnlineSpatialNet(nn.Module):
         """One frame: x_t [B,F,Cin] -> y_t [B,F,Cout]; `state` is updated in place."""
         B, F, Cin = x_t.shape
         assert B == state.batch and F == self.num_freqs and Cin == self.dim_input, (x_t.shape, state.batch)
-        if state.graph is not None:
-            state.x_in.copy_(x_t, non_blocking=True)
-            state.graph.replay()
-            return state.y_out
-        return self._step_launches(x_t, state)
+        with _lib.device_of(state.h):
+            if state.graph is not None:
+                state.x_in.copy_(x_t, non_blocking=True)
+                state.graph.replay()
+                return state.y_out
+            return self._step_launches(x_t, state)
 
     def _step_launches(self, x_t: Tensor, state: OnlineState) -> Tensor:
         B, F, Cin = x_t.shape

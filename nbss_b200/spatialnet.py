@@ -281,7 +281,8 @@ class SpatialNet(nn.Module):
         if padding != "zeros": unsupported.append("padding")
         if dim_squeeze != 8: unsupported.append("dim_squeeze != 8")
         if unsupported:
-            raise NotImplementedError("nbss_b200.SpatialNet (round 1) supports the SpatialNet-small configuration only: " + ", ".join(unsupported))
+            raise NotImplementedError("nbss_b200.SpatialNet supports the SpatialNet-small layer widths only (DESIGN.md §1; the large model is "
+                                      "SURVEY §8f rank-4 work that is not built): " + ", ".join(unsupported))
         self.encoder = nn.Conv1d(dim_input, dim_hidden, encoder_kernel_size, stride=1, padding="same")
         full, layers = None, []
         for l in range(num_layers):
@@ -354,13 +355,14 @@ class SpatialNet(nn.Module):
 
     def forward(self, x: Tensor, return_attn_score: bool = False):
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        if needs_grad:
-            y = _SpatialNetFn.apply(self, x, *[p for _, p in self._unique_params()])
-        else:
-            self._poll_device_errors()
-            y, _, errs = self.engine.forward(self._param_dict(), x.detach().float().contiguous(), save=False)
-            self._last_errs = errs
-            self._post_device_error_check(x.device)
+        with ops._lib.device_of(x):  # launches go to the current stream of x's device (autograd sets it for the backward)
+            if needs_grad:
+                y = _SpatialNetFn.apply(self, x, *[p for _, p in self._unique_params()])
+            else:
+                self._poll_device_errors()
+                y, _, errs = self.engine.forward(self._param_dict(), x.detach().float().contiguous(), save=False)
+                self._last_errs = errs
+                self._post_device_error_check(x.device)
         if return_attn_score:
             return y, [None] * len(self.layers)  # the reference also returns None here (SpatialNet.py:97 quirk)
         return y

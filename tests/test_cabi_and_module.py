@@ -23,6 +23,44 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
 
 
+def test_cabi_error_behaviour_without_a_gpu():
+    """Every entry point validates its arguments BEFORE touching CUDA and answers with the status codes of include/nbss_b200.h
+    (-1 shape, -2 null pointer, -3 unsupported); nothing throws, nothing is launched — so this runs without a GPU.  The dummy
+    non-null addresses are never dereferenced on the host."""
+    import ctypes as C
+
+    L = _lib.lib()
+    nul, d = C.c_void_p(0), C.c_void_p(0x1000)
+    assert L.nbss_version() == 200
+    L.nbss_workspace_bytes.restype = C.c_longlong
+    assert L.nbss_workspace_bytes(32, 129, 250, 0) == 0
+    per_layer = L.nbss_workspace_bytes(32, 129, 250, 1)
+    assert 4.0e9 < per_layer < 9.0e9  # DESIGN.md §2: ~4.4 GB saved per layer at batch 32 + transient gradient operands
+    assert L.nbss_workspace_bytes(0, 129, 250, 1) == -1
+    L.nbss_layer_image_bytes.restype = C.c_uint
+    assert L.nbss_layer_image_bytes() == 626688            # csrc/layout.cuh IMG_LAYER_BYTES
+    L.nbss_fconv_image_bytes.restype = C.c_uint
+    assert L.nbss_fconv_image_bytes() == 2 * 46080          # forward + transposed F-conv images
+    # null pointers
+    assert L.nbss_mhsa_fwd(nul, d, 4, 250, d, d, d, d, d, nul, nul, nul, nul, 0, nul, nul) == -2
+    assert L.nbss_fconv_tc_fwd(d, nul, 1, 129, 250, d, d, d, d, d, 0, nul, nul) == -2
+    assert L.nbss_pack_layer_weights(d, d, d, nul, d, d, d, d, 0, 0, nul) == -2
+    assert L.nbss_sisdr_pit_fwd(nul, d, 1, 2, C.c_longlong(100), 0, d, d, nul, nul, nul, nul) == -2
+    # shapes: the training kernels hold one (b,f) slab of at most 256 frames per CTA
+    assert L.nbss_mhsa_fwd(d, d, 4, 257, d, d, d, d, d, nul, nul, nul, nul, 0, nul, nul) == -1
+    assert L.nbss_mhsa_fwd(d, d, 0, 250, d, d, d, d, d, nul, nul, nul, nul, 0, nul, nul) == -1
+    assert L.nbss_ffn_fwd(d, d, 4, 0, d, d, d, d, d, d, d, d, d, d, nul, nul, nul, nul, nul, nul, 0, nul, nul) == -1
+    assert L.nbss_fconv_tc_fwd(d, d, 0, 129, 250, d, d, d, d, d, 0, nul, nul) == -1
+    assert L.nbss_sisdr_pit_fwd(d, d, 0, 2, C.c_longlong(100), 0, d, d, nul, nul, nul, nul) == -1
+    # unsupported configurations
+    assert L.nbss_mhsa_fwd_nh(d, d, 4, 250, d, d, d, d, d, nul, nul, nul, nul, nul, 3, 0, nul, nul) == -3   # heads: 4 or 2
+    assert L.nbss_ffn_fwd(d, d, 4, 250, d, d, d, d, d, d, d, d, d, d, nul, nul, nul, nul, nul, nul, 2, nul, nul) == -3  # fmt
+    assert L.nbss_sisdr_pit_fwd(d, d, 1, 3, C.c_longlong(100), 0, d, d, nul, nul, nul, nul) == -3           # 2 speakers
+    # the Python wrapper turns a status into NbssError with the entry point's name
+    with pytest.raises(_lib.NbssError, match="nbss_mhsa_fwd.*shape"):
+        _lib.check(-1, "nbss_mhsa_fwd")
+
+
 def test_state_dict_contract_matches_reference_names_and_shapes():
     net = SpatialNet(dim_input=12, dim_output=4, dim_squeeze=8, num_layers=8, num_freqs=129, dim_hidden=96, dim_ffn=192, num_heads=4)
     sd = net.state_dict()

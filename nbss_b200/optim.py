@@ -62,6 +62,57 @@ class FlatClipAdam:
         # UMMA weight images must be rebuilt explicitly
         self.module.engine.invalidate_images()
 
+    # ------------------------------------------------------------------------------------------------ checkpoint / resume
+    # The reference's trainer saves and restores ``torch.optim.Adam``'s state inside the Lightning checkpoint
+    # (``optimizer_states``; models/utils/general_steps.py:243-271 builds the optimizer over ``self.parameters()``, i.e. the
+    # arch's parameters in registration order).  state_dict() / load_state_dict() speak that format, so a run can move between
+    # the reference's optimizer and this one in either direction.
+    def state_dict(self) -> dict:
+        state, off = {}, 0
+        step = self.step_count.detach().cpu().reshape(())  # torch.optim.Adam keeps `step` as a CPU scalar (non-capturable default)
+        for i, p in enumerate(self._params):
+            n = p.numel()
+            state[i] = {"step": step.clone(),
+                        "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
+            off += n
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+                 "params": list(range(len(self._params)))}
+        return {"state": state, "param_groups": [group], "max_norm": self.max_norm}
+
+    @torch.no_grad()
+    def load_state_dict(self, sd: dict) -> None:
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self._params):
+            raise ValueError(f"FlatClipAdam.load_state_dict: expected one param group over {len(self._params)} tensors "
+                             f"(the arch's parameters in registration order), got {[len(g['params']) for g in groups]}")
+        g = groups[0]
+        if g.get("weight_decay", 0) or g.get("amsgrad", False) or g.get("maximize", False):
+            raise NotImplementedError("FlatClipAdam implements plain Adam (no weight decay / amsgrad / maximize)")
+        self.lr, self.betas, self.eps = float(g["lr"]), tuple(float(b) for b in g["betas"]), float(g["eps"])
+        if "max_norm" in sd:
+            self.max_norm = float(sd["max_norm"])
+        state = sd.get("state", {})
+        if not state:  # an optimizer that has not stepped yet
+            self.exp_avg.zero_()
+            self.exp_avg_sq.zero_()
+            self.step_count.zero_()
+            return
+        steps, off = set(), 0
+        for i, (idx, p) in enumerate(zip(g["params"], self._params)):
+            st = state.get(idx, state.get(str(idx)))
+            n = p.numel()
+            if st is None or tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"FlatClipAdam.load_state_dict: state of parameter {i} is missing or has the wrong shape")
+            self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(float(st["step"]))
+            off += n
+        if len(steps) != 1:
+            raise ValueError(f"FlatClipAdam.load_state_dict: the parameters carry different step counts {sorted(steps)}")
+        self.step_count.fill_(steps.pop())
+
     def grad_norm(self) -> torch.Tensor:
         """Total gradient norm before clipping of the last step (device scalar), what clip_grad_norm_ returns."""
         return self.gnorm_sq.sqrt().float()

@@ -101,3 +101,53 @@ def test_same_init_as_reference_under_same_seed():
     assert list(rsd.keys()) == list(msd.keys())
     for k in rsd:
         assert torch.equal(rsd[k], msd[k]), k
+
+
+def test_flat_clip_adam_state_dict_speaks_torch_adam_format():
+    """CPU (host logic only; the update kernel itself is a GPU test): FlatClipAdam.state_dict() loads into torch.optim.Adam over
+    the same parameters and torch.optim.Adam's state_dict() loads back — the checkpoint / resume path of the reference's trainer
+    (Lightning stores optimizer.state_dict(), models/utils/general_steps.py:243-271)."""
+    from nbss_b200.optim import FlatClipAdam
+
+    net = SpatialNet(dim_input=12, dim_output=4, dim_squeeze=8, num_layers=1, num_freqs=17, dim_hidden=96, dim_ffn=192, num_heads=4)
+    params = [p for _, p in net._unique_params()]
+    n = sum(p.numel() for p in params)
+    opt = FlatClipAdam.__new__(FlatClipAdam)  # the constructor insists on CUDA parameters; the state logic does not
+    opt.module, opt._params, opt.n = net, params, n
+    opt.lr, opt.betas, opt.eps, opt.max_norm = 1e-3, (0.9, 0.999), 1e-8, 5.0
+    opt.exp_avg, opt.exp_avg_sq = torch.zeros(n), torch.zeros(n)
+    opt.step_count = torch.zeros(1)
+
+    ref = torch.optim.Adam(params, lr=3e-4)
+    g = torch.Generator().manual_seed(0)
+    for _ in range(3):
+        for p in params:
+            p.grad = torch.randn(p.shape, generator=g)
+        ref.step()
+    opt.load_state_dict(ref.state_dict())
+    assert opt.lr == 3e-4 and opt.step_count.item() == 3.0
+    off = 0
+    for i, p in enumerate(params):
+        assert torch.equal(opt.exp_avg[off:off + p.numel()].view_as(p), ref.state[p]["exp_avg"])
+        assert torch.equal(opt.exp_avg_sq[off:off + p.numel()].view_as(p), ref.state[p]["exp_avg_sq"])
+        off += p.numel()
+    ref2 = torch.optim.Adam(params, lr=1.0)
+    ref2.load_state_dict(opt.state_dict())  # torch validates the group / state structure
+    assert ref2.param_groups[0]["lr"] == 3e-4
+    for p in params:
+        assert torch.equal(ref2.state[p]["exp_avg"], ref.state[p]["exp_avg"]) and float(ref2.state[p]["step"]) == 3.0
+    for p in params:  # and the restored torch optimizer steps exactly like the original one
+        p.grad = torch.randn(p.shape, generator=g)
+    before = [p.detach().clone() for p in params]
+    ref.step()
+    after_ref = [p.detach().clone() for p in params]
+    with torch.no_grad():
+        for p, b in zip(params, before):
+            p.copy_(b)
+    ref2.step()
+    for p, a in zip(params, after_ref):
+        assert torch.equal(p.detach(), a)
+    with pytest.raises(ValueError):
+        opt.load_state_dict({"state": {}, "param_groups": [{"params": [0, 1], "lr": 1e-3, "betas": (0.9, 0.999), "eps": 1e-8}]})
+    opt.load_state_dict(torch.optim.Adam(params, lr=1e-3).state_dict())  # fresh optimizer: empty state
+    assert opt.step_count.item() == 0.0 and not opt.exp_avg.any()

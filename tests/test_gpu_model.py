@@ -171,6 +171,43 @@ def test_si_sdr_pit_loss(B, Ts, zero_mean):
 
 
 @pytest.mark.gpu
+def test_flat_clip_adam_resume_across_optimizers():
+    """Checkpoint / resume: FlatClipAdam.state_dict() is torch.optim.Adam's format (what Lightning stores), in both directions —
+    after two steps the two optimizers swap states and the third step still agrees to 2e-6."""
+    import copy
+
+    from nbss_b200.optim import FlatClipAdam
+
+    cfg = dict(O.SMALL_CFG, num_layers=1)
+    net = _net(cfg, O.synth_params(cfg, 13))
+    ref = copy.deepcopy(net)
+    ref_params = [p for _, p in ref.named_parameters()]
+    opt_ref = torch.optim.Adam(ref_params, lr=1e-3)
+    opt = FlatClipAdam(net, lr=1e-3, max_norm=5.0)
+    g = torch.Generator().manual_seed(5)
+    for it in range(3):
+        if it == 2:  # swap: each optimizer continues from the OTHER one's saved state
+            sd_flat, sd_torch = opt.state_dict(), copy.deepcopy(opt_ref.state_dict())
+            opt = FlatClipAdam(net, lr=7.0, max_norm=5.0)
+            opt.load_state_dict(sd_torch)
+            opt_ref = torch.optim.Adam(ref_params, lr=7.0)
+            opt_ref.load_state_dict(sd_flat)
+            assert opt.lr == 1e-3 and opt_ref.param_groups[0]["lr"] == 1e-3 and opt.step_count.item() == 2.0
+        x = torch.randn(1, 129, 24, 12, generator=g).cuda()
+        dy = 2e-4 * torch.randn(1, 129, 24, 4, generator=g).cuda()
+        opt.zero_grad(set_to_none=True)
+        net(x).backward(dy)
+        for (_, p1), p2 in zip(net.named_parameters(), ref_params):
+            p2.grad = p1.grad.detach().clone()
+        torch.nn.utils.clip_grad_norm_(ref_params, 5.0)
+        opt_ref.step()
+        opt.step()
+        torch.cuda.synchronize()
+        for (n1, p1), p2 in zip(net.named_parameters(), ref_params):
+            assert torch.allclose(p1, p2, rtol=0, atol=2e-6), (it, n1, (p1 - p2).abs().max().item())
+
+
+@pytest.mark.gpu
 def test_si_sdr_pit_loss_torchmetrics_known_answer():
     """csrc/loss.cu on the vector torchmetrics publishes in the doctest of permutation_invariant_training (the library
     models/io/loss.py:5-9 calls): best SI-SDR -5.1091 dB with the identity permutation (tests/golden/torchmetrics_kat.json)."""

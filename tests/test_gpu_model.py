@@ -297,6 +297,9 @@ def test_forward_against_the_unmodified_reference_module():
         assert O.rel_l2(orc, ref) < 2e-5
         e = O.rel_l2(y.cpu(), ref)
         assert e < 1e-3, f"rel-L2 vs the unmodified reference {e:.3e}"
-    finally:
+    finally:  # leave neither the path nor a partial `models` package behind for other tests
         if added and ref_dir in sys.path:
             sys.path.remove(ref_dir)
+        if added:
+            for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+                del sys.modules[k]

@@ -2,7 +2,7 @@
 
 The reference is a script repository without packaging metadata (no setup.py / pyproject.toml), so `pip install --target
 oracle/_ref /root/reference` has nothing to install; this script does what that install would have done for the path: it COPIES,
-byte for byte, the eight files `TrainModule.forward` executes from /root/reference into oracle/_ref/ — a directory
+byte for byte, the eight files `TrainModule.forward` executes and `models/arch/NBC2.py` from /root/reference into oracle/_ref/ — a directory
 that is git-ignored (no reference source enters the history) but travels to the GPU box with the snapshot — and writes their SHA-256
 next to them (MANIFEST.json).  `__graft_entry__.build()` runs it when /root/reference exists (in the build container); on the GPU box
 the already-copied files are used.  TEST / BASELINE INFRASTRUCTURE: only bench.py's `--impl reference` arm and its `cpu_baseline` leg
@@ -35,6 +35,7 @@ FILES = [
     "models/arch/base/linear_group.py",
     "models/io/stft.py",
     "models/io/norm.py",
+    "models/arch/NBC2.py",  # BASELINE configs[3] (§8 a14): only tests/test_gpu_nbc2.py compares against it
 ]
 
 

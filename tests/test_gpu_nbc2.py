@@ -75,3 +75,46 @@ def test_nbc2_state_dict_and_no_cpu_path():
         assert tuple(sd[k].shape) == tuple(shp), k
     with pytest.raises(Exception):
         net(torch.zeros(1, 9, 8, 16))
+
+
+@pytest.mark.gpu
+def test_nbc2_forward_against_the_unmodified_reference_module():
+    """Parity with the reference ITSELF on the GPU box: the unmodified `models.arch.NBC2.NBC2` (byte-for-byte copy in the git-ignored
+    oracle/_ref, oracle/make_ref.py) on the host in fp32, same case as test_nbc2_forward[(3, 33, 100)].  Skipped where oracle/_ref
+    was never built."""
+    import os
+    import sys
+
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "models", "arch", "NBC2.py")):
+        pytest.skip("oracle/_ref not built (no /root/reference where build() ran)")
+    added = ref_dir not in sys.path
+    if added:
+        sys.path.insert(0, ref_dir)
+    try:
+        try:
+            from models.arch.NBC2 import NBC2 as RefNBC2
+        except Exception as e:
+            pytest.skip(f"reference module not importable here: {type(e).__name__}: {e}")
+        B, F, T = 3, 33, 100
+        cfg = dict(N2.NBC2_SMALL, n_layers=8, num_freqs=F)
+        P = N2.synth_params(cfg, 11)
+        ref_net = RefNBC2(dim_input=16, dim_output=4, n_layers=8, dim_hidden=96, dim_ffn=192, num_freqs=F,
+                          block_kwargs={'n_heads': 2, 'dropout': 0, 'conv_kernel_size': 3, 'n_conv_groups': 8, 'norms': ("LN", "GBN", "GBN"),
+                                        'group_batch_norm_kwargs': {'share_along_sequence_dim': False}}).eval()  # NBC2.py:294-311
+        ref_net.load_state_dict({k: v.clone() for k, v in P.items()}, strict=True)
+        net = _net(cfg, P)
+        x = torch.randn(B, F, T, 16, generator=torch.Generator().manual_seed(F + T))
+        y = net(x.cuda())
+        torch.cuda.synchronize()
+        net.check_device_errors()
+        with torch.no_grad():
+            ref = ref_net(x)
+        e = O.rel_l2(y.cpu(), ref)
+        assert e < 1e-3, f"rel-L2 vs the unmodified reference {e:.3e}"
+    finally:
+        if added and ref_dir in sys.path:
+            sys.path.remove(ref_dir)
+        if added:
+            for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+                del sys.modules[k]

@@ -103,7 +103,7 @@ def cpu_oracle_subprocess(threads, reps, timeout_s=420):
         return None, None, f"cpu baseline unavailable: {type(e).__name__}", "port"
 
 
-REF_DIR = os.path.join(ROOT, "oracle", "_ref")  # unmodified reference files of the path (oracle/make_ref.py; git-ignored, travels)
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")  # unmodified reference files of the path (oracle/make_ref.py; git-ignored, travels)
 
 
 def reference_available() -> bool:
@@ -111,7 +111,7 @@ def reference_available() -> bool:
 
 
 def reference_modules(num_layers=None):
-    """The reference's own SpatialNet / STFT / Norm objects (imported from oracle/_ref, unmodified) carrying the oracle's synthetic
+    """The reference's own SpatialNet / STFT / Norm objects (imported from baseline/_ref, unmodified) carrying the oracle's synthetic
     parameters, plus TrainModule.forward (SharedTrainer.py:104-132) restated around them — 12 lines without arithmetic of their own;
     SharedTrainer.py itself needs pytorch_lightning, which the image does not have."""
     from oracle import spatialnet_oracle as O
@@ -144,7 +144,7 @@ def reference_modules(num_layers=None):
 
 
 def cpu_reference_step(threads, b=4, reps=2):
-    """One training pass of the path on the host cores through the UNMODIFIED reference modules when oracle/_ref holds them
+    """One training pass of the path on the host cores through the UNMODIFIED reference modules when baseline/_ref holds them
     (kind "reference"), else through the op-set port (kind "port").  Returns (frames/s, seconds, sample description, kind)."""
     if not reference_available():
         return cpu_oracle_step(threads, b, reps) + ("port",)
@@ -167,11 +167,11 @@ def cpu_reference_step(threads, b=4, reps=2):
         t = min(timed)
         note = f"1 warm-up + {len(ts) - 1} timed (best)" if len(ts) > 1 else "single cold pass (host too slow for a warm-up within the bound)"
         return (b * CFG["T"] / t, t, f"B={b} utterance(s) x T=250 frames, wave->wave fwd+bwd through the unmodified reference modules "
-                f"(oracle/_ref: models.arch.SpatialNet, models.io.stft / norm; TrainModule.forward glue and the torchmetrics loss restated), "
+                f"(baseline/_ref: models.arch.SpatialNet, models.io.stft / norm; TrainModule.forward glue and the torchmetrics loss restated), "
                 f"{threads} threads, {note}", "reference")
     except Exception as e:  # a broken copy must not take the arm down: fall back to the port and say so
         fps, t, sample = cpu_oracle_step(threads, b, reps)
-        return fps, t, sample + f" [oracle/_ref failed: {type(e).__name__}: {e}]"[:300], "port"
+        return fps, t, sample + f" [baseline/_ref failed: {type(e).__name__}: {e}]"[:300], "port"
 
 
 def cpu_oracle_step(threads, b=4, reps=2):

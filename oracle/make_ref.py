@@ -1,12 +1,12 @@
-"""Recipe for `oracle/_ref/`: the UNMODIFIED reference files of the hot path, for the CPU reference arm of bench.py.
+"""Recipe for `baseline/_ref/`: the UNMODIFIED reference files of the hot path, for the CPU reference arm of bench.py.
 
 The reference is a script repository without packaging metadata (no setup.py / pyproject.toml), so `pip install --target
-oracle/_ref /root/reference` has nothing to install; this script does what that install would have done for the path: it COPIES,
-byte for byte, the eight files `TrainModule.forward` executes and `models/arch/NBC2.py` from /root/reference into oracle/_ref/ — a directory
+baseline/_ref /root/reference` has nothing to install; this script does what that install would have done for the path: it COPIES,
+byte for byte, the eight files `TrainModule.forward` executes and `models/arch/NBC2.py` from /root/reference into baseline/_ref/ — a directory
 that is git-ignored (no reference source enters the history) but travels to the GPU box with the snapshot — and writes their SHA-256
 next to them (MANIFEST.json).  `__graft_entry__.build()` runs it when /root/reference exists (in the build container); on the GPU box
 the already-copied files are used.  TEST / BASELINE INFRASTRUCTURE: only bench.py's `--impl reference` arm and its `cpu_baseline` leg
-import from oracle/_ref; the product package never does.
+import from baseline/_ref; the product package never does.
 
     models/arch/SpatialNet.py                       the network                       (§8 a4-a9)
     models/arch/base/{norm,non_linear,linear_group}.py   its norm / activation / LinearGroup modules
@@ -39,8 +39,8 @@ FILES = [
 ]
 
 
-def make_ref(src: str = "/root/reference", dst: str = os.path.join(ROOT, "oracle", "_ref")) -> bool:
-    """Returns True when oracle/_ref holds the files (copied now, or already there and `src` is absent)."""
+def make_ref(src: str = "/root/reference", dst: str = os.path.join(ROOT, "baseline", "_ref")) -> bool:
+    """Returns True when baseline/_ref holds the files (copied now, or already there and `src` is absent)."""
     if not os.path.isdir(os.path.join(src, "models")):
         return os.path.exists(os.path.join(dst, "MANIFEST.json"))
     manifest = {}
@@ -56,4 +56,4 @@ def make_ref(src: str = "/root/reference", dst: str = os.path.join(ROOT, "oracle
 
 if __name__ == "__main__":
     ok = make_ref(*sys.argv[1:3])
-    print("oracle/_ref:", "ready" if ok else "unavailable (no /root/reference and no earlier copy)")
+    print("baseline/_ref:", "ready" if ok else "unavailable (no /root/reference and no earlier copy)")

@@ -18,24 +18,24 @@ def test_reference_arm_prints_one_json_line():
     assert len(lines) == 1, lines
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and KEYS <= set(d) and {"cores", "kind", "sample", "value"} <= set(d["cpu_baseline"])
-    # "reference" = the unmodified reference modules copied into oracle/_ref by oracle/make_ref.py (present wherever build() ran with
+    # "reference" = the unmodified reference modules copied into baseline/_ref by oracle/make_ref.py (present wherever build() ran with
     # /root/reference in reach); "port" = the op-set restatement, the fallback
-    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "MANIFEST.json"))
+    have_ref = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "MANIFEST.json"))
     assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port"), d["cpu_baseline"]
     assert d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0
 
 
 def test_reference_arm_modules_are_unmodified_and_agree_with_the_port():
-    """oracle/_ref (when present): every file still has the SHA-256 recorded when it was copied and — in the build container — is
+    """baseline/_ref (when present): every file still has the SHA-256 recorded when it was copied and — in the build container — is
     byte-identical to /root/reference; the copied modules + the restated TrainModule.forward compute what the op-set port computes."""
     import hashlib
 
     import pytest
     import torch
 
-    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
     if not os.path.exists(os.path.join(ref_dir, "MANIFEST.json")):
-        pytest.skip("oracle/_ref not built (no /root/reference here)")
+        pytest.skip("baseline/_ref not built (no /root/reference here)")
     man = json.load(open(os.path.join(ref_dir, "MANIFEST.json")))["files"]
     assert "models/arch/SpatialNet.py" in man and "models/io/stft.py" in man
     for rel, sha in man.items():

@@ -264,15 +264,15 @@ def test_flat_clip_adam_matches_torch():
 @pytest.mark.gpu
 def test_forward_against_the_unmodified_reference_module():
     """Parity with the reference ITSELF on the GPU box: the unmodified `models.arch.SpatialNet.SpatialNet` (byte-for-byte copy in the
-    git-ignored oracle/_ref, made by oracle/make_ref.py in the build container) runs on the host in fp32 on the input of
+    git-ignored baseline/_ref, made by oracle/make_ref.py in the build container) runs on the host in fp32 on the input of
     test_forward_small_6ch_f129[250]; the CUDA path is within 1e-3 of it, and the oracle within 2e-5 (what pins the oracle here too).
-    Skipped where oracle/_ref was never built."""
+    Skipped where baseline/_ref was never built."""
     import os
     import sys
 
-    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
     if not os.path.exists(os.path.join(ref_dir, "models", "arch", "SpatialNet.py")):
-        pytest.skip("oracle/_ref not built (no /root/reference where build() ran)")
+        pytest.skip("baseline/_ref not built (no /root/reference where build() ran)")
     added = ref_dir not in sys.path
     if added:
         sys.path.insert(0, ref_dir)

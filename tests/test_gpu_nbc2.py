@@ -80,14 +80,14 @@ def test_nbc2_state_dict_and_no_cpu_path():
 @pytest.mark.gpu
 def test_nbc2_forward_against_the_unmodified_reference_module():
     """Parity with the reference ITSELF on the GPU box: the unmodified `models.arch.NBC2.NBC2` (byte-for-byte copy in the git-ignored
-    oracle/_ref, oracle/make_ref.py) on the host in fp32, same case as test_nbc2_forward[(3, 33, 100)].  Skipped where oracle/_ref
+    baseline/_ref, oracle/make_ref.py) on the host in fp32, same case as test_nbc2_forward[(3, 33, 100)].  Skipped where baseline/_ref
     was never built."""
     import os
     import sys
 
-    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
     if not os.path.exists(os.path.join(ref_dir, "models", "arch", "NBC2.py")):
-        pytest.skip("oracle/_ref not built (no /root/reference where build() ran)")
+        pytest.skip("baseline/_ref not built (no /root/reference where build() ran)")
     added = ref_dir not in sys.path
     if added:
         sys.path.insert(0, ref_dir)
